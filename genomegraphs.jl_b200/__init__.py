@@ -1,0 +1,12 @@
+"""genomegraphs.jl_b200 -- B200-native (sm_100a) de Bruijn graph construction path of
+GenomeGraphs.jl: hand-written CUDA kernels behind a C ABI (libggb200.so), a Python host
+mirror of the Julia call surface (host.py) and the Julia host files (julia/).
+
+The directory name carries a dot, so import it through `__graft_entry__.load_package()`
+(registered in sys.modules as `genomegraphs_b200`).
+"""
+from . import _native  # noqa: F401
+from .host import *  # noqa: F401,F403
+from .host import (CANONICAL, NONCANONICAL, Context, GraphArrays, GraphStrandPosition, MerCounts, SDGLink, SDGNode,  # noqa: F401
+                   SequenceDistanceGraph, UniqueMerIndex, dbg_, dbg_arrays, dbg_from_reads, empty_graph, extract_kmers, freq,
+                   mer, pack_reads, serial_mem, spectra, synth_genome, synth_reads)

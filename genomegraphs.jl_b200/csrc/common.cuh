@@ -1,0 +1,264 @@
+// common.cuh -- context, error handling, stream-ordered allocation, k-mer word type.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/ggb200.h"
+
+typedef uint8_t u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef int64_t i64;
+
+#define GG_NSTAGE 9
+enum { ST_PACK = 0, ST_EXTRACT, ST_SORT, ST_COUNT, ST_FILTER, ST_LOOKUP, ST_UNITIG, ST_LINKS, ST_TOTAL };
+
+struct gg_ctx {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    // timing of the last pipeline call
+    cudaEvent_t ev[2 * GG_NSTAGE];
+    bool ev_used[GG_NSTAGE];
+    float ms[GG_NSTAGE];
+    u64 launches = 0;
+    // small pinned scratch for device->host scalars
+    u64 *h_scalar = nullptr;  // 64 x u64
+};
+
+struct GgError {
+    int code;
+    std::string msg;
+};
+
+#define GG_THROW(code, ...)                                   \
+    do {                                                      \
+        char _b[512];                                         \
+        snprintf(_b, sizeof(_b), __VA_ARGS__);                \
+        throw GgError{code, std::string(_b)};                 \
+    } while (0)
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t _e = (call);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            GG_THROW(_e == cudaErrorMemoryAllocation ? GG_ERR_OOM : GG_ERR_CUDA, "%s:%d %s: %s", \
+                     __FILE__, __LINE__, #call, cudaGetErrorString(_e));                      \
+    } while (0)
+
+// every kernel launch goes through this so that gpu_launches can be reported
+#define LAUNCH(ctx, kernel, grid, block, smem, ...)                                  \
+    do {                                                                             \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);             \
+        (ctx)->launches++;                                                           \
+        CK(cudaGetLastError());                                                      \
+    } while (0)
+
+static inline u64 ceil_div(u64 a, u64 b) { return (a + b - 1) / b; }
+
+// stream-ordered allocation from the device's default memory pool (cached: the release
+// threshold is raised in gg_ctx_create, so steady-state calls do not hit the driver)
+template <class T>
+static T *dalloc(gg_ctx *ctx, u64 count) {
+    void *p = nullptr;
+    u64 bytes = count * sizeof(T);
+    if (bytes == 0) bytes = 16;
+    CK(cudaMallocAsync(&p, bytes, ctx->stream));
+    return (T *)p;
+}
+static inline void dfree(gg_ctx *ctx, void *p) {
+    if (p) cudaFreeAsync(p, ctx->stream);
+}
+// RAII temp buffer
+template <class T>
+struct DBuf {
+    gg_ctx *ctx = nullptr;
+    T *p = nullptr;
+    u64 n = 0;
+    DBuf() {}
+    DBuf(gg_ctx *c, u64 count) : ctx(c), n(count) { p = dalloc<T>(c, count); }
+    DBuf(const DBuf &) = delete;
+    DBuf &operator=(const DBuf &) = delete;
+    DBuf(DBuf &&o) noexcept : ctx(o.ctx), p(o.p), n(o.n) { o.p = nullptr; }
+    DBuf &operator=(DBuf &&o) noexcept {
+        if (this != &o) { release(); ctx = o.ctx; p = o.p; n = o.n; o.p = nullptr; }
+        return *this;
+    }
+    void alloc(gg_ctx *c, u64 count) { release(); ctx = c; n = count; p = dalloc<T>(c, count); }
+    void release() { if (p) { dfree(ctx, p); p = nullptr; } }
+    T *take() { T *r = p; p = nullptr; return r; }
+    ~DBuf() { release(); }
+};
+
+static inline void stage_begin(gg_ctx *ctx, int s) {
+    if (!ctx->ev_used[s]) { cudaEventRecord(ctx->ev[2 * s], ctx->stream); ctx->ev_used[s] = true; }
+}
+static inline void stage_end(gg_ctx *ctx, int s) { cudaEventRecord(ctx->ev[2 * s + 1], ctx->stream); }
+
+// read a device scalar (blocking on the context's stream)
+template <class T>
+static T read_scalar(gg_ctx *ctx, const T *d) {
+    CK(cudaMemcpyAsync(ctx->h_scalar, d, sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    T v;
+    memcpy(&v, ctx->h_scalar, sizeof(T));
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// k-mer value: W little-endian u64 words, w[0] MOST significant; 2k bits right-aligned.
+// ------------------------------------------------------------------------------------------
+template <int W>
+struct Kmer {
+    u64 w[W];
+};
+
+__host__ __device__ __forceinline__ u64 rev2_u64(u64 x) {  // reverse the 32 2-bit groups
+#ifdef __CUDA_ARCH__
+    u64 y = __brevll(x);
+    return ((y >> 1) & 0x5555555555555555ULL) | ((y & 0x5555555555555555ULL) << 1);
+#else
+    x = __builtin_bswap64(x);
+    x = ((x >> 4) & 0x0F0F0F0F0F0F0F0FULL) | ((x & 0x0F0F0F0F0F0F0F0FULL) << 4);
+    x = ((x >> 2) & 0x3333333333333333ULL) | ((x & 0x3333333333333333ULL) << 2);
+    return x;
+#endif
+}
+
+template <int W>
+__host__ __device__ __forceinline__ int km_cmp(const Kmer<W> &a, const Kmer<W> &b) {
+#pragma unroll
+    for (int i = 0; i < W; ++i)
+        if (a.w[i] != b.w[i]) return a.w[i] < b.w[i] ? -1 : 1;
+    return 0;
+}
+template <int W>
+__host__ __device__ __forceinline__ bool km_eq(const Kmer<W> &a, const Kmer<W> &b) {
+    bool e = true;
+#pragma unroll
+    for (int i = 0; i < W; ++i) e = e && (a.w[i] == b.w[i]);
+    return e;
+}
+template <int W>
+__host__ __device__ __forceinline__ bool km_lt(const Kmer<W> &a, const Kmer<W> &b) { return km_cmp(a, b) < 0; }
+
+// logical right shift of the W*64-bit value by s bits (0 <= s < 64*W)
+template <int W>
+__host__ __device__ __forceinline__ Kmer<W> km_shr(const Kmer<W> &x, int s) {
+    Kmer<W> r;
+    int ws = s >> 6, bs = s & 63;
+#pragma unroll
+    for (int i = W - 1; i >= 0; --i) {
+        u64 lo = 0, hi = 0;
+#pragma unroll
+        for (int j = 0; j < W; ++j) {  // select without dynamic register indexing
+            if (j == i - ws) lo = x.w[j];
+            if (j == i - ws - 1) hi = x.w[j];
+        }
+        r.w[i] = bs ? ((lo >> bs) | (hi << (64 - bs))) : lo;
+    }
+    return r;
+}
+// low 2k bits mask applied in place
+template <int W>
+__host__ __device__ __forceinline__ Kmer<W> km_mask(const Kmer<W> &x, int k) {
+    Kmer<W> r;
+    int bits = 2 * k;
+#pragma unroll
+    for (int i = W - 1; i >= 0; --i) {
+        int b = bits - 64 * (W - 1 - i);  // bits available to word i
+        u64 m = b >= 64 ? ~0ULL : (b > 0 ? ((1ULL << b) - 1) : 0ULL);
+        r.w[i] = x.w[i] & m;
+    }
+    return r;
+}
+template <int W>
+__host__ __device__ __forceinline__ Kmer<W> km_rc(const Kmer<W> &x, int k) {
+    Kmer<W> t;
+#pragma unroll
+    for (int i = 0; i < W; ++i) t.w[W - 1 - i] = rev2_u64(~x.w[i]);
+    return km_shr<W>(t, 64 * W - 2 * k);
+}
+// ((x << 2) | b) masked to 2k bits : forward neighbour (src/dbg.jl:30-34)
+template <int W>
+__host__ __device__ __forceinline__ Kmer<W> km_fw_nb(const Kmer<W> &x, u32 b, int k) {
+    Kmer<W> r;
+#pragma unroll
+    for (int i = 0; i < W; ++i) r.w[i] = (x.w[i] << 2) | ((i + 1 < W) ? (x.w[i + 1] >> 62) : (u64)b);
+    return km_mask<W>(r, k);
+}
+// (x >> 2) | (b << 2(k-1)) : backward neighbour (src/dbg.jl:36-42)
+template <int W>
+__host__ __device__ __forceinline__ Kmer<W> km_bw_nb(const Kmer<W> &x, u32 b, int k) {
+    Kmer<W> r;
+#pragma unroll
+    for (int i = W - 1; i >= 0; --i) r.w[i] = (x.w[i] >> 2) | ((i > 0) ? (x.w[i - 1] << 62) : 0ULL);
+    int pos = 2 * (k - 1);
+#pragma unroll
+    for (int i = 0; i < W; ++i)
+        if (i == W - 1 - (pos >> 6)) r.w[i] |= ((u64)b) << (pos & 63);
+    return r;
+}
+// 2-bit code of base j (0 = first base) of a k-mer
+template <int W>
+__host__ __device__ __forceinline__ u32 km_base(const Kmer<W> &x, int j, int k) {
+    int pos = 2 * (k - 1 - j);
+    u64 v = 0;
+#pragma unroll
+    for (int i = 0; i < W; ++i)
+        if (i == W - 1 - (pos >> 6)) v = x.w[i];
+    return (u32)((v >> (pos & 63)) & 3ULL);
+}
+template <int W>
+__host__ __device__ __forceinline__ Kmer<W> km_load(const u64 *p, u64 i) {
+    Kmer<W> r;
+#pragma unroll
+    for (int j = 0; j < W; ++j) r.w[j] = p[i * W + j];
+    return r;
+}
+template <int W>
+__host__ __device__ __forceinline__ void km_store(u64 *p, u64 i, const Kmer<W> &x) {
+#pragma unroll
+    for (int j = 0; j < W; ++j) p[i * W + j] = x.w[j];
+}
+#ifdef __CUDACC__
+// vectorised variants (keys are 8*W-byte aligned)
+template <>
+__device__ __forceinline__ Kmer<2> km_load<2>(const u64 *p, u64 i) {
+    ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(p + i * 2);
+    Kmer<2> r; r.w[0] = v.x; r.w[1] = v.y; return r;
+}
+template <>
+__device__ __forceinline__ void km_store<2>(u64 *p, u64 i, const Kmer<2> &x) {
+    *reinterpret_cast<ulonglong2 *>(p + i * 2) = make_ulonglong2(x.w[0], x.w[1]);
+}
+template <>
+__device__ __forceinline__ Kmer<4> km_load<4>(const u64 *p, u64 i) {
+    const ulonglong2 *q = reinterpret_cast<const ulonglong2 *>(p + i * 4);
+    ulonglong2 a = q[0], b = q[1];
+    Kmer<4> r; r.w[0] = a.x; r.w[1] = a.y; r.w[2] = b.x; r.w[3] = b.y; return r;
+}
+template <>
+__device__ __forceinline__ void km_store<4>(u64 *p, u64 i, const Kmer<4> &x) {
+    ulonglong2 *q = reinterpret_cast<ulonglong2 *>(p + i * 4);
+    q[0] = make_ulonglong2(x.w[0], x.w[1]);
+    q[1] = make_ulonglong2(x.w[2], x.w[3]);
+}
+#endif
+
+static inline int kmer_words(int k) { return k < 1 ? 0 : k <= 32 ? 1 : k <= 64 ? 2 : k <= 128 ? 4 : 0; }
+
+#define DISPATCH_W(W_, ...)                              \
+    switch (W_) {                                        \
+        case 1: { constexpr int W = 1; __VA_ARGS__; } break; \
+        case 2: { constexpr int W = 2; __VA_ARGS__; } break; \
+        case 4: { constexpr int W = 4; __VA_ARGS__; } break; \
+        default: GG_THROW(GG_ERR_ARG, "unsupported word count %d", (int)(W_)); \
+    }

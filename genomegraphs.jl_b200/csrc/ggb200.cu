@@ -1,0 +1,561 @@
+// ggb200.cu -- C ABI of libggb200.so (see include/ggb200.h).  Single translation unit:
+// the kernels live in the .cuh files included below.
+#include "common.cuh"
+#include "prims.cuh"
+#include "pack.cuh"
+#include "sort.cuh"
+#include "graph.cuh"
+#include "umi.cuh"
+#include "synth.cuh"
+
+struct gg_counts {
+    gg_ctx *ctx = nullptr;
+    int k = 0, W = 0;
+    u64 n_unique = 0, n_instances = 0;
+    u64 *d_keys = nullptr;   // n_unique * W, sorted ascending
+    u32 *d_counts = nullptr; // n_unique
+};
+
+#define API_BEGIN(ctx_) \
+    gg_ctx *_c = (ctx_); \
+    if (!_c) return GG_ERR_ARG; \
+    try {
+#define API_END \
+    } catch (const GgError &e) { \
+        _c->err = e.msg; \
+        cudaGetLastError(); \
+        return e.code; \
+    } catch (const std::bad_alloc &) { \
+        _c->err = "host allocation failed"; \
+        return GG_ERR_OOM; \
+    } catch (...) { \
+        _c->err = "unknown failure"; \
+        return GG_ERR_CUDA; \
+    } \
+    return GG_OK;
+
+static void timing_reset(gg_ctx *ctx) {
+    for (int i = 0; i < GG_NSTAGE; ++i) { ctx->ev_used[i] = false; ctx->ms[i] = 0.f; }
+    ctx->launches = 0;
+}
+static void timing_collect(gg_ctx *ctx) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < GG_NSTAGE; ++i)
+        if (ctx->ev_used[i]) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ctx->ev[2 * i], ctx->ev[2 * i + 1]) == cudaSuccess) ctx->ms[i] = ms;
+        }
+}
+
+extern "C" {
+
+int gg_version(void) { return 100; }
+int gg_kmer_words(int k) { return kmer_words(k); }
+
+int gg_ctx_create(int device, gg_ctx **out) {
+    if (!out) return GG_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return GG_ERR_CUDA;  // no CPU fallback
+    }
+    gg_ctx *ctx = new (std::nothrow) gg_ctx();
+    if (!ctx) return GG_ERR_OOM;
+    ctx->device = device;
+    try {
+        CK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        ctx->num_sms = prop.multiProcessorCount;
+        CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2 * GG_NSTAGE; ++i) CK(cudaEventCreate(&ctx->ev[i]));
+        CK(cudaHostAlloc((void **)&ctx->h_scalar, 64 * sizeof(u64), cudaHostAllocDefault));
+        cudaMemPool_t pool;
+        CK(cudaDeviceGetDefaultMemPool(&pool, device));
+        u64 thr = ~0ULL;  // keep freed blocks cached in the pool
+        CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        timing_reset(ctx);
+    } catch (const GgError &) {
+        delete ctx;
+        cudaGetLastError();
+        return GG_ERR_CUDA;
+    }
+    *out = ctx;
+    return GG_OK;
+}
+void gg_ctx_destroy(gg_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < 2 * GG_NSTAGE; ++i) cudaEventDestroy(ctx->ev[i]);
+    cudaFreeHost(ctx->h_scalar);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+const char *gg_last_error(gg_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int gg_host_alloc(gg_ctx *ctx, uint64_t bytes, void **out) {
+    API_BEGIN(ctx)
+    if (!out) GG_THROW(GG_ERR_ARG, "null output");
+    CK(cudaSetDevice(_c->device));
+    CK(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    API_END
+}
+void gg_host_free(gg_ctx *ctx, void *p) { (void)ctx; if (p) cudaFreeHost(p); }
+int gg_dev_alloc(gg_ctx *ctx, uint64_t bytes, void **out) {
+    API_BEGIN(ctx)
+    if (!out) GG_THROW(GG_ERR_ARG, "null output");
+    CK(cudaSetDevice(_c->device));
+    CK(cudaMalloc(out, bytes ? bytes : 16));
+    API_END
+}
+void gg_dev_free(gg_ctx *ctx, void *p) { (void)ctx; if (p) cudaFree(p); }
+int gg_memcpy_h2d(gg_ctx *ctx, void *dst, const void *src, uint64_t bytes) {
+    API_BEGIN(ctx)
+    CK(cudaSetDevice(_c->device));
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, _c->stream));
+    CK(cudaStreamSynchronize(_c->stream));
+    API_END
+}
+int gg_memcpy_d2h(gg_ctx *ctx, void *dst, const void *src, uint64_t bytes) {
+    API_BEGIN(ctx)
+    CK(cudaSetDevice(_c->device));
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, _c->stream));
+    CK(cudaStreamSynchronize(_c->stream));
+    API_END
+}
+int gg_ctx_last_timings(gg_ctx *ctx, float ms[9], uint64_t *kernel_launches) {
+    if (!ctx) return GG_ERR_ARG;
+    if (ms) for (int i = 0; i < GG_NSTAGE; ++i) ms[i] = ctx->ms[i];
+    if (kernel_launches) *kernel_launches = ctx->launches;
+    return GG_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------ pipelines -------------------------------------------
+static void check_k(int k) {
+    if (kmer_words(k) == 0) GG_THROW(GG_ERR_ARG, "k = %d is outside 1..%d", k, GG_MAX_K);
+}
+
+// device reads -> all k-mers in read order (device), returns N
+template <int W>
+static u64 extract_all(gg_ctx *ctx, const u8 *d_seq, const u64 *d_offs, u64 nreads, u64 nbytes, int k, int canonical, DBuf<u64> &keys, u64 extra_words) {
+    stage_begin(ctx, ST_PACK);
+    PackedReads pr;
+    pack_reads(ctx, d_seq, d_offs, nreads, nbytes, pr);
+    DBuf<u32> valid;
+    window_valid_mask(ctx, pr, k, valid);
+    stage_end(ctx, ST_PACK);
+    stage_begin(ctx, ST_EXTRACT);
+    ExtractF<W> ef{valid.p, pr.packed.p, nullptr, k, canonical};
+    Compactor<ExtractF<W>> cp(ctx, nbytes);
+    u64 n = cp.count(ef);
+    keys.alloc(ctx, n * W + extra_words);
+    ef.out = keys.p;
+    cp.emit(ef);
+    stage_end(ctx, ST_EXTRACT);
+    return n;
+}
+
+template <int W>
+static gg_counts *count_kmers_dev_impl(gg_ctx *ctx, const u8 *d_seq, const u64 *d_offs, u64 nreads, u64 nbytes, int k, int canonical) {
+    gg_counts *c = new gg_counts();
+    c->ctx = ctx; c->k = k; c->W = W;
+    try {
+        DBuf<u64> keys;
+        u64 n = extract_all<W>(ctx, d_seq, d_offs, nreads, nbytes, k, canonical, keys, 0);
+        c->n_instances = n;
+        stage_begin(ctx, ST_SORT);
+        DBuf<u64> alt(ctx, n * W);
+        u64 *a = keys.p, *b = alt.p;
+        std::vector<BitRange> ranges = {{0, 2 * k}};
+        radix_sort<W>(ctx, &a, &b, nullptr, nullptr, n, ranges);
+        stage_end(ctx, ST_SORT);
+        stage_begin(ctx, ST_COUNT);
+        DBuf<u64> ukeys;
+        DBuf<u32> counts;
+        c->n_unique = run_length_count<W>(ctx, a, n, ukeys, counts);
+        c->d_keys = ukeys.take();
+        c->d_counts = counts.take();
+        stage_end(ctx, ST_COUNT);
+        return c;
+    } catch (...) {
+        dfree(ctx, c->d_keys); dfree(ctx, c->d_counts);
+        delete c;
+        throw;
+    }
+}
+
+template <int W>
+static void filter_impl(gg_counts *c, u64 min_freq, int u8sat) {
+    gg_ctx *ctx = c->ctx;
+    stage_begin(ctx, ST_FILTER);
+    FilterF<W> f{c->d_keys, c->d_counts, nullptr, nullptr, min_freq, u8sat};
+    Compactor<FilterF<W>> cp(ctx, c->n_unique);
+    u64 nk = cp.count(f);
+    DBuf<u64> okeys(ctx, nk * W);
+    DBuf<u32> ocounts(ctx, nk);
+    f.okeys = okeys.p; f.ocounts = ocounts.p;
+    cp.emit(f);
+    dfree(ctx, c->d_keys); dfree(ctx, c->d_counts);
+    c->d_keys = okeys.take();
+    c->d_counts = ocounts.take();
+    c->n_unique = nk;
+    stage_end(ctx, ST_FILTER);
+}
+
+template <int W>
+__global__ void is_sorted_kernel(const u64 *__restrict__ keys, u64 n, u32 *__restrict__ flag) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i + 1 >= n) return;
+    if (km_cmp<W>(km_load<W>(keys, i), km_load<W>(keys, i + 1)) > 0) *flag = 1;
+}
+
+// stage device input from host buffers (padded so that 128-bit loads stay in bounds)
+struct StagedReads {
+    DBuf<u8> seq;
+    DBuf<u64> offs;
+    u64 nbytes = 0;
+};
+static void stage_reads(gg_ctx *ctx, const u8 *seq, const u64 *offs, u64 nreads, StagedReads &s) {
+    if (!offs) GG_THROW(GG_ERR_ARG, "read_offsets is null");
+    s.nbytes = offs[nreads];
+    for (u64 i = 0; i < nreads; ++i)
+        if (offs[i] > offs[i + 1]) GG_THROW(GG_ERR_ARG, "read_offsets must be non-decreasing (read %llu)", (unsigned long long)i);
+    if (s.nbytes && !seq) GG_THROW(GG_ERR_ARG, "seq_bytes is null");
+    s.seq.alloc(ctx, s.nbytes + 32);
+    s.offs.alloc(ctx, nreads + 1);
+    if (s.nbytes) CK(cudaMemcpyAsync(s.seq.p, seq, s.nbytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(s.offs.p, offs, (nreads + 1) * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+}
+
+extern "C" {
+
+int gg_count_kmers_dev(gg_ctx *ctx, const uint8_t *d_seq, const uint64_t *d_offs, uint64_t nreads, uint64_t nbytes, int k,
+                       int canonical, gg_counts **out) {
+    API_BEGIN(ctx)
+    if (!out) GG_THROW(GG_ERR_ARG, "null output");
+    *out = nullptr;
+    check_k(k);
+    CK(cudaSetDevice(_c->device));
+    timing_reset(_c);
+    stage_begin(_c, ST_TOTAL);
+    DISPATCH_W(kmer_words(k), *out = count_kmers_dev_impl<W>(_c, d_seq, d_offs, nreads, nbytes, k, canonical));
+    stage_end(_c, ST_TOTAL);
+    timing_collect(_c);
+    API_END
+}
+int gg_count_kmers(gg_ctx *ctx, const uint8_t *seq, const uint64_t *offs, uint64_t nreads, int k, int canonical, gg_counts **out) {
+    API_BEGIN(ctx)
+    if (!out) GG_THROW(GG_ERR_ARG, "null output");
+    *out = nullptr;
+    check_k(k);
+    CK(cudaSetDevice(_c->device));
+    timing_reset(_c);
+    StagedReads s;
+    stage_reads(_c, seq, offs, nreads, s);
+    stage_begin(_c, ST_TOTAL);
+    DISPATCH_W(kmer_words(k), *out = count_kmers_dev_impl<W>(_c, s.seq.p, s.offs.p, nreads, s.nbytes, k, canonical));
+    stage_end(_c, ST_TOTAL);
+    timing_collect(_c);
+    API_END
+}
+int gg_counts_from_kmers(gg_ctx *ctx, const uint64_t *words, const uint32_t *counts, uint64_t n, int k, gg_counts **out) {
+    API_BEGIN(ctx)
+    if (!out) GG_THROW(GG_ERR_ARG, "null output");
+    *out = nullptr;
+    check_k(k);
+    if (n && !words) GG_THROW(GG_ERR_ARG, "kmer_words is null");
+    CK(cudaSetDevice(_c->device));
+    int W = kmer_words(k);
+    gg_counts *c = new gg_counts();
+    c->ctx = _c; c->k = k; c->W = W; c->n_unique = n; c->n_instances = n;
+    try {
+        DBuf<u64> keys(_c, n * W), alt(_c, n * W), pay, pay_alt;
+        DBuf<u32> cnt(_c, n);
+        if (n) CK(cudaMemcpyAsync(keys.p, words, n * W * sizeof(u64), cudaMemcpyHostToDevice, _c->stream));
+        if (n && counts) CK(cudaMemcpyAsync(cnt.p, counts, n * sizeof(u32), cudaMemcpyHostToDevice, _c->stream));
+        else if (n) LAUNCH(_c, fill_counts_kernel, (unsigned)ceil_div(n, 256), 256, 0, cnt.p, n, 1u);
+        // issorted(kmerlist) || sort!(kmerlist)  (src/dbg.jl:98-100)
+        DBuf<u32> flag(_c, 1);
+        CK(cudaMemsetAsync(flag.p, 0, sizeof(u32), _c->stream));
+        if (n > 1) {
+            DISPATCH_W(W, LAUNCH(_c, is_sorted_kernel<W>, (unsigned)ceil_div(n, 256), 256, 0, keys.p, n, flag.p));
+        }
+        u64 *a = keys.p, *b = alt.p;
+        if (n > 1 && read_scalar<u32>(_c, flag.p)) {
+            if (counts) GG_THROW(GG_ERR_ARG, "k-mers with counts must be sorted ascending");
+            std::vector<BitRange> ranges = {{0, 2 * k}};
+            DISPATCH_W(W, radix_sort<W>(_c, &a, &b, nullptr, nullptr, n, ranges));
+        }
+        if (a == keys.p) { c->d_keys = keys.take(); } else { c->d_keys = alt.take(); }
+        c->d_counts = cnt.take();
+        CK(cudaStreamSynchronize(_c->stream));
+    } catch (...) {
+        delete c;
+        throw;
+    }
+    *out = c;
+    API_END
+}
+int gg_counts_sizes(gg_counts *c, uint64_t *n_unique, uint64_t *n_instances, int *k, int *words) {
+    if (!c) return GG_ERR_ARG;
+    if (n_unique) *n_unique = c->n_unique;
+    if (n_instances) *n_instances = c->n_instances;
+    if (k) *k = c->k;
+    if (words) *words = c->W;
+    return GG_OK;
+}
+int gg_counts_filter(gg_counts *c, uint64_t min_freq, int u8_saturated) {
+    if (!c) return GG_ERR_ARG;
+    API_BEGIN(c->ctx)
+    CK(cudaSetDevice(_c->device));
+    DISPATCH_W(c->W, filter_impl<W>(c, min_freq, u8_saturated));
+    CK(cudaStreamSynchronize(_c->stream));
+    API_END
+}
+__global__ void sat_u8_kernel(const u32 *__restrict__ in, u64 n, u8 *__restrict__ out) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (u8)(in[i] > 255u ? 255u : in[i]);
+}
+int gg_counts_export(gg_counts *c, uint64_t *kmer_words_out, uint8_t *counts_u8, uint32_t *counts_u32) {
+    if (!c) return GG_ERR_ARG;
+    API_BEGIN(c->ctx)
+    CK(cudaSetDevice(_c->device));
+    u64 n = c->n_unique;
+    if (n && kmer_words_out) CK(cudaMemcpyAsync(kmer_words_out, c->d_keys, n * c->W * sizeof(u64), cudaMemcpyDeviceToHost, _c->stream));
+    if (n && counts_u32) CK(cudaMemcpyAsync(counts_u32, c->d_counts, n * sizeof(u32), cudaMemcpyDeviceToHost, _c->stream));
+    if (n && counts_u8) {
+        DBuf<u8> t(_c, n);
+        LAUNCH(_c, sat_u8_kernel, (unsigned)ceil_div(n, 256), 256, 0, c->d_counts, n, t.p);
+        CK(cudaMemcpyAsync(counts_u8, t.p, n, cudaMemcpyDeviceToHost, _c->stream));
+        CK(cudaStreamSynchronize(_c->stream));
+    }
+    CK(cudaStreamSynchronize(_c->stream));
+    API_END
+}
+int gg_counts_spectrum(gg_counts *c, uint64_t hist[256]) {
+    if (!c || !hist) return GG_ERR_ARG;
+    API_BEGIN(c->ctx)
+    CK(cudaSetDevice(_c->device));
+    DBuf<u64> h(_c, 256);
+    CK(cudaMemsetAsync(h.p, 0, 256 * sizeof(u64), _c->stream));
+    if (c->n_unique) {
+        u64 blocks = ceil_div(c->n_unique, 256 * 16);
+        if (blocks > (u64)_c->num_sms * 8) blocks = (u64)_c->num_sms * 8;
+        LAUNCH(_c, spectrum_kernel, (unsigned)blocks, 256, 0, c->d_counts, c->n_unique, (unsigned long long *)h.p);
+    }
+    CK(cudaMemcpyAsync(hist, h.p, 256 * sizeof(u64), cudaMemcpyDeviceToHost, _c->stream));
+    CK(cudaStreamSynchronize(_c->stream));
+    API_END
+}
+void gg_counts_free(gg_counts *c) {
+    if (!c) return;
+    cudaSetDevice(c->ctx->device);
+    dfree(c->ctx, c->d_keys);
+    dfree(c->ctx, c->d_counts);
+    delete c;
+}
+
+int gg_extract_kmers(gg_ctx *ctx, const uint8_t *seq, const uint64_t *offs, uint64_t nreads, int k, int canonical,
+                     uint64_t *out_words, uint64_t *n_kmers) {
+    API_BEGIN(ctx)
+    if (!n_kmers) GG_THROW(GG_ERR_ARG, "n_kmers is null");
+    check_k(k);
+    CK(cudaSetDevice(_c->device));
+    timing_reset(_c);
+    StagedReads s;
+    stage_reads(_c, seq, offs, nreads, s);
+    int W = kmer_words(k);
+    DBuf<u64> keys;
+    u64 n = 0;
+    DISPATCH_W(W, n = extract_all<W>(_c, s.seq.p, s.offs.p, nreads, s.nbytes, k, canonical, keys, 0));
+    if (out_words && n) {
+        if (*n_kmers < n) GG_THROW(GG_ERR_ARG, "output holds %llu k-mers, %llu needed", (unsigned long long)*n_kmers, (unsigned long long)n);
+        CK(cudaMemcpyAsync(out_words, keys.p, n * W * sizeof(u64), cudaMemcpyDeviceToHost, _c->stream));
+    }
+    CK(cudaStreamSynchronize(_c->stream));
+    *n_kmers = n;
+    API_END
+}
+
+// ------------------------------------- graph ----------------------------------------------
+int gg_dbg_build(gg_ctx *ctx, gg_counts *counts, gg_graph **out) {
+    API_BEGIN(ctx)
+    if (!out || !counts) GG_THROW(GG_ERR_ARG, "null argument");
+    *out = nullptr;
+    CK(cudaSetDevice(_c->device));
+    timing_reset(_c);
+    stage_begin(_c, ST_TOTAL);
+    DISPATCH_W(counts->W, *out = build_graph<W>(_c, counts->d_keys, counts->n_unique, counts->k));
+    stage_end(_c, ST_TOTAL);
+    timing_collect(_c);
+    API_END
+}
+static void dbg_from_reads_dev(gg_ctx *ctx, const u8 *d_seq, const u64 *d_offs, u64 nreads, u64 nbytes, int k, u64 min_freq, gg_graph **out) {
+    gg_counts *c = nullptr;
+    stage_begin(ctx, ST_TOTAL);
+    DISPATCH_W(kmer_words(k), c = count_kmers_dev_impl<W>(ctx, d_seq, d_offs, nreads, nbytes, k, 1));
+    try {
+        DISPATCH_W(c->W, filter_impl<W>(c, min_freq, 0));
+        DISPATCH_W(c->W, *out = build_graph<W>(ctx, c->d_keys, c->n_unique, c->k));
+    } catch (...) {
+        gg_counts_free(c);
+        throw;
+    }
+    gg_counts_free(c);
+    stage_end(ctx, ST_TOTAL);
+    timing_collect(ctx);
+}
+int gg_dbg_from_reads_dev(gg_ctx *ctx, const uint8_t *d_seq, const uint64_t *d_offs, uint64_t nreads, uint64_t nbytes, int k,
+                          uint64_t min_freq, gg_graph **out) {
+    API_BEGIN(ctx)
+    if (!out) GG_THROW(GG_ERR_ARG, "null output");
+    *out = nullptr;
+    check_k(k);
+    CK(cudaSetDevice(_c->device));
+    timing_reset(_c);
+    dbg_from_reads_dev(_c, d_seq, d_offs, nreads, nbytes, k, min_freq, out);
+    API_END
+}
+int gg_dbg_from_reads(gg_ctx *ctx, const uint8_t *seq, const uint64_t *offs, uint64_t nreads, int k, uint64_t min_freq, gg_graph **out) {
+    API_BEGIN(ctx)
+    if (!out) GG_THROW(GG_ERR_ARG, "null output");
+    *out = nullptr;
+    check_k(k);
+    CK(cudaSetDevice(_c->device));
+    timing_reset(_c);
+    StagedReads s;
+    stage_reads(_c, seq, offs, nreads, s);
+    dbg_from_reads_dev(_c, s.seq.p, s.offs.p, nreads, s.nbytes, k, min_freq, out);
+    API_END
+}
+int gg_graph_sizes(gg_graph *g, uint64_t *n_nodes, uint64_t *total_bases, uint64_t *n_link_entries, int *k) {
+    if (!g) return GG_ERR_ARG;
+    if (n_nodes) *n_nodes = g->n_nodes;
+    if (total_bases) *total_bases = g->total_bases;
+    if (n_link_entries) *n_link_entries = g->n_link_entries;
+    if (k) *k = g->k;
+    return GG_OK;
+}
+int gg_graph_export(gg_graph *g, uint64_t *node_offsets, uint8_t *bases_ascii, uint64_t *link_row_offsets, int64_t *link_triples) {
+    if (!g) return GG_ERR_ARG;
+    API_BEGIN(g->ctx)
+    CK(cudaSetDevice(_c->device));
+    if (node_offsets) CK(cudaMemcpyAsync(node_offsets, g->d_node_off, (g->n_nodes + 1) * sizeof(u64), cudaMemcpyDeviceToHost, _c->stream));
+    if (bases_ascii && g->total_bases) CK(cudaMemcpyAsync(bases_ascii, g->d_bases, g->total_bases, cudaMemcpyDeviceToHost, _c->stream));
+    if (link_row_offsets) CK(cudaMemcpyAsync(link_row_offsets, g->d_link_row, (g->n_nodes + 1) * sizeof(u64), cudaMemcpyDeviceToHost, _c->stream));
+    if (link_triples && g->n_link_entries)
+        CK(cudaMemcpyAsync(link_triples, g->d_link_tri, 3 * g->n_link_entries * sizeof(i64), cudaMemcpyDeviceToHost, _c->stream));
+    CK(cudaStreamSynchronize(_c->stream));
+    API_END
+}
+__global__ void checksum_kernel(const u8 *__restrict__ bases, u64 nb, const i64 *__restrict__ tri, u64 nt, unsigned long long *out) {
+    u64 acc = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += (u64)gridDim.x * blockDim.x)
+        acc += sy_mix(i * 4 + (u64)bases[i]);
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nt; i += (u64)gridDim.x * blockDim.x)
+        acc += sy_mix(0x5bd1e995ULL + i) ^ sy_mix((u64)tri[i]);
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(FULL_MASK, acc, d);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, (unsigned long long)acc);
+}
+int gg_graph_checksum(gg_graph *g, uint64_t *checksum) {
+    if (!g || !checksum) return GG_ERR_ARG;
+    API_BEGIN(g->ctx)
+    CK(cudaSetDevice(_c->device));
+    DBuf<u64> acc(_c, 1);
+    CK(cudaMemsetAsync(acc.p, 0, sizeof(u64), _c->stream));
+    LAUNCH(_c, checksum_kernel, (unsigned)(_c->num_sms * 4), 256, 0, g->d_bases, g->total_bases, g->d_link_tri, 3 * g->n_link_entries, (unsigned long long *)acc.p);
+    *checksum = read_scalar<u64>(_c, acc.p) + g->n_nodes * 0x9E3779B97F4A7C15ULL;
+    API_END
+}
+void gg_graph_free(gg_graph *g) {
+    if (!g) return;
+    cudaSetDevice(g->ctx->device);
+    dfree(g->ctx, g->d_node_off); dfree(g->ctx, g->d_bases); dfree(g->ctx, g->d_link_row); dfree(g->ctx, g->d_link_tri);
+    delete g;
+}
+
+// ------------------------------------- UMI -------------------------------------------------
+int gg_unique_mer_index(gg_ctx *ctx, const uint8_t *bases, const uint64_t *node_offsets, uint64_t n_nodes, int k, gg_umi **out) {
+    API_BEGIN(ctx)
+    if (!out) GG_THROW(GG_ERR_ARG, "null output");
+    *out = nullptr;
+    check_k(k);
+    CK(cudaSetDevice(_c->device));
+    timing_reset(_c);
+    StagedReads s;
+    stage_reads(_c, bases, node_offsets, n_nodes, s);
+    DISPATCH_W(kmer_words(k), *out = build_umi<W>(_c, s.seq.p, s.offs.p, n_nodes, s.nbytes, k));
+    API_END
+}
+int gg_umi_sizes(gg_umi *u, uint64_t *n_unique, uint64_t *n_nodes, int *k, int *words) {
+    if (!u) return GG_ERR_ARG;
+    if (n_unique) *n_unique = u->n_unique;
+    if (n_nodes) *n_nodes = u->n_nodes;
+    if (k) *k = u->k;
+    if (words) *words = u->W;
+    return GG_OK;
+}
+int gg_umi_export(gg_umi *u, uint64_t *kmer_words_out, int64_t *node, uint32_t *pos, uint64_t *unique_per_node, uint64_t *total_per_node) {
+    if (!u) return GG_ERR_ARG;
+    API_BEGIN(u->ctx)
+    CK(cudaSetDevice(_c->device));
+    u64 n = u->n_unique;
+    if (n && kmer_words_out) CK(cudaMemcpyAsync(kmer_words_out, u->d_keys, n * u->W * sizeof(u64), cudaMemcpyDeviceToHost, _c->stream));
+    if (n && (node || pos)) {
+        DBuf<i64> dn(_c, n);
+        DBuf<u32> dp(_c, n);
+        LAUNCH(_c, umi_unpack_kernel, (unsigned)ceil_div(n, 256), 256, 0, u->d_pay, n, dn.p, dp.p);
+        if (node) CK(cudaMemcpyAsync(node, dn.p, n * sizeof(i64), cudaMemcpyDeviceToHost, _c->stream));
+        if (pos) CK(cudaMemcpyAsync(pos, dp.p, n * sizeof(u32), cudaMemcpyDeviceToHost, _c->stream));
+        CK(cudaStreamSynchronize(_c->stream));
+    }
+    if (u->n_nodes && unique_per_node) CK(cudaMemcpyAsync(unique_per_node, u->d_unique_per_node, u->n_nodes * sizeof(u64), cudaMemcpyDeviceToHost, _c->stream));
+    if (u->n_nodes && total_per_node) CK(cudaMemcpyAsync(total_per_node, u->d_total_per_node, u->n_nodes * sizeof(u64), cudaMemcpyDeviceToHost, _c->stream));
+    CK(cudaStreamSynchronize(_c->stream));
+    API_END
+}
+void gg_umi_free(gg_umi *u) {
+    if (!u) return;
+    cudaSetDevice(u->ctx->device);
+    dfree(u->ctx, u->d_keys); dfree(u->ctx, u->d_pay); dfree(u->ctx, u->d_unique_per_node); dfree(u->ctx, u->d_total_per_node);
+    delete u;
+}
+
+// ------------------------------------- synth ------------------------------------------------
+static int synth_check(u64 genome_len, u32 read_len, int paired, u32 frag_len) {
+    u64 F = paired ? frag_len : read_len;
+    if (read_len == 0 || F < read_len || genome_len < F) return GG_ERR_ARG;
+    return GG_OK;
+}
+int gg_synth_reads_host(uint64_t seed, uint64_t genome_len, uint64_t nreads, uint32_t read_len, int paired, uint32_t frag_len,
+                        uint32_t err_ppm, uint32_t n_ppm, uint8_t *out) {
+    if (!out || synth_check(genome_len, read_len, paired, frag_len) != GG_OK) return GG_ERR_ARG;
+    SynthParams P = synth_params(seed, genome_len, nreads, read_len, paired, frag_len, err_ppm, n_ppm);
+#pragma omp parallel for schedule(static)
+    for (long long r = 0; r < (long long)nreads; ++r)
+        for (u32 p = 0; p < read_len; ++p) out[(u64)r * read_len + p] = synth_base(P, (u64)r, p);
+    return GG_OK;
+}
+int gg_synth_reads_dev(gg_ctx *ctx, uint64_t seed, uint64_t genome_len, uint64_t nreads, uint32_t read_len, int paired,
+                       uint32_t frag_len, uint32_t err_ppm, uint32_t n_ppm, uint8_t *d_out) {
+    API_BEGIN(ctx)
+    if (!d_out || synth_check(genome_len, read_len, paired, frag_len) != GG_OK) GG_THROW(GG_ERR_ARG, "bad synthetic read parameters");
+    CK(cudaSetDevice(_c->device));
+    SynthParams P = synth_params(seed, genome_len, nreads, read_len, paired, frag_len, err_ppm, n_ppm);
+    LAUNCH(_c, synth_reads_kernel, (unsigned)(_c->num_sms * 16), 256, 0, P, d_out);
+    CK(cudaStreamSynchronize(_c->stream));
+    API_END
+}
+int gg_synth_genome_host(uint64_t seed, uint64_t genome_len, uint8_t *out) {
+    if (!out) return GG_ERR_ARG;
+    u64 gkey = sy_key(seed, 1);
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < (long long)genome_len; ++i) out[i] = code_to_ascii(sy_genome_base(gkey, (u64)i));
+    return GG_OK;
+}
+
+}  // extern "C"

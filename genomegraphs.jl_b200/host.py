@@ -1,0 +1,432 @@
+"""Python host mirror of the GenomeGraphs.jl call surface for the DBG construction path.
+
+Same names, argument meaning and error behaviour as the reference (Julia `!` suffix is
+spelled `_`): `serial_mem(k, CANONICAL)(reads)`, `mer`/`freq`, `empty_graph`, `dbg_`
+(`dbg!`, src/dbg.jl:261-278), `SequenceDistanceGraph` / `SDGNode` / `SDGLink`
+(src/Graphs.jl:65-68,163-167,232-243), `UniqueMerIndex` (src/GraphIndexes.jl:27-102).
+Everything computational is a call into libggb200.so (CUDA, sm_100a); there is no CPU path.
+The Julia host files that `ccall` the same ABI are under genomegraphs.jl_b200/julia/.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+
+CANONICAL = 1
+NONCANONICAL = 0
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Context:
+    """One GPU, one private stream (gg_ctx).  A process-wide default is created on demand."""
+
+    _default = None
+
+    def __init__(self, device=0):
+        h = C.c_void_p()
+        code = N.lib().gg_ctx_create(int(device), C.byref(h))
+        if code != N.GG_OK:
+            raise N.GGError(code, "no usable CUDA device %d (libggb200 has no CPU fallback)" % device)
+        self.h = h
+        self.device = device
+
+    @classmethod
+    def default(cls):
+        if cls._default is None:
+            cls._default = cls(0)
+        return cls._default
+
+    def close(self):
+        if self.h:
+            N.lib().gg_ctx_destroy(self.h)
+            self.h = None
+
+    def last_timings(self):
+        ms = (C.c_float * 9)()
+        n = C.c_uint64()
+        N.lib().gg_ctx_last_timings(self.h, ms, C.byref(n))
+        names = ["pack", "extract", "sort", "count", "filter", "lookup", "unitigs", "links", "total"]
+        return dict(zip(names, [float(x) for x in ms])), int(n.value)
+
+
+def pack_reads(reads):
+    """list of str/bytes -> (seq_bytes uint8[n], read_offsets uint64[nreads+1])."""
+    bs = [r.encode() if isinstance(r, str) else bytes(r) for r in reads]
+    offs = np.zeros(len(bs) + 1, dtype=np.uint64)
+    if bs:
+        offs[1:] = np.cumsum([len(b) for b in bs], dtype=np.uint64)
+    seq = np.frombuffer(b"".join(bs), dtype=np.uint8) if bs else np.zeros(0, dtype=np.uint8)
+    return seq, offs
+
+
+def _as_reads(reads):
+    if isinstance(reads, tuple) and len(reads) == 2:
+        seq = np.ascontiguousarray(reads[0], dtype=np.uint8)
+        offs = np.ascontiguousarray(reads[1], dtype=np.uint64)
+        return seq, offs
+    return pack_reads(reads)
+
+
+class MerCounts:
+    """`Vector{MerCount{M}}` held on the device (gg_counts): sorted unique k-mers + counts."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self.h = ctx, handle
+
+    def _sizes(self):
+        nu, ni, k, w = C.c_uint64(), C.c_uint64(), C.c_int(), C.c_int()
+        N.check(self.ctx.h, N.lib().gg_counts_sizes(self.h, C.byref(nu), C.byref(ni), C.byref(k), C.byref(w)))
+        return nu.value, ni.value, k.value, w.value
+
+    def __len__(self):
+        return self._sizes()[0]
+
+    @property
+    def k(self):
+        return self._sizes()[2]
+
+    @property
+    def n_instances(self):
+        return self._sizes()[1]
+
+    def export(self):
+        """-> (kmer words (U, W) uint64, counts uint32, freq uint8 saturated)."""
+        nu, _, _, w = self._sizes()
+        keys = np.zeros((nu, w), dtype=np.uint64)
+        c32 = np.zeros(nu, dtype=np.uint32)
+        c8 = np.zeros(nu, dtype=np.uint8)
+        N.check(self.ctx.h, N.lib().gg_counts_export(self.h, _ptr(keys), _ptr(c8), _ptr(c32)))
+        return keys, c32, c8
+
+    def filter_(self, min_freq, u8_saturated=False):
+        """filter!(x -> freq(x) >= min_freq, counts) -- mutates, like src/dbg.jl:275."""
+        N.check(self.ctx.h, N.lib().gg_counts_filter(self.h, int(min_freq), int(bool(u8_saturated))))
+        return self
+
+    def spectrum(self):
+        h = np.zeros(256, dtype=np.uint64)
+        N.check(self.ctx.h, N.lib().gg_counts_spectrum(self.h, h.ctypes.data_as(N.u64p)))
+        return h
+
+    def free(self):
+        if self.h:
+            N.lib().gg_counts_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def mer(counts):
+    """mer.(counts): the k-mer words."""
+    return counts.export()[0]
+
+
+def freq(counts):
+    """freq.(counts): UInt8-saturated counts (KmerAnalysis MerCount)."""
+    return counts.export()[2]
+
+
+def spectra(counts):
+    return counts.spectrum()
+
+
+def serial_mem(k, mode=CANONICAL, ctx=None):
+    """`serial_mem(DNAMer{k}, CANONICAL)` -> counter; `counter(reads)` -> MerCounts
+    (docs/src/man/assembly.md:126-128).  reads: list of str/bytes or (seq_bytes, offsets)."""
+    if N.lib().gg_kmer_words(int(k)) == 0:
+        raise ValueError("k must be in 1..128")
+
+    def counter(reads):
+        c = ctx or Context.default()
+        seq, offs = _as_reads(reads)
+        h = C.c_void_p()
+        N.check(c.h, N.lib().gg_count_kmers(c.h, _ptr(seq) if seq.size else None, _ptr(offs), len(offs) - 1, int(k), int(mode), C.byref(h)))
+        return MerCounts(c, h)
+
+    return counter
+
+
+def extract_kmers(reads, k, mode=CANONICAL, ctx=None):
+    """each(M, seq) + canonical over all reads, in read order -> (n, W) uint64."""
+    c = ctx or Context.default()
+    seq, offs = _as_reads(reads)
+    w = N.lib().gg_kmer_words(int(k))
+    if w == 0:
+        raise ValueError("k must be in 1..128")
+    n = C.c_uint64(0)
+    sp = _ptr(seq) if seq.size else None
+    N.check(c.h, N.lib().gg_extract_kmers(c.h, sp, _ptr(offs), len(offs) - 1, int(k), int(mode), None, C.byref(n)))
+    out = np.zeros((n.value, w), dtype=np.uint64)
+    if n.value:
+        N.check(c.h, N.lib().gg_extract_kmers(c.h, sp, _ptr(offs), len(offs) - 1, int(k), int(mode), _ptr(out), C.byref(n)))
+    return out
+
+
+class SDGNode:
+    """src/Graphs.jl:65-68"""
+    __slots__ = ("seq", "deleted")
+
+    def __init__(self, seq, deleted=False):
+        self.seq, self.deleted = seq, deleted
+
+    def __eq__(self, o):
+        return isinstance(o, SDGNode) and self.seq == o.seq and self.deleted == o.deleted
+
+    def __repr__(self):
+        return "SDGNode(%r, %r)" % (self.seq, self.deleted)
+
+
+class SDGLink:
+    """src/Graphs.jl:163-167; `==` ignores dist (:183-185)."""
+    __slots__ = ("source", "destination", "dist")
+
+    def __init__(self, source, destination, dist=0):
+        self.source, self.destination, self.dist = int(source), int(destination), int(dist)
+
+    def __eq__(self, o):
+        return isinstance(o, SDGLink) and self.source == o.source and self.destination == o.destination
+
+    def astuple(self):
+        return (self.source, self.destination, self.dist)
+
+    def __repr__(self):
+        return "SDGLink(%d, %d, %d)" % self.astuple()
+
+
+class SequenceDistanceGraph:
+    """src/Graphs.jl:232-235: nodes::Vector{SDGNode}, links::Vector{Vector{SDGLink}}."""
+
+    def __init__(self):
+        self.nodes = []
+        self.links = []
+
+    def n_nodes(self):
+        return len(self.nodes)
+
+    def add_node_(self, seq):
+        """add_node! src/Graphs.jl:418-422,442-444"""
+        self.nodes.append(seq if isinstance(seq, SDGNode) else SDGNode(seq, False))
+        self.links.append([])
+        return len(self.nodes)
+
+    def _check_node_id(self, i):
+        if not (0 < abs(i) <= len(self.nodes)):
+            raise IndexError("Sequence graph has no node with ID of %d" % i)
+
+    def add_link_(self, source, dest, dist):
+        """add_link! src/Graphs.jl:473-476"""
+        self._check_node_id(source)
+        self._check_node_id(dest)
+        self.links[abs(source) - 1].append(SDGLink(source, dest, dist))
+        self.links[abs(dest) - 1].append(SDGLink(dest, source, dist))
+
+    def sequence(self, n):
+        """src/Graphs.jl:592-600"""
+        self._check_node_id(n)
+        s = self.nodes[abs(n) - 1].seq
+        if n < 0:
+            s = s[::-1].translate(str.maketrans("ACGT", "TGCA"))
+        return s
+
+    def link_tuples(self):
+        return [[l.astuple() for l in ls] for ls in self.links]
+
+    def write_to_gfa1(self, filename):
+        """src/Graphs.jl:892-926: <filename>.gfa + <filename>.fasta"""
+        fasta_filename = filename + ".fasta"
+        with open(filename + ".gfa", "w") as gfa, open(fasta_filename, "w") as fa:
+            gfa.write("H\tVN:Z:1.0\n")
+            for nid, n in enumerate(self.nodes, start=1):
+                if n.deleted:
+                    continue
+                gfa.write("S\tseq%d\t*\tLN:i:%d\tUR:Z:%s\n" % (nid, len(n.seq), fasta_filename))
+                fa.write(">seq%d\n%s\n" % (nid, n.seq))
+            for ls in self.links:
+                for l in ls:
+                    if l.source <= l.destination:
+                        a = "seq%d\t-" % l.source if l.source > 0 else "seq%d\t+" % -l.source
+                        b = "seq%d\t+" % l.destination if l.destination > 0 else "seq%d\t-" % -l.destination
+                        gfa.write("L\t%s\t%s\t%dM\n" % (a, b, -l.dist if l.dist < 0 else 0))
+
+
+def empty_graph(_seqtype=None):
+    """empty_graph(LongSequence{DNAAlphabet{4}}) src/GenomeGraphs.jl:85"""
+    return SequenceDistanceGraph()
+
+
+class GraphArrays:
+    """Raw export of a gg_graph (CSR arrays), for large graphs where Python objects are too slow."""
+
+    def __init__(self, k, node_offsets, bases, link_row_offsets, link_triples):
+        self.k = k
+        self.node_offsets, self.bases = node_offsets, bases
+        self.link_row_offsets, self.link_triples = link_row_offsets, link_triples
+
+    @property
+    def n_nodes(self):
+        return len(self.node_offsets) - 1
+
+    def node_strings(self):
+        b = self.bases.tobytes().decode()
+        o = self.node_offsets
+        return [b[int(o[i]):int(o[i + 1])] for i in range(self.n_nodes)]
+
+    def link_lists(self):
+        t = self.link_triples.reshape(-1, 3)
+        r = self.link_row_offsets
+        return [[tuple(int(x) for x in t[j]) for j in range(int(r[i]), int(r[i + 1]))] for i in range(self.n_nodes)]
+
+
+def _export_graph(ctx, gh):
+    nn, nb, nl, k = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_int()
+    N.check(ctx.h, N.lib().gg_graph_sizes(gh, C.byref(nn), C.byref(nb), C.byref(nl), C.byref(k)))
+    node_off = np.zeros(nn.value + 1, dtype=np.uint64)
+    bases = np.zeros(nb.value, dtype=np.uint8)
+    link_row = np.zeros(nn.value + 1, dtype=np.uint64)
+    tri = np.zeros(3 * nl.value, dtype=np.int64)
+    N.check(ctx.h, N.lib().gg_graph_export(gh, _ptr(node_off), _ptr(bases) if nb.value else None, _ptr(link_row), _ptr(tri) if nl.value else None))
+    return GraphArrays(k.value, node_off, bases, link_row, tri)
+
+
+def _kmers_to_counts(ctx, kmers, k):
+    a = np.ascontiguousarray(kmers, dtype=np.uint64)
+    w = N.lib().gg_kmer_words(int(k))
+    if w == 0:
+        raise ValueError("k must be in 1..128")
+    a = a.reshape(-1, w)
+    h = C.c_void_p()
+    N.check(ctx.h, N.lib().gg_counts_from_kmers(ctx.h, _ptr(a) if a.size else None, None, a.shape[0], int(k), C.byref(h)))
+    return MerCounts(ctx, h)
+
+
+def dbg_arrays(kmers_or_counts, k=None, min_freq=None, ctx=None):
+    """Device DBG build returning raw arrays (GraphArrays)."""
+    c = ctx or Context.default()
+    if isinstance(kmers_or_counts, MerCounts):
+        counts, own = kmers_or_counts, False
+        if min_freq is not None:
+            counts.filter_(min_freq)
+    else:
+        if k is None:
+            raise ValueError("Didn't provide a collection of kmers for the `kmers` parameter did ya?")  # src/dbg.jl:263
+        counts, own = _kmers_to_counts(c, kmers_or_counts, k), True
+    gh = C.c_void_p()
+    try:
+        N.check(c.h, N.lib().gg_dbg_build(c.h, counts.h, C.byref(gh)))
+        return _export_graph(c, gh)
+    finally:
+        if gh:
+            N.lib().gg_graph_free(gh)
+        if own:
+            counts.free()
+
+
+def dbg_(sdg, kmers_or_counts, min_freq=None, k=None, ctx=None):
+    """dbg!(sdg, kmers) (src/dbg.jl:261-272) and dbg!(sg, counted_kmers, min_freq) (:274-278).
+    kmers: (n, W) uint64 words with k given, or a MerCounts (filtered in place when min_freq
+    is given, exactly like the reference mutates the caller's vector)."""
+    if not isinstance(kmers_or_counts, MerCounts) and k is None:
+        raise ValueError("Didn't provide a collection of kmers for the `kmers` parameter did ya?")
+    ga = dbg_arrays(kmers_or_counts, k=k, min_freq=min_freq, ctx=ctx)
+    base = len(sdg.nodes)
+    if base != 0:
+        raise ValueError("dbg! expects an empty graph")  # node ids in links are absolute
+    for s in ga.node_strings():
+        sdg.add_node_(s)
+    for i, ls in enumerate(ga.link_lists()):
+        sdg.links[i].extend(SDGLink(*t) for t in ls)
+    return sdg
+
+
+def dbg_from_reads(reads, k, min_freq, ctx=None):
+    """reads -> graph arrays in one device pipeline (count, filter, build)."""
+    c = ctx or Context.default()
+    seq, offs = _as_reads(reads)
+    gh = C.c_void_p()
+    N.check(c.h, N.lib().gg_dbg_from_reads(c.h, _ptr(seq) if seq.size else None, _ptr(offs), len(offs) - 1, int(k), int(min_freq), C.byref(gh)))
+    try:
+        return _export_graph(c, gh)
+    finally:
+        N.lib().gg_graph_free(gh)
+
+
+class GraphStrandPosition:
+    """src/GraphIndexes.jl:14-17"""
+    __slots__ = ("node", "position")
+
+    def __init__(self, node, position):
+        self.node, self.position = int(node), int(position)
+
+    def __eq__(self, o):
+        return (self.node, self.position) == (o.node, o.position)
+
+    def __repr__(self):
+        return "(Node: %d, Base position: %d)" % (self.node, self.position)
+
+
+class UniqueMerIndex:
+    """UniqueMerIndex{M}(graph) src/GraphIndexes.jl:62-102 (intended semantics)."""
+
+    def __init__(self, graph, k, ctx=None):
+        c = ctx or Context.default()
+        seqs = [n.seq for n in graph.nodes] if isinstance(graph, SequenceDistanceGraph) else list(graph)
+        seq, offs = pack_reads(seqs)
+        h = C.c_void_p()
+        N.check(c.h, N.lib().gg_unique_mer_index(c.h, _ptr(seq) if seq.size else None, _ptr(offs), len(seqs), int(k), C.byref(h)))
+        try:
+            nu, nn, kk, w = C.c_uint64(), C.c_uint64(), C.c_int(), C.c_int()
+            N.check(c.h, N.lib().gg_umi_sizes(h, C.byref(nu), C.byref(nn), C.byref(kk), C.byref(w)))
+            self.k, self.words = kk.value, w.value
+            self.keys = np.zeros((nu.value, w.value), dtype=np.uint64)
+            self.node = np.zeros(nu.value, dtype=np.int64)
+            self.pos = np.zeros(nu.value, dtype=np.uint32)
+            self.unique_mers_per_node = np.zeros(nn.value, dtype=np.uint64)
+            self.total_mers_per_node = np.zeros(nn.value, dtype=np.uint64)
+            N.check(c.h, N.lib().gg_umi_export(h, _ptr(self.keys) if nu.value else None, _ptr(self.node) if nu.value else None,
+                                               _ptr(self.pos) if nu.value else None,
+                                               _ptr(self.unique_mers_per_node) if nn.value else None,
+                                               _ptr(self.total_mers_per_node) if nn.value else None))
+        finally:
+            N.lib().gg_umi_free(h)
+        self._dict = None
+
+    @property
+    def mer_to_graphposition(self):
+        if self._dict is None:
+            self._dict = {tuple(int(x) for x in self.keys[i]): GraphStrandPosition(self.node[i], self.pos[i]) for i in range(len(self.keys))}
+        return self._dict
+
+    def find_unique_mer(self, mer_words):
+        """src/GraphIndexes.jl:37-41 -> (exists, GraphStrandPosition)"""
+        key = tuple(int(x) for x in np.atleast_1d(np.asarray(mer_words, dtype=np.uint64)))
+        pos = self.mer_to_graphposition.get(key, GraphStrandPosition(0, 0))
+        return pos != GraphStrandPosition(0, 0), pos
+
+    def isunmappable(self, nodeid):
+        """src/GraphIndexes.jl:33-35"""
+        return self.unique_mers_per_node[abs(int(nodeid)) - 1] == 0
+
+
+def synth_reads(seed, genome_len, nreads, read_len, paired=False, frag_len=0, err_ppm=0, n_ppm=0):
+    """Deterministic synthetic reads (host generator) -> (seq_bytes, offsets)."""
+    out = np.zeros(int(nreads) * int(read_len), dtype=np.uint8)
+    code = N.lib().gg_synth_reads_host(int(seed), int(genome_len), int(nreads), int(read_len), int(bool(paired)), int(frag_len),
+                                       int(err_ppm), int(n_ppm), _ptr(out))
+    if code != N.GG_OK:
+        raise ValueError("bad synthetic read parameters")
+    offs = np.arange(int(nreads) + 1, dtype=np.uint64) * np.uint64(read_len)
+    return out, offs
+
+
+def synth_genome(seed, genome_len):
+    out = np.zeros(int(genome_len), dtype=np.uint8)
+    N.check(None, N.lib().gg_synth_genome_host(int(seed), int(genome_len), _ptr(out)))
+    return out

@@ -1,0 +1,153 @@
+/*
+ * ggb200.h -- C ABI of libggb200.so: the B200-native (sm_100a) de Bruijn graph
+ * construction path of GenomeGraphs.jl.
+ *
+ * The reference (BioJulia/GenomeGraphs.jl v0.2.0) has no FFI / plugin interface: its
+ * boundary is a Julia call surface.  Each entry point below names the reference
+ * interface it replaces (paths relative to the reference repository); the Julia host
+ * files under genomegraphs.jl_b200/julia/ bind these with `ccall`, the Python host
+ * mirror (genomegraphs.jl_b200/host.py) with ctypes -- see INTEGRATION.md.
+ *
+ * Conventions
+ *  - every function returns GG_OK (0) or a negative gg_status; nothing throws across the ABI;
+ *    gg_last_error(ctx) gives the message of the last failure on that context.
+ *  - opaque handles (gg_counts, gg_graph, gg_umi) own DEVICE memory; the caller allocates
+ *    host export buffers after the matching *_sizes call (Julia: GC.@preserve).
+ *  - one context = one GPU = one private CUDA stream; calls on a context are blocking and
+ *    must be serialised by the caller (the reference is single-threaded as well).
+ *  - there is NO CPU fallback: without a CUDA device gg_ctx_create fails with GG_ERR_CUDA.
+ *
+ * k-mer words: W = 1 (k <= 32), 2 (k <= 64), 4 (k <= 128) little-endian uint64 per k-mer,
+ * MOST significant word first; 2 bits per base (A0 C1 G2 T3), first base in the most
+ * significant of the 2k used bits, value right-aligned (BioSequences Mer / BigMer layout:
+ * W=1 is the UInt64 of a Mer, W=2 the (hi, lo) halves of a BigMer's UInt128).
+ */
+#ifndef GGB200_H
+#define GGB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gg_ctx gg_ctx;
+typedef struct gg_counts gg_counts; /* sorted unique k-mers + counts (Vector{MerCount{M}}) */
+typedef struct gg_graph gg_graph;   /* SequenceDistanceGraph: unitig nodes + links */
+typedef struct gg_umi gg_umi;       /* UniqueMerIndex */
+
+typedef enum {
+    GG_OK = 0,
+    GG_ERR_ARG = -1,     /* bad argument (reference: ArgumentError, src/dbg.jl:262-264) */
+    GG_ERR_CUDA = -2,    /* CUDA runtime failure / no device */
+    GG_ERR_OOM = -3,     /* device or host allocation failed */
+    GG_ERR_LIMIT = -4    /* size exceeds an implementation limit */
+} gg_status;
+
+#define GG_MAX_K 128
+
+int gg_version(void);
+/* words per k-mer for k (0 if k is outside 1..GG_MAX_K) */
+int gg_kmer_words(int k);
+
+/* ---- context ------------------------------------------------------------------------ */
+int gg_ctx_create(int device, gg_ctx **out);
+void gg_ctx_destroy(gg_ctx *ctx);
+const char *gg_last_error(gg_ctx *ctx);
+/* pinned host memory for fast host<->device copies of read buffers */
+int gg_host_alloc(gg_ctx *ctx, uint64_t bytes, void **out);
+void gg_host_free(gg_ctx *ctx, void *p);
+/* plain device buffers (benchmarks keep inputs resident in HBM with these) */
+int gg_dev_alloc(gg_ctx *ctx, uint64_t bytes, void **out);
+void gg_dev_free(gg_ctx *ctx, void *p);
+int gg_memcpy_h2d(gg_ctx *ctx, void *dst_dev, const void *src_host, uint64_t bytes);
+int gg_memcpy_d2h(gg_ctx *ctx, void *dst_host, const void *src_dev, uint64_t bytes);
+/* device time (ms, CUDA events on the context's stream) of the stages of the last pipeline
+ * call: [0] pack, [1] extract, [2] sort, [3] count/RLE, [4] filter, [5] neighbour lookup,
+ * [6] unitigs, [7] links, [8] total; and the number of kernel launches it issued. */
+int gg_ctx_last_timings(gg_ctx *ctx, float ms[9], uint64_t *kernel_launches);
+
+/* ---- reads -> k-mer counts ------------------------------------------------------------
+ * Replaces `serial_mem(DNAMer{K}, CANONICAL)(reads)` of KmerAnalysis.jl (re-exported at
+ * src/GenomeGraphs.jl:39-48; call site docs/src/man/assembly.md:126-128): every window of
+ * k bases of every read (windows holding a non-ACGT symbol are skipped), canonicalised when
+ * canonical != 0, sorted ascending, run-length collapsed.
+ * seq_bytes: the reads' bases (ASCII, any case) concatenated; read i is
+ * seq_bytes[read_offsets[i] .. read_offsets[i+1]) ; read_offsets has nreads + 1 entries.
+ * gg_count_kmers takes HOST buffers (copies inside the call); gg_count_kmers_dev takes
+ * DEVICE buffers of the same layout (nbytes = read_offsets[nreads]). */
+int gg_count_kmers(gg_ctx *ctx, const uint8_t *seq_bytes, const uint64_t *read_offsets,
+                   uint64_t nreads, int k, int canonical, gg_counts **out);
+int gg_count_kmers_dev(gg_ctx *ctx, const uint8_t *d_seq_bytes, const uint64_t *d_read_offsets,
+                       uint64_t nreads, uint64_t nbytes, int k, int canonical, gg_counts **out);
+/* wrap an existing k-mer vector (host, any order, canonical and duplicate-free as
+ * src/dbg.jl:261 requires); counts may be NULL (then all 1).  Sorted on the device when
+ * needed (src/dbg.jl:98-100). */
+int gg_counts_from_kmers(gg_ctx *ctx, const uint64_t *kmer_words, const uint32_t *counts,
+                         uint64_t n, int k, gg_counts **out);
+int gg_counts_sizes(gg_counts *c, uint64_t *n_unique, uint64_t *n_instances, int *k, int *words);
+/* `filter!(x -> freq(x) >= min_freq, counts)` (src/dbg.jl:275): in place, order kept.
+ * u8_saturated != 0 compares the MerCount UInt8 view min(count, 255). */
+int gg_counts_filter(gg_counts *c, uint64_t min_freq, int u8_saturated);
+/* any of the three output pointers may be NULL */
+int gg_counts_export(gg_counts *c, uint64_t *kmer_words, uint8_t *counts_u8_saturated, uint32_t *counts_u32);
+/* `spectra(counts)` of KmerAnalysis.jl (docs/src/man/assembly.md:159): 256-bin histogram of
+ * min(count, 255) */
+int gg_counts_spectrum(gg_counts *c, uint64_t hist[256]);
+void gg_counts_free(gg_counts *c);
+
+/* staged entry points (tests / measurement) */
+/* k-mers of all windows in read order (each(M, seq) + canonical, src/GraphIndexes.jl:78-82).
+ * Call with out_words == NULL to get *n_kmers first. */
+int gg_extract_kmers(gg_ctx *ctx, const uint8_t *seq_bytes, const uint64_t *read_offsets,
+                     uint64_t nreads, int k, int canonical, uint64_t *out_words, uint64_t *n_kmers);
+
+/* ---- k-mers -> SequenceDistanceGraph ---------------------------------------------------
+ * Replaces `dbg!(sdg, kmers)` (src/dbg.jl:261-272: build_unitigs! :94-185 +
+ * connect_unitigs_by_overlaps! :224-240) on the k-mers currently held by `counts`
+ * (after gg_counts_filter this is `dbg!(sg, counted_kmers, min_freq)`, src/dbg.jl:274-278).
+ * Node ids, node orientation (canonical!) and per-node link order equal the reference's. */
+int gg_dbg_build(gg_ctx *ctx, gg_counts *counts, gg_graph **out);
+/* reads -> graph in one call (count, filter, build); HOST / DEVICE input variants */
+int gg_dbg_from_reads(gg_ctx *ctx, const uint8_t *seq_bytes, const uint64_t *read_offsets,
+                      uint64_t nreads, int k, uint64_t min_freq, gg_graph **out);
+int gg_dbg_from_reads_dev(gg_ctx *ctx, const uint8_t *d_seq_bytes, const uint64_t *d_read_offsets,
+                          uint64_t nreads, uint64_t nbytes, int k, uint64_t min_freq, gg_graph **out);
+int gg_graph_sizes(gg_graph *g, uint64_t *n_nodes, uint64_t *total_bases, uint64_t *n_link_entries, int *k);
+/* node i (id i+1, src/Graphs.jl:418-422) is bases_ascii[node_offsets[i] .. node_offsets[i+1]);
+ * links of node i (src/Graphs.jl:198,473-476) are the (source, destination, dist) int64
+ * triples link_triples[3*link_row_offsets[i] .. 3*link_row_offsets[i+1]) in push order. */
+int gg_graph_export(gg_graph *g, uint64_t *node_offsets, uint8_t *bases_ascii,
+                    uint64_t *link_row_offsets, int64_t *link_triples);
+/* small summary read back without exporting: sum over nodes of an order-independent hash */
+int gg_graph_checksum(gg_graph *g, uint64_t *checksum);
+void gg_graph_free(gg_graph *g);
+
+/* ---- UniqueMerIndex ---------------------------------------------------------------------
+ * Replaces `UniqueMerIndex{M}(graph)` (src/GraphIndexes.jl:62-102, intended semantics: the
+ * unique_mers_per_node vector has n_nodes entries).  Node sequences are passed as ASCII. */
+int gg_unique_mer_index(gg_ctx *ctx, const uint8_t *node_bases_ascii, const uint64_t *node_offsets,
+                        uint64_t n_nodes, int k, gg_umi **out);
+int gg_umi_sizes(gg_umi *u, uint64_t *n_unique, uint64_t *n_nodes, int *k, int *words);
+/* keys sorted ascending; node = +-id (sign = strand, src/GraphIndexes.jl:80), pos 1-based */
+int gg_umi_export(gg_umi *u, uint64_t *kmer_words, int64_t *node, uint32_t *pos,
+                  uint64_t *unique_mers_per_node, uint64_t *total_mers_per_node);
+void gg_umi_free(gg_umi *u);
+
+/* ---- deterministic synthetic reads -----------------------------------
+ * Counter-based generator (splitmix64 keyed by seed and index): the host and device
+ * variants produce identical bytes.  Genome of genome_len i.i.d. uniform bases; nreads
+ * reads of read_len bases; paired != 0: reads 2j / 2j+1 are the forward start and the
+ * reverse-complemented end of fragment j (FwRv) of frag_len bases; substitution errors with
+ * probability err_ppm / 1e6 per base; n_ppm / 1e6 of the bases become 'N'.
+ * Output: nreads * read_len ASCII bytes (read i at i * read_len). */
+int gg_synth_reads_host(uint64_t seed, uint64_t genome_len, uint64_t nreads, uint32_t read_len,
+                        int paired, uint32_t frag_len, uint32_t err_ppm, uint32_t n_ppm, uint8_t *out);
+int gg_synth_reads_dev(gg_ctx *ctx, uint64_t seed, uint64_t genome_len, uint64_t nreads, uint32_t read_len,
+                       int paired, uint32_t frag_len, uint32_t err_ppm, uint32_t n_ppm, uint8_t *d_out);
+int gg_synth_genome_host(uint64_t seed, uint64_t genome_len, uint8_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GGB200_H */

@@ -1,0 +1,81 @@
+"""CPU-side checks of the boundary: the C-ABI library builds, loads and exports every symbol
+include/ggb200.h declares; no compute call is made (there is no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import __graft_entry__ as G
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    return G.build()
+
+
+def test_header_symbols_exported(pkg):
+    hdr = open(os.path.join(ROOT, "include", "ggb200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(gg_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    lib = C.CDLL(pkg._native.SO_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    # the ctypes table mirrors the header one to one
+    assert declared == set(pkg._native.SIGNATURES)
+
+
+def test_kmer_words(pkg):
+    L = pkg._native.lib()
+    assert [L.gg_kmer_words(k) for k in (0, 1, 32, 33, 64, 65, 128, 129)] == [0, 1, 1, 2, 2, 4, 4, 0]
+
+
+def test_no_cpu_fallback(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(pkg._native.GGError):
+        pkg.Context(0)
+
+
+def test_product_does_not_import_oracle():
+    pkgdir = os.path.join(ROOT, "genomegraphs.jl_b200")
+    for dp, _, fs in os.walk(pkgdir):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")):
+                txt = open(os.path.join(dp, f), errors="replace").read()
+                assert "ggoracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_synth_reads_host_semantics(pkg):
+    """reads are substrings of the synthetic genome (either strand); paired mates face each other."""
+    G_, L, F = 5000, 60, 200
+    genome = pkg.synth_genome(7, G_).tobytes().decode()
+    comp = str.maketrans("ACGT", "TGCA")
+    rcg = genome[::-1].translate(comp)
+    seq, offs = pkg.synth_reads(7, G_, 400, L, paired=True, frag_len=F)
+    assert offs.tolist() == [i * L for i in range(401)]
+    reads = [seq[i * L:(i + 1) * L].tobytes().decode() for i in range(400)]
+    for j in range(200):
+        r1, r2 = reads[2 * j], reads[2 * j + 1]
+        p = genome.find(r1)
+        if p >= 0:                       # forward fragment: mate 2 is the rc of the fragment end
+            assert genome[p + F - L:p + F] == r2[::-1].translate(comp)
+        else:
+            q = rcg.find(r1)
+            assert q >= 0
+            assert rcg[q + F - L:q + F] == r2[::-1].translate(comp)
+    # determinism + error / N injection rates
+    seq2, _ = pkg.synth_reads(7, G_, 400, L, paired=True, frag_len=F)
+    assert np.array_equal(seq, seq2)
+    e, _ = pkg.synth_reads(7, G_, 400, L, paired=True, frag_len=F, err_ppm=100000)
+    frac = float(np.mean(e != seq))
+    assert 0.07 < frac < 0.13
+    n, _ = pkg.synth_reads(7, G_, 400, L, paired=True, frag_len=F, n_ppm=50000)
+    assert 0.03 < float(np.mean(n == ord("N"))) < 0.07
+    with pytest.raises(ValueError):
+        pkg.synth_reads(7, 10, 4, 60)
