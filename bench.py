@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- DBG build throughput (input k-mers/sec) on B200, contract per the task brief.
+
+A "step" is one pass of the whole hot path over one batch of synthetic reads:
+reads (ASCII) -> 2-bit pack -> canonical k-mers -> sort + run-length counts -> min-count
+filter -> unitig nodes -> (k-1)-overlap links.  Workload = BASELINE.json configs[1]
+(C2): 4,641,652 bp uniform genome, 50x 150 bp paired reads (fragment
+700, 0.1 % substitutions), k = 31, min-count 2.
+
+  value  : whole-job input k-mers/s with the read buffers already resident in HBM
+  e2e    : same metric through the host-buffer C-ABI call (gg_dbg_from_reads) + full export of
+           the graph to host memory, H2D / D2H inside the timed region
+  roofline / cpu_baseline : see DESIGN.md, "Measurement"
+
+`--impl reference` times the CPU restatement of the reference algorithm (oracle/, kind "port":
+the Julia reference cannot run here) on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as G  # noqa: E402
+
+WORKLOADS = {
+    # name: genome_len, coverage, read_len, frag_len, err_ppm, k, min_freq
+    "c2_ecoli50x_k31": dict(genome_len=4641652, cov=50, read_len=150, frag_len=700, err_ppm=1000, k=31, min_freq=2),
+    "c2_ecoli50x_k63": dict(genome_len=4641652, cov=50, read_len=150, frag_len=700, err_ppm=1000, k=63, min_freq=2),
+    "c3_100mbp30x_k31": dict(genome_len=100000000, cov=30, read_len=150, frag_len=700, err_ppm=10000, k=31, min_freq=2),
+    "c5_100mbp30x_k127": dict(genome_len=100000000, cov=30, read_len=150, frag_len=700, err_ppm=10000, k=127, min_freq=2),
+    "tiny": dict(genome_len=200000, cov=30, read_len=150, frag_len=500, err_ppm=2000, k=31, min_freq=2),
+}
+
+# algorithmic (compulsory) bytes per k-mer INSTANCE for the kernels that can dominate; W = key bytes
+ALG_BYTES = {
+    "radix_scatter_kernel": lambda W: 2 * W,       # read every key once, write every key once
+    "radix_hist_kernel": lambda W: W,              # read every key once
+    "extract_emit_kernel": lambda W: 0.3125 + W,   # 0.25 B/base packed + masks read, W written
+    "extract_count_kernel": lambda W: 0.0625,
+}
+
+
+def nreads_for(w):
+    return 2 * int(round(w["cov"] * w["genome_len"] / (2.0 * w["read_len"])))
+
+
+def kmers_per_read(w):
+    return max(0, w["read_len"] - w["k"] + 1)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args, w, rank, world):
+    """CPU arm: the oracle (C restatement of the reference algorithm) on a bounded sample."""
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    pkg = G.load_package()
+    frac = args.cpu_sample_frac
+    glen = max(int(w["genome_len"] * frac), 4 * w["frag_len"])
+    ws = dict(w, genome_len=glen)
+    nreads = nreads_for(ws)
+    seq, offs = pkg.synth_reads(1, glen, nreads, w["read_len"], True, w["frag_len"], w["err_ppm"])
+    n_inst = nreads * kmers_per_read(w)
+    threads = O.lib().ggo_max_threads()
+
+    def step():
+        keys, cnt = O.count_kmers(seq, offs, w["k"], threads=threads)
+        g = O.dbg(O.filter_counts(keys, cnt, w["k"], w["min_freq"]), w["k"])
+        return g.n_nodes
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = n_inst * args.steps / dt
+    sample = "genome %d bp (%.3g of the workload's), %d reads, %d k-mer instances per step; counting with %d OpenMP threads, unitig walk sequential" % (
+        glen, frac, nreads, n_inst, threads)
+    out = {
+        "impl": "reference", "metric": "DBG build: input k-mers/sec", "value": v, "unit": "k-mers/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64" if w["k"] <= 32 else "u128" if w["k"] <= 64 else "u256", "data": "synthetic",
+        "config": {"workload": args.workload, **w, "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "k-mers/s", "cores": threads, "kind": "port", "sample": sample,
+                         "note": "C restatement of the Julia algorithm (oracle/), not Julia itself; JULIA_NUM_THREADS n/a (the reference is single-threaded)"},
+        "e2e": {"value": v, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2_ecoli50x_k31", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-sample-frac", type=float, default=0.25)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload])
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+
+    if args.impl == "reference":
+        run_reference(args, w, rank, world)
+        return
+
+    pkg = G.build() if rank == 0 or world == 1 else None
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+        if pkg is None:
+            pkg = G.load_package()
+    N = pkg._native
+    L = N.lib()
+    ctx = pkg.Context(local_rank)
+    H = ctx.h
+    k, min_freq, rl = w["k"], w["min_freq"], w["read_len"]
+    W = 8 * L.gg_kmer_words(k)
+    nreads = nreads_for(w)
+    nbytes = nreads * rl
+    n_inst = nreads * kmers_per_read(w)
+    seed = 1 + rank  # every rank owns a different shard of reads (weak scaling)
+
+    # ---- inputs: generated on the device, kept resident in HBM; pinned host copy for the e2e leg
+    d_seq, d_offs, h_seq = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    N.check(H, L.gg_dev_alloc(H, nbytes + 64, C.byref(d_seq)))
+    N.check(H, L.gg_dev_alloc(H, 8 * (nreads + 1), C.byref(d_offs)))
+    N.check(H, L.gg_synth_reads_dev(H, seed, w["genome_len"], nreads, rl, 1, w["frag_len"], w["err_ppm"], 0, d_seq))
+    offs = np.arange(nreads + 1, dtype=np.uint64) * np.uint64(rl)
+    N.check(H, L.gg_memcpy_h2d(H, d_offs, offs.ctypes.data_as(C.c_void_p), offs.nbytes))
+    N.check(H, L.gg_host_alloc(H, nbytes + 64, C.byref(h_seq)))
+    N.check(H, L.gg_memcpy_d2h(H, h_seq, d_seq, nbytes))
+
+    def barrier():
+        L.gg_ctx_sync(H)
+        if dist is not None:
+            import torch
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    def step_dev():
+        gh = C.c_void_p()
+        N.check(H, L.gg_dbg_from_reads_dev(H, d_seq, d_offs, nreads, nbytes, k, min_freq, C.byref(gh)))
+        return gh
+
+    def graph_sizes(gh):
+        nn, nb, nl, kk = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_int()
+        N.check(H, L.gg_graph_sizes(gh, C.byref(nn), C.byref(nb), C.byref(nl), C.byref(kk)))
+        return nn.value, nb.value, nl.value
+
+    # ---- warm-up (also fills the memory pool) ----
+    launches = 0
+    sizes = None
+    for _ in range(args.warmup):
+        gh = step_dev()
+        sizes = graph_sizes(gh)
+        L.gg_graph_free(gh)
+        launches = ctx.last_timings()[1]
+
+    # ---- timed: K steps, inputs resident in HBM (232 MB of reads > 126 MB L2) ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    N.check(H, L.gg_ctx_event_record(H, 0))
+    t0 = time.perf_counter()
+    stage_ms = None
+    for _ in range(args.steps):
+        gh = step_dev()
+        L.gg_graph_free(gh)
+    N.check(H, L.gg_ctx_event_record(H, 1))
+    barrier()
+    wall = time.perf_counter() - t0
+    ev_ms = C.c_float()
+    N.check(H, L.gg_ctx_event_elapsed_ms(H, 0, 1, C.byref(ev_ms)))
+    stage_ms, launches = ctx.last_timings()
+    dev_s = ev_ms.value / 1e3
+
+    # ---- e2e: host buffers in, full graph out, every step ----
+    nn, nb, nl = sizes
+    out_off = np.zeros(nn + 1, dtype=np.uint64); out_bases = np.zeros(max(nb, 1), dtype=np.uint8)
+    out_row = np.zeros(nn + 1, dtype=np.uint64); out_tri = np.zeros(max(3 * nl, 1), dtype=np.int64)
+
+    def step_e2e():
+        gh = C.c_void_p()
+        N.check(H, L.gg_dbg_from_reads(H, h_seq, offs.ctypes.data_as(C.c_void_p), nreads, k, min_freq, C.byref(gh)))
+        N.check(H, L.gg_graph_export(gh, out_off.ctypes.data_as(C.c_void_p), out_bases.ctypes.data_as(C.c_void_p),
+                                     out_row.ctypes.data_as(C.c_void_p), out_tri.ctypes.data_as(C.c_void_p)))
+        L.gg_graph_free(gh)
+
+    step_e2e()
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t1
+    clocks = sampler.stop()
+
+    # ---- max over ranks / sum of work ----
+    if dist is not None:
+        import torch
+        t = torch.tensor([dev_s, e2e_s, wall], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_s, e2e_s, wall = (float(x) for x in t.tolist())
+    total_inst = n_inst * world
+
+    # ---- roofline of the dominant kernel: one extra, untimed, profiled step ----
+    roofline, top = None, []
+    if rank == 0:
+        L.gg_ctx_set_profile(H, 1)
+        gh = step_dev()
+        L.gg_graph_free(gh)
+        L.gg_ctx_set_profile(H, 0)
+        prof = []
+        for ln in L.gg_ctx_kernel_profile(H).decode().splitlines():
+            name, cnt, ms = ln.split("\t")
+            prof.append((name.split("<")[0].strip("( "), int(cnt), float(ms)))
+        agg = {}
+        for name, cnt, ms in prof:
+            a = agg.setdefault(name, [0, 0.0]); a[0] += cnt; a[1] += ms
+        tot_ms = sum(v[1] for v in agg.values())
+        top = sorted(agg.items(), key=lambda kv: -kv[1][1])[:8]
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak, peak_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json hbm_gbs)") if peaks.get("hbm_gbs") else (6650.0, "fallback (B200_PROFILING.md)")
+        name, (cnt, ms) = top[0]
+        per_inst = ALG_BYTES.get(name, lambda W_: None)(W)
+        if per_inst is not None:
+            achieved = per_inst * n_inst / (ms / cnt / 1e3) / 1e9
+            roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "traffic": None, "launches_per_step": cnt, "avg_launch_ms": ms / cnt, "share_of_kernel_time": ms / tot_ms,
+                        "alg_bytes_per_launch": per_inst * n_inst, "peak_source": peak_src}
+        else:
+            roofline = {"bound": "hbm", "kernel": name, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
+                        "launches_per_step": cnt, "avg_launch_ms": ms / cnt, "share_of_kernel_time": ms / tot_ms, "peak_source": peak_src,
+                        "note": "latency-bound pointer chasing; no streaming byte model"}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        frac = args.cpu_sample_frac
+        glen = int(w["genome_len"] * frac)
+        ws = dict(w, genome_len=glen)
+        nr = nreads_for(ws)
+        sseq, soffs = pkg.synth_reads(1, glen, nr, rl, True, w["frag_len"], w["err_ppm"])
+        tc = time.perf_counter()
+        keys, cnt = O.count_kmers(sseq, soffs, k, threads=1)
+        og = O.dbg(O.filter_counts(keys, cnt, k, min_freq), k)
+        tc = time.perf_counter() - tc
+        cpu = {"value": nr * kmers_per_read(w) / tc, "unit": "k-mers/s", "cores": 1, "kind": "port",
+               "sample": "same workload at %.3g of the genome length (%d bp, %d reads, %d k-mer instances), 1 thread as the reference runs; %.1f s" % (
+                   frac, glen, nr, nr * kmers_per_read(w), tc),
+               "host_cpus": os.cpu_count(), "nodes": og.n_nodes,
+               "note": "C restatement of the Julia algorithm (oracle/), not Julia itself; JULIA_NUM_THREADS n/a"}
+
+    if rank == 0:
+        h2d = nbytes + offs.nbytes
+        d2h = out_off.nbytes + nb + out_row.nbytes + 3 * nl * 8
+        out = {
+            "metric": "DBG build: input k-mers/sec", "value": total_inst * args.steps / dev_s, "unit": "k-mers/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64" if k <= 32 else "u128" if k <= 64 else "u256", "data": "synthetic",
+            "config": {"workload": args.workload, **w, "reads_per_gpu": nreads, "kmer_instances_per_gpu": n_inst,
+                       "input_bytes_per_gpu": nbytes, "l2_policy": "inputs (%.0f MB of reads + %.0f MB of k-mers per step) larger than the 126 MB L2" % (nbytes / 1e6, n_inst * W / 1e6),
+                       "parallelism": "1 process per GPU, independent read shards per rank (no data-path collective yet)",
+                       "graph": {"nodes": nn, "bases": nb, "link_entries": nl}},
+            "wall_ms_per_step": 1e3 * wall / args.steps,
+            "stage_ms_last_step": stage_ms,
+            "hbm_gbs_effective": None,
+            "e2e": {"value": total_inst * args.steps / e2e_s, "unit": "k-mers/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": launches * args.steps,
+            "gpu_launches_per_step": launches,
+            "clocks": clocks,
+            "roofline": roofline,
+            "top_kernels_ms": [{"kernel": n_, "launches": v[0], "ms": round(v[1], 4)} for n_, v in top],
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(out), flush=True)
+
+    L.gg_dev_free(H, d_seq); L.gg_dev_free(H, d_offs); L.gg_host_free(H, h_seq)
+    ctx.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

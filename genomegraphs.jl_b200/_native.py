@@ -36,6 +36,11 @@ SIGNATURES = {
     "gg_memcpy_h2d": (C.c_int, [vp, vp, vp, C.c_uint64]),
     "gg_memcpy_d2h": (C.c_int, [vp, vp, vp, C.c_uint64]),
     "gg_ctx_last_timings": (C.c_int, [vp, f32p, u64p]),
+    "gg_ctx_event_record": (C.c_int, [vp, C.c_int]),
+    "gg_ctx_event_elapsed_ms": (C.c_int, [vp, C.c_int, C.c_int, f32p]),
+    "gg_ctx_sync": (C.c_int, [vp]),
+    "gg_ctx_set_profile": (C.c_int, [vp, C.c_int]),
+    "gg_ctx_kernel_profile": (C.c_char_p, [vp]),
     "gg_count_kmers": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_int, C.c_int, vpp]),
     "gg_count_kmers_dev": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_uint64, C.c_int, C.c_int, vpp]),
     "gg_counts_from_kmers": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_int, vpp]),

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <new>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -31,6 +32,14 @@ struct gg_ctx {
     u64 launches = 0;
     // small pinned scratch for device->host scalars
     u64 *h_scalar = nullptr;  // 64 x u64
+    // optional per-kernel profiling (gg_ctx_set_profile): events around every launch
+    bool profile = false;
+    struct ProfRec { std::string name; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> ev_pool;
+    std::string prof_text;
+    // user events (gg_ctx_event_record / gg_ctx_event_elapsed_ms)
+    cudaEvent_t user_ev[8];
 };
 
 struct GgError {
@@ -54,10 +63,20 @@ struct GgError {
     } while (0)
 
 // every kernel launch goes through this so that gpu_launches can be reported
-#define LAUNCH(ctx, kernel, grid, block, smem, ...)                                  \
+static inline cudaEvent_t prof_event(gg_ctx *ctx) {
+    cudaEvent_t e;
+    if (!ctx->ev_pool.empty()) { e = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); return e; }
+    cudaEventCreate(&e);
+    return e;
+}
+#define LAUNCH(ctx, kernel, grid, block, smem, ...) LAUNCH_NAMED(ctx, #kernel, kernel, grid, block, smem, __VA_ARGS__)
+#define LAUNCH_NAMED(ctx, kname, kernel, grid, block, smem, ...)                     \
     do {                                                                             \
+        cudaEvent_t _pa = nullptr, _pb = nullptr;                                    \
+        if ((ctx)->profile) { _pa = prof_event(ctx); _pb = prof_event(ctx); cudaEventRecord(_pa, (ctx)->stream); } \
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);             \
         (ctx)->launches++;                                                           \
+        if ((ctx)->profile) { cudaEventRecord(_pb, (ctx)->stream); (ctx)->prof.push_back({std::string(kname), _pa, _pb}); } \
         CK(cudaGetLastError());                                                      \
     } while (0)
 

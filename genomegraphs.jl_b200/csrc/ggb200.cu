@@ -37,9 +37,33 @@ struct gg_counts {
 static void timing_reset(gg_ctx *ctx) {
     for (int i = 0; i < GG_NSTAGE; ++i) { ctx->ev_used[i] = false; ctx->ms[i] = 0.f; }
     ctx->launches = 0;
+    for (auto &r : ctx->prof) { ctx->ev_pool.push_back(r.a); ctx->ev_pool.push_back(r.b); }
+    ctx->prof.clear();
+}
+static void profile_collect(gg_ctx *ctx) {
+    if (ctx->prof.empty()) return;
+    std::map<std::string, std::pair<u64, double>> acc;
+    std::vector<std::string> order;
+    for (auto &r : ctx->prof) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        auto it = acc.find(r.name);
+        if (it == acc.end()) { acc[r.name] = {1, ms}; order.push_back(r.name); }
+        else { it->second.first++; it->second.second += ms; }
+        ctx->ev_pool.push_back(r.a);
+        ctx->ev_pool.push_back(r.b);
+    }
+    ctx->prof.clear();
+    ctx->prof_text.clear();
+    char line[512];
+    for (auto &n : order) {
+        snprintf(line, sizeof(line), "%s\t%llu\t%.6f\n", n.c_str(), (unsigned long long)acc[n].first, acc[n].second);
+        ctx->prof_text += line;
+    }
 }
 static void timing_collect(gg_ctx *ctx) {
     CK(cudaStreamSynchronize(ctx->stream));
+    profile_collect(ctx);
     for (int i = 0; i < GG_NSTAGE; ++i)
         if (ctx->ev_used[i]) {
             float ms = 0.f;
@@ -70,6 +94,7 @@ int gg_ctx_create(int device, gg_ctx **out) {
         ctx->num_sms = prop.multiProcessorCount;
         CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         for (int i = 0; i < 2 * GG_NSTAGE; ++i) CK(cudaEventCreate(&ctx->ev[i]));
+        for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&ctx->user_ev[i]));
         CK(cudaHostAlloc((void **)&ctx->h_scalar, 64 * sizeof(u64), cudaHostAllocDefault));
         cudaMemPool_t pool;
         CK(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -89,6 +114,9 @@ void gg_ctx_destroy(gg_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 2 * GG_NSTAGE; ++i) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->user_ev[i]);
+    for (auto &r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     cudaFreeHost(ctx->h_scalar);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -125,6 +153,33 @@ int gg_memcpy_d2h(gg_ctx *ctx, void *dst, const void *src, uint64_t bytes) {
     CK(cudaStreamSynchronize(_c->stream));
     API_END
 }
+int gg_ctx_set_profile(gg_ctx *ctx, int enabled) {
+    if (!ctx) return GG_ERR_ARG;
+    ctx->profile = enabled != 0;
+    return GG_OK;
+}
+const char *gg_ctx_kernel_profile(gg_ctx *ctx) { return ctx ? ctx->prof_text.c_str() : ""; }
+int gg_ctx_event_record(gg_ctx *ctx, int slot) {
+    API_BEGIN(ctx)
+    if (slot < 0 || slot >= 8) GG_THROW(GG_ERR_ARG, "event slot out of range");
+    CK(cudaSetDevice(_c->device));
+    CK(cudaEventRecord(_c->user_ev[slot], _c->stream));
+    API_END
+}
+int gg_ctx_event_elapsed_ms(gg_ctx *ctx, int slot_a, int slot_b, float *ms) {
+    API_BEGIN(ctx)
+    if (slot_a < 0 || slot_a >= 8 || slot_b < 0 || slot_b >= 8 || !ms) GG_THROW(GG_ERR_ARG, "bad event slot");
+    CK(cudaSetDevice(_c->device));
+    CK(cudaEventSynchronize(_c->user_ev[slot_b]));
+    CK(cudaEventElapsedTime(ms, _c->user_ev[slot_a], _c->user_ev[slot_b]));
+    API_END
+}
+int gg_ctx_sync(gg_ctx *ctx) {
+    API_BEGIN(ctx)
+    CK(cudaSetDevice(_c->device));
+    CK(cudaStreamSynchronize(_c->stream));
+    API_END
+}
 int gg_ctx_last_timings(gg_ctx *ctx, float ms[9], uint64_t *kernel_launches) {
     if (!ctx) return GG_ERR_ARG;
     if (ms) for (int i = 0; i < GG_NSTAGE; ++i) ms[i] = ctx->ms[i];
@@ -150,7 +205,7 @@ static u64 extract_all(gg_ctx *ctx, const u8 *d_seq, const u64 *d_offs, u64 nrea
     stage_end(ctx, ST_PACK);
     stage_begin(ctx, ST_EXTRACT);
     ExtractF<W> ef{valid.p, pr.packed.p, nullptr, k, canonical};
-    Compactor<ExtractF<W>> cp(ctx, nbytes);
+    Compactor<ExtractF<W>> cp(ctx, nbytes, "extract");
     u64 n = cp.count(ef);
     keys.alloc(ctx, n * W + extra_words);
     ef.out = keys.p;
@@ -193,7 +248,7 @@ static void filter_impl(gg_counts *c, u64 min_freq, int u8sat) {
     gg_ctx *ctx = c->ctx;
     stage_begin(ctx, ST_FILTER);
     FilterF<W> f{c->d_keys, c->d_counts, nullptr, nullptr, min_freq, u8sat};
-    Compactor<FilterF<W>> cp(ctx, c->n_unique);
+    Compactor<FilterF<W>> cp(ctx, c->n_unique, "filter");
     u64 nk = cp.count(f);
     DBuf<u64> okeys(ctx, nk * W);
     DBuf<u32> ocounts(ctx, nk);

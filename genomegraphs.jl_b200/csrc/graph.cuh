@@ -427,7 +427,7 @@ static void build_links(gg_ctx *ctx, gg_graph *g, const u64 *keys, const u32 *no
     }
     constexpr int KW = W + 1;
     OverlapF<W> f{keys, node_first, node_last, nullptr, nn, k, 1};
-    Compactor<OverlapF<W>> cin(ctx, 2 * nn), cout_(ctx, 2 * nn);
+    Compactor<OverlapF<W>> cin(ctx, 2 * nn, "overlap"), cout_(ctx, 2 * nn, "overlap");
     u64 ni = cin.count(f);
     u64 no = 2 * nn - ni;
     DBuf<u64> in(ctx, (ni + 1) * KW), in_alt(ctx, (ni + 1) * KW), out(ctx, (no + 1) * KW), out_alt(ctx, (no + 1) * KW);

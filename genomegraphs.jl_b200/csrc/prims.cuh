@@ -164,17 +164,19 @@ struct Compactor {
     u64 n, ntiles;
     DBuf<u32> tiles;
     DBuf<u64> total;
-    Compactor(gg_ctx *c, u64 n_) : ctx(c), n(n_), ntiles(ceil_div(n_ ? n_ : 1, CP_TILE)), tiles(c, ntiles), total(c, 1) {}
+    std::string tag;
+    Compactor(gg_ctx *c, u64 n_, const char *tag_ = "compact")
+        : ctx(c), n(n_), ntiles(ceil_div(n_ ? n_ : 1, CP_TILE)), tiles(c, ntiles), total(c, 1), tag(tag_) {}
     // phase 1: count + scan; returns the total on the host (one stream sync)
     u64 count(const F &f) {
         if (n == 0) return 0;
-        LAUNCH(ctx, compact_count_kernel<F>, (unsigned)ntiles, CP_THREADS, 0, f, n, tiles.p);
+        LAUNCH_NAMED(ctx, tag + "_count_kernel", compact_count_kernel<F>, (unsigned)ntiles, CP_THREADS, 0, f, n, tiles.p);
         exclusive_scan_u32(ctx, tiles.p, tiles.p, ntiles, total.p);
         return read_scalar<u64>(ctx, total.p);
     }
     // phase 2
     void emit(const F &f) {
         if (n == 0) return;
-        LAUNCH(ctx, compact_emit_kernel<F>, (unsigned)ntiles, CP_THREADS, 0, f, n, tiles.p);
+        LAUNCH_NAMED(ctx, tag + "_emit_kernel", compact_emit_kernel<F>, (unsigned)ntiles, CP_THREADS, 0, f, n, tiles.p);
     }
 };

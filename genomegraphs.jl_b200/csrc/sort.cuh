@@ -193,7 +193,7 @@ template <int W>
 static u64 run_length_count(gg_ctx *ctx, const u64 *sorted, u64 n, DBuf<u64> &ukeys, DBuf<u32> &counts) {
     if (n == 0) { ukeys.alloc(ctx, 1); counts.alloc(ctx, 1); return 0; }
     RunHeadF<W> f{sorted, nullptr, nullptr};
-    Compactor<RunHeadF<W>> cp(ctx, n);
+    Compactor<RunHeadF<W>> cp(ctx, n, "runhead");
     u64 nu = cp.count(f);
     ukeys.alloc(ctx, nu * W);
     DBuf<u32> headpos(ctx, nu);

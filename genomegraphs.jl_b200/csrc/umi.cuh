@@ -91,7 +91,7 @@ static gg_umi *build_umi(gg_ctx *ctx, const u8 *d_seq, const u64 *d_offs, u64 nn
         DBuf<u32> valid;
         window_valid_mask(ctx, pr, k, valid);
         ExtractPayF<W> ef{valid.p, pr.packed.p, d_offs, nn, nullptr, nullptr, k};
-        Compactor<ExtractPayF<W>> cp(ctx, nbytes);
+        Compactor<ExtractPayF<W>> cp(ctx, nbytes, "umi_extract");
         u64 n = cp.count(ef);
         DBuf<u64> keys(ctx, n * W), keys_alt(ctx, n * W), pay(ctx, n + 1), pay_alt(ctx, n + 1);
         ef.out = keys.p; ef.pay = pay.p;
@@ -100,7 +100,7 @@ static gg_umi *build_umi(gg_ctx *ctx, const u8 *d_seq, const u64 *d_offs, u64 nn
         std::vector<BitRange> ranges = {{0, 2 * k}};
         radix_sort<W>(ctx, &a, &b, &pa, &pb, n, ranges);
         UniqueRunF<W> uf{a, pa, n, nullptr, nullptr, (unsigned long long *)u->d_unique_per_node};
-        Compactor<UniqueRunF<W>> cu(ctx, n);
+        Compactor<UniqueRunF<W>> cu(ctx, n, "umi_unique");
         u64 nu = cu.count(uf);
         u->n_unique = nu;
         u->d_keys = dalloc<u64>(ctx, nu * W);

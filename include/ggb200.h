@@ -66,6 +66,15 @@ int gg_memcpy_d2h(gg_ctx *ctx, void *dst_host, const void *src_dev, uint64_t byt
  * call: [0] pack, [1] extract, [2] sort, [3] count/RLE, [4] filter, [5] neighbour lookup,
  * [6] unitigs, [7] links, [8] total; and the number of kernel launches it issued. */
 int gg_ctx_last_timings(gg_ctx *ctx, float ms[9], uint64_t *kernel_launches);
+/* measurement helpers: CUDA events on the context's (launching) stream, slots 0..7 */
+int gg_ctx_event_record(gg_ctx *ctx, int slot);
+int gg_ctx_event_elapsed_ms(gg_ctx *ctx, int slot_a, int slot_b, float *ms);
+int gg_ctx_sync(gg_ctx *ctx);
+/* per-kernel profile of the next pipeline calls (events around every launch; slows the call
+ * down, never enabled inside a timed region).  gg_ctx_kernel_profile returns
+ * "kernel\tlaunches\ttotal_ms\n" lines for the last pipeline call. */
+int gg_ctx_set_profile(gg_ctx *ctx, int enabled);
+const char *gg_ctx_kernel_profile(gg_ctx *ctx);
 
 /* ---- reads -> k-mer counts ------------------------------------------------------------
  * Replaces `serial_mem(DNAMer{K}, CANONICAL)(reads)` of KmerAnalysis.jl (re-exported at
