@@ -4,6 +4,7 @@
 #include "prims.cuh"
 #include "pack.cuh"
 #include "sort.cuh"
+#include "msdcount.cuh"
 #include "graph.cuh"
 #include "umi.cuh"
 #include "synth.cuh"
@@ -214,11 +215,31 @@ static u64 extract_all(gg_ctx *ctx, const u8 *d_seq, const u64 *d_offs, u64 nrea
     return n;
 }
 
+// min_freq > 1 drops rarer k-mers inside the counting kernels (fused filter of the reads -> graph
+// pipeline); *filtered tells the caller whether that happened.
 template <int W>
-static gg_counts *count_kmers_dev_impl(gg_ctx *ctx, const u8 *d_seq, const u64 *d_offs, u64 nreads, u64 nbytes, int k, int canonical) {
+static gg_counts *count_kmers_dev_impl(gg_ctx *ctx, const u8 *d_seq, const u64 *d_offs, u64 nreads, u64 nbytes, int k, int canonical,
+                                       u64 min_freq = 1, bool *filtered = nullptr) {
     gg_counts *c = new gg_counts();
     c->ctx = ctx; c->k = k; c->W = W;
+    if (filtered) *filtered = false;
     try {
+        if (W == 1 && !getenv("GG_FORCE_LSD")) {
+            stage_begin(ctx, ST_PACK);
+            PackedReads pr;
+            pack_reads(ctx, d_seq, d_offs, nreads, nbytes, pr);
+            DBuf<u32> valid;
+            window_valid_mask(ctx, pr, k, valid);
+            stage_end(ctx, ST_PACK);
+            DBuf<u64> ukeys;
+            DBuf<u32> counts;
+            u32 mf = min_freq > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)min_freq;
+            c->n_unique = msd_count(ctx, pr, valid.p, k, canonical, mf < 1 ? 1 : mf, ukeys, counts, &c->n_instances);
+            c->d_keys = ukeys.take();
+            c->d_counts = counts.take();
+            if (filtered) *filtered = true;
+            return c;
+        }
         DBuf<u64> keys;
         u64 n = extract_all<W>(ctx, d_seq, d_offs, nreads, nbytes, k, canonical, keys, 0);
         c->n_instances = n;
@@ -452,9 +473,10 @@ int gg_dbg_build(gg_ctx *ctx, gg_counts *counts, gg_graph **out) {
 static void dbg_from_reads_dev(gg_ctx *ctx, const u8 *d_seq, const u64 *d_offs, u64 nreads, u64 nbytes, int k, u64 min_freq, gg_graph **out) {
     gg_counts *c = nullptr;
     stage_begin(ctx, ST_TOTAL);
-    DISPATCH_W(kmer_words(k), c = count_kmers_dev_impl<W>(ctx, d_seq, d_offs, nreads, nbytes, k, 1));
+    bool filtered = false;
+    DISPATCH_W(kmer_words(k), c = count_kmers_dev_impl<W>(ctx, d_seq, d_offs, nreads, nbytes, k, 1, min_freq, &filtered));
     try {
-        DISPATCH_W(c->W, filter_impl<W>(c, min_freq, 0));
+        if (!filtered) { DISPATCH_W(c->W, filter_impl<W>(c, min_freq, 0)); }
         DISPATCH_W(c->W, *out = build_graph<W>(ctx, c->d_keys, c->n_unique, c->k));
     } catch (...) {
         gg_counts_free(c);

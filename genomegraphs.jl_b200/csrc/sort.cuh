@@ -128,6 +128,115 @@ __global__ void __launch_bounds__(256) radix_scatter_kernel(const u64 *__restric
     }
 }
 
+// Small inputs (graph link records, tiny k-mer sets): ONE launch, one CTA, all digit passes inside
+// (a pass of the tiled path costs five launches, which dominates below ~64 K keys).
+#define RADIX_SMALL_N 65536
+#define RADIX_MAX_PASSES 40
+struct RadixPasses {
+    int n;
+    short bit[RADIX_MAX_PASSES];
+    signed char nbits[RADIX_MAX_PASSES];
+};
+template <int KW, bool PAY>
+__global__ void __launch_bounds__(256) radix_small_kernel(u64 *k0, u64 *k1, u64 *p0, u64 *p1, u32 n, RadixPasses pl) {
+    constexpr int ITEMS = RadixCfg<KW>::ITEMS;
+    constexpr int TILE = RadixCfg<KW>::TILE;
+    extern __shared__ __align__(16) u8 smem_raw[];
+    u64 *skeys = reinterpret_cast<u64 *>(smem_raw);
+    u64 *spay = skeys + (size_t)TILE * KW;
+    __shared__ u32 whist[8][256];
+    __shared__ u32 lbase[256];
+    __shared__ u32 gbase[256];
+    __shared__ u32 ws[33];
+    const u32 tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    u64 *kin = k0, *kout = k1, *pin = p0, *pout = p1;
+    for (int pass = 0; pass < pl.n; ++pass) {
+        const int bit = pl.bit[pass], nbits = pl.nbits[pass];
+        gbase[tid] = 0;
+        __syncthreads();
+        for (u32 i = tid; i < n; i += 256) atomicAdd(&gbase[key_digit<KW>(km_load<KW>(kin, i), bit, nbits)], 1u);
+        __syncthreads();
+        {
+            u32 c = gbase[tid], tot;
+            u32 ex = block_excl_scan(c, ws, &tot);
+            gbase[tid] = ex;
+        }
+        __syncthreads();
+        for (u32 tbase = 0; tbase < n; tbase += TILE) {
+            const u32 wbase = tbase + wid * (32 * ITEMS);
+            for (int i = tid; i < 8 * 256; i += 256) (&whist[0][0])[i] = 0;
+            __syncthreads();
+            Kmer<KW> key[ITEMS];
+            u64 pay[ITEMS];
+            u32 dg[ITEMS], rk[ITEMS];
+            u32 inmask = 0;
+#pragma unroll
+            for (int it = 0; it < ITEMS; ++it) {
+                u32 idx = wbase + it * 32 + lane;
+                bool in = idx < n;
+                dg[it] = 0; rk[it] = 0;
+                if (in) {
+                    key[it] = km_load<KW>(kin, idx);
+                    if (PAY) pay[it] = pin[idx];
+                }
+                u32 act = __ballot_sync(FULL_MASK, in);
+                if (in) {
+                    u32 d = key_digit<KW>(key[it], bit, nbits);
+                    u32 peers = __match_any_sync(act, d);
+                    int leader = __ffs(peers) - 1;
+                    u32 old = 0;
+                    if ((int)lane == leader) {
+                        old = whist[wid][d];
+                        whist[wid][d] = old + __popc(peers);
+                    }
+                    old = __shfl_sync(peers, old, leader);
+                    rk[it] = old + __popc(peers & lanemask_lt());
+                    dg[it] = d;
+                    inmask |= 1u << it;
+                }
+                __syncwarp();
+            }
+            __syncthreads();
+            u32 dtot;
+            {
+                u32 run = 0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) { u32 t = whist[w][tid]; whist[w][tid] = run; run += t; }
+                dtot = run;
+                u32 tot;
+                lbase[tid] = block_excl_scan(run, ws, &tot);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int it = 0; it < ITEMS; ++it) {
+                if ((inmask >> it) & 1u) {
+                    u32 pos = lbase[dg[it]] + whist[wid][dg[it]] + rk[it];
+#pragma unroll
+                    for (int j = 0; j < KW; ++j) skeys[(size_t)pos * KW + j] = key[it].w[j];
+                    if (PAY) spay[pos] = pay[it];
+                }
+            }
+            __syncthreads();
+            u32 rem = n - tbase;
+            u32 cnt = rem < (u32)TILE ? rem : (u32)TILE;
+            for (u32 i = tid; i < cnt; i += 256) {
+                Kmer<KW> x = km_load<KW>(skeys, i);
+                u32 d = key_digit<KW>(x, bit, nbits);
+                u32 dst = gbase[d] + (i - lbase[d]);
+                km_store<KW>(kout, dst, x);
+                if (PAY) pout[dst] = spay[i];
+            }
+            __syncthreads();
+            gbase[tid] += dtot;  // running base of digit `tid` for the next tile
+            __syncthreads();
+        }
+        __threadfence();
+        __syncthreads();
+        u64 *t = kin; kin = kout; kout = t;
+        t = pin; pin = pout; pout = t;
+    }
+}
+
 // Stable LSD radix sort over the given bit ranges (least significant range first).
 // On return the sorted data is in *keys (and *pay); *keys_alt / *pay_alt hold scratch.
 template <int KW>
@@ -142,9 +251,32 @@ static void radix_sort(gg_ctx *ctx, u64 **keys, u64 **keys_alt, u64 **pay, u64 *
     size_t smem = (size_t)TILE * KW * 8 + (has_pay ? (size_t)TILE * 8 : 0);
     static bool attr_set[2] = {false, false};
     if (!attr_set[has_pay]) {
-        if (has_pay) CK(cudaFuncSetAttribute(radix_scatter_kernel<KW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else CK(cudaFuncSetAttribute(radix_scatter_kernel<KW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (has_pay) {
+            CK(cudaFuncSetAttribute(radix_scatter_kernel<KW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(radix_small_kernel<KW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        } else {
+            CK(cudaFuncSetAttribute(radix_scatter_kernel<KW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(radix_small_kernel<KW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
         attr_set[has_pay] = true;
+    }
+    if (n <= RADIX_SMALL_N) {
+        RadixPasses pl;
+        pl.n = 0;
+        for (const BitRange &r : ranges)
+            for (int bit = r.lo; bit < r.hi; bit += 8) {
+                if (pl.n >= RADIX_MAX_PASSES) GG_THROW(GG_ERR_LIMIT, "too many radix passes");
+                pl.bit[pl.n] = (short)bit;
+                pl.nbits[pl.n] = (signed char)(r.hi - bit < 8 ? r.hi - bit : 8);
+                ++pl.n;
+            }
+        if (has_pay) LAUNCH(ctx, (radix_small_kernel<KW, true>), 1, 256, smem, *keys, *keys_alt, *pay, *pay_alt, (u32)n, pl);
+        else LAUNCH(ctx, (radix_small_kernel<KW, false>), 1, 256, smem, *keys, *keys_alt, (u64 *)nullptr, (u64 *)nullptr, (u32)n, pl);
+        if (pl.n & 1) {
+            std::swap(*keys, *keys_alt);
+            if (has_pay) std::swap(*pay, *pay_alt);
+        }
+        return;
     }
     for (const BitRange &r : ranges) {
         for (int bit = r.lo; bit < r.hi; bit += 8) {
