@@ -5,25 +5,28 @@
 // run-length collapse (docs/src/man/assembly.md:126-128).  Output is identical (sorted unique
 // k-mers + counts); the route is an MSD formulation sized for HBM traffic:
 //
-//   A  msd_hist_kernel     roll over the packed reads, histogram of the top b0 key bits
-//   B  msd_scatter_kernel  roll again, stage a tile in shared memory grouped by bucket, write
-//                          each bucket run with one reservation (atomicAdd) per (tile, bucket)
-//   C  msd_bucket_kernel   one CTA per bucket (dynamic ticket): 8-bit sub-partition A->B through
-//                          CTA-private cursors, then leaves of <= CAP keys are counted in a
-//                          shared-memory hash table, the distinct keys are put in order by an
-//                          order-preserving binning + rank-by-counting, and written in place.
-//                          Oversized children recurse (8 more bits); a range with no bits left
-//                          is one run.
-//   D  msd_gather_kernel   per-bucket unique runs -> dense output arrays
+//   A  msd_hist_kernel      roll over the packed reads, histogram of the top b0 key bits
+//   B  msd_scatter_kernel   one roll per 32 windows (keys stay in registers), tile staged in
+//                           shared memory grouped by bucket, one reservation per (tile, bucket)
+//   C  msd_hist1_kernel     per level-0 bucket, histogram of the next b1 bits
+//   D  msd_scatter1_kernel  same staging scheme, keys -> 2^(b0+b1) ordered children
+//   E  task list            runs of consecutive small children (<= CAP keys together)
+//   F  msd_task_kernel      one CTA per task: keys counted in a shared-memory hash table, the
+//                           distinct keys put in order by order-preserving bins + rank-by-counting
+//                           and written in place.  A child larger than CAP is partitioned again
+//                           by the CTA (8 bits per level, depth first); a range with no key bits
+//                           left is one run.
+//   G  msd_gather_kernel    per-task unique runs -> dense output arrays
 //
-// Algorithmic bytes per k-mer instance (W = 8): A 0.31 read; B 0.31 read + 8 written;
-// C 8 read + 8 written + 8 read (sub-partition, mostly L2) + 12 U/N written; D 24 U/N.
+// Algorithmic bytes per k-mer instance (8-byte keys): A 0.31 read; B 0.31 read + 8 written;
+// C 8 read; D 8 read + 8 written; F 8 read + 12 U/N written; G 24 U/N.
 #pragma once
 #include "pack.cuh"
 #include "sort.cuh"
 
 #define MSD_MAX_B0 11
-#define MSD_UNROLL 8  // independent global loads in flight per thread in the bucket kernel
+#define MSD_MAX_B1 10
+#define MSD_UNROLL 8  // independent global loads in flight per thread in the task kernel
 #define MSD_EMPTY 0xFFFFFFFFFFFFFFFFULL  // never a valid key: all-T k-mers are not canonical, and 2k < 64 otherwise
 
 // 32 consecutive windows starting at base 32 t (k <= 32): f(key, j) for every valid window j
@@ -64,6 +67,32 @@ __global__ void __launch_bounds__(256) msd_hist_kernel(const u64 *__restrict__ p
         if (h[i]) atomicAdd(&ghist[i], h[i]);
 }
 
+// shared tail of the two scatter kernels: bins counted in hist[0..nb) -> per-bin reservation in
+// the global cursors, hist becomes the in-tile running cursor, delta the global-minus-local base
+template <int BPT>
+__device__ __forceinline__ u32 msd_reserve(u32 *hist, u32 *delta, int nb, u32 *__restrict__ cursor, u32 *ws) {
+    const int bpt = (nb + 255) / 256;  // <= BPT
+    const int lo = min(nb, (int)threadIdx.x * bpt), hi = min(nb, lo + bpt);
+    u32 s = 0;
+    u32 cnts[BPT], res[BPT];
+#pragma unroll
+    for (int q = 0; q < BPT; ++q) { cnts[q] = (lo + q < hi) ? hist[lo + q] : 0; s += cnts[q]; }
+#pragma unroll
+    for (int q = 0; q < BPT; ++q) res[q] = cnts[q] ? atomicAdd(&cursor[lo + q], cnts[q]) : 0;  // independent: all in flight together
+    u32 total;
+    u32 run = block_excl_scan(s, ws, &total);
+#pragma unroll
+    for (int q = 0; q < BPT; ++q) {
+        if (lo + q < hi) {
+            delta[lo + q] = res[q] - run;
+            hist[lo + q] = run;
+            run += cnts[q];
+        }
+    }
+    __syncthreads();
+    return total;
+}
+
 // tile = 256 words = 8192 window positions
 #define MSD_TILE_KEYS 8192
 __global__ void __launch_bounds__(256) msd_scatter_kernel(const u64 *__restrict__ packed, const u32 *__restrict__ valid, u64 nwords,
@@ -85,26 +114,7 @@ __global__ void __launch_bounds__(256) msd_scatter_kernel(const u64 *__restrict_
         roll32(packed, valid, t, k, canonical, [&](u64 key, int j) { keys[j] = key; atomicAdd(&hist[msd_digit0(key, sh, b0)], 1u); });
     }
     __syncthreads();
-    // exclusive scan over the bins (thread owns a contiguous chunk), one global reservation per non-empty bin
-    const int bpt = (nb + 255) / 256;  // <= 8
-    const int lo = min(nb, (int)threadIdx.x * bpt), hi = min(nb, lo + bpt);
-    u32 s = 0;
-    u32 cnts[8], res[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) { cnts[q] = (lo + q < hi) ? hist[lo + q] : 0; s += cnts[q]; }
-#pragma unroll
-    for (int q = 0; q < 8; ++q) res[q] = cnts[q] ? atomicAdd(&cursor[lo + q], cnts[q]) : 0;  // independent: all in flight together
-    u32 total;
-    u32 run = block_excl_scan(s, ws, &total);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        if (lo + q < hi) {
-            delta[lo + q] = res[q] - run;
-            hist[lo + q] = run;  // becomes the running cursor of the bin inside the tile
-            run += cnts[q];
-        }
-    }
-    __syncthreads();
+    const u32 total = msd_reserve<8>(hist, delta, nb, cursor, ws);
 #pragma unroll
     for (int j = 0; j < 32; ++j)
         if ((vm >> (31 - j)) & 1u) skeys[atomicAdd(&hist[msd_digit0(keys[j], sh, b0)], 1u)] = keys[j];
@@ -115,21 +125,110 @@ __global__ void __launch_bounds__(256) msd_scatter_kernel(const u64 *__restrict_
     }
 }
 
-// ------------------------------- per-bucket CTA ---------------------------------------------
-#define MSD_MAXD 10
+// ------------------------------ level 1: bucket-aligned tiles --------------------------------
+#define MSD_T1 4096  // keys per tile (16 per thread)
+__global__ void msd_tilecount_kernel(const u32 *__restrict__ bstart, u32 nb, u32 *__restrict__ tcount) {
+    u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b <= nb) tcount[b] = b < nb ? (bstart[b + 1] - bstart[b] + MSD_T1 - 1) / MSD_T1 : 0;
+}
+// tile t -> (bucket, key range)
+__device__ __forceinline__ bool msd_tile_range(const u32 *__restrict__ tstart, const u32 *__restrict__ bstart, u32 nb, u32 t, u32 &b,
+                                               u32 &s, u32 &e) {
+    if (t >= tstart[nb]) return false;
+    u32 lo = 0, hi = nb;  // largest b with tstart[b] <= t
+    while (hi - lo > 1) {
+        u32 mid = (lo + hi) >> 1;
+        if (tstart[mid] <= t) lo = mid; else hi = mid;
+    }
+    b = lo;
+    s = bstart[b] + (t - tstart[b]) * MSD_T1;
+    e = min(bstart[b + 1], s + MSD_T1);
+    return true;
+}
+__global__ void __launch_bounds__(256) msd_hist1_kernel(const u64 *__restrict__ A, const u32 *__restrict__ tstart,
+                                                        const u32 *__restrict__ bstart, u32 nb0, int sh1, int b1,
+                                                        u32 *__restrict__ hist1) {
+    __shared__ u32 h[1 << MSD_MAX_B1];
+    u32 b, s, e;
+    if (!msd_tile_range(tstart, bstart, nb0, blockIdx.x, b, s, e)) return;
+    const int nb = 1 << b1;
+    const u32 dm = (u32)nb - 1u;
+    for (int i = threadIdx.x; i < nb; i += 256) h[i] = 0;
+    __syncthreads();
+    u64 kk[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) { u32 i = s + u * 256 + threadIdx.x; kk[u] = i < e ? A[i] : 0; }
+#pragma unroll
+    for (int u = 0; u < 16; ++u)
+        if (s + u * 256 + threadIdx.x < e) atomicAdd(&h[(u32)(kk[u] >> sh1) & dm], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb; i += 256)
+        if (h[i]) atomicAdd(&hist1[((u64)b << b1) + i], h[i]);
+}
+__global__ void __launch_bounds__(256) msd_scatter1_kernel(const u64 *__restrict__ A, const u32 *__restrict__ tstart,
+                                                           const u32 *__restrict__ bstart, u32 nb0, int sh1, int b1,
+                                                           u32 *__restrict__ cursor1, u64 *__restrict__ B) {
+    __shared__ u64 skeys[MSD_T1];
+    __shared__ u32 hist[1 << MSD_MAX_B1];
+    __shared__ u32 delta[1 << MSD_MAX_B1];
+    __shared__ u32 ws[33];
+    u32 b, s, e;
+    if (!msd_tile_range(tstart, bstart, nb0, blockIdx.x, b, s, e)) return;
+    const int nb = 1 << b1;
+    const u32 dm = (u32)nb - 1u;
+    for (int i = threadIdx.x; i < nb; i += 256) hist[i] = 0;
+    __syncthreads();
+    u64 kk[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) { u32 i = s + u * 256 + threadIdx.x; kk[u] = i < e ? A[i] : 0; }
+#pragma unroll
+    for (int u = 0; u < 16; ++u)
+        if (s + u * 256 + threadIdx.x < e) atomicAdd(&hist[(u32)(kk[u] >> sh1) & dm], 1u);
+    __syncthreads();
+    const u32 total = msd_reserve<4>(hist, delta, nb, cursor1 + ((u64)b << b1), ws);
+#pragma unroll
+    for (int u = 0; u < 16; ++u)
+        if (s + u * 256 + threadIdx.x < e) skeys[atomicAdd(&hist[(u32)(kk[u] >> sh1) & dm], 1u)] = kk[u];
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < total; i += 256) {
+        u64 key = skeys[i];
+        B[delta[(u32)(key >> sh1) & dm] + i] = key;
+    }
+}
+__global__ void msd_copy_u32_kernel(const u32 *__restrict__ in, u64 n, u32 *__restrict__ out) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+}
+
+// ---- task list: consecutive children are merged while they stay small -----------------------
+// A child larger than SMALL keys is a task of its own; otherwise children whose first key falls
+// in the same window of GW keys form one task, so a merged task holds <= GW + SMALL <= CAP keys.
+struct MsdTaskF {
+    const u32 *off;  // nchild + 1
+    u32 *tasks;
+    u32 gw, small;
+    __device__ bool pred(u64 c) const {
+        if (c == 0) return true;
+        u32 o0 = off[c - 1], o1 = off[c], o2 = off[c + 1];
+        return (o2 - o1) > small || (o1 - o0) > small || (o1 / gw) != (o0 / gw);
+    }
+    __device__ void emit(u64 c, u64 dst) const { tasks[dst] = (u32)c; }
+};
+
+// ------------------------------- per-task CTA ------------------------------------------------
+#define MSD_MAXD 9
 struct MsdFrame {
     u32 start, size;      // range (absolute key index) being partitioned
     int shift_before;     // key bits [0, shift_before) still vary inside the range
     int bits;             // digit = bits [shift_before - bits, shift_before)
-    int dst;              // buffer (0 = A, 1 = B) that holds the partitioned children
+    int dst;              // buffer (0 = the task's own buffer, 1 = the other one) holding the children
     u32 ntasks;
     u32 off[257];         // child offsets relative to start
     u16 task[258];        // first child of every task; task[ntasks] = nchildren
 };
 
-template <int THREADS, int CAP>
+template <int THREADS, int CAP, int HT>
 struct MsdSmem {
-    static constexpr int HT = 2 * CAP;
     static constexpr int BINS = 1024;
     u64 tab[HT];
     u64 lkey[CAP];
@@ -139,7 +238,7 @@ struct MsdSmem {
     u32 bincur[BINS];
     u32 pcur[256];
     u32 ws[33];
-    u32 s_bucket, s_nd, s_out;
+    u32 s_task, s_nd, s_out;
     MsdFrame frames[MSD_MAXD];
 };
 
@@ -157,8 +256,8 @@ __device__ __forceinline__ u32 block_scan_array(u32 *arr, int n, u32 *ws) {
     return total;
 }
 
-template <int THREADS, int CAP>
-__device__ void msd_partition(MsdSmem<THREADS, CAP> &S, MsdFrame &f, const u64 *src, u64 *dst) {
+template <int THREADS, int CAP, int HT>
+__device__ void msd_partition(MsdSmem<THREADS, CAP, HT> &S, MsdFrame &f, const u64 *src, u64 *dst) {
     const int nch = 1 << f.bits, sh = f.shift_before - f.bits;
     const u32 dm = (u32)nch - 1u;
     for (int i = threadIdx.x; i <= 256; i += THREADS) f.off[i] = 0;
@@ -187,7 +286,7 @@ __device__ void msd_partition(MsdSmem<THREADS, CAP> &S, MsdFrame &f, const u64 *
             if (i0 + u * THREADS < f.size) dp[atomicAdd(&S.pcur[(u32)(kk[u] >> sh) & dm], 1u)] = kk[u];
     }
     __syncthreads();
-    // tasks: runs of consecutive small children whose starts share a window of G keys; big children alone
+    // sub-tasks: same merging rule as MsdTaskF with GW = SMALL = CAP / 2
     constexpr u32 G = CAP / 2;
     u32 flag = 0;
     const int c = threadIdx.x;
@@ -205,12 +304,11 @@ __device__ void msd_partition(MsdSmem<THREADS, CAP> &S, MsdFrame &f, const u64 *
 }
 
 // count the n keys of buf[start ..) in the hash table, order the distinct ones, append them
-template <int THREADS, int CAP>
-__device__ void msd_leaf(MsdSmem<THREADS, CAP> &S, const u64 *buf, u32 start, u32 n, int shift, u64 *okeys, u32 *ocnt, u32 obase,
+template <int THREADS, int CAP, int HT>
+__device__ void msd_leaf(MsdSmem<THREADS, CAP, HT> &S, const u64 *buf, u32 start, u32 n, int shift, u64 *okeys, u32 *ocnt, u32 obase,
                          u32 min_freq) {
-    constexpr int HT = 2 * CAP;
     constexpr int LOG_HT = (HT == 2048) ? 11 : (HT == 4096) ? 12 : (HT == 8192) ? 13 : (HT == 16384) ? 14 : 0;
-    static_assert(LOG_HT != 0, "unsupported CAP");
+    static_assert(LOG_HT != 0 && HT % THREADS == 0 && CAP <= HT * 3 / 4, "unsupported leaf geometry");
     for (int i = threadIdx.x; i < HT; i += THREADS) { S.tab[i] = MSD_EMPTY; S.tcnt[i] = 0; }
     if (threadIdx.x == 0) S.s_nd = 0;
     __syncthreads();
@@ -286,23 +384,38 @@ __device__ void msd_leaf(MsdSmem<THREADS, CAP> &S, const u64 *buf, u32 start, u3
     __syncthreads();
 }
 
-template <int THREADS, int CAP>
-__global__ void __launch_bounds__(THREADS) msd_bucket_kernel(u64 *A, u64 *B, u32 *cnt_out, const u32 *__restrict__ bstart,
-                                                             u32 nbuckets, int shift0, u32 *__restrict__ nu_out, u32 *ticket,
-                                                             u32 min_freq) {
+// X: buffer holding the children (read, then overwritten in place with the unique keys);
+// Y: the other buffer (scratch of the depth-first fallback).
+template <int THREADS, int CAP, int HT>
+__global__ void __launch_bounds__(THREADS) msd_task_kernel(u64 *X, u64 *Y, u32 *cnt_out, const u32 *__restrict__ off1,
+                                                           const u32 *__restrict__ tasks, u32 ntasks, u32 nchild, int shiftc,
+                                                           u32 *__restrict__ nu_out, u32 *ticket, u32 min_freq) {
     extern __shared__ __align__(16) u8 smem_raw[];
-    MsdSmem<THREADS, CAP> &S = *reinterpret_cast<MsdSmem<THREADS, CAP> *>(smem_raw);
+    MsdSmem<THREADS, CAP, HT> &S = *reinterpret_cast<MsdSmem<THREADS, CAP, HT> *>(smem_raw);
     for (;;) {
         __syncthreads();
-        if (threadIdx.x == 0) { S.s_bucket = atomicAdd(ticket, 1u); S.s_out = 0; }
+        if (threadIdx.x == 0) { S.s_task = atomicAdd(ticket, 1u); S.s_out = 0; }
         __syncthreads();
-        const u32 b = S.s_bucket;
-        if (b >= nbuckets) break;
-        const u32 bs = bstart[b], bsize = bstart[b + 1] - bs;
-        if (bsize == 0) { if (threadIdx.x == 0) nu_out[b] = 0; continue; }
+        const u32 t = S.s_task;
+        if (t >= ntasks) break;
+        const u32 c0 = tasks[t], c1 = (t + 1 < ntasks) ? tasks[t + 1] : nchild;
+        const u32 bs = off1[c0], bsize = off1[c1] - bs;
+        if (bsize == 0) { if (threadIdx.x == 0) nu_out[t] = 0; continue; }
+        // key bits that vary inside the task: the child's own bits plus the differing child-index bits
+        const u32 x = c0 ^ (c1 - 1);
+        const int shift0 = shiftc + (x ? 32 - __clz(x) : 0);
         if (bsize <= (u32)CAP) {
-            msd_leaf<THREADS, CAP>(S, A, bs, bsize, shift0, A, cnt_out, bs, min_freq);
-            if (threadIdx.x == 0) nu_out[b] = S.s_nd;
+            msd_leaf<THREADS, CAP, HT>(S, X, bs, bsize, shift0, X, cnt_out, bs, min_freq);
+            if (threadIdx.x == 0) nu_out[t] = S.s_nd;
+            continue;
+        }
+        // a single child larger than CAP: partition it again, depth first
+        if (shift0 == 0) {  // no varying bits: the whole child is one k-mer
+            if (threadIdx.x == 0) {
+                u32 keep = bsize >= min_freq;
+                if (keep) cnt_out[bs] = bsize;  // X[bs] already holds the key
+                nu_out[t] = keep;
+            }
             continue;
         }
         u32 cur[MSD_MAXD];
@@ -312,36 +425,28 @@ __global__ void __launch_bounds__(THREADS) msd_bucket_kernel(u64 *A, u64 *B, u32
             f.start = bs; f.size = bsize; f.shift_before = shift0; f.bits = shift0 < 8 ? shift0 : 8; f.dst = 1;
         }
         __syncthreads();
-        if (shift0 == 0) {  // no varying bits: the whole bucket is one k-mer
-            if (threadIdx.x == 0) {
-                u32 keep = bsize >= min_freq;
-                if (keep) { u64 key = A[bs]; A[bs] = key; cnt_out[bs] = bsize; }
-                nu_out[b] = keep;
-            }
-            continue;
-        }
-        msd_partition<THREADS, CAP>(S, S.frames[0], A, B);
+        msd_partition<THREADS, CAP, HT>(S, S.frames[0], X, Y);
         cur[0] = 0;
         while (depth >= 0) {
             MsdFrame &f = S.frames[depth];
             if (cur[depth] == f.ntasks) { --depth; continue; }
-            const u32 c0 = f.task[cur[depth]], c1 = f.task[cur[depth] + 1];
+            const u32 d0 = f.task[cur[depth]], d1 = f.task[cur[depth] + 1];
             ++cur[depth];
-            const u32 s = f.off[c0], n = f.off[c1] - s;
+            const u32 s = f.off[d0], n = f.off[d1] - s;
             if (n == 0) continue;
             if (n <= (u32)CAP) {
                 const u32 ob = bs + S.s_out;
-                msd_leaf<THREADS, CAP>(S, f.dst ? B : A, f.start + s, n, f.shift_before, A, cnt_out, ob, min_freq);
+                msd_leaf<THREADS, CAP, HT>(S, f.dst ? Y : X, f.start + s, n, f.shift_before, X, cnt_out, ob, min_freq);
                 if (threadIdx.x == 0) S.s_out += S.s_nd;
                 __syncthreads();
                 continue;
             }
             const int child_shift = f.shift_before - f.bits;
             if (child_shift == 0 || depth + 1 >= MSD_MAXD) {
-                // all n keys of this child are the same k-mer (child_shift == 0 always holds here: 8 levels cover 64 bits)
+                // all n keys of this child are the same k-mer (8 levels of 8 bits cover the 64-bit key)
                 if (threadIdx.x == 0 && n >= min_freq) {
-                    u64 key = (f.dst ? B : A)[f.start + s];
-                    A[bs + S.s_out] = key;
+                    u64 key = (f.dst ? Y : X)[f.start + s];
+                    X[bs + S.s_out] = key;
                     cnt_out[bs + S.s_out] = n;
                     S.s_out += 1;
                 }
@@ -353,57 +458,62 @@ __global__ void __launch_bounds__(THREADS) msd_bucket_kernel(u64 *A, u64 *B, u32
                 g.start = f.start + s; g.size = n; g.shift_before = child_shift; g.bits = child_shift < 8 ? child_shift : 8; g.dst = 1 - f.dst;
             }
             __syncthreads();
-            msd_partition<THREADS, CAP>(S, S.frames[depth + 1], f.dst ? B : A, f.dst ? A : B);
+            msd_partition<THREADS, CAP, HT>(S, S.frames[depth + 1], f.dst ? Y : X, f.dst ? X : Y);
             ++depth;
             cur[depth] = 0;
         }
         __syncthreads();
-        if (threadIdx.x == 0) nu_out[b] = S.s_out;
+        if (threadIdx.x == 0) nu_out[t] = S.s_out;
     }
 }
 
-__global__ void __launch_bounds__(256) msd_gather_kernel(const u64 *__restrict__ A, const u32 *__restrict__ cnt, const u32 *__restrict__ bstart,
-                                                         const u32 *__restrict__ nu, const u32 *__restrict__ ustart, u32 nbuckets,
-                                                         u64 *__restrict__ okeys, u32 *__restrict__ ocnt) {
-    for (u32 b = blockIdx.x; b < nbuckets; b += gridDim.x) {
-        const u32 n = nu[b], s = bstart[b], d = ustart[b];
+__global__ void __launch_bounds__(256) msd_gather_kernel(const u64 *__restrict__ X, const u32 *__restrict__ cnt, const u32 *__restrict__ off1,
+                                                         const u32 *__restrict__ tasks, const u32 *__restrict__ nu,
+                                                         const u32 *__restrict__ ustart, u32 ntasks, u64 *__restrict__ okeys,
+                                                         u32 *__restrict__ ocnt) {
+    for (u32 t = blockIdx.x; t < ntasks; t += gridDim.x) {
+        const u32 n = nu[t], s = off1[tasks[t]], d = ustart[t];
         for (u32 i = threadIdx.x; i < n; i += 256) {
-            okeys[d + i] = A[s + i];
+            okeys[d + i] = X[s + i];
             ocnt[d + i] = cnt[s + i];
         }
     }
 }
-__global__ void msd_cursor_init_kernel(const u32 *__restrict__ bstart, u32 nb, u32 *__restrict__ cursor) {
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nb) cursor[i] = bstart[i];
-}
 
 struct MsdTune {
-    int b0_max = 9;      // level-0 digit bits (<= MSD_MAX_B0)
-    int variant = 3;     // 3: 1024 threads, CAP 4096, 1 CTA/SM (best measured); 0: 512/4096/1; 1: 256/2048/2; 2: 512/2048/2; 4: 256/1024/3
-    int keys_per_bucket_log2 = 16;
+    int b0_max = 10;       // level-0 digit bits (<= MSD_MAX_B0)
+    int b1_max = 9;        // level-1 digit bits (<= MSD_MAX_B1)
+    int child_log2 = 9;    // target keys per child = 2^child_log2
+    int variant = 0;       // task kernel geometry, see msd_launch_tasks
+    int gw = 0, small = 0; // task merging window / small-child threshold (0 = from the variant)
 };
 static MsdTune msd_tune() {
     MsdTune t;
     if (const char *e = getenv("GG_MSD_B0")) t.b0_max = atoi(e);
+    if (const char *e = getenv("GG_MSD_B1")) t.b1_max = atoi(e);
+    if (const char *e = getenv("GG_MSD_CHILD")) t.child_log2 = atoi(e);
     if (const char *e = getenv("GG_MSD_VARIANT")) t.variant = atoi(e);
-    if (const char *e = getenv("GG_MSD_KPB")) t.keys_per_bucket_log2 = atoi(e);
+    if (const char *e = getenv("GG_MSD_GW")) t.gw = atoi(e);
+    if (const char *e = getenv("GG_MSD_SMALL")) t.small = atoi(e);
     if (t.b0_max > MSD_MAX_B0) t.b0_max = MSD_MAX_B0;
     if (t.b0_max < 0) t.b0_max = 0;
+    if (t.b1_max > MSD_MAX_B1) t.b1_max = MSD_MAX_B1;
+    if (t.b1_max < 0) t.b1_max = 0;
     return t;
 }
 
-template <int THREADS, int CAP>
-static void msd_launch_bucket(gg_ctx *ctx, u64 *A, u64 *B, u32 *cnt, const u32 *bstart, u32 nb, int shift0, u32 *nu, u32 *ticket, u32 min_freq, int ctas_per_sm) {
-    size_t smem = sizeof(MsdSmem<THREADS, CAP>);
+template <int THREADS, int CAP, int HT>
+static void msd_launch_tasks(gg_ctx *ctx, int ctas_per_sm, u64 *X, u64 *Y, u32 *cnt, const u32 *off1, const u32 *tasks, u32 ntasks,
+                             u32 nchild, int shiftc, u32 *nu, u32 *ticket, u32 min_freq) {
+    size_t smem = sizeof(MsdSmem<THREADS, CAP, HT>);
     static bool set = false;
     if (!set) {
-        CK(cudaFuncSetAttribute(msd_bucket_kernel<THREADS, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(msd_task_kernel<THREADS, CAP, HT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         set = true;
     }
     u32 grid = (u32)ctx->num_sms * ctas_per_sm;
-    if (grid > nb) grid = nb;
-    LAUNCH(ctx, (msd_bucket_kernel<THREADS, CAP>), grid, THREADS, smem, A, B, cnt, bstart, nb, shift0, nu, ticket, min_freq);
+    if (grid > ntasks) grid = ntasks;
+    LAUNCH(ctx, (msd_task_kernel<THREADS, CAP, HT>), grid, THREADS, smem, X, Y, cnt, off1, tasks, ntasks, nchild, shiftc, nu, ticket, min_freq);
 }
 
 // packed reads -> sorted unique k-mers + counts (count >= min_freq only).  k <= 32.
@@ -414,20 +524,27 @@ static u64 msd_count(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int k
     const u64 nwords = pr.nwords;
     *n_instances = 0;
     if (nwords == 0) { ukeys.alloc(ctx, 1); ucounts.alloc(ctx, 1); return 0; }
-    // the number of windows bounds N; pick b0 from it (cheap upper bound: one window per base)
-    int b0 = 0;
-    while (b0 < tune.b0_max && (pr.nbases >> (b0 + tune.keys_per_bucket_log2)) > 0) ++b0;
+    // digit widths from the number of windows (upper bound of N): children of ~2^child_log2 keys
+    int bt = 0;
+    while (bt < 21 && (pr.nbases >> (bt + tune.child_log2)) > 0) ++bt;
+    int b0 = (bt + 1) / 2;
+    if (b0 > tune.b0_max) b0 = tune.b0_max;
     if (b0 > 2 * k) b0 = 2 * k;
-    const u32 nb = 1u << b0;
+    int b1 = bt - b0;
+    if (b1 > tune.b1_max) b1 = tune.b1_max;
+    if (b1 > 2 * k - b0) b1 = 2 * k - b0;
+    const u32 nb0 = 1u << b0;
+    const u64 nchild = (u64)nb0 << b1;
+    const int shiftc = 2 * k - b0 - b1;
     // ---- A: histogram ----
     stage_begin(ctx, ST_EXTRACT);
-    DBuf<u32> hist(ctx, nb + 1), bstart(ctx, nb + 1), cursor(ctx, nb), nu(ctx, nb), ustart(ctx, nb + 1), ticket(ctx, 1);
+    DBuf<u32> hist(ctx, nb0 + 1), bstart(ctx, nb0 + 1), cursor(ctx, nb0), tcount(ctx, nb0 + 1), tstart(ctx, nb0 + 1), ticket(ctx, 1);
     DBuf<u64> tot(ctx, 1);
-    CK(cudaMemsetAsync(hist.p, 0, (nb + 1) * sizeof(u32), ctx->stream));
+    CK(cudaMemsetAsync(hist.p, 0, (nb0 + 1) * sizeof(u32), ctx->stream));
     u64 hgrid = ceil_div(nwords, 256);
     if (hgrid > (u64)ctx->num_sms * 8) hgrid = (u64)ctx->num_sms * 8;
     LAUNCH(ctx, msd_hist_kernel, (unsigned)hgrid, 256, 0, pr.packed.p, valid, nwords, k, canonical, b0, hist.p);
-    exclusive_scan_u32(ctx, hist.p, bstart.p, nb + 1, tot.p);
+    exclusive_scan_u32(ctx, hist.p, bstart.p, nb0 + 1, tot.p);
     const u64 N = read_scalar<u64>(ctx, tot.p);
     *n_instances = N;
     if (N == 0) { stage_end(ctx, ST_EXTRACT); ukeys.alloc(ctx, 1); ucounts.alloc(ctx, 1); return 0; }
@@ -435,30 +552,56 @@ static u64 msd_count(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int k
     // ---- B: extract + scatter ----
     DBuf<u64> A(ctx, N), B(ctx, N);
     DBuf<u32> cnt(ctx, N);
-    LAUNCH(ctx, msd_cursor_init_kernel, (unsigned)ceil_div(nb, 256), 256, 0, bstart.p, nb, cursor.p);
+    LAUNCH(ctx, msd_copy_u32_kernel, (unsigned)ceil_div(nb0, 256), 256, 0, bstart.p, (u64)nb0, cursor.p);
     size_t smemB = (size_t)MSD_TILE_KEYS * 8 + 2 * (size_t)(1 << MSD_MAX_B0) * 4;
     static bool setB = false;
     if (!setB) { CK(cudaFuncSetAttribute(msd_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB)); setB = true; }
     LAUNCH(ctx, msd_scatter_kernel, (unsigned)ceil_div(nwords, 256), 256, smemB, pr.packed.p, valid, nwords, k, canonical, b0, cursor.p, A.p);
     stage_end(ctx, ST_EXTRACT);
-    // ---- C: per-bucket counting ----
+    // ---- C, D: level-1 partition (children in X) ----
     stage_begin(ctx, ST_SORT);
+    DBuf<u32> off1(ctx, nchild + 1), tasks(ctx, nchild + 1);
+    u64 *X = A.p, *Y = B.p;
+    if (b1 > 0) {
+        DBuf<u32> hist1(ctx, nchild + 1), cursor1(ctx, nchild);
+        CK(cudaMemsetAsync(hist1.p, 0, (nchild + 1) * sizeof(u32), ctx->stream));
+        LAUNCH(ctx, msd_tilecount_kernel, (unsigned)ceil_div(nb0 + 1, 256), 256, 0, bstart.p, nb0, tcount.p);
+        exclusive_scan_u32(ctx, tcount.p, tstart.p, nb0 + 1, nullptr);
+        const unsigned tgrid = (unsigned)(ceil_div(N, MSD_T1) + nb0);
+        LAUNCH(ctx, msd_hist1_kernel, tgrid, 256, 0, A.p, tstart.p, bstart.p, nb0, shiftc, b1, hist1.p);
+        exclusive_scan_u32(ctx, hist1.p, off1.p, nchild + 1, nullptr);
+        LAUNCH(ctx, msd_copy_u32_kernel, (unsigned)ceil_div(nchild, 256), 256, 0, off1.p, nchild, cursor1.p);
+        LAUNCH(ctx, msd_scatter1_kernel, tgrid, 256, 0, A.p, tstart.p, bstart.p, nb0, shiftc, b1, cursor1.p, B.p);
+        X = B.p;
+        Y = A.p;
+    } else {
+        LAUNCH(ctx, msd_copy_u32_kernel, (unsigned)ceil_div(nchild + 1, 256), 256, 0, bstart.p, nchild + 1, off1.p);
+    }
+    // ---- E: tasks ----
+    int variant = tune.variant;
+    u32 cap = variant == 1 ? 6144u : variant == 2 ? 1536u : 3072u;
+    MsdTaskF tf{off1.p, tasks.p, tune.gw ? (u32)tune.gw : cap * 2 / 3, tune.small ? (u32)tune.small : cap / 3};
+    if (tf.gw + tf.small > cap) GG_THROW(GG_ERR_ARG, "GG_MSD_GW + GG_MSD_SMALL exceed the leaf capacity %u", cap);
+    Compactor<MsdTaskF> tc(ctx, nchild, "msd_tasks");
+    const u32 ntasks = (u32)tc.count(tf);
+    tc.emit(tf);
+    // ---- F: per-task counting ----
+    DBuf<u32> nu(ctx, ntasks + 1), ustart(ctx, ntasks + 1);
     CK(cudaMemsetAsync(ticket.p, 0, sizeof(u32), ctx->stream));
-    if (tune.variant == 1) msd_launch_bucket<256, 2048>(ctx, A.p, B.p, cnt.p, bstart.p, nb, 2 * k - b0, nu.p, ticket.p, min_freq, 2);
-    else if (tune.variant == 2) msd_launch_bucket<512, 2048>(ctx, A.p, B.p, cnt.p, bstart.p, nb, 2 * k - b0, nu.p, ticket.p, min_freq, 2);
-    else if (tune.variant == 3) msd_launch_bucket<1024, 4096>(ctx, A.p, B.p, cnt.p, bstart.p, nb, 2 * k - b0, nu.p, ticket.p, min_freq, 1);
-    else if (tune.variant == 4) msd_launch_bucket<256, 1024>(ctx, A.p, B.p, cnt.p, bstart.p, nb, 2 * k - b0, nu.p, ticket.p, min_freq, 3);
-    else msd_launch_bucket<512, 4096>(ctx, A.p, B.p, cnt.p, bstart.p, nb, 2 * k - b0, nu.p, ticket.p, min_freq, 1);
+    if (variant == 1) msd_launch_tasks<1024, 6144, 8192>(ctx, 1, X, Y, cnt.p, off1.p, tasks.p, ntasks, (u32)nchild, shiftc, nu.p, ticket.p, min_freq);
+    else if (variant == 2) msd_launch_tasks<256, 1536, 2048>(ctx, 3, X, Y, cnt.p, off1.p, tasks.p, ntasks, (u32)nchild, shiftc, nu.p, ticket.p, min_freq);
+    else if (variant == 3) msd_launch_tasks<256, 3072, 4096>(ctx, 2, X, Y, cnt.p, off1.p, tasks.p, ntasks, (u32)nchild, shiftc, nu.p, ticket.p, min_freq);
+    else msd_launch_tasks<512, 3072, 4096>(ctx, 2, X, Y, cnt.p, off1.p, tasks.p, ntasks, (u32)nchild, shiftc, nu.p, ticket.p, min_freq);
     stage_end(ctx, ST_SORT);
-    // ---- D: gather ----
+    // ---- G: gather ----
     stage_begin(ctx, ST_COUNT);
-    exclusive_scan_u32(ctx, nu.p, ustart.p, nb, tot.p);
+    exclusive_scan_u32(ctx, nu.p, ustart.p, ntasks, tot.p);
     const u64 U = read_scalar<u64>(ctx, tot.p);
     ukeys.alloc(ctx, U ? U : 1);
     ucounts.alloc(ctx, U ? U : 1);
     if (U) {
-        u32 ggrid = nb < (u32)ctx->num_sms * 8 ? nb : (u32)ctx->num_sms * 8;
-        LAUNCH(ctx, msd_gather_kernel, ggrid, 256, 0, A.p, cnt.p, bstart.p, nu.p, ustart.p, nb, ukeys.p, ucounts.p);
+        u32 ggrid = ntasks < (u32)ctx->num_sms * 16 ? ntasks : (u32)ctx->num_sms * 16;
+        LAUNCH(ctx, msd_gather_kernel, ggrid, 256, 0, X, cnt.p, off1.p, tasks.p, nu.p, ustart.p, ntasks, ukeys.p, ucounts.p);
     }
     stage_end(ctx, ST_COUNT);
     return U;
