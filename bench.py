@@ -39,13 +39,30 @@ WORKLOADS = {
     "tiny": dict(genome_len=200000, cov=30, read_len=150, frag_len=500, err_ppm=2000, k=31, min_freq=2),
 }
 
-# algorithmic (compulsory) bytes per k-mer INSTANCE for the kernels that can dominate; W = key bytes
+# algorithmic (compulsory) bytes per LAUNCH of the kernels that can dominate ("Kernels"):
+# every input element read once, every output element written once.  N = k-mer instances,
+# nb = input bases, U = distinct k-mers kept by the min-count filter, W = key bytes.
+def _stream_bytes(nb):  # packed words (8 B / 32 bases) + window-valid masks (4 B / 32 bases)
+    return 12.0 * ((nb + 31) // 32)
+
+
 ALG_BYTES = {
-    "radix_scatter_kernel": lambda W: 2 * W,       # read every key once, write every key once
-    "radix_hist_kernel": lambda W: W,              # read every key once
-    "extract_emit_kernel": lambda W: 0.3125 + W,   # 0.25 B/base packed + masks read, W written
-    "extract_count_kernel": lambda W: 0.0625,
+    "msd_hist_kernel": lambda N, nb, U, W: _stream_bytes(nb),
+    "msd_scatter_kernel": lambda N, nb, U, W: _stream_bytes(nb) + W * N,
+    "msd_hist1_kernel": lambda N, nb, U, W: W * N,
+    "msd_scatter1_kernel": lambda N, nb, U, W: 2.0 * W * N,
+    "msd_task_kernel": lambda N, nb, U, W: W * N + (W + 4.0) * U,
+    "msd_gather_kernel": lambda N, nb, U, W: 2.0 * (W + 4.0) * U,
+    "radix_scatter_kernel": lambda N, nb, U, W: 2.0 * W * N,   # per pass
+    "radix_hist_kernel": lambda N, nb, U, W: 1.0 * W * N,
+    "extract_emit_kernel": lambda N, nb, U, W: _stream_bytes(nb) + W * N,
+    "pack_kernel": lambda N, nb, U, W: 1.375 * nb,             # 1 B ASCII in, 2 bits + 1 bad bit out
 }
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
+# captures of the default workload (profiles/README.md); null where no capture exists
+NCU_TRAFFIC = {}
 
 
 def nreads_for(w):
@@ -289,17 +306,43 @@ def main():
         except Exception:
             pass
         peak, peak_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json hbm_gbs)") if peaks.get("hbm_gbs") else (6650.0, "fallback (B200_PROFILING.md)")
+        # distinct k-mers kept by the filter (writes of the counting kernels), outside any timed region
+        ch = C.c_void_p()
+        N.check(H, L.gg_count_kmers_dev(H, d_seq, d_offs, nreads, nbytes, k, 1, C.byref(ch)))
+        nu_all = C.c_uint64()
+        N.check(H, L.gg_counts_sizes(ch, C.byref(nu_all), None, None, None))
+        N.check(H, L.gg_counts_filter(ch, min_freq, 0))
+        nu_kept = C.c_uint64()
+        N.check(H, L.gg_counts_sizes(ch, C.byref(nu_kept), None, None, None))
+        L.gg_counts_free(ch)
+        distinct = {"all": nu_all.value, "kept": nu_kept.value}
+
+        def model(kname, kcnt, kms):
+            f = ALG_BYTES.get(kname)
+            if f is None:
+                return None
+            by = f(float(n_inst), float(nbytes), float(nu_kept.value), float(W))
+            gbs = by / (kms / kcnt / 1e3) / 1e9
+            return by, gbs
+
         name, (cnt, ms) = top[0]
-        per_inst = ALG_BYTES.get(name, lambda W_: None)(W)
-        if per_inst is not None:
-            achieved = per_inst * n_inst / (ms / cnt / 1e3) / 1e9
-            roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": None, "launches_per_step": cnt, "avg_launch_ms": ms / cnt, "share_of_kernel_time": ms / tot_ms,
-                        "alg_bytes_per_launch": per_inst * n_inst, "peak_source": peak_src}
+        m = model(name, cnt, ms)
+        if m is not None:
+            roofline = {"bound": "hbm", "kernel": name, "achieved": m[1], "peak": peak, "unit": "GB/s", "frac": m[1] / peak,
+                        "traffic": NCU_TRAFFIC.get(name), "launches_per_step": cnt, "avg_launch_ms": ms / cnt, "share_of_kernel_time": ms / tot_ms,
+                        "alg_bytes_per_launch": m[0], "peak_source": peak_src}
         else:
             roofline = {"bound": "hbm", "kernel": name, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
                         "launches_per_step": cnt, "avg_launch_ms": ms / cnt, "share_of_kernel_time": ms / tot_ms, "peak_source": peak_src,
                         "note": "latency-bound pointer chasing; no streaming byte model"}
+        kernel_rooflines = []
+        for kname, (kcnt, kms) in top:
+            m = model(kname, kcnt, kms)
+            if m is not None:
+                kernel_rooflines.append({"kernel": kname, "alg_bytes_per_launch": m[0], "avg_launch_ms": kms / kcnt,
+                                         "achieved_gbs": round(m[1], 1), "frac": round(m[1] / peak, 4)})
+        roofline["distinct_kmers"] = distinct
+        roofline["other_kernels"] = kernel_rooflines
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----
     cpu = None

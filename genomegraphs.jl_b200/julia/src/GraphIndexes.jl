@@ -1,0 +1,50 @@
+# UniqueMerIndex built on the GPU (reference src/GraphIndexes.jl:14-17, :27-41, :62-102; the
+# constructor there references unimported names and mis-sizes unique_mers_per_node -- this file
+# implements the documented intent: one entry per node).
+module GraphIndexes
+
+export UniqueMerIndex, GraphStrandPosition, find_unique_mer, isunmappable
+
+using BioSequences
+import ..Graphs
+import ..LibGG
+
+struct GraphStrandPosition
+    node::Graphs.NodeID   # sign = strand of the canonical k-mer relative to the node
+    position::UInt32      # 1-based start of the k-mer in the node sequence
+end
+Base.show(io::IO, x::GraphStrandPosition) = print(io, "(Node: ", x.node, ", Base position: ", x.position, ')')
+
+struct UniqueMerIndex{M<:AbstractMer}
+    mer_to_graphposition::Dict{M,GraphStrandPosition}
+    unique_mers_per_node::Vector{UInt64}
+    total_mers_per_node::Vector{UInt64}
+end
+
+isunmappable(idx::UniqueMerIndex, nodeid::Graphs.NodeID) = idx.unique_mers_per_node[abs(nodeid)] == 0
+
+function find_unique_mer(idx::UniqueMerIndex{M}, mer::M) where {M<:AbstractMer}
+    pos = get(idx.mer_to_graphposition, mer, GraphStrandPosition(0, 0))
+    return pos != GraphStrandPosition(0, 0), pos
+end
+
+mer_from_words(::Type{M}, w, i) where {M<:Mer} = M(w[i])
+mer_from_words(::Type{M}, w, i) where {M<:BigMer} = M((UInt128(w[2i - 1]) << 64) | UInt128(w[2i]))
+
+function UniqueMerIndex{M}(sg::Graphs.SequenceDistanceGraph; ctx::LibGG.Context = LibGG.default_context()) where {M<:AbstractMer}
+    buf = IOBuffer()
+    offs = UInt64[0]
+    for n in Graphs.nodes(sg)
+        print(buf, n.seq)
+        push!(offs, UInt64(position(buf)))
+    end
+    words, node, pos, upn, tpn, _ = LibGG.unique_mer_index(ctx, take!(buf), offs, BioSequences.ksize(M))
+    d = Dict{M,GraphStrandPosition}()
+    sizehint!(d, length(node))
+    for i in eachindex(node)
+        d[mer_from_words(M, words, i)] = GraphStrandPosition(node[i], pos[i])
+    end
+    return UniqueMerIndex{M}(d, upn, tpn)
+end
+
+end # module GraphIndexes
