@@ -224,7 +224,7 @@ static gg_counts *count_kmers_dev_impl(gg_ctx *ctx, const u8 *d_seq, const u64 *
     c->ctx = ctx; c->k = k; c->W = W;
     if (filtered) *filtered = false;
     try {
-        if (W == 1 && !getenv("GG_FORCE_LSD")) {
+        if (W == 1 && msd_supported(k, canonical) && !getenv("GG_FORCE_LSD")) {
             stage_begin(ctx, ST_PACK);
             PackedReads pr;
             pack_reads(ctx, d_seq, d_offs, nreads, nbytes, pr);

@@ -5,29 +5,37 @@
 // run-length collapse (docs/src/man/assembly.md:126-128).  Output is identical (sorted unique
 // k-mers + counts); the route is an MSD formulation sized for HBM traffic:
 //
-//   A  msd_hist_kernel      roll over the packed reads, histogram of the top b0 key bits
+//   A  msd_hist_kernel      roll over the packed reads: histogram of the top 12 key bits and a
+//                           distinct-count estimate (hash-sampled slice of the key space)
+//      plan                 children of ~3072 DISTINCT keys: b0 (<= 12) + b1 (<= 10) digit bits
 //   B  msd_scatter_kernel   one roll per 32 windows (keys stay in registers), tile staged in
 //                           shared memory grouped by bucket, one reservation per (tile, bucket)
-//   C  msd_hist1_kernel     per level-0 bucket, histogram of the next b1 bits
+//   C  msd_hist1_kernel     (only when b1 > 0) per level-0 bucket, histogram of the next b1 bits
 //   D  msd_scatter1_kernel  same staging scheme, keys -> 2^(b0+b1) ordered children
-//   E  task list            runs of consecutive small children (<= CAP keys together)
-//   F  msd_task_kernel      one CTA per task: keys counted in a shared-memory hash table, the
-//                           distinct keys put in order by order-preserving bins + rank-by-counting
-//                           and written in place.  A child larger than CAP is partitioned again
-//                           by the CTA (8 bits per level, depth first); a range with no key bits
-//                           left is one run.
-//   G  msd_gather_kernel    per-task unique runs -> dense output arrays
+//   E  msd_leaf_kernel      one CTA per child: all instances streamed through a shared-memory
+//                           hash table (capacity bounds DISTINCT keys, not instances), distinct
+//                           keys put in order by order-preserving bins + rank-by-counting.  A
+//                           child whose table overflows is partitioned again by the CTA (8 bits
+//                           per level, depth first).
+//   F  msd_gather_kernel    per-child unique runs -> dense output arrays
 //
-// Algorithmic bytes per k-mer instance (8-byte keys): A 0.31 read; B 0.31 read + 8 written;
-// C 8 read; D 8 read + 8 written; F 8 read + 12 U/N written; G 24 U/N.
+// A bucket / child may be given as several segments (virtual buckets): in the multi-GPU path
+// the segments are the pieces received from the ranks (dist.cuh).
+//
+// Algorithmic bytes per k-mer instance (8-byte keys, U = distinct kept): A 0.47 read;
+// B 0.47 read + 8 written; C 8 read; D 8 read + 8 written; E 8 read + 12 U/N written; F 24 U/N.
 #pragma once
 #include "pack.cuh"
 #include "sort.cuh"
 
-#define MSD_MAX_B0 11
+#define MSD_HB 12      // resolution of the pass-A histogram (bits) = largest level-0 digit
 #define MSD_MAX_B1 10
-#define MSD_UNROLL 8  // independent global loads in flight per thread in the task kernel
-#define MSD_EMPTY 0xFFFFFFFFFFFFFFFFULL  // never a valid key: all-T k-mers are not canonical, and 2k < 64 otherwise
+#define MSD_UNROLL 8   // independent global loads in flight per thread in the leaf kernel
+#define MSD_EMPTY 0xFFFFFFFFFFFFFFFFULL  // never a valid key: all-T k-mers are not canonical, 2k < 64 otherwise (see msd_supported)
+#define MSD_GOLD 0x9E3779B97F4A7C15ULL
+#define EST_LOG 20     // slots of the distinct-estimate table
+
+static inline bool msd_supported(int k, int canonical) { return k <= 32 && (canonical || k < 32); }
 
 // 32 consecutive windows starting at base 32 t (k <= 32): f(key, j) for every valid window j
 template <class F>
@@ -52,23 +60,63 @@ __device__ __forceinline__ void roll32(const u64 *__restrict__ packed, const u32
     }
 }
 
+
 __device__ __forceinline__ u32 msd_digit0(u64 key, int sh, int b0) { return b0 ? (u32)(key >> sh) : 0u; }
 
+// ---- pass A: 12-bit histogram + distinct estimate -------------------------------------------
+// Estimate: keys whose hash falls into a 2^-est_shift slice of the hash space are inserted into a
+// global open-addressing set; (#occupied << est_shift) estimates the number of distinct keys.
 __global__ void __launch_bounds__(256) msd_hist_kernel(const u64 *__restrict__ packed, const u32 *__restrict__ valid, u64 nwords,
-                                                       int k, int canonical, int b0, u32 *__restrict__ ghist) {
-    __shared__ u32 h[1 << MSD_MAX_B0];
-    const int nb = 1 << b0, sh = 2 * k - b0;
+                                                       int k, int canonical, int hb, u32 *__restrict__ ghist, u32 est_max,
+                                                       unsigned long long *__restrict__ est_tab) {
+    __shared__ u32 h[1 << MSD_HB];
+    const int nb = 1 << hb, sh = 2 * k - hb;
     for (int i = threadIdx.x; i < nb; i += 256) h[i] = 0;
     __syncthreads();
     for (u64 t = (u64)blockIdx.x * 256 + threadIdx.x; t < nwords; t += (u64)gridDim.x * 256)
-        roll32(packed, valid, t, k, canonical, [&](u64 key, int) { atomicAdd(&h[msd_digit0(key, sh, b0)], 1u); });
+        roll32(packed, valid, t, k, canonical, [&](u64 key, int) {
+            atomicAdd(&h[msd_digit0(key, sh, hb)], 1u);
+            const u32 p = (u32)key * 0x9E3779B1u;  // hash of the last 16 bases: a sampler, not an identity
+            if (p <= est_max) {
+                u32 slot = (u32)(((u64)key * MSD_GOLD) >> (64 - EST_LOG));
+                for (int probe = 0; probe < 64; ++probe) {
+                    unsigned long long cur = est_tab[slot];
+                    if (cur == (unsigned long long)key) break;
+                    if (cur == MSD_EMPTY) {
+                        cur = atomicCAS(&est_tab[slot], (unsigned long long)MSD_EMPTY, (unsigned long long)key);
+                        if (cur == MSD_EMPTY || cur == (unsigned long long)key) break;
+                    }
+                    slot = (slot + 1) & ((1u << EST_LOG) - 1u);
+                }
+            }
+        });
     __syncthreads();
     for (int i = threadIdx.x; i < nb; i += 256)
         if (h[i]) atomicAdd(&ghist[i], h[i]);
 }
+// out[0] += number of occupied estimate slots; out[1] += sum of the histogram (N)
+__global__ void __launch_bounds__(256) msd_est_count_kernel(const unsigned long long *__restrict__ est_tab, const u32 *__restrict__ hist,
+                                                            u32 nb, unsigned long long *__restrict__ out) {
+    u64 occ = 0, n = 0;
+    for (u32 i = blockIdx.x * 256 + threadIdx.x; i < (1u << EST_LOG); i += gridDim.x * 256) occ += est_tab[i] != MSD_EMPTY;
+    for (u32 i = blockIdx.x * 256 + threadIdx.x; i < nb; i += gridDim.x * 256) n += hist[i];
+    for (int d = 16; d > 0; d >>= 1) { occ += __shfl_xor_sync(FULL_MASK, occ, d); n += __shfl_xor_sync(FULL_MASK, n, d); }
+    if (lane_id() == 0) { if (occ) atomicAdd(&out[0], (unsigned long long)occ); if (n) atomicAdd(&out[1], (unsigned long long)n); }
+}
+// 2^hb-bin histogram -> 2^b0 bins (b0 <= hb)
+__global__ void msd_collapse_kernel(const u32 *__restrict__ hist, int hb, int b0, u32 *__restrict__ out) {
+    u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > (1u << b0)) return;
+    u32 s = 0;
+    if (b < (1u << b0)) {
+        const u32 g = 1u << (hb - b0);
+        for (u32 i = 0; i < g; ++i) s += hist[b * g + i];
+    }
+    out[b] = s;
+}
 
 // shared tail of the two scatter kernels: bins counted in hist[0..nb) -> per-bin reservation in
-// the global cursors, hist becomes the in-tile running cursor, delta the global-minus-local base
+// the global cursors; hist becomes the in-tile running cursor, delta the global-minus-local base
 template <int BPT>
 __device__ __forceinline__ u32 msd_reserve(u32 *hist, u32 *delta, int nb, u32 *__restrict__ cursor, u32 *ws) {
     const int bpt = (nb + 255) / 256;  // <= BPT
@@ -93,14 +141,14 @@ __device__ __forceinline__ u32 msd_reserve(u32 *hist, u32 *delta, int nb, u32 *_
     return total;
 }
 
-// tile = 256 words = 8192 window positions
+// ---- pass B: tile = 256 words = 8192 window positions ------------------------------------------
 #define MSD_TILE_KEYS 8192
-__global__ void __launch_bounds__(256) msd_scatter_kernel(const u64 *__restrict__ packed, const u32 *__restrict__ valid, u64 nwords,
-                                                          int k, int canonical, int b0, u32 *__restrict__ cursor, u64 *__restrict__ out) {
+__global__ void __launch_bounds__(256, 2) msd_scatter_kernel(const u64 *__restrict__ packed, const u32 *__restrict__ valid, u64 nwords,
+                                                             int k, int canonical, int b0, u32 *__restrict__ cursor, u64 *__restrict__ out) {
     extern __shared__ __align__(16) u8 smem_raw[];
     u64 *skeys = reinterpret_cast<u64 *>(smem_raw);                      // MSD_TILE_KEYS
-    u32 *hist = reinterpret_cast<u32 *>(skeys + MSD_TILE_KEYS);          // 2^b0
-    u32 *delta = hist + (1 << MSD_MAX_B0);                               // 2^b0
+    u32 *hist = reinterpret_cast<u32 *>(skeys + MSD_TILE_KEYS);          // 2^MSD_HB
+    u32 *delta = hist + (1 << MSD_HB);                                   // 2^MSD_HB
     __shared__ u32 ws[33];
     const int nb = 1 << b0, sh = 2 * k - b0;
     const u64 t = (u64)blockIdx.x * 256 + threadIdx.x;
@@ -114,7 +162,7 @@ __global__ void __launch_bounds__(256) msd_scatter_kernel(const u64 *__restrict_
         roll32(packed, valid, t, k, canonical, [&](u64 key, int j) { keys[j] = key; atomicAdd(&hist[msd_digit0(key, sh, b0)], 1u); });
     }
     __syncthreads();
-    const u32 total = msd_reserve<8>(hist, delta, nb, cursor, ws);
+    const u32 total = msd_reserve<(1 << MSD_HB) / 256>(hist, delta, nb, cursor, ws);
 #pragma unroll
     for (int j = 0; j < 32; ++j)
         if ((vm >> (31 - j)) & 1u) skeys[atomicAdd(&hist[msd_digit0(keys[j], sh, b0)], 1u)] = keys[j];
@@ -125,32 +173,36 @@ __global__ void __launch_bounds__(256) msd_scatter_kernel(const u64 *__restrict_
     }
 }
 
-// ------------------------------ level 1: bucket-aligned tiles --------------------------------
+// ---- level 1 over virtual buckets ---------------------------------------------------------------
+// Virtual bucket vb = (local bucket bl) * nsrc + src: keys IN[vbeg[vb] .. vbeg[vb] + vcnt[vb]), all
+// of level-0 bucket bl.  Single GPU: nsrc = 1.  Tiles never straddle a virtual bucket.
 #define MSD_T1 4096  // keys per tile (16 per thread)
-__global__ void msd_tilecount_kernel(const u32 *__restrict__ bstart, u32 nb, u32 *__restrict__ tcount) {
+__global__ void msd_tilecount_kernel(const u32 *__restrict__ vcnt, u32 nvb, u32 *__restrict__ tcount) {
     u32 b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b <= nb) tcount[b] = b < nb ? (bstart[b + 1] - bstart[b] + MSD_T1 - 1) / MSD_T1 : 0;
+    if (b <= nvb) tcount[b] = b < nvb ? (vcnt[b] + MSD_T1 - 1) / MSD_T1 : 0;
 }
-// tile t -> (bucket, key range)
-__device__ __forceinline__ bool msd_tile_range(const u32 *__restrict__ tstart, const u32 *__restrict__ bstart, u32 nb, u32 t, u32 &b,
-                                               u32 &s, u32 &e) {
-    if (t >= tstart[nb]) return false;
-    u32 lo = 0, hi = nb;  // largest b with tstart[b] <= t
+__device__ __forceinline__ bool msd_tile_range(const u32 *__restrict__ tstart, const u32 *__restrict__ vbeg, const u32 *__restrict__ vcnt,
+                                               u32 nvb, u32 t, u32 &vb, u32 &s, u32 &e) {
+    if (t >= tstart[nvb]) return false;
+    u32 lo = 0, hi = nvb;  // largest vb with tstart[vb] <= t
     while (hi - lo > 1) {
         u32 mid = (lo + hi) >> 1;
         if (tstart[mid] <= t) lo = mid; else hi = mid;
     }
-    b = lo;
-    s = bstart[b] + (t - tstart[b]) * MSD_T1;
-    e = min(bstart[b + 1], s + MSD_T1);
+    vb = lo;
+    const u32 b0 = vbeg[vb];
+    s = b0 + (t - tstart[vb]) * MSD_T1;
+    e = min(b0 + vcnt[vb], s + MSD_T1);
     return true;
 }
+__device__ __forceinline__ u32 msd_digit1(u64 key, int sh1, u32 dm) { return dm ? ((u32)(key >> sh1) & dm) : 0u; }
+
 __global__ void __launch_bounds__(256) msd_hist1_kernel(const u64 *__restrict__ A, const u32 *__restrict__ tstart,
-                                                        const u32 *__restrict__ bstart, u32 nb0, int sh1, int b1,
-                                                        u32 *__restrict__ hist1) {
+                                                        const u32 *__restrict__ vbeg, const u32 *__restrict__ vcnt, u32 nvb, u32 nsrc,
+                                                        int sh1, int b1, u32 *__restrict__ hist1) {
     __shared__ u32 h[1 << MSD_MAX_B1];
-    u32 b, s, e;
-    if (!msd_tile_range(tstart, bstart, nb0, blockIdx.x, b, s, e)) return;
+    u32 vb, s, e;
+    if (!msd_tile_range(tstart, vbeg, vcnt, nvb, blockIdx.x, vb, s, e)) return;
     const int nb = 1 << b1;
     const u32 dm = (u32)nb - 1u;
     for (int i = threadIdx.x; i < nb; i += 256) h[i] = 0;
@@ -160,20 +212,21 @@ __global__ void __launch_bounds__(256) msd_hist1_kernel(const u64 *__restrict__ 
     for (int u = 0; u < 16; ++u) { u32 i = s + u * 256 + threadIdx.x; kk[u] = i < e ? A[i] : 0; }
 #pragma unroll
     for (int u = 0; u < 16; ++u)
-        if (s + u * 256 + threadIdx.x < e) atomicAdd(&h[(u32)(kk[u] >> sh1) & dm], 1u);
+        if (s + u * 256 + threadIdx.x < e) atomicAdd(&h[msd_digit1(kk[u], sh1, dm)], 1u);
     __syncthreads();
+    const u64 cb = (u64)(vb / nsrc) << b1;
     for (int i = threadIdx.x; i < nb; i += 256)
-        if (h[i]) atomicAdd(&hist1[((u64)b << b1) + i], h[i]);
+        if (h[i]) atomicAdd(&hist1[cb + i], h[i]);
 }
 __global__ void __launch_bounds__(256) msd_scatter1_kernel(const u64 *__restrict__ A, const u32 *__restrict__ tstart,
-                                                           const u32 *__restrict__ bstart, u32 nb0, int sh1, int b1,
-                                                           u32 *__restrict__ cursor1, u64 *__restrict__ B) {
+                                                           const u32 *__restrict__ vbeg, const u32 *__restrict__ vcnt, u32 nvb, u32 nsrc,
+                                                           int sh1, int b1, u32 *__restrict__ cursor1, u64 *__restrict__ B) {
     __shared__ u64 skeys[MSD_T1];
     __shared__ u32 hist[1 << MSD_MAX_B1];
     __shared__ u32 delta[1 << MSD_MAX_B1];
     __shared__ u32 ws[33];
-    u32 b, s, e;
-    if (!msd_tile_range(tstart, bstart, nb0, blockIdx.x, b, s, e)) return;
+    u32 vb, s, e;
+    if (!msd_tile_range(tstart, vbeg, vcnt, nvb, blockIdx.x, vb, s, e)) return;
     const int nb = 1 << b1;
     const u32 dm = (u32)nb - 1u;
     for (int i = threadIdx.x; i < nb; i += 256) hist[i] = 0;
@@ -183,16 +236,16 @@ __global__ void __launch_bounds__(256) msd_scatter1_kernel(const u64 *__restrict
     for (int u = 0; u < 16; ++u) { u32 i = s + u * 256 + threadIdx.x; kk[u] = i < e ? A[i] : 0; }
 #pragma unroll
     for (int u = 0; u < 16; ++u)
-        if (s + u * 256 + threadIdx.x < e) atomicAdd(&hist[(u32)(kk[u] >> sh1) & dm], 1u);
+        if (s + u * 256 + threadIdx.x < e) atomicAdd(&hist[msd_digit1(kk[u], sh1, dm)], 1u);
     __syncthreads();
-    const u32 total = msd_reserve<4>(hist, delta, nb, cursor1 + ((u64)b << b1), ws);
+    const u32 total = msd_reserve<(1 << MSD_MAX_B1) / 256>(hist, delta, nb, cursor1 + ((u64)(vb / nsrc) << b1), ws);
 #pragma unroll
     for (int u = 0; u < 16; ++u)
-        if (s + u * 256 + threadIdx.x < e) skeys[atomicAdd(&hist[(u32)(kk[u] >> sh1) & dm], 1u)] = kk[u];
+        if (s + u * 256 + threadIdx.x < e) skeys[atomicAdd(&hist[msd_digit1(kk[u], sh1, dm)], 1u)] = kk[u];
     __syncthreads();
     for (u32 i = threadIdx.x; i < total; i += 256) {
         u64 key = skeys[i];
-        B[delta[(u32)(key >> sh1) & dm] + i] = key;
+        B[delta[msd_digit1(key, sh1, dm)] + i] = key;
     }
 }
 __global__ void msd_copy_u32_kernel(const u32 *__restrict__ in, u64 n, u32 *__restrict__ out) {
@@ -200,46 +253,25 @@ __global__ void msd_copy_u32_kernel(const u32 *__restrict__ in, u64 n, u32 *__re
     if (i < n) out[i] = in[i];
 }
 
-// ---- task list: consecutive children are merged while they stay small -----------------------
-// A child larger than SMALL keys is a task of its own; otherwise children whose first key falls
-// in the same window of GW keys form one task, so a merged task holds <= GW + SMALL <= CAP keys.
-struct MsdTaskF {
-    const u32 *off;  // nchild + 1
-    u32 *tasks;
-    u32 gw, small;
-    __device__ bool pred(u64 c) const {
-        if (c == 0) return true;
-        u32 o0 = off[c - 1], o1 = off[c], o2 = off[c + 1];
-        return (o2 - o1) > small || (o1 - o0) > small || (o1 / gw) != (o0 / gw);
-    }
-    __device__ void emit(u64 c, u64 dst) const { tasks[dst] = (u32)c; }
-};
-
-// ------------------------------- per-task CTA ------------------------------------------------
+// ------------------------------- pass E: one CTA per child ---------------------------------------
 #define MSD_MAXD 9
-struct MsdFrame {
-    u32 start, size;      // range (absolute key index) being partitioned
-    int shift_before;     // key bits [0, shift_before) still vary inside the range
-    int bits;             // digit = bits [shift_before - bits, shift_before)
-    int dst;              // buffer (0 = the task's own buffer, 1 = the other one) holding the children
-    u32 ntasks;
-    u32 off[257];         // child offsets relative to start
-    u16 task[258];        // first child of every task; task[ntasks] = nchildren
-};
+#define LEAF_BINS 1024
+#define LEAF_MAX_PROBE 96   // a longer probe sequence means the table is too full: partition instead
+#define FSCR_STRIDE 260     // per-depth scratch: 257 offsets (+ padding)
 
-template <int THREADS, int CAP, int HT>
-struct MsdSmem {
-    static constexpr int BINS = 1024;
+template <int THREADS, int LOG_HT>
+struct LeafSmem {
+    static constexpr int HT = 1 << LOG_HT;
     u64 tab[HT];
-    u64 lkey[CAP];
     u32 tcnt[HT];
-    u32 lcnt[CAP];
-    u32 bins[BINS + 1];
-    u32 bincur[BINS];
+    u32 bins[LEAF_BINS + 1];
+    u32 bincur[LEAF_BINS];
     u32 pcur[256];
+    u64 red[64];
     u32 ws[33];
-    u32 s_task, s_nd, s_out;
-    MsdFrame frames[MSD_MAXD];
+    u32 s_task, s_ovf, s_nd;
+    u32 sub_beg, sub_cnt;
+    u64 s_min, s_max;
 };
 
 template <int THREADS>
@@ -256,223 +288,235 @@ __device__ __forceinline__ u32 block_scan_array(u32 *arr, int n, u32 *ws) {
     return total;
 }
 
-template <int THREADS, int CAP, int HT>
-__device__ void msd_partition(MsdSmem<THREADS, CAP, HT> &S, MsdFrame &f, const u64 *src, u64 *dst) {
-    const int nch = 1 << f.bits, sh = f.shift_before - f.bits;
-    const u32 dm = (u32)nch - 1u;
-    for (int i = threadIdx.x; i <= 256; i += THREADS) f.off[i] = 0;
-    __syncthreads();
-    const u64 *sp = src + f.start;
-    for (u32 i0 = threadIdx.x; i0 < f.size; i0 += MSD_UNROLL * THREADS) {  // batch the loads: memory-level parallelism
-        u64 kk[MSD_UNROLL];
-#pragma unroll
-        for (int u = 0; u < MSD_UNROLL; ++u) { u32 i = i0 + u * THREADS; kk[u] = i < f.size ? sp[i] : 0; }
-#pragma unroll
-        for (int u = 0; u < MSD_UNROLL; ++u)
-            if (i0 + u * THREADS < f.size) atomicAdd(&f.off[(u32)(kk[u] >> sh) & dm], 1u);
+// Count the keys of nseg segments IN[segbeg[s] .. +segcnt[s]) in the hash table; the distinct keys
+// with count >= min_freq are put in order and written to OK/OC[obase ..); SK[obase ..) is staging.
+// Returns false (nothing written) when the table got too full; *nd_out = number written.
+// SK may alias the input; OK must not alias SK.
+template <int THREADS, int LOG_HT>
+__device__ bool msd_leaf(LeafSmem<THREADS, LOG_HT> &S, const u64 *IN, const u32 *segbeg, const u32 *segcnt, u32 nseg, u64 *SK,
+                         u64 *OK, u32 *OC, u32 obase, u32 min_freq, u32 *nd_out) {
+    constexpr int HT = 1 << LOG_HT;
+    constexpr u32 HM = HT - 1;
+    {
+        ulonglong2 *t2 = reinterpret_cast<ulonglong2 *>(S.tab);
+        for (int i = threadIdx.x; i < HT / 2; i += THREADS) t2[i] = make_ulonglong2(MSD_EMPTY, MSD_EMPTY);
+        uint4 *c4 = reinterpret_cast<uint4 *>(S.tcnt);
+        for (int i = threadIdx.x; i < HT / 4; i += THREADS) c4[i] = make_uint4(0, 0, 0, 0);
+        if (threadIdx.x == 0) S.s_ovf = 0;
     }
     __syncthreads();
-    block_scan_array<THREADS>(f.off, 256, S.ws);
-    if (threadIdx.x < 256) S.pcur[threadIdx.x] = f.off[threadIdx.x];
-    if (threadIdx.x == 0) f.off[256] = f.size;
-    __syncthreads();
-    u64 *dp = dst + f.start;
-    for (u32 i0 = threadIdx.x; i0 < f.size; i0 += MSD_UNROLL * THREADS) {
-        u64 kk[MSD_UNROLL];
+    volatile u32 *ovf = &S.s_ovf;
+    for (u32 sg = 0; sg < nseg; ++sg) {
+        const u64 *bp = IN + segbeg[sg];
+        const u32 n = segcnt[sg];
+        u64 cur[MSD_UNROLL], nxt[MSD_UNROLL];
 #pragma unroll
-        for (int u = 0; u < MSD_UNROLL; ++u) { u32 i = i0 + u * THREADS; kk[u] = i < f.size ? sp[i] : 0; }
+        for (int u = 0; u < MSD_UNROLL; ++u) { u32 i = threadIdx.x + u * THREADS; cur[u] = i < n ? bp[i] : MSD_EMPTY; }
+        for (u32 i0 = threadIdx.x; i0 < n; i0 += MSD_UNROLL * THREADS) {
+            const u32 i1 = i0 + MSD_UNROLL * THREADS;  // next batch in flight while this one is inserted
 #pragma unroll
-        for (int u = 0; u < MSD_UNROLL; ++u)
-            if (i0 + u * THREADS < f.size) dp[atomicAdd(&S.pcur[(u32)(kk[u] >> sh) & dm], 1u)] = kk[u];
-    }
-    __syncthreads();
-    // sub-tasks: same merging rule as MsdTaskF with GW = SMALL = CAP / 2
-    constexpr u32 G = CAP / 2;
-    u32 flag = 0;
-    const int c = threadIdx.x;
-    if (c < 256) {
-        u32 sz = f.off[c + 1] - f.off[c];
-        bool big = sz > G;
-        bool prevbig = c > 0 && (f.off[c] - f.off[c - 1]) > G;
-        flag = (c == 0 || big || prevbig || (f.off[c] / G != f.off[c - 1] / G)) ? 1u : 0u;
-    }
-    u32 total;
-    u32 idx = block_excl_scan(flag, S.ws, &total);
-    if (flag) f.task[idx] = (u16)c;
-    if (threadIdx.x == 0) { f.task[total] = 256; f.ntasks = total; }
-    __syncthreads();
-}
-
-// count the n keys of buf[start ..) in the hash table, order the distinct ones, append them
-template <int THREADS, int CAP, int HT>
-__device__ void msd_leaf(MsdSmem<THREADS, CAP, HT> &S, const u64 *buf, u32 start, u32 n, int shift, u64 *okeys, u32 *ocnt, u32 obase,
-                         u32 min_freq) {
-    constexpr int LOG_HT = (HT == 2048) ? 11 : (HT == 4096) ? 12 : (HT == 8192) ? 13 : (HT == 16384) ? 14 : 0;
-    static_assert(LOG_HT != 0 && HT % THREADS == 0 && CAP <= HT * 3 / 4, "unsupported leaf geometry");
-    for (int i = threadIdx.x; i < HT; i += THREADS) { S.tab[i] = MSD_EMPTY; S.tcnt[i] = 0; }
-    if (threadIdx.x == 0) S.s_nd = 0;
-    __syncthreads();
-    const u64 *bp = buf + start;
-    for (u32 i0 = threadIdx.x; i0 < n; i0 += MSD_UNROLL * THREADS) {
-        u64 kk[MSD_UNROLL];
+            for (int u = 0; u < MSD_UNROLL; ++u) { u32 i = i1 + u * THREADS; nxt[u] = i < n ? bp[i] : MSD_EMPTY; }
 #pragma unroll
-        for (int u = 0; u < MSD_UNROLL; ++u) { u32 i = i0 + u * THREADS; kk[u] = i < n ? bp[i] : MSD_EMPTY; }
-#pragma unroll
-        for (int u = 0; u < MSD_UNROLL; ++u) {
-            const u64 key = kk[u];
-            if (key == MSD_EMPTY) continue;
-            u32 slot = (u32)((key * 0x9E3779B97F4A7C15ULL) >> (64 - LOG_HT));
-            for (;;) {
-                u64 cur = S.tab[slot];
-                if (cur == MSD_EMPTY) cur = atomicCAS((unsigned long long *)&S.tab[slot], (unsigned long long)MSD_EMPTY, (unsigned long long)key);
-                if (cur == MSD_EMPTY || cur == key) { atomicAdd(&S.tcnt[slot], 1u); break; }
-                slot = (slot + 1) & (HT - 1);
+            for (int u = 0; u < MSD_UNROLL; ++u) {
+                const u64 key = cur[u];
+                if (key == MSD_EMPTY) continue;
+                u32 slot = (u32)((key * MSD_GOLD) >> (64 - LOG_HT));
+                int probes = 0;
+                for (;;) {
+                    u64 c = S.tab[slot];
+                    if (c == MSD_EMPTY) c = atomicCAS((unsigned long long *)&S.tab[slot], (unsigned long long)MSD_EMPTY, (unsigned long long)key);
+                    if (c == MSD_EMPTY || c == key) { atomicAdd(&S.tcnt[slot], 1u); break; }
+                    slot = (slot + 1) & HM;
+                    if (++probes > LEAF_MAX_PROBE) { *ovf = 1; break; }
+                }
             }
+            if (*ovf) break;
+#pragma unroll
+            for (int u = 0; u < MSD_UNROLL; ++u) cur[u] = nxt[u];
         }
+        if (*ovf) break;
     }
     __syncthreads();
-    // compact the occupied slots that pass the min-count filter (warp-aggregated append)
-    for (int base = 0; base < HT; base += THREADS) {
-        int slot = base + threadIdx.x;
-        u64 key = S.tab[slot];
-        u32 c = S.tcnt[slot];
-        bool keep = key != MSD_EMPTY && c >= min_freq;
-        u32 b = __ballot_sync(FULL_MASK, keep);
-        u32 wbase = 0;
-        if (lane_id() == 0 && b) wbase = atomicAdd(&S.s_nd, (u32)__popc(b));
-        wbase = __shfl_sync(FULL_MASK, wbase, 0);
-        if (keep) {
-            u32 p = wbase + __popc(b & lanemask_lt());
-            S.lkey[p] = key;
-            S.lcnt[p] = c;
+    if (S.s_ovf) return false;
+    // ---- range of the kept keys (their common prefix is skipped by the ordering bins) ----
+    u64 mn = ~0ULL, mx = 0;
+    for (int slot = threadIdx.x; slot < HT; slot += THREADS) {
+        const u64 key = S.tab[slot];
+        if (key != MSD_EMPTY && S.tcnt[slot] >= min_freq) { mn = key < mn ? key : mn; mx = key > mx ? key : mx; }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        u64 a = __shfl_xor_sync(FULL_MASK, mn, d), b = __shfl_xor_sync(FULL_MASK, mx, d);
+        mn = a < mn ? a : mn; mx = b > mx ? b : mx;
+    }
+    if (lane_id() == 0) { S.red[threadIdx.x >> 5] = mn; S.red[32 + (threadIdx.x >> 5)] = mx; }
+    for (int i = threadIdx.x; i <= LEAF_BINS; i += THREADS) S.bins[i] = 0;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        u64 a = threadIdx.x < THREADS / 32 ? S.red[threadIdx.x] : ~0ULL, b = threadIdx.x < THREADS / 32 ? S.red[32 + threadIdx.x] : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            u64 a2 = __shfl_xor_sync(FULL_MASK, a, d), b2 = __shfl_xor_sync(FULL_MASK, b, d);
+            a = a2 < a ? a2 : a; b = b2 > b ? b2 : b;
         }
+        if (threadIdx.x == 0) { S.s_min = a; S.s_max = b; }
     }
     __syncthreads();
-    const u32 nd = S.s_nd;
-    if (nd == 0) return;
-    // order-preserving bins over the top bb varying bits, then rank by counting inside the bin
-    int bb = 0;
-    while ((1u << (bb + 3)) <= nd && bb < 10) ++bb;  // ~4..8 keys per bin on uniform keys
-    if (bb > shift) bb = shift;
-    const int nbins = 1 << bb, bsh = shift - bb;
-    const u32 bm = (u32)nbins - 1u;
-    for (int i = threadIdx.x; i <= nbins; i += THREADS) S.bins[i] = 0;
+    mn = S.s_min; mx = S.s_max;
+    if (mn > mx) { *nd_out = 0; return true; }  // nothing kept
+    const int hi = 64 - __clzll((long long)(mn ^ mx));  // bits [0, hi) vary (0 when a single key)
+    const int bb = hi < 10 ? hi : 10, bsh = hi - bb;
+    const u32 bm = (1u << bb) - 1u;
+    const int nbins = 1 << bb;
+    for (int slot = threadIdx.x; slot < HT; slot += THREADS) {
+        const u64 key = S.tab[slot];
+        if (key != MSD_EMPTY && S.tcnt[slot] >= min_freq) atomicAdd(&S.bins[(u32)(key >> bsh) & bm], 1u);
+    }
     __syncthreads();
-    for (u32 i = threadIdx.x; i < nd; i += THREADS) atomicAdd(&S.bins[bb ? ((u32)(S.lkey[i] >> bsh) & bm) : 0u], 1u);
-    __syncthreads();
-    block_scan_array<THREADS>(S.bins, nbins, S.ws);
+    const u32 nd = block_scan_array<THREADS>(S.bins, nbins, S.ws);
     for (int i = threadIdx.x; i < nbins; i += THREADS) S.bincur[i] = S.bins[i];
     if (threadIdx.x == 0) S.bins[nbins] = nd;
     __syncthreads();
-    u64 *lkey2 = S.tab;   // the table is dead now: reuse it for the binned order
-    u32 *lcnt2 = S.tcnt;
-    for (u32 i = threadIdx.x; i < nd; i += THREADS) {
-        u64 key = S.lkey[i];
-        u32 r = atomicAdd(&S.bincur[bb ? ((u32)(key >> bsh) & bm) : 0u], 1u);
-        lkey2[r] = key;
-        lcnt2[r] = S.lcnt[i];
+    u64 *sk = SK + obase;
+    for (int slot = threadIdx.x; slot < HT; slot += THREADS) {
+        const u64 key = S.tab[slot];
+        if (key != MSD_EMPTY && S.tcnt[slot] >= min_freq) sk[atomicAdd(&S.bincur[(u32)(key >> bsh) & bm], 1u)] = key;
     }
     __syncthreads();
     for (u32 j = threadIdx.x; j < nd; j += THREADS) {
-        u64 key = lkey2[j];
-        u32 b = bb ? ((u32)(key >> bsh) & bm) : 0u;
-        u32 lo = S.bins[b], hi = S.bins[b + 1], rank = 0;
-        for (u32 q = lo; q < hi; ++q) rank += lkey2[q] < key;
-        okeys[obase + lo + rank] = key;
-        ocnt[obase + lo + rank] = lcnt2[j];
+        const u64 key = sk[j];
+        const u32 b = (u32)(key >> bsh) & bm;
+        const u32 lo = S.bins[b], hi2 = S.bins[b + 1];
+        u32 rank = 0;
+        for (u32 q = lo; q < hi2; ++q) rank += sk[q] < key;
+        u32 slot = (u32)((key * MSD_GOLD) >> (64 - LOG_HT));
+        while (S.tab[slot] != key) slot = (slot + 1) & HM;
+        OK[obase + lo + rank] = key;
+        OC[obase + lo + rank] = S.tcnt[slot];
+    }
+    __syncthreads();
+    *nd_out = nd;
+    return true;
+}
+
+// radix partition of nseg segments by key bits [sh, sh + bits) into DST[dbase ..); the 257 child
+// offsets (relative) go to offs (global scratch)
+template <int THREADS, int LOG_HT>
+__device__ void msd_partition(LeafSmem<THREADS, LOG_HT> &S, const u64 *SRC, const u32 *segbeg, const u32 *segcnt, u32 nseg, u64 *DST,
+                              u32 dbase, int sh, int bits, u32 *offs) {
+    const u32 dm = (1u << bits) - 1u;
+    for (int i = threadIdx.x; i <= 256; i += THREADS) S.bins[i] = 0;
+    __syncthreads();
+    for (u32 sg = 0; sg < nseg; ++sg) {
+        const u64 *sp = SRC + segbeg[sg];
+        const u32 n = segcnt[sg];
+        for (u32 i0 = threadIdx.x; i0 < n; i0 += MSD_UNROLL * THREADS) {
+            u64 kk[MSD_UNROLL];
+#pragma unroll
+            for (int u = 0; u < MSD_UNROLL; ++u) { u32 i = i0 + u * THREADS; kk[u] = i < n ? sp[i] : 0; }
+#pragma unroll
+            for (int u = 0; u < MSD_UNROLL; ++u)
+                if (i0 + u * THREADS < n) atomicAdd(&S.bins[(u32)(kk[u] >> sh) & dm], 1u);
+        }
+    }
+    __syncthreads();
+    const u32 total = block_scan_array<THREADS>(S.bins, 256, S.ws);
+    if (threadIdx.x < 256) { S.pcur[threadIdx.x] = S.bins[threadIdx.x]; offs[threadIdx.x] = S.bins[threadIdx.x]; }
+    if (threadIdx.x == 0) offs[256] = total;
+    __syncthreads();
+    u64 *dp = DST + dbase;
+    for (u32 sg = 0; sg < nseg; ++sg) {
+        const u64 *sp = SRC + segbeg[sg];
+        const u32 n = segcnt[sg];
+        for (u32 i0 = threadIdx.x; i0 < n; i0 += MSD_UNROLL * THREADS) {
+            u64 kk[MSD_UNROLL];
+#pragma unroll
+            for (int u = 0; u < MSD_UNROLL; ++u) { u32 i = i0 + u * THREADS; kk[u] = i < n ? sp[i] : 0; }
+#pragma unroll
+            for (int u = 0; u < MSD_UNROLL; ++u)
+                if (i0 + u * THREADS < n) dp[atomicAdd(&S.pcur[(u32)(kk[u] >> sh) & dm], 1u)] = kk[u];
+        }
     }
     __syncthreads();
 }
 
-// X: buffer holding the children (read, then overwritten in place with the unique keys);
-// Y: the other buffer (scratch of the depth-first fallback).
-template <int THREADS, int CAP, int HT>
-__global__ void __launch_bounds__(THREADS) msd_task_kernel(u64 *X, u64 *Y, u32 *cnt_out, const u32 *__restrict__ off1,
-                                                           const u32 *__restrict__ tasks, u32 ntasks, u32 nchild, int shiftc,
-                                                           u32 *__restrict__ nu_out, u32 *ticket, u32 min_freq) {
+// IN: buffer holding the children (child c = nseg segments segbeg/segcnt[c * nseg ..]);
+// O / OC: output keys / counts, child c writes [off[c], off[c] + nu[c]); SB: scratch keys, same size.
+// O may alias IN when nseg == 1 and segbeg == off (counted in place).
+template <int THREADS, int LOG_HT>
+__global__ void __launch_bounds__(THREADS) msd_leaf_kernel(const u64 *IN, u64 *SB, u64 *O, u32 *OC, const u32 *__restrict__ segbeg,
+                                                           const u32 *__restrict__ segcnt, u32 nseg, const u32 *__restrict__ off,
+                                                           u32 nchild, int shiftc, u32 *__restrict__ nu_out, u32 *ticket, u32 min_freq,
+                                                           u32 *fscr) {
     extern __shared__ __align__(16) u8 smem_raw[];
-    MsdSmem<THREADS, CAP, HT> &S = *reinterpret_cast<MsdSmem<THREADS, CAP, HT> *>(smem_raw);
+    LeafSmem<THREADS, LOG_HT> &S = *reinterpret_cast<LeafSmem<THREADS, LOG_HT> *>(smem_raw);
+    u32 *myscr = fscr + (size_t)blockIdx.x * MSD_MAXD * FSCR_STRIDE;
     for (;;) {
         __syncthreads();
-        if (threadIdx.x == 0) { S.s_task = atomicAdd(ticket, 1u); S.s_out = 0; }
+        if (threadIdx.x == 0) S.s_task = atomicAdd(ticket, 1u);
         __syncthreads();
-        const u32 t = S.s_task;
-        if (t >= ntasks) break;
-        const u32 c0 = tasks[t], c1 = (t + 1 < ntasks) ? tasks[t + 1] : nchild;
-        const u32 bs = off1[c0], bsize = off1[c1] - bs;
-        if (bsize == 0) { if (threadIdx.x == 0) nu_out[t] = 0; continue; }
-        // key bits that vary inside the task: the child's own bits plus the differing child-index bits
-        const u32 x = c0 ^ (c1 - 1);
-        const int shift0 = shiftc + (x ? 32 - __clz(x) : 0);
-        if (bsize <= (u32)CAP) {
-            msd_leaf<THREADS, CAP, HT>(S, X, bs, bsize, shift0, X, cnt_out, bs, min_freq);
-            if (threadIdx.x == 0) nu_out[t] = S.s_nd;
-            continue;
-        }
-        // a single child larger than CAP: partition it again, depth first
-        if (shift0 == 0) {  // no varying bits: the whole child is one k-mer
+        const u32 c = S.s_task;
+        if (c >= nchild) break;
+        const u32 ob = off[c], bsize = off[c + 1] - ob;
+        if (bsize == 0) { if (threadIdx.x == 0) nu_out[c] = 0; continue; }
+        if (shiftc == 0) {  // no varying bits: the whole child is one k-mer
             if (threadIdx.x == 0) {
                 u32 keep = bsize >= min_freq;
-                if (keep) cnt_out[bs] = bsize;  // X[bs] already holds the key
-                nu_out[t] = keep;
+                if (keep) { O[ob] = IN[segbeg[(size_t)c * nseg]]; OC[ob] = bsize; }
+                nu_out[c] = keep;
             }
             continue;
         }
-        u32 cur[MSD_MAXD];
+        u32 nd;
+        if (msd_leaf<THREADS, LOG_HT>(S, IN, segbeg + (size_t)c * nseg, segcnt + (size_t)c * nseg, nseg, SB, O, OC, ob, min_freq, &nd)) {
+            if (threadIdx.x == 0) nu_out[c] = nd;
+            continue;
+        }
+        // ---- too many distinct keys for the table: partition again, depth first (uniform control flow) ----
+        u32 f_start[MSD_MAXD], f_cur[MSD_MAXD];
+        int f_sb[MSD_MAXD], f_bits[MSD_MAXD], f_dst[MSD_MAXD];  // dst: 0 = SB, 1 = O
+        u32 s_out = 0;
         int depth = 0;
-        if (threadIdx.x == 0) {
-            MsdFrame &f = S.frames[0];
-            f.start = bs; f.size = bsize; f.shift_before = shift0; f.bits = shift0 < 8 ? shift0 : 8; f.dst = 1;
-        }
-        __syncthreads();
-        msd_partition<THREADS, CAP, HT>(S, S.frames[0], X, Y);
-        cur[0] = 0;
+        f_start[0] = ob; f_sb[0] = shiftc; f_bits[0] = shiftc < 8 ? shiftc : 8; f_dst[0] = 0; f_cur[0] = 0;
+        msd_partition<THREADS, LOG_HT>(S, IN, segbeg + (size_t)c * nseg, segcnt + (size_t)c * nseg, nseg, SB, ob, f_sb[0] - f_bits[0], f_bits[0], myscr);
         while (depth >= 0) {
-            MsdFrame &f = S.frames[depth];
-            if (cur[depth] == f.ntasks) { --depth; continue; }
-            const u32 d0 = f.task[cur[depth]], d1 = f.task[cur[depth] + 1];
-            ++cur[depth];
-            const u32 s = f.off[d0], n = f.off[d1] - s;
+            if (f_cur[depth] == 256u) { --depth; continue; }
+            const u32 d = f_cur[depth]++;
+            const u32 *fo = myscr + depth * FSCR_STRIDE;
+            const u32 s = fo[d], n = fo[d + 1] - s;
             if (n == 0) continue;
-            if (n <= (u32)CAP) {
-                const u32 ob = bs + S.s_out;
-                msd_leaf<THREADS, CAP, HT>(S, f.dst ? Y : X, f.start + s, n, f.shift_before, X, cnt_out, ob, min_freq);
-                if (threadIdx.x == 0) S.s_out += S.s_nd;
+            u64 *buf = f_dst[depth] ? O : SB;
+            const u32 abs0 = f_start[depth] + s;
+            const int child_shift = f_sb[depth] - f_bits[depth];
+            if (child_shift == 0 || depth + 1 >= MSD_MAXD) {  // all n keys are the same k-mer
+                __syncthreads();
+                if (threadIdx.x == 0 && n >= min_freq) { u64 key = buf[abs0]; O[ob + s_out] = key; OC[ob + s_out] = n; }
+                if (n >= min_freq) s_out += 1;
                 __syncthreads();
                 continue;
             }
-            const int child_shift = f.shift_before - f.bits;
-            if (child_shift == 0 || depth + 1 >= MSD_MAXD) {
-                // all n keys of this child are the same k-mer (8 levels of 8 bits cover the 64-bit key)
-                if (threadIdx.x == 0 && n >= min_freq) {
-                    u64 key = (f.dst ? Y : X)[f.start + s];
-                    X[bs + S.s_out] = key;
-                    cnt_out[bs + S.s_out] = n;
-                    S.s_out += 1;
-                }
-                __syncthreads();
-                continue;
-            }
-            if (threadIdx.x == 0) {
-                MsdFrame &g = S.frames[depth + 1];
-                g.start = f.start + s; g.size = n; g.shift_before = child_shift; g.bits = child_shift < 8 ? child_shift : 8; g.dst = 1 - f.dst;
-            }
+            if (threadIdx.x == 0) { S.sub_beg = abs0; S.sub_cnt = n; }
             __syncthreads();
-            msd_partition<THREADS, CAP, HT>(S, S.frames[depth + 1], f.dst ? Y : X, f.dst ? X : Y);
+            if (msd_leaf<THREADS, LOG_HT>(S, buf, &S.sub_beg, &S.sub_cnt, 1, SB, O, OC, ob + s_out, min_freq, &nd)) {
+                s_out += nd;
+                continue;
+            }
+            f_start[depth + 1] = abs0; f_sb[depth + 1] = child_shift; f_bits[depth + 1] = child_shift < 8 ? child_shift : 8;
+            f_dst[depth + 1] = 1 - f_dst[depth]; f_cur[depth + 1] = 0;
+            msd_partition<THREADS, LOG_HT>(S, buf, &S.sub_beg, &S.sub_cnt, 1, f_dst[depth + 1] ? O : SB, abs0,
+                                           f_sb[depth + 1] - f_bits[depth + 1], f_bits[depth + 1], myscr + (depth + 1) * FSCR_STRIDE);
             ++depth;
-            cur[depth] = 0;
         }
         __syncthreads();
-        if (threadIdx.x == 0) nu_out[t] = S.s_out;
+        if (threadIdx.x == 0) nu_out[c] = s_out;
     }
 }
 
-__global__ void __launch_bounds__(256) msd_gather_kernel(const u64 *__restrict__ X, const u32 *__restrict__ cnt, const u32 *__restrict__ off1,
-                                                         const u32 *__restrict__ tasks, const u32 *__restrict__ nu,
-                                                         const u32 *__restrict__ ustart, u32 ntasks, u64 *__restrict__ okeys,
-                                                         u32 *__restrict__ ocnt) {
-    for (u32 t = blockIdx.x; t < ntasks; t += gridDim.x) {
-        const u32 n = nu[t], s = off1[tasks[t]], d = ustart[t];
+__global__ void __launch_bounds__(256) msd_gather_kernel(const u64 *__restrict__ X, const u32 *__restrict__ cnt, const u32 *__restrict__ off,
+                                                         const u32 *__restrict__ nu, const u32 *__restrict__ ustart, u32 nchild,
+                                                         u64 *__restrict__ okeys, u32 *__restrict__ ocnt) {
+    for (u32 t = blockIdx.x; t < nchild; t += gridDim.x) {
+        const u32 n = nu[t], s = off[t], d = ustart[t];
         for (u32 i = threadIdx.x; i < n; i += 256) {
             okeys[d + i] = X[s + i];
             ocnt[d + i] = cnt[s + i];
@@ -480,129 +524,200 @@ __global__ void __launch_bounds__(256) msd_gather_kernel(const u64 *__restrict__
     }
 }
 
+// ------------------------------------- host side -------------------------------------------------
 struct MsdTune {
-    int b0_max = 10;       // level-0 digit bits (<= MSD_MAX_B0)
-    int b1_max = 9;        // level-1 digit bits (<= MSD_MAX_B1)
-    int child_log2 = 9;    // target keys per child = 2^child_log2
-    int variant = 0;       // task kernel geometry, see msd_launch_tasks
-    int gw = 0, small = 0; // task merging window / small-child threshold (0 = from the variant)
+    int b0_max = 8;          // preferred level-0 digit bits (grows up to MSD_HB when level 1 is full)
+    int b1_max = MSD_MAX_B1; // level-1 digit bits
+    u32 dt = 3072;           // target DISTINCT keys per child (leaf table: 8192 slots)
+    u32 it_log2 = 16;        // target instances per child (bounds the work of one CTA)
+    int variant = 0;         // leaf geometry, see msd_launch_leaf
 };
 static MsdTune msd_tune() {
     MsdTune t;
     if (const char *e = getenv("GG_MSD_B0")) t.b0_max = atoi(e);
     if (const char *e = getenv("GG_MSD_B1")) t.b1_max = atoi(e);
-    if (const char *e = getenv("GG_MSD_CHILD")) t.child_log2 = atoi(e);
+    if (const char *e = getenv("GG_MSD_DT")) t.dt = (u32)atoi(e);
+    if (const char *e = getenv("GG_MSD_IT")) t.it_log2 = (u32)atoi(e);
     if (const char *e = getenv("GG_MSD_VARIANT")) t.variant = atoi(e);
-    if (const char *e = getenv("GG_MSD_GW")) t.gw = atoi(e);
-    if (const char *e = getenv("GG_MSD_SMALL")) t.small = atoi(e);
-    if (t.b0_max > MSD_MAX_B0) t.b0_max = MSD_MAX_B0;
+    if (t.b0_max > MSD_HB) t.b0_max = MSD_HB;
     if (t.b0_max < 0) t.b0_max = 0;
     if (t.b1_max > MSD_MAX_B1) t.b1_max = MSD_MAX_B1;
     if (t.b1_max < 0) t.b1_max = 0;
+    if (t.dt < 16) t.dt = 16;
     return t;
 }
 
-template <int THREADS, int CAP, int HT>
-static void msd_launch_tasks(gg_ctx *ctx, int ctas_per_sm, u64 *X, u64 *Y, u32 *cnt, const u32 *off1, const u32 *tasks, u32 ntasks,
-                             u32 nchild, int shiftc, u32 *nu, u32 *ticket, u32 min_freq) {
-    size_t smem = sizeof(MsdSmem<THREADS, CAP, HT>);
+struct MsdPlan {
+    int hb = 0;      // histogram bits of pass A
+    int b0 = 0, b1 = 0;
+    int shiftc = 0;  // key bits below the child digits
+};
+static inline int msd_hist_bits(int k) { return 2 * k < MSD_HB ? 2 * k : MSD_HB; }
+// children of ~dt distinct keys and <= 2^it_log2 instances
+static MsdPlan msd_plan(u64 distinct_est, u64 n_instances, int k, const MsdTune &t) {
+    MsdPlan p;
+    p.hb = msd_hist_bits(k);
+    int bits = 0;
+    while (bits < 22 && (distinct_est >> bits) > t.dt) ++bits;
+    while (bits < 22 && (n_instances >> bits) > (1ULL << t.it_log2)) ++bits;
+    // level 0 prefers few buckets (long runs per tile, cheap reservations); level 1 takes the rest,
+    // and level 0 widens only when level 1 is at its maximum
+    p.b0 = bits < t.b0_max ? bits : t.b0_max;
+    p.b1 = bits - p.b0;
+    if (p.b1 > t.b1_max) { p.b0 += p.b1 - t.b1_max; p.b1 = t.b1_max; }
+    if (p.b0 > MSD_HB) p.b0 = MSD_HB;
+    if (p.b0 > p.hb) p.b0 = p.hb;
+    if (p.b1 > 2 * k - p.b0) p.b1 = 2 * k - p.b0;
+    p.shiftc = 2 * k - p.b0 - p.b1;
+    return p;
+}
+
+// pass A: hist (2^hb + 1 entries, last 0); returns N and the distinct estimate of THIS GPU's reads
+static void msd_pass_a(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int k, int canonical, DBuf<u32> &hist, u64 *N, u64 *distinct_est) {
+    const int hb = msd_hist_bits(k);
+    const u32 nb = 1u << hb;
+    hist.alloc(ctx, nb + 1);
+    CK(cudaMemsetAsync(hist.p, 0, (nb + 1) * sizeof(u32), ctx->stream));
+    *N = 0; *distinct_est = 0;
+    if (pr.nwords == 0) return;
+    int est_shift = 0;
+    while (est_shift < 30 && (pr.nbases >> est_shift) > (1ULL << (EST_LOG - 1))) ++est_shift;
+    DBuf<u64> est(ctx, 1ULL << EST_LOG), res(ctx, 2);
+    CK(cudaMemsetAsync(est.p, 0xFF, sizeof(u64) << EST_LOG, ctx->stream));
+    CK(cudaMemsetAsync(res.p, 0, 2 * sizeof(u64), ctx->stream));
+    u64 hgrid = ceil_div(pr.nwords, 256);
+    if (hgrid > (u64)ctx->num_sms * 8) hgrid = (u64)ctx->num_sms * 8;
+    LAUNCH(ctx, msd_hist_kernel, (unsigned)hgrid, 256, 0, pr.packed.p, valid, pr.nwords, k, canonical, hb, hist.p, est_shift ? (0xFFFFFFFFu >> est_shift) : 0xFFFFFFFFu,
+           (unsigned long long *)est.p);
+    LAUNCH(ctx, msd_est_count_kernel, (unsigned)(ctx->num_sms * 2), 256, 0, (const unsigned long long *)est.p, hist.p, nb, (unsigned long long *)res.p);
+    CK(cudaMemcpyAsync(ctx->h_scalar, res.p, 2 * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *distinct_est = ctx->h_scalar[0] << est_shift;
+    *N = ctx->h_scalar[1];
+}
+
+// pass B: keys scattered into 2^b0 buckets; hist0 (nb0 + 1, last 0) and bstart (nb0 + 1) describe them
+static void msd_pass_b(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int k, int canonical, const MsdPlan &pl, const u32 *hist,
+                       u64 N, DBuf<u32> &hist0, DBuf<u32> &bstart, DBuf<u64> &A) {
+    const u32 nb0 = 1u << pl.b0;
+    hist0.alloc(ctx, nb0 + 1);
+    bstart.alloc(ctx, nb0 + 1);
+    DBuf<u32> cursor(ctx, nb0);
+    LAUNCH(ctx, msd_collapse_kernel, (unsigned)ceil_div(nb0 + 1, 256), 256, 0, hist, pl.hb, pl.b0, hist0.p);
+    exclusive_scan_u32(ctx, hist0.p, bstart.p, nb0 + 1, nullptr);
+    LAUNCH(ctx, msd_copy_u32_kernel, (unsigned)ceil_div(nb0, 256), 256, 0, bstart.p, (u64)nb0, cursor.p);
+    A.alloc(ctx, N ? N : 1);
+    if (N == 0) return;
+    size_t smemB = (size_t)MSD_TILE_KEYS * 8 + 2 * (size_t)(1 << MSD_HB) * 4;
+    static bool setB = false;
+    if (!setB) { CK(cudaFuncSetAttribute(msd_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB)); setB = true; }
+    LAUNCH(ctx, msd_scatter_kernel, (unsigned)ceil_div(pr.nwords, 256), 256, smemB, pr.packed.p, valid, pr.nwords, k, canonical, pl.b0, cursor.p, A.p);
+}
+
+__global__ void msd_child_total_kernel(const u32 *__restrict__ vcnt, u32 nsrc, u32 nchild, u32 *__restrict__ ctot) {
+    u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > nchild) return;
+    u32 s = 0;
+    if (c < nchild) for (u32 i = 0; i < nsrc; ++i) s += vcnt[(size_t)c * nsrc + i];
+    ctot[c] = s;
+}
+
+template <int THREADS, int LOG_HT>
+static void msd_launch_leaf(gg_ctx *ctx, int ctas_per_sm, const u64 *IN, u64 *SB, u64 *O, u32 *OC, const u32 *segbeg, const u32 *segcnt,
+                            u32 nseg, const u32 *off, u32 nchild, int shiftc, u32 *nu, u32 *ticket, u32 min_freq) {
+    size_t smem = sizeof(LeafSmem<THREADS, LOG_HT>);
     static bool set = false;
     if (!set) {
-        CK(cudaFuncSetAttribute(msd_task_kernel<THREADS, CAP, HT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(msd_leaf_kernel<THREADS, LOG_HT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         set = true;
     }
     u32 grid = (u32)ctx->num_sms * ctas_per_sm;
-    if (grid > ntasks) grid = ntasks;
-    LAUNCH(ctx, (msd_task_kernel<THREADS, CAP, HT>), grid, THREADS, smem, X, Y, cnt, off1, tasks, ntasks, nchild, shiftc, nu, ticket, min_freq);
+    if (grid > nchild) grid = nchild;
+    DBuf<u32> fscr(ctx, (u64)grid * MSD_MAXD * FSCR_STRIDE);
+    LAUNCH(ctx, (msd_leaf_kernel<THREADS, LOG_HT>), grid, THREADS, smem, IN, SB, O, OC, segbeg, segcnt, nseg, off, nchild, shiftc, nu, ticket,
+           min_freq, fscr.p);
 }
 
-// packed reads -> sorted unique k-mers + counts (count >= min_freq only).  k <= 32.
-// Returns U; *n_instances = number of k-mer windows.
-static u64 msd_count(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int k, int canonical, u32 min_freq,
-                     DBuf<u64> &ukeys, DBuf<u32> &ucounts, u64 *n_instances) {
-    const MsdTune tune = msd_tune();
-    const u64 nwords = pr.nwords;
-    *n_instances = 0;
-    if (nwords == 0) { ukeys.alloc(ctx, 1); ucounts.alloc(ctx, 1); return 0; }
-    // digit widths from the number of windows (upper bound of N): children of ~2^child_log2 keys
-    int bt = 0;
-    while (bt < 21 && (pr.nbases >> (bt + tune.child_log2)) > 0) ++bt;
-    int b0 = (bt + 1) / 2;
-    if (b0 > tune.b0_max) b0 = tune.b0_max;
-    if (b0 > 2 * k) b0 = 2 * k;
-    int b1 = bt - b0;
-    if (b1 > tune.b1_max) b1 = tune.b1_max;
-    if (b1 > 2 * k - b0) b1 = 2 * k - b0;
-    const u32 nb0 = 1u << b0;
-    const u64 nchild = (u64)nb0 << b1;
-    const int shiftc = 2 * k - b0 - b1;
-    // ---- A: histogram ----
-    stage_begin(ctx, ST_EXTRACT);
-    DBuf<u32> hist(ctx, nb0 + 1), bstart(ctx, nb0 + 1), cursor(ctx, nb0), tcount(ctx, nb0 + 1), tstart(ctx, nb0 + 1), ticket(ctx, 1);
+// Level-0 buckets -> sorted unique keys + counts (count >= min_freq).
+// IN holds n_in keys; local bucket bl (0 .. nb_local) consists of the nsrc virtual buckets
+// vb = bl * nsrc + s: IN[vbeg[vb] .. + vcnt[vb]).  IN is consumed (used as scratch).
+static u64 msd_finish(gg_ctx *ctx, DBuf<u64> &IN, u64 n_in, const u32 *vbeg, const u32 *vcnt, u32 nb_local, u32 nsrc, const MsdPlan &pl,
+                      const MsdTune &tune, u32 min_freq, DBuf<u64> &ukeys, DBuf<u32> &ucounts) {
+    if (n_in == 0) { ukeys.alloc(ctx, 1); ucounts.alloc(ctx, 1); return 0; }
+    const u32 nvb = nb_local * nsrc;
+    const u64 nchild = (u64)nb_local << pl.b1;
+    DBuf<u64> S1(ctx, n_in), S2;
+    DBuf<u32> OC(ctx, n_in), off(ctx, nchild + 1), ticket(ctx, 1), nu(ctx, nchild + 1), ustart(ctx, nchild + 1);
     DBuf<u64> tot(ctx, 1);
-    CK(cudaMemsetAsync(hist.p, 0, (nb0 + 1) * sizeof(u32), ctx->stream));
-    u64 hgrid = ceil_div(nwords, 256);
-    if (hgrid > (u64)ctx->num_sms * 8) hgrid = (u64)ctx->num_sms * 8;
-    LAUNCH(ctx, msd_hist_kernel, (unsigned)hgrid, 256, 0, pr.packed.p, valid, nwords, k, canonical, b0, hist.p);
-    exclusive_scan_u32(ctx, hist.p, bstart.p, nb0 + 1, tot.p);
-    const u64 N = read_scalar<u64>(ctx, tot.p);
-    *n_instances = N;
-    if (N == 0) { stage_end(ctx, ST_EXTRACT); ukeys.alloc(ctx, 1); ucounts.alloc(ctx, 1); return 0; }
-    if (N >= 0xFFFFFFFFull) GG_THROW(GG_ERR_LIMIT, "%llu k-mer instances exceed the 2^32-1 per-call limit", (unsigned long long)N);
-    // ---- B: extract + scatter ----
-    DBuf<u64> A(ctx, N), B(ctx, N);
-    DBuf<u32> cnt(ctx, N);
-    LAUNCH(ctx, msd_copy_u32_kernel, (unsigned)ceil_div(nb0, 256), 256, 0, bstart.p, (u64)nb0, cursor.p);
-    size_t smemB = (size_t)MSD_TILE_KEYS * 8 + 2 * (size_t)(1 << MSD_MAX_B0) * 4;
-    static bool setB = false;
-    if (!setB) { CK(cudaFuncSetAttribute(msd_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB)); setB = true; }
-    LAUNCH(ctx, msd_scatter_kernel, (unsigned)ceil_div(nwords, 256), 256, smemB, pr.packed.p, valid, nwords, k, canonical, b0, cursor.p, A.p);
-    stage_end(ctx, ST_EXTRACT);
-    // ---- C, D: level-1 partition (children in X) ----
+    const u64 *leaf_in;
+    u64 *leaf_sb, *leaf_o;
+    const u32 *segbeg, *segcnt;
+    u32 nseg;
+    DBuf<u32> hist1, ctot;
     stage_begin(ctx, ST_SORT);
-    DBuf<u32> off1(ctx, nchild + 1), tasks(ctx, nchild + 1);
-    u64 *X = A.p, *Y = B.p;
-    if (b1 > 0) {
-        DBuf<u32> hist1(ctx, nchild + 1), cursor1(ctx, nchild);
+    if (pl.b1 > 0) {
+        // ---- C, D: level-1 partition into S1 ----
+        DBuf<u32> tcount(ctx, nvb + 1), tstart(ctx, nvb + 1), cursor1(ctx, nchild);
+        hist1.alloc(ctx, nchild + 1);
         CK(cudaMemsetAsync(hist1.p, 0, (nchild + 1) * sizeof(u32), ctx->stream));
-        LAUNCH(ctx, msd_tilecount_kernel, (unsigned)ceil_div(nb0 + 1, 256), 256, 0, bstart.p, nb0, tcount.p);
-        exclusive_scan_u32(ctx, tcount.p, tstart.p, nb0 + 1, nullptr);
-        const unsigned tgrid = (unsigned)(ceil_div(N, MSD_T1) + nb0);
-        LAUNCH(ctx, msd_hist1_kernel, tgrid, 256, 0, A.p, tstart.p, bstart.p, nb0, shiftc, b1, hist1.p);
-        exclusive_scan_u32(ctx, hist1.p, off1.p, nchild + 1, nullptr);
-        LAUNCH(ctx, msd_copy_u32_kernel, (unsigned)ceil_div(nchild, 256), 256, 0, off1.p, nchild, cursor1.p);
-        LAUNCH(ctx, msd_scatter1_kernel, tgrid, 256, 0, A.p, tstart.p, bstart.p, nb0, shiftc, b1, cursor1.p, B.p);
-        X = B.p;
-        Y = A.p;
+        LAUNCH(ctx, msd_tilecount_kernel, (unsigned)ceil_div(nvb + 1, 256), 256, 0, vcnt, nvb, tcount.p);
+        exclusive_scan_u32(ctx, tcount.p, tstart.p, nvb + 1, nullptr);
+        const unsigned tgrid = (unsigned)(ceil_div(n_in, MSD_T1) + nvb);
+        LAUNCH(ctx, msd_hist1_kernel, tgrid, 256, 0, IN.p, tstart.p, vbeg, vcnt, nvb, nsrc, pl.shiftc, pl.b1, hist1.p);
+        exclusive_scan_u32(ctx, hist1.p, off.p, nchild + 1, nullptr);
+        LAUNCH(ctx, msd_copy_u32_kernel, (unsigned)ceil_div(nchild, 256), 256, 0, off.p, nchild, cursor1.p);
+        LAUNCH(ctx, msd_scatter1_kernel, tgrid, 256, 0, IN.p, tstart.p, vbeg, vcnt, nvb, nsrc, pl.shiftc, pl.b1, cursor1.p, S1.p);
+        leaf_in = S1.p; leaf_o = S1.p; leaf_sb = IN.p;
+        segbeg = off.p; segcnt = hist1.p; nseg = 1;
     } else {
-        LAUNCH(ctx, msd_copy_u32_kernel, (unsigned)ceil_div(nchild + 1, 256), 256, 0, bstart.p, nchild + 1, off1.p);
+        ctot.alloc(ctx, nchild + 1);
+        LAUNCH(ctx, msd_child_total_kernel, (unsigned)ceil_div(nchild + 1, 256), 256, 0, vcnt, nsrc, (u32)nchild, ctot.p);
+        exclusive_scan_u32(ctx, ctot.p, off.p, nchild + 1, nullptr);
+        leaf_in = IN.p; leaf_sb = S1.p;
+        segbeg = vbeg; segcnt = vcnt; nseg = nsrc;
+        if (nsrc == 1) leaf_o = IN.p;  // contiguous buckets: off == vbeg, counted in place
+        else { S2.alloc(ctx, n_in); leaf_o = S2.p; }
     }
-    // ---- E: tasks ----
-    int variant = tune.variant;
-    u32 cap = variant == 1 ? 6144u : variant == 2 ? 1536u : 3072u;
-    MsdTaskF tf{off1.p, tasks.p, tune.gw ? (u32)tune.gw : cap * 2 / 3, tune.small ? (u32)tune.small : cap / 3};
-    if (tf.gw + tf.small > cap) GG_THROW(GG_ERR_ARG, "GG_MSD_GW + GG_MSD_SMALL exceed the leaf capacity %u", cap);
-    Compactor<MsdTaskF> tc(ctx, nchild, "msd_tasks");
-    const u32 ntasks = (u32)tc.count(tf);
-    tc.emit(tf);
-    // ---- F: per-task counting ----
-    DBuf<u32> nu(ctx, ntasks + 1), ustart(ctx, ntasks + 1);
+    // ---- E: leaves ----
     CK(cudaMemsetAsync(ticket.p, 0, sizeof(u32), ctx->stream));
-    if (variant == 1) msd_launch_tasks<1024, 6144, 8192>(ctx, 1, X, Y, cnt.p, off1.p, tasks.p, ntasks, (u32)nchild, shiftc, nu.p, ticket.p, min_freq);
-    else if (variant == 2) msd_launch_tasks<256, 1536, 2048>(ctx, 3, X, Y, cnt.p, off1.p, tasks.p, ntasks, (u32)nchild, shiftc, nu.p, ticket.p, min_freq);
-    else if (variant == 3) msd_launch_tasks<256, 3072, 4096>(ctx, 2, X, Y, cnt.p, off1.p, tasks.p, ntasks, (u32)nchild, shiftc, nu.p, ticket.p, min_freq);
-    else msd_launch_tasks<512, 3072, 4096>(ctx, 2, X, Y, cnt.p, off1.p, tasks.p, ntasks, (u32)nchild, shiftc, nu.p, ticket.p, min_freq);
+    if (tune.variant == 1)
+        msd_launch_leaf<1024, 14>(ctx, 1, leaf_in, leaf_sb, leaf_o, OC.p, segbeg, segcnt, nseg, off.p, (u32)nchild, pl.shiftc, nu.p, ticket.p, min_freq);
+    else if (tune.variant == 2)
+        msd_launch_leaf<256, 12>(ctx, 4, leaf_in, leaf_sb, leaf_o, OC.p, segbeg, segcnt, nseg, off.p, (u32)nchild, pl.shiftc, nu.p, ticket.p, min_freq);
+    else
+        msd_launch_leaf<512, 13>(ctx, 2, leaf_in, leaf_sb, leaf_o, OC.p, segbeg, segcnt, nseg, off.p, (u32)nchild, pl.shiftc, nu.p, ticket.p, min_freq);
     stage_end(ctx, ST_SORT);
-    // ---- G: gather ----
+    // ---- F: gather ----
     stage_begin(ctx, ST_COUNT);
-    exclusive_scan_u32(ctx, nu.p, ustart.p, ntasks, tot.p);
+    exclusive_scan_u32(ctx, nu.p, ustart.p, nchild, tot.p);
     const u64 U = read_scalar<u64>(ctx, tot.p);
     ukeys.alloc(ctx, U ? U : 1);
     ucounts.alloc(ctx, U ? U : 1);
     if (U) {
-        u32 ggrid = ntasks < (u32)ctx->num_sms * 16 ? ntasks : (u32)ctx->num_sms * 16;
-        LAUNCH(ctx, msd_gather_kernel, ggrid, 256, 0, X, cnt.p, off1.p, tasks.p, nu.p, ustart.p, ntasks, ukeys.p, ucounts.p);
+        u32 ggrid = nchild < (u64)ctx->num_sms * 16 ? (u32)nchild : (u32)ctx->num_sms * 16;
+        LAUNCH(ctx, msd_gather_kernel, ggrid, 256, 0, leaf_o, OC.p, off.p, nu.p, ustart.p, (u32)nchild, ukeys.p, ucounts.p);
     }
     stage_end(ctx, ST_COUNT);
     return U;
+}
+
+// packed reads -> sorted unique k-mers + counts (count >= min_freq only).  msd_supported(k, canonical).
+// Returns U; *n_instances = number of k-mer windows.
+static u64 msd_count(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int k, int canonical, u32 min_freq,
+                     DBuf<u64> &ukeys, DBuf<u32> &ucounts, u64 *n_instances) {
+    const MsdTune tune = msd_tune();
+    *n_instances = 0;
+    if (pr.nwords == 0) { ukeys.alloc(ctx, 1); ucounts.alloc(ctx, 1); return 0; }
+    stage_begin(ctx, ST_EXTRACT);
+    DBuf<u32> hist, hist0, bstart;
+    DBuf<u64> A;
+    u64 N = 0, dest = 0;
+    msd_pass_a(ctx, pr, valid, k, canonical, hist, &N, &dest);
+    *n_instances = N;
+    if (N == 0) { stage_end(ctx, ST_EXTRACT); ukeys.alloc(ctx, 1); ucounts.alloc(ctx, 1); return 0; }
+    if (N >= 0xFFFFFFFFull) GG_THROW(GG_ERR_LIMIT, "%llu k-mer instances exceed the 2^32-1 per-call limit", (unsigned long long)N);
+    const MsdPlan pl = msd_plan(dest, N, k, tune);
+    msd_pass_b(ctx, pr, valid, k, canonical, pl, hist.p, N, hist0, bstart, A);
+    stage_end(ctx, ST_EXTRACT);
+    return msd_finish(ctx, A, N, bstart.p, hist0.p, 1u << pl.b0, 1, pl, tune, min_freq, ukeys, ucounts);
 }
