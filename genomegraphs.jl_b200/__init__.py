@@ -6,6 +6,7 @@ The directory name carries a dot, so import it through `__graft_entry__.load_pac
 (registered in sys.modules as `genomegraphs_b200`).
 """
 from . import _native  # noqa: F401
+from . import dist  # noqa: F401
 from .host import *  # noqa: F401,F403
 from .host import (CANONICAL, NONCANONICAL, Context, GraphArrays, GraphStrandPosition, MerCounts, SDGLink, SDGNode,  # noqa: F401
                    SequenceDistanceGraph, UniqueMerIndex, dbg_, dbg_arrays, dbg_from_reads, empty_graph, extract_kmers, freq,

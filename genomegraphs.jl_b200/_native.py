@@ -64,6 +64,15 @@ SIGNATURES = {
     "gg_synth_reads_host": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, vp]),
     "gg_synth_reads_dev": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, vp]),
     "gg_synth_genome_host": (C.c_int, [C.c_uint64, C.c_uint64, vp]),
+    "gg_synth_reads_range_dev": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, vp]),
+    "gg_synth_reads_range_host": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, vp]),
+    "gg_comm_unique_id": (C.c_int, [vp]),
+    "gg_comm_create": (C.c_int, [vp, vp, C.c_int, C.c_int, vpp]),
+    "gg_comm_destroy": (None, [vp]),
+    "gg_dist_splitters": (C.c_int, [vp, C.c_uint32, C.c_int, vp]),
+    "gg_dist_count_kmers_dev": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_uint64, vpp, u64p]),
+    "gg_counts_allgather": (C.c_int, [vp, vp, vpp]),
+    "gg_dist_dbg_from_reads_dev": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, vpp, u64p]),
 }
 
 _LIB = None

@@ -5,6 +5,7 @@
 #include "pack.cuh"
 #include "sort.cuh"
 #include "msdcount.cuh"
+#include "dist.cuh"
 #include "graph.cuh"
 #include "umi.cuh"
 #include "synth.cuh"
@@ -602,30 +603,191 @@ void gg_umi_free(gg_umi *u) {
     delete u;
 }
 
+// ------------------------------------- multi-GPU ---------------------------------------------
+int gg_comm_unique_id(uint8_t id[GG_COMM_ID_BYTES]) {
+    NcclApi *nc = nccl_api();
+    if (!nc || !id) return GG_ERR_CUDA;
+    static_assert(sizeof(ncclUniqueId) <= GG_COMM_ID_BYTES, "unique id size");
+    ncclUniqueId u;
+    if (nc->GetUniqueId(&u) != ncclSuccess) return GG_ERR_CUDA;
+    memset(id, 0, GG_COMM_ID_BYTES);
+    memcpy(id, &u, sizeof(u));
+    return GG_OK;
+}
+int gg_comm_create(gg_ctx *ctx, const uint8_t id[GG_COMM_ID_BYTES], int rank, int world, gg_comm **out) {
+    API_BEGIN(ctx)
+    if (!out || !id || world < 1 || rank < 0 || rank >= world) GG_THROW(GG_ERR_ARG, "bad communicator arguments");
+    *out = nullptr;
+    NcclApi *nc = nccl_api();
+    if (!nc) GG_THROW(GG_ERR_CUDA, "libnccl.so.2 could not be loaded");
+    CK(cudaSetDevice(_c->device));
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof(u));
+    gg_comm *cm = new gg_comm();
+    cm->ctx = _c; cm->rank = rank; cm->world = world;
+    ncclResult_t r = nc->CommInitRank(&cm->comm, world, u, rank);
+    if (r != ncclSuccess) { delete cm; GG_THROW(GG_ERR_CUDA, "ncclCommInitRank: %s", nc->GetErrorString(r)); }
+    *out = cm;
+    API_END
+}
+void gg_comm_destroy(gg_comm *cm) {
+    if (!cm) return;
+    cudaSetDevice(cm->ctx->device);
+    cudaStreamSynchronize(cm->ctx->stream);
+    if (cm->comm) nccl_api()->CommDestroy(cm->comm);
+    delete cm;
+}
+int gg_dist_splitters(const uint64_t *hist, uint32_t nb, int world, uint32_t *first) {
+    if (!hist || !first || world < 1) return GG_ERR_ARG;
+    dist_splitters(hist, nb, world, first);
+    return GG_OK;
+}
+}  // extern "C"
+
+static gg_counts *dist_count_impl(gg_comm *cm, const u8 *d_seq, const u64 *d_offs, u64 nreads, u64 nbytes, int k, int canonical, u64 min_freq,
+                                  u64 *n_glob) {
+    gg_ctx *ctx = cm->ctx;
+    if (!msd_supported(k, canonical)) GG_THROW(GG_ERR_LIMIT, "the multi-GPU path covers k <= 32 (k = 32 canonical only) in this version");
+    gg_counts *c = new gg_counts();
+    c->ctx = ctx; c->k = k; c->W = 1;
+    try {
+        stage_begin(ctx, ST_PACK);
+        PackedReads pr;
+        pack_reads(ctx, d_seq, d_offs, nreads, nbytes, pr);
+        DBuf<u32> valid;
+        window_valid_mask(ctx, pr, k, valid);
+        stage_end(ctx, ST_PACK);
+        DBuf<u64> ukeys;
+        DBuf<u32> counts;
+        u32 mf = min_freq > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)min_freq;
+        u64 ng = 0;
+        c->n_unique = dist_msd_count(cm, pr, valid.p, k, canonical, mf < 1 ? 1 : mf, ukeys, counts, &c->n_instances, &ng);
+        if (n_glob) *n_glob = ng;
+        c->d_keys = ukeys.take();
+        c->d_counts = counts.take();
+        return c;
+    } catch (...) {
+        dfree(ctx, c->d_keys); dfree(ctx, c->d_counts);
+        delete c;
+        throw;
+    }
+}
+// every rank's slice -> the whole table on every rank (slices are in key order by rank)
+static gg_counts *counts_allgather_impl(gg_comm *cm, gg_counts *c) {
+    NcclApi *nc = nccl_api();
+    gg_ctx *ctx = cm->ctx;
+    const int P = cm->world;
+    DBuf<u64> sz(ctx, P + 2);
+    u64 mine[2] = {c->n_unique, c->n_instances};
+    CK(cudaMemcpyAsync(sz.p + P, mine, sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    NCK(nc->AllGather(sz.p + P, sz.p, 1, ncclUint64, cm->comm, ctx->stream));
+    std::vector<u64> n(P), off(P), zero(P, 0), mycnt(P, c->n_unique);
+    CK(cudaMemcpyAsync(n.data(), sz.p, P * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    u64 total = 0;
+    for (int p = 0; p < P; ++p) { off[p] = total; total += n[p]; }
+    gg_counts *f = new gg_counts();
+    f->ctx = ctx; f->k = c->k; f->W = c->W; f->n_unique = total; f->n_instances = c->n_instances;
+    try {
+        f->d_keys = dalloc<u64>(ctx, total * c->W);
+        f->d_counts = dalloc<u32>(ctx, total);
+        dist_alltoallv(cm, c->d_keys, zero.data(), mycnt.data(), f->d_keys, off.data(), n.data(), sizeof(u64) * c->W);
+        dist_alltoallv(cm, c->d_counts, zero.data(), mycnt.data(), f->d_counts, off.data(), n.data(), sizeof(u32));
+        CK(cudaStreamSynchronize(ctx->stream));
+    } catch (...) {
+        dfree(ctx, f->d_keys); dfree(ctx, f->d_counts);
+        delete f;
+        throw;
+    }
+    return f;
+}
+
+extern "C" {
+int gg_dist_count_kmers_dev(gg_comm *cm, const uint8_t *d_seq, const uint64_t *d_offs, uint64_t nreads, uint64_t nbytes, int k,
+                            int canonical, uint64_t min_freq, gg_counts **out, uint64_t *n_instances_global) {
+    if (!cm) return GG_ERR_ARG;
+    API_BEGIN(cm->ctx)
+    if (!out) GG_THROW(GG_ERR_ARG, "null output");
+    *out = nullptr;
+    check_k(k);
+    CK(cudaSetDevice(_c->device));
+    timing_reset(_c);
+    stage_begin(_c, ST_TOTAL);
+    *out = dist_count_impl(cm, d_seq, d_offs, nreads, nbytes, k, canonical, min_freq, n_instances_global);
+    stage_end(_c, ST_TOTAL);
+    timing_collect(_c);
+    API_END
+}
+int gg_counts_allgather(gg_comm *cm, gg_counts *local, gg_counts **full) {
+    if (!cm) return GG_ERR_ARG;
+    API_BEGIN(cm->ctx)
+    if (!local || !full) GG_THROW(GG_ERR_ARG, "null argument");
+    *full = nullptr;
+    CK(cudaSetDevice(_c->device));
+    *full = counts_allgather_impl(cm, local);
+    API_END
+}
+int gg_dist_dbg_from_reads_dev(gg_comm *cm, const uint8_t *d_seq, const uint64_t *d_offs, uint64_t nreads, uint64_t nbytes, int k,
+                               uint64_t min_freq, gg_graph **out, uint64_t *n_instances_global) {
+    if (!cm) return GG_ERR_ARG;
+    API_BEGIN(cm->ctx)
+    if (!out) GG_THROW(GG_ERR_ARG, "null output");
+    *out = nullptr;
+    check_k(k);
+    CK(cudaSetDevice(_c->device));
+    timing_reset(_c);
+    stage_begin(_c, ST_TOTAL);
+    gg_counts *c = dist_count_impl(cm, d_seq, d_offs, nreads, nbytes, k, 1, min_freq, n_instances_global), *f = nullptr;
+    try {
+        stage_begin(_c, ST_FILTER);  // the all-gather of the kept k-mers is booked under "filter"
+        f = counts_allgather_impl(cm, c);
+        stage_end(_c, ST_FILTER);
+        DISPATCH_W(f->W, *out = build_graph<W>(_c, f->d_keys, f->n_unique, f->k));
+    } catch (...) {
+        gg_counts_free(c);
+        gg_counts_free(f);
+        throw;
+    }
+    gg_counts_free(c);
+    gg_counts_free(f);
+    stage_end(_c, ST_TOTAL);
+    timing_collect(_c);
+    API_END
+}
+
 // ------------------------------------- synth ------------------------------------------------
 static int synth_check(u64 genome_len, u32 read_len, int paired, u32 frag_len) {
     u64 F = paired ? frag_len : read_len;
     if (read_len == 0 || F < read_len || genome_len < F) return GG_ERR_ARG;
     return GG_OK;
 }
-int gg_synth_reads_host(uint64_t seed, uint64_t genome_len, uint64_t nreads, uint32_t read_len, int paired, uint32_t frag_len,
-                        uint32_t err_ppm, uint32_t n_ppm, uint8_t *out) {
-    if (!out || synth_check(genome_len, read_len, paired, frag_len) != GG_OK) return GG_ERR_ARG;
+int gg_synth_reads_range_host(uint64_t seed, uint64_t genome_len, uint64_t first_read, uint64_t nreads, uint32_t read_len, int paired,
+                              uint32_t frag_len, uint32_t err_ppm, uint32_t n_ppm, uint8_t *out) {
+    if (!out || synth_check(genome_len, read_len, paired, frag_len) != GG_OK || (paired && (first_read & 1))) return GG_ERR_ARG;
     SynthParams P = synth_params(seed, genome_len, nreads, read_len, paired, frag_len, err_ppm, n_ppm);
 #pragma omp parallel for schedule(static)
     for (long long r = 0; r < (long long)nreads; ++r)
-        for (u32 p = 0; p < read_len; ++p) out[(u64)r * read_len + p] = synth_base(P, (u64)r, p);
+        for (u32 p = 0; p < read_len; ++p) out[(u64)r * read_len + p] = synth_base(P, first_read + (u64)r, p);
     return GG_OK;
+}
+int gg_synth_reads_host(uint64_t seed, uint64_t genome_len, uint64_t nreads, uint32_t read_len, int paired, uint32_t frag_len,
+                        uint32_t err_ppm, uint32_t n_ppm, uint8_t *out) {
+    return gg_synth_reads_range_host(seed, genome_len, 0, nreads, read_len, paired, frag_len, err_ppm, n_ppm, out);
+}
+int gg_synth_reads_range_dev(gg_ctx *ctx, uint64_t seed, uint64_t genome_len, uint64_t first_read, uint64_t nreads, uint32_t read_len,
+                             int paired, uint32_t frag_len, uint32_t err_ppm, uint32_t n_ppm, uint8_t *d_out) {
+    API_BEGIN(ctx)
+    if (!d_out || synth_check(genome_len, read_len, paired, frag_len) != GG_OK || (paired && (first_read & 1)))
+        GG_THROW(GG_ERR_ARG, "bad synthetic read parameters");
+    CK(cudaSetDevice(_c->device));
+    SynthParams P = synth_params(seed, genome_len, nreads, read_len, paired, frag_len, err_ppm, n_ppm);
+    LAUNCH(_c, synth_reads_kernel, (unsigned)(_c->num_sms * 16), 256, 0, P, first_read, d_out);
+    CK(cudaStreamSynchronize(_c->stream));
+    API_END
 }
 int gg_synth_reads_dev(gg_ctx *ctx, uint64_t seed, uint64_t genome_len, uint64_t nreads, uint32_t read_len, int paired,
                        uint32_t frag_len, uint32_t err_ppm, uint32_t n_ppm, uint8_t *d_out) {
-    API_BEGIN(ctx)
-    if (!d_out || synth_check(genome_len, read_len, paired, frag_len) != GG_OK) GG_THROW(GG_ERR_ARG, "bad synthetic read parameters");
-    CK(cudaSetDevice(_c->device));
-    SynthParams P = synth_params(seed, genome_len, nreads, read_len, paired, frag_len, err_ppm, n_ppm);
-    LAUNCH(_c, synth_reads_kernel, (unsigned)(_c->num_sms * 16), 256, 0, P, d_out);
-    CK(cudaStreamSynchronize(_c->stream));
-    API_END
+    return gg_synth_reads_range_dev(ctx, seed, genome_len, 0, nreads, read_len, paired, frag_len, err_ppm, n_ppm, d_out);
 }
 int gg_synth_genome_host(uint64_t seed, uint64_t genome_len, uint8_t *out) {
     if (!out) return GG_ERR_ARG;

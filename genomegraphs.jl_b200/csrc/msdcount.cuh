@@ -27,6 +27,7 @@
 #pragma once
 #include "pack.cuh"
 #include "sort.cuh"
+#include <math.h>
 
 #define MSD_HB 12      // resolution of the pass-A histogram (bits) = largest level-0 digit
 #define MSD_MAX_B1 10
@@ -64,11 +65,12 @@ __device__ __forceinline__ void roll32(const u64 *__restrict__ packed, const u32
 __device__ __forceinline__ u32 msd_digit0(u64 key, int sh, int b0) { return b0 ? (u32)(key >> sh) : 0u; }
 
 // ---- pass A: 12-bit histogram + distinct estimate -------------------------------------------
-// Estimate: keys whose hash falls into a 2^-est_shift slice of the hash space are inserted into a
-// global open-addressing set; (#occupied << est_shift) estimates the number of distinct keys.
+// Estimate (linear counting): keys whose sampler hash falls into a 2^-est_shift slice set one byte
+// of a 2^EST_LOG-byte map; with Z zero bytes left, distinct ~= 2^EST_LOG * ln(2^EST_LOG / Z) << est_shift.
+// The map of several GPUs merges with an elementwise max (dist.cuh).
 __global__ void __launch_bounds__(256) msd_hist_kernel(const u64 *__restrict__ packed, const u32 *__restrict__ valid, u64 nwords,
                                                        int k, int canonical, int hb, u32 *__restrict__ ghist, u32 est_max,
-                                                       unsigned long long *__restrict__ est_tab) {
+                                                       u8 *__restrict__ est_map) {
     __shared__ u32 h[1 << MSD_HB];
     const int nb = 1 << hb, sh = 2 * k - hb;
     for (int i = threadIdx.x; i < nb; i += 256) h[i] = 0;
@@ -77,28 +79,21 @@ __global__ void __launch_bounds__(256) msd_hist_kernel(const u64 *__restrict__ p
         roll32(packed, valid, t, k, canonical, [&](u64 key, int) {
             atomicAdd(&h[msd_digit0(key, sh, hb)], 1u);
             const u32 p = (u32)key * 0x9E3779B1u;  // hash of the last 16 bases: a sampler, not an identity
-            if (p <= est_max) {
-                u32 slot = (u32)(((u64)key * MSD_GOLD) >> (64 - EST_LOG));
-                for (int probe = 0; probe < 64; ++probe) {
-                    unsigned long long cur = est_tab[slot];
-                    if (cur == (unsigned long long)key) break;
-                    if (cur == MSD_EMPTY) {
-                        cur = atomicCAS(&est_tab[slot], (unsigned long long)MSD_EMPTY, (unsigned long long)key);
-                        if (cur == MSD_EMPTY || cur == (unsigned long long)key) break;
-                    }
-                    slot = (slot + 1) & ((1u << EST_LOG) - 1u);
-                }
-            }
+            if (p <= est_max) est_map[(u32)((key * MSD_GOLD) >> (64 - EST_LOG))] = 1;
         });
     __syncthreads();
     for (int i = threadIdx.x; i < nb; i += 256)
         if (h[i]) atomicAdd(&ghist[i], h[i]);
 }
-// out[0] += number of occupied estimate slots; out[1] += sum of the histogram (N)
-__global__ void __launch_bounds__(256) msd_est_count_kernel(const unsigned long long *__restrict__ est_tab, const u32 *__restrict__ hist,
+// out[0] += number of set map bytes; out[1] += sum of the histogram (N)
+__global__ void __launch_bounds__(256) msd_est_count_kernel(const u8 *__restrict__ est_map, const u32 *__restrict__ hist,
                                                             u32 nb, unsigned long long *__restrict__ out) {
     u64 occ = 0, n = 0;
-    for (u32 i = blockIdx.x * 256 + threadIdx.x; i < (1u << EST_LOG); i += gridDim.x * 256) occ += est_tab[i] != MSD_EMPTY;
+    const uint4 *m4 = reinterpret_cast<const uint4 *>(est_map);
+    for (u32 i = blockIdx.x * 256 + threadIdx.x; i < (1u << EST_LOG) / 16; i += gridDim.x * 256) {
+        uint4 v = m4[i];
+        occ += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);  // bytes are 0 or 1
+    }
     for (u32 i = blockIdx.x * 256 + threadIdx.x; i < nb; i += gridDim.x * 256) n += hist[i];
     for (int d = 16; d > 0; d >>= 1) { occ += __shfl_xor_sync(FULL_MASK, occ, d); n += __shfl_xor_sync(FULL_MASK, n, d); }
     if (lane_id() == 0) { if (occ) atomicAdd(&out[0], (unsigned long long)occ); if (n) atomicAdd(&out[1], (unsigned long long)n); }
@@ -572,27 +567,41 @@ static MsdPlan msd_plan(u64 distinct_est, u64 n_instances, int k, const MsdTune 
     return p;
 }
 
-// pass A: hist (2^hb + 1 entries, last 0); returns N and the distinct estimate of THIS GPU's reads
-static void msd_pass_a(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int k, int canonical, DBuf<u32> &hist, u64 *N, u64 *distinct_est) {
+static inline int msd_est_shift(u64 nbases) {
+    int s = 0;
+    while (s < 30 && (nbases >> s) > (1ULL << (EST_LOG - 1))) ++s;
+    return s;
+}
+static inline u64 msd_est_value(u64 set_bytes, int est_shift) {
+    const double m = (double)(1ULL << EST_LOG);
+    double z = m - (double)set_bytes;
+    if (z < 1.0) z = 1.0;
+    return (u64)(m * log(m / z)) << est_shift;
+}
+// pass A, launch: hist (2^hb + 1 entries, last 0) and the estimate map (2^EST_LOG bytes); est_shift
+// must be the same on every GPU whose maps are merged
+static void msd_pass_a_launch(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int k, int canonical, int est_shift, DBuf<u32> &hist,
+                              DBuf<u8> &est) {
     const int hb = msd_hist_bits(k);
     const u32 nb = 1u << hb;
     hist.alloc(ctx, nb + 1);
+    est.alloc(ctx, 1ULL << EST_LOG);
     CK(cudaMemsetAsync(hist.p, 0, (nb + 1) * sizeof(u32), ctx->stream));
-    *N = 0; *distinct_est = 0;
+    CK(cudaMemsetAsync(est.p, 0, 1ULL << EST_LOG, ctx->stream));
     if (pr.nwords == 0) return;
-    int est_shift = 0;
-    while (est_shift < 30 && (pr.nbases >> est_shift) > (1ULL << (EST_LOG - 1))) ++est_shift;
-    DBuf<u64> est(ctx, 1ULL << EST_LOG), res(ctx, 2);
-    CK(cudaMemsetAsync(est.p, 0xFF, sizeof(u64) << EST_LOG, ctx->stream));
-    CK(cudaMemsetAsync(res.p, 0, 2 * sizeof(u64), ctx->stream));
     u64 hgrid = ceil_div(pr.nwords, 256);
     if (hgrid > (u64)ctx->num_sms * 8) hgrid = (u64)ctx->num_sms * 8;
-    LAUNCH(ctx, msd_hist_kernel, (unsigned)hgrid, 256, 0, pr.packed.p, valid, pr.nwords, k, canonical, hb, hist.p, est_shift ? (0xFFFFFFFFu >> est_shift) : 0xFFFFFFFFu,
-           (unsigned long long *)est.p);
-    LAUNCH(ctx, msd_est_count_kernel, (unsigned)(ctx->num_sms * 2), 256, 0, (const unsigned long long *)est.p, hist.p, nb, (unsigned long long *)res.p);
+    LAUNCH(ctx, msd_hist_kernel, (unsigned)hgrid, 256, 0, pr.packed.p, valid, pr.nwords, k, canonical, hb, hist.p,
+           est_shift ? (0xFFFFFFFFu >> est_shift) : 0xFFFFFFFFu, est.p);
+}
+// pass A, read back: N = sum of hist, distinct estimate from the map
+static void msd_pass_a_read(gg_ctx *ctx, const u32 *hist, u32 nb, const u8 *est, int est_shift, u64 *N, u64 *distinct_est) {
+    DBuf<u64> res(ctx, 2);
+    CK(cudaMemsetAsync(res.p, 0, 2 * sizeof(u64), ctx->stream));
+    LAUNCH(ctx, msd_est_count_kernel, (unsigned)(ctx->num_sms * 2), 256, 0, est, hist, nb, (unsigned long long *)res.p);
     CK(cudaMemcpyAsync(ctx->h_scalar, res.p, 2 * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    *distinct_est = ctx->h_scalar[0] << est_shift;
+    *distinct_est = msd_est_value(ctx->h_scalar[0], est_shift);
     *N = ctx->h_scalar[1];
 }
 
@@ -712,7 +721,11 @@ static u64 msd_count(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int k
     DBuf<u32> hist, hist0, bstart;
     DBuf<u64> A;
     u64 N = 0, dest = 0;
-    msd_pass_a(ctx, pr, valid, k, canonical, hist, &N, &dest);
+    DBuf<u8> est;
+    const int est_shift = msd_est_shift(pr.nbases);
+    msd_pass_a_launch(ctx, pr, valid, k, canonical, est_shift, hist, est);
+    msd_pass_a_read(ctx, hist.p, 1u << msd_hist_bits(k), est.p, est_shift, &N, &dest);
+    est.release();
     *n_instances = N;
     if (N == 0) { stage_end(ctx, ST_EXTRACT); ukeys.alloc(ctx, 1); ucounts.alloc(ctx, 1); return 0; }
     if (N >= 0xFFFFFFFFull) GG_THROW(GG_ERR_LIMIT, "%llu k-mer instances exceed the 2^32-1 per-call limit", (unsigned long long)N);

@@ -58,8 +58,8 @@ __host__ __device__ __forceinline__ u8 synth_base(const SynthParams &P, u64 r, u
     }
     return (u8)(0x54474341u >> (8 * b));
 }
-__global__ void synth_reads_kernel(SynthParams P, u8 *__restrict__ out) {
+__global__ void synth_reads_kernel(SynthParams P, u64 first_read, u8 *__restrict__ out) {
     u64 total = P.nreads * (u64)P.read_len;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (u64)gridDim.x * blockDim.x)
-        out[i] = synth_base(P, i / P.read_len, (u32)(i % P.read_len));
+        out[i] = synth_base(P, first_read + i / P.read_len, (u32)(i % P.read_len));
 }

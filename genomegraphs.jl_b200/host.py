@@ -114,7 +114,8 @@ class MerCounts:
 
     def free(self):
         if self.h:
-            N.lib().gg_counts_free(self.h)
+            if self.ctx.h:  # a closed context has already released the device
+                N.lib().gg_counts_free(self.h)
             self.h = None
 
     def __del__(self):
@@ -415,11 +416,12 @@ class UniqueMerIndex:
         return self.unique_mers_per_node[abs(int(nodeid)) - 1] == 0
 
 
-def synth_reads(seed, genome_len, nreads, read_len, paired=False, frag_len=0, err_ppm=0, n_ppm=0):
-    """Deterministic synthetic reads (host generator) -> (seq_bytes, offsets)."""
+def synth_reads(seed, genome_len, nreads, read_len, paired=False, frag_len=0, err_ppm=0, n_ppm=0, first_read=0):
+    """Deterministic synthetic reads (host generator) -> (seq_bytes, offsets).  `first_read` selects
+    reads first_read .. first_read + nreads of the same job (a rank's shard)."""
     out = np.zeros(int(nreads) * int(read_len), dtype=np.uint8)
-    code = N.lib().gg_synth_reads_host(int(seed), int(genome_len), int(nreads), int(read_len), int(bool(paired)), int(frag_len),
-                                       int(err_ppm), int(n_ppm), _ptr(out))
+    code = N.lib().gg_synth_reads_range_host(int(seed), int(genome_len), int(first_read), int(nreads), int(read_len), int(bool(paired)),
+                                             int(frag_len), int(err_ppm), int(n_ppm), _ptr(out))
     if code != N.GG_OK:
         raise ValueError("bad synthetic read parameters")
     offs = np.arange(int(nreads) + 1, dtype=np.uint64) * np.uint64(read_len)

@@ -143,6 +143,38 @@ int gg_umi_export(gg_umi *u, uint64_t *kmer_words, int64_t *node, uint32_t *pos,
                   uint64_t *unique_mers_per_node, uint64_t *total_mers_per_node);
 void gg_umi_free(gg_umi *u);
 
+/* ---- multi-GPU (one process per GPU) ------------------------------------------------------
+ * Replaces the role of KmerAnalysis `dist_mem` (re-export src/GenomeGraphs.jl:46-47, prose
+ * docs/src/man/assembly.md:108-117: workers count read ranges, sorted count vectors are
+ * merged).  Every rank passes ITS shard of the reads; k-mers are range-partitioned over the
+ * ranks on the all-gathered level-0 histogram and exchanged once (NCCL send/recv over
+ * NVLink); rank r returns the r-th contiguous slice of the global sorted table, so the
+ * concatenation over ranks equals the single-GPU gg_count_kmers result.  k <= 32 in this
+ * version (GG_ERR_LIMIT otherwise).
+ * Bootstrap: rank 0 calls gg_comm_unique_id and ships the bytes to the other ranks by any
+ * host channel (the Python host uses torch.distributed, Julia would use Distributed / MPI);
+ * every rank then calls gg_comm_create on its own context.  Collective calls must be made
+ * by all ranks in the same order. */
+typedef struct gg_comm gg_comm;
+#define GG_COMM_ID_BYTES 128
+int gg_comm_unique_id(uint8_t id[GG_COMM_ID_BYTES]);
+int gg_comm_create(gg_ctx *ctx, const uint8_t id[GG_COMM_ID_BYTES], int rank, int world, gg_comm **out);
+void gg_comm_destroy(gg_comm *comm);
+/* owner ranges of the histogram buckets: rank q owns [first[q], first[q + 1]); first has
+ * world + 1 entries.  Pure host function (no GPU needed). */
+int gg_dist_splitters(const uint64_t *hist, uint32_t n_buckets, int world, uint32_t *first);
+/* min_freq > 1 drops rarer k-mers on the owner (every k-mer has exactly one owner, so the
+ * counts are complete).  *n_instances_global = k-mer windows over all ranks. */
+int gg_dist_count_kmers_dev(gg_comm *comm, const uint8_t *d_seq_bytes, const uint64_t *d_read_offsets, uint64_t nreads,
+                            uint64_t nbytes, int k, int canonical, uint64_t min_freq, gg_counts **out,
+                            uint64_t *n_instances_global);
+/* slices of all ranks -> the whole sorted table on every rank */
+int gg_counts_allgather(gg_comm *comm, gg_counts *local, gg_counts **full);
+/* reads -> graph: distributed count + filter, all-gather of the kept k-mers, graph stage on
+ * every rank (each rank returns the same graph). */
+int gg_dist_dbg_from_reads_dev(gg_comm *comm, const uint8_t *d_seq_bytes, const uint64_t *d_read_offsets, uint64_t nreads,
+                               uint64_t nbytes, int k, uint64_t min_freq, gg_graph **out, uint64_t *n_instances_global);
+
 /* ---- deterministic synthetic reads -----------------------------------
  * Counter-based generator (splitmix64 keyed by seed and index): the host and device
  * variants produce identical bytes.  Genome of genome_len i.i.d. uniform bases; nreads
@@ -154,6 +186,13 @@ int gg_synth_reads_host(uint64_t seed, uint64_t genome_len, uint64_t nreads, uin
                         int paired, uint32_t frag_len, uint32_t err_ppm, uint32_t n_ppm, uint8_t *out);
 int gg_synth_reads_dev(gg_ctx *ctx, uint64_t seed, uint64_t genome_len, uint64_t nreads, uint32_t read_len,
                        int paired, uint32_t frag_len, uint32_t err_ppm, uint32_t n_ppm, uint8_t *d_out);
+/* reads first_read .. first_read + nreads of the same job (a rank's shard); first_read must be
+ * even when paired */
+int gg_synth_reads_range_dev(gg_ctx *ctx, uint64_t seed, uint64_t genome_len, uint64_t first_read, uint64_t nreads,
+                             uint32_t read_len, int paired, uint32_t frag_len, uint32_t err_ppm, uint32_t n_ppm,
+                             uint8_t *d_out);
+int gg_synth_reads_range_host(uint64_t seed, uint64_t genome_len, uint64_t first_read, uint64_t nreads, uint32_t read_len,
+                              int paired, uint32_t frag_len, uint32_t err_ppm, uint32_t n_ppm, uint8_t *out);
 int gg_synth_genome_host(uint64_t seed, uint64_t genome_len, uint8_t *out);
 
 #ifdef __cplusplus
