@@ -51,7 +51,7 @@ ALG_BYTES = {
     "msd_scatter_kernel": lambda N, nb, U, W: _stream_bytes(nb) + W * N,
     "msd_hist1_kernel": lambda N, nb, U, W: W * N,
     "msd_scatter1_kernel": lambda N, nb, U, W: 2.0 * W * N,
-    "msd_task_kernel": lambda N, nb, U, W: W * N + (W + 4.0) * U,
+    "msd_leaf_kernel": lambda N, nb, U, W: W * N + (W + 4.0) * U,
     "msd_gather_kernel": lambda N, nb, U, W: 2.0 * (W + 4.0) * U,
     "radix_scatter_kernel": lambda N, nb, U, W: 2.0 * W * N,   # per pass
     "radix_hist_kernel": lambda N, nb, U, W: 1.0 * W * N,
@@ -94,7 +94,12 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def mark(self):
+        """index of the next sample: brackets the timed region (the sampler itself is started before
+        the warm-up so that nvidia-smi's start-up never lands inside a timed region)"""
+        return len(self.lines)
+
+    def stop(self, first=0, last=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -103,7 +108,8 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        window = self.lines[first:last] or self.lines[max(0, first - 1):]  # a region shorter than one period: nearest sample
+        for ln in window:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -199,13 +205,17 @@ def main():
     nreads = nreads_for(w)
     nbytes = nreads * rl
     n_inst = nreads * kmers_per_read(w)
-    seed = 1 + rank  # every rank owns a different shard of reads (weak scaling)
+    # Weak scaling: ONE job whose size grows with the GPU count -- genome world x genome_len, world x nreads
+    # reads; rank r owns reads [r * nreads, (r + 1) * nreads) and (after the exchange) one key range.
+    seed = 1
+    genome_total = w["genome_len"] * world
+    comm = pkg.dist.Comm.from_torch(ctx) if world > 1 else None
 
     # ---- inputs: generated on the device, kept resident in HBM; pinned host copy for the e2e leg
     d_seq, d_offs, h_seq = C.c_void_p(), C.c_void_p(), C.c_void_p()
     N.check(H, L.gg_dev_alloc(H, nbytes + 64, C.byref(d_seq)))
     N.check(H, L.gg_dev_alloc(H, 8 * (nreads + 1), C.byref(d_offs)))
-    N.check(H, L.gg_synth_reads_dev(H, seed, w["genome_len"], nreads, rl, 1, w["frag_len"], w["err_ppm"], 0, d_seq))
+    N.check(H, L.gg_synth_reads_range_dev(H, seed, genome_total, rank * nreads, nreads, rl, 1, w["frag_len"], w["err_ppm"], 0, d_seq))
     offs = np.arange(nreads + 1, dtype=np.uint64) * np.uint64(rl)
     N.check(H, L.gg_memcpy_h2d(H, d_offs, offs.ctypes.data_as(C.c_void_p), offs.nbytes))
     N.check(H, L.gg_host_alloc(H, nbytes + 64, C.byref(h_seq)))
@@ -220,13 +230,19 @@ def main():
 
     def step_dev():
         gh = C.c_void_p()
-        N.check(H, L.gg_dbg_from_reads_dev(H, d_seq, d_offs, nreads, nbytes, k, min_freq, C.byref(gh)))
+        if comm is None:
+            N.check(H, L.gg_dbg_from_reads_dev(H, d_seq, d_offs, nreads, nbytes, k, min_freq, C.byref(gh)))
+        else:  # distributed count (one NCCL exchange) + all-gather of the kept k-mers + graph stage
+            N.check(H, L.gg_dist_dbg_from_reads_dev(comm.h, d_seq, d_offs, nreads, nbytes, k, min_freq, C.byref(gh), None))
         return gh
 
     def graph_sizes(gh):
         nn, nb, nl, kk = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_int()
         N.check(H, L.gg_graph_sizes(gh, C.byref(nn), C.byref(nb), C.byref(nl), C.byref(kk)))
         return nn.value, nb.value, nl.value
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
 
     # ---- warm-up (also fills the memory pool) ----
     launches = 0
@@ -238,9 +254,8 @@ def main():
         launches = ctx.last_timings()[1]
 
     # ---- timed: K steps, inputs resident in HBM (232 MB of reads > 126 MB L2) ----
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
+    s_first = sampler.mark()
     N.check(H, L.gg_ctx_event_record(H, 0))
     t0 = time.perf_counter()
     stage_ms = None
@@ -260,9 +275,19 @@ def main():
     out_off = np.zeros(nn + 1, dtype=np.uint64); out_bases = np.zeros(max(nb, 1), dtype=np.uint8)
     out_row = np.zeros(nn + 1, dtype=np.uint64); out_tri = np.zeros(max(3 * nl, 1), dtype=np.int64)
 
+    d_seq2, d_offs2 = C.c_void_p(), C.c_void_p()
+    if comm is not None:
+        N.check(H, L.gg_dev_alloc(H, nbytes + 64, C.byref(d_seq2)))
+        N.check(H, L.gg_dev_alloc(H, 8 * (nreads + 1), C.byref(d_offs2)))
+
     def step_e2e():
         gh = C.c_void_p()
-        N.check(H, L.gg_dbg_from_reads(H, h_seq, offs.ctypes.data_as(C.c_void_p), nreads, k, min_freq, C.byref(gh)))
+        if comm is None:
+            N.check(H, L.gg_dbg_from_reads(H, h_seq, offs.ctypes.data_as(C.c_void_p), nreads, k, min_freq, C.byref(gh)))
+        else:  # host buffers of this rank's shard -> device, distributed build, graph back to the host
+            N.check(H, L.gg_memcpy_h2d(H, d_seq2, h_seq, nbytes))
+            N.check(H, L.gg_memcpy_h2d(H, d_offs2, offs.ctypes.data_as(C.c_void_p), offs.nbytes))
+            N.check(H, L.gg_dist_dbg_from_reads_dev(comm.h, d_seq2, d_offs2, nreads, nbytes, k, min_freq, C.byref(gh), None))
         N.check(H, L.gg_graph_export(gh, out_off.ctypes.data_as(C.c_void_p), out_bases.ctypes.data_as(C.c_void_p),
                                      out_row.ctypes.data_as(C.c_void_p), out_tri.ctypes.data_as(C.c_void_p)))
         L.gg_graph_free(gh)
@@ -274,7 +299,7 @@ def main():
         step_e2e()
     barrier()
     e2e_s = time.perf_counter() - t1
-    clocks = sampler.stop()
+    clocks = sampler.stop(s_first, sampler.mark())
 
     # ---- max over ranks / sum of work ----
     if dist is not None:
@@ -286,13 +311,26 @@ def main():
 
     # ---- roofline of the dominant kernel: one extra, untimed, profiled step ----
     roofline, top = None, []
+    L.gg_ctx_set_profile(H, 1)   # every rank runs the step (it is collective for N > 1); rank 0 reports its own kernels
+    gh = step_dev()
+    L.gg_graph_free(gh)
+    L.gg_ctx_set_profile(H, 0)
+    prof_text = L.gg_ctx_kernel_profile(H).decode()
+    # distinct k-mers (all / kept by the filter) of this rank's key range: the writes of the counting kernels
+    ch = C.c_void_p()
+    if comm is None:
+        N.check(H, L.gg_count_kmers_dev(H, d_seq, d_offs, nreads, nbytes, k, 1, C.byref(ch)))
+    else:
+        N.check(H, L.gg_dist_count_kmers_dev(comm.h, d_seq, d_offs, nreads, nbytes, k, 1, 1, C.byref(ch), None))
+    nu_all = C.c_uint64()
+    N.check(H, L.gg_counts_sizes(ch, C.byref(nu_all), None, None, None))
+    N.check(H, L.gg_counts_filter(ch, min_freq, 0))
+    nu_kept = C.c_uint64()
+    N.check(H, L.gg_counts_sizes(ch, C.byref(nu_kept), None, None, None))
+    L.gg_counts_free(ch)
     if rank == 0:
-        L.gg_ctx_set_profile(H, 1)
-        gh = step_dev()
-        L.gg_graph_free(gh)
-        L.gg_ctx_set_profile(H, 0)
         prof = []
-        for ln in L.gg_ctx_kernel_profile(H).decode().splitlines():
+        for ln in prof_text.splitlines():
             name, cnt, ms = ln.split("\t")
             prof.append((name.split("<")[0].strip("( "), int(cnt), float(ms)))
         agg = {}
@@ -306,15 +344,6 @@ def main():
         except Exception:
             pass
         peak, peak_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json hbm_gbs)") if peaks.get("hbm_gbs") else (6650.0, "fallback (B200_PROFILING.md)")
-        # distinct k-mers kept by the filter (writes of the counting kernels), outside any timed region
-        ch = C.c_void_p()
-        N.check(H, L.gg_count_kmers_dev(H, d_seq, d_offs, nreads, nbytes, k, 1, C.byref(ch)))
-        nu_all = C.c_uint64()
-        N.check(H, L.gg_counts_sizes(ch, C.byref(nu_all), None, None, None))
-        N.check(H, L.gg_counts_filter(ch, min_freq, 0))
-        nu_kept = C.c_uint64()
-        N.check(H, L.gg_counts_sizes(ch, C.byref(nu_kept), None, None, None))
-        L.gg_counts_free(ch)
         distinct = {"all": nu_all.value, "kept": nu_kept.value}
 
         def model(kname, kcnt, kms):
@@ -373,7 +402,9 @@ def main():
             "dtype": "u64" if k <= 32 else "u128" if k <= 64 else "u256", "data": "synthetic",
             "config": {"workload": args.workload, **w, "reads_per_gpu": nreads, "kmer_instances_per_gpu": n_inst,
                        "input_bytes_per_gpu": nbytes, "l2_policy": "inputs (%.0f MB of reads + %.0f MB of k-mers per step) larger than the 126 MB L2" % (nbytes / 1e6, n_inst * W / 1e6),
-                       "parallelism": "1 process per GPU, independent read shards per rank (no data-path collective yet)",
+                       "genome_len_total": genome_total,
+                       "parallelism": ("1 GPU" if world == 1 else "1 process per GPU; reads sharded by index, k-mers range-partitioned over the ranks "
+                                       "with one NCCL send/recv exchange, kept k-mers all-gathered, graph stage replicated"),
                        "graph": {"nodes": nn, "bases": nb, "link_entries": nl}},
             "wall_ms_per_step": 1e3 * wall / args.steps,
             "stage_ms_last_step": stage_ms,
@@ -390,6 +421,9 @@ def main():
         print(json.dumps(out), flush=True)
 
     L.gg_dev_free(H, d_seq); L.gg_dev_free(H, d_offs); L.gg_host_free(H, h_seq)
+    if comm is not None:
+        L.gg_dev_free(H, d_seq2); L.gg_dev_free(H, d_offs2)
+        comm.close()
     ctx.close()
     if dist is not None:
         dist.barrier()
