@@ -137,20 +137,20 @@ __global__ void wyllie_kernel(const u64 *__restrict__ in, u64 *__restrict__ out,
     if (!(np & V_TERM)) *active = 1;
 }
 // ---- splitter-based list ranking (work-efficient front end of the Wyllie rounds) -----------
-// Splitters = path heads + a 1/32 hash sample.  Every splitter walks to the next splitter (or
-// to the tail), labelling the vertices it passes; the 32x smaller list of splitters is ranked by
+// Splitters = path heads + a 2^-sl hash sample.  Every splitter walks to the next splitter (or
+// to the tail), labelling the vertices it passes; the 2^sl times smaller list of splitters is ranked by
 // pointer jumping; every vertex then derives (tail, distance to tail) from its splitter.
 // Vertices on cycles keep a non-terminal record and go through the cycle path below.
-__device__ __forceinline__ bool hash_splitter(u32 v) { return ((v * 0x9E3779B1u) >> 27) == 0u; }
+__device__ __forceinline__ bool hash_splitter(u32 v, int sl) { return ((v * 0x9E3779B1u) >> (32 - sl)) == 0u; }
 __global__ void split_flag_kernel(const u32 *__restrict__ succ, const u8 *__restrict__ flags, const u64 *__restrict__ rec, u64 nv,
-                                  u32 *__restrict__ sflag) {
+                                  int sl, u32 *__restrict__ sflag) {
     u64 vv = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (vv >= nv) return;
     u32 v = (u32)vv;
     if ((u32)rec[v] == V_NONE) { sflag[v] = 0; return; }
     u32 mv = ((flags[v >> 1] >> 6) & 1u) ? v : (v ^ 1u);
     bool head = succ[mv] == V_NONE;  // pred(v) does not exist  <=>  the mirror vertex has no successor
-    sflag[v] = (head || hash_splitter(v)) ? 1u : 0u;
+    sflag[v] = (head || hash_splitter(v, sl)) ? 1u : 0u;
 }
 __global__ void split_list_kernel(const u32 *__restrict__ sflag, const u32 *__restrict__ sidx, u64 nv, u32 *__restrict__ red_vertex) {
     u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -159,7 +159,7 @@ __global__ void split_list_kernel(const u32 *__restrict__ sflag, const u32 *__re
 // one thread per splitter (dense: every lane of a warp walks).  A walk can only run into a
 // hash-sampled splitter: heads have no predecessor, so no memory lookup is needed for the test.
 __global__ void split_walk_kernel(const u32 *__restrict__ succ, const u32 *__restrict__ red_vertex, const u32 *__restrict__ sidx, u64 ns,
-                                  u32 *__restrict__ owner, u32 *__restrict__ local, u64 *__restrict__ red_rec,
+                                  int sl, u32 *__restrict__ owner, u32 *__restrict__ local, u64 *__restrict__ red_rec,
                                   u32 *__restrict__ red_tail) {
     u64 ii = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (ii >= ns) return;
@@ -168,7 +168,7 @@ __global__ void split_walk_kernel(const u32 *__restrict__ succ, const u32 *__res
     for (;;) {
         u32 n = succ[u];
         if (n == V_NONE) { red_rec[i] = ((u64)d << 32) | (i | V_TERM); red_tail[i] = u; break; }
-        if (hash_splitter(n)) { red_rec[i] = ((u64)(d + 1) << 32) | sidx[n]; red_tail[i] = V_NONE; break; }
+        if (hash_splitter(n, sl)) { red_rec[i] = ((u64)(d + 1) << 32) | sidx[n]; red_tail[i] = V_NONE; break; }
         ++d;
         owner[n] = i;
         local[n] = d;
@@ -583,14 +583,15 @@ static gg_graph *build_graph(gg_ctx *ctx, const u64 *keys, u64 U, int k) {
         } else {
             DBuf<u32> sflag(ctx, nv), sidx(ctx, nv), owner(ctx, nv), local(ctx, nv);
             DBuf<u64> stot(ctx, 1);
-            LAUNCH(ctx, split_flag_kernel, (unsigned)ceil_div(nv, 256), 256, 0, succ.p, flags.p, rin, nv, sflag.p);
+            const int sl = getenv("GG_SPLIT_LOG") ? atoi(getenv("GG_SPLIT_LOG")) : 4;  // splitters: heads + a 2^-sl hash sample
+            LAUNCH(ctx, split_flag_kernel, (unsigned)ceil_div(nv, 256), 256, 0, succ.p, flags.p, rin, nv, sl, sflag.p);
             exclusive_scan_u32(ctx, sflag.p, sidx.p, nv, stot.p);
             const u64 ns = read_scalar<u64>(ctx, stot.p);
             CK(cudaMemsetAsync(owner.p, 0xFF, nv * sizeof(u32), ctx->stream));
             DBuf<u64> redA(ctx, ns + 1), redB(ctx, ns + 1);
             DBuf<u32> red_tail(ctx, ns + 1), red_vertex(ctx, ns + 1);
             LAUNCH(ctx, split_list_kernel, (unsigned)ceil_div(nv, 256), 256, 0, sflag.p, sidx.p, nv, red_vertex.p);
-            if (ns) LAUNCH(ctx, split_walk_kernel, (unsigned)ceil_div(ns, 128), 128, 0, succ.p, red_vertex.p, sidx.p, ns, owner.p, local.p, redA.p, red_tail.p);
+            if (ns) LAUNCH(ctx, split_walk_kernel, (unsigned)ceil_div(ns, 128), 128, 0, succ.p, red_vertex.p, sidx.p, ns, sl, owner.p, local.p, redA.p, red_tail.p);
             u64 *ra = redA.p, *rb = redB.p;
             if (ns) {
                 const int rounds = ilog2_ceil(ns) + 2;  // fixed count: no host round trips

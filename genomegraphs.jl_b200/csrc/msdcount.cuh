@@ -38,29 +38,26 @@
 
 static inline bool msd_supported(int k, int canonical) { return k <= 32 && (canonical || k < 32); }
 
-// 32 consecutive windows starting at base 32 t (k <= 32): f(key, j) for every valid window j
+// 32 consecutive windows starting at base 32 t (k <= 32): f(key, j) for every valid window j.
+// Forward and reverse-complement words are kept LEFT-aligned (k-mer in the top 2k bits) so that every
+// per-window shift has a compile-time amount: the forward word is a funnel shift of the two packed
+// words, the reverse complement rolls by one base (>> 2, new complemented base into the top 2 bits).
 template <class F>
 __device__ __forceinline__ void roll32(const u64 *__restrict__ packed, const u32 *__restrict__ valid, u64 t, int k, int canonical, F &&f) {
     const u32 vm = valid[t];
     if (vm == 0) return;
     const u64 a0 = packed[t], a1 = packed[t + 1];
-    const u64 mask = k == 32 ? ~0ULL : ((1ULL << (2 * k)) - 1ULL);
-    const int top = 2 * (k - 1);
-    u64 fw = a0 >> (64 - 2 * k);
-    u64 rc = rev2_u64(~fw) >> (64 - 2 * k);
+    const int s = 64 - 2 * k;  // 0 .. 62
+    const u64 topmask = ~0ULL << s;
+    const u64 nbc = ~(k == 32 ? a1 : ((a0 << (2 * k)) | (a1 >> s)));  // complemented bases k, k+1, ... of the tile
+    u64 rl = rev2_u64(~a0) << s;                                       // reverse complement of window 0
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-        if ((vm >> (31 - j)) & 1u) f((canonical && rc < fw) ? rc : fw, j);
-        if (j < 31) {
-            int o = k + j;  // base index relative to 32 t, 1 .. 62
-            u64 w = o < 32 ? a0 : a1;
-            u64 nb = (w >> (62 - 2 * (o & 31))) & 3ULL;
-            fw = ((fw << 2) | nb) & mask;
-            rc = (rc >> 2) | ((3ULL - nb) << top);
-        }
+        const u64 fl = (j == 0 ? a0 : ((a0 << (2 * j)) | (a1 >> (64 - 2 * j)))) & topmask;
+        if ((vm >> (31 - j)) & 1u) f(((canonical && rl < fl) ? rl : fl) >> s, j);
+        if (j < 31) rl = ((rl >> 2) & topmask) | ((nbc << (2 * j)) & 0xC000000000000000ULL);
     }
 }
-
 
 __device__ __forceinline__ u32 msd_digit0(u64 key, int sh, int b0) { return b0 ? (u32)(key >> sh) : 0u; }
 

@@ -132,6 +132,24 @@ __global__ void __launch_bounds__(256) valid_kernel(const u32 *__restrict__ bad,
     valid[j] = ~inv;
 }
 
+// k <= 32: every window lies inside two mask words, so the sliding OR runs on one u64
+__global__ void __launch_bounds__(256) valid32_kernel(const u32 *__restrict__ bad, const u32 *__restrict__ brk, u64 nwords, int k,
+                                                      u32 *__restrict__ valid) {
+    u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nwords) return;
+    const u64 B = ((u64)bad[j] << 32) | bad[j + 1], R = ((u64)brk[j] << 32) | brk[j + 1];  // MSB-first positions 0 .. 63
+    const int m = k - 1;
+    u64 acc = 0;
+    if (m > 0) {
+        acc = B | (R << 1);
+        int sz = 1;
+        while (2 * sz <= m) { acc |= acc << sz; sz *= 2; }
+        if (sz < m) acc |= acc << (m - sz);
+    }
+    const u64 inv = acc | (B << m);
+    valid[j] = ~(u32)(inv >> 32);
+}
+
 static void pack_reads(gg_ctx *ctx, const u8 *d_seq, const u64 *d_offs, u64 nreads, u64 nbytes, PackedReads &pr) {
     pr.nbases = nbytes;
     pr.nwords = ceil_div(nbytes, 32);
@@ -154,7 +172,8 @@ static void pack_reads(gg_ctx *ctx, const u8 *d_seq, const u64 *d_offs, u64 nrea
 // valid-window mask for a given k (nwords u32)
 static void window_valid_mask(gg_ctx *ctx, const PackedReads &pr, int k, DBuf<u32> &valid) {
     valid.alloc(ctx, pr.nwords ? pr.nwords : 1);
-    if (pr.nwords) LAUNCH(ctx, valid_kernel, (unsigned)ceil_div(pr.nwords, 256), 256, 0, pr.bad.p, pr.brk.p, pr.nwords, k, valid.p);
+    if (pr.nwords && k <= 32) LAUNCH(ctx, valid32_kernel, (unsigned)ceil_div(pr.nwords, 256), 256, 0, pr.bad.p, pr.brk.p, pr.nwords, k, valid.p);
+    else if (pr.nwords) LAUNCH(ctx, valid_kernel, (unsigned)ceil_div(pr.nwords, 256), 256, 0, pr.bad.p, pr.brk.p, pr.nwords, k, valid.p);
 }
 
 // ---------------------------------- K2: k-mer at position p -------------------------------

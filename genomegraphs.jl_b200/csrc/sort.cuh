@@ -237,6 +237,59 @@ __global__ void __launch_bounds__(256) radix_small_kernel(u64 *k0, u64 *k1, u64 
     }
 }
 
+// ---- rank sort: n <= RANK_SORT_N records, one launch over the whole GPU ---------------------------
+// rank(i) = #{ j : key_j < key_i, or key_j == key_i and j < i } over the masked key bits: the same
+// permutation as a stable LSD radix sort over those bits, in O(n^2 / threads) compares instead of
+// ceil(bits / 8) dependent single-CTA passes.
+#define RANK_SORT_N 12288
+template <int KW>
+struct KeyMask {
+    u64 m[KW];
+};
+// 32 records per CTA, 8 lanes per record: lane `sub` compares against the tile entries q = sub (mod 8)
+template <int KW, bool PAY>
+__global__ void __launch_bounds__(256) rank_sort_kernel(const u64 *__restrict__ kin, u64 *__restrict__ kout, const u64 *__restrict__ pin,
+                                                        u64 *__restrict__ pout, u32 n, KeyMask<KW> km) {
+    __shared__ u64 tile[256 * KW];
+    const u32 i = blockIdx.x * 32 + (threadIdx.x >> 3), sub = threadIdx.x & 7u;
+    const bool live = i < n;
+    Kmer<KW> x, xm;
+#pragma unroll
+    for (int j = 0; j < KW; ++j) { x.w[j] = 0; xm.w[j] = 0; }
+    if (live) {
+        x = km_load<KW>(kin, i);
+#pragma unroll
+        for (int j = 0; j < KW; ++j) xm.w[j] = x.w[j] & km.m[j];
+    }
+    u32 rank = 0;
+    for (u32 t0 = 0; t0 < n; t0 += 256) {
+        __syncthreads();
+        if (t0 + threadIdx.x < n) {
+#pragma unroll
+            for (int j = 0; j < KW; ++j) tile[threadIdx.x * KW + j] = kin[(u64)(t0 + threadIdx.x) * KW + j] & km.m[j];
+        }
+        __syncthreads();
+        const u32 cnt = n - t0 < 256u ? n - t0 : 256u;
+        if (live) {
+#pragma unroll 4
+            for (u32 q = sub; q < cnt; q += 8) {
+                Kmer<KW> y;
+#pragma unroll
+                for (int j = 0; j < KW; ++j) y.w[j] = tile[q * KW + j];
+                const int c = km_cmp<KW>(y, xm);
+                rank += (c < 0 || (c == 0 && t0 + q < i)) ? 1u : 0u;
+            }
+        }
+    }
+    rank += __shfl_xor_sync(FULL_MASK, rank, 1);
+    rank += __shfl_xor_sync(FULL_MASK, rank, 2);
+    rank += __shfl_xor_sync(FULL_MASK, rank, 4);
+    if (live && sub == 0) {
+        km_store<KW>(kout, rank, x);
+        if (PAY) pout[rank] = pin[i];
+    }
+}
+
 // Stable LSD radix sort over the given bit ranges (least significant range first).
 // On return the sorted data is in *keys (and *pay); *keys_alt / *pay_alt hold scratch.
 template <int KW>
@@ -259,6 +312,19 @@ static void radix_sort(gg_ctx *ctx, u64 **keys, u64 **keys_alt, u64 **pay, u64 *
             CK(cudaFuncSetAttribute(radix_small_kernel<KW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         }
         attr_set[has_pay] = true;
+    }
+    if (n <= RANK_SORT_N) {
+        KeyMask<KW> km;
+        for (int j = 0; j < KW; ++j) km.m[j] = 0;
+        for (const BitRange &r : ranges)
+            for (int bit = r.lo; bit < r.hi; ++bit) km.m[KW - 1 - (bit >> 6)] |= 1ULL << (bit & 63);
+        // ranges are given least significant first and must not interleave within a word in a way that changes
+        // the lexicographic order: every caller passes disjoint ranges in ascending significance
+        if (has_pay) LAUNCH(ctx, (rank_sort_kernel<KW, true>), (unsigned)ceil_div(n, 32), 256, 0, *keys, *keys_alt, *pay, *pay_alt, (u32)n, km);
+        else LAUNCH(ctx, (rank_sort_kernel<KW, false>), (unsigned)ceil_div(n, 32), 256, 0, *keys, *keys_alt, (const u64 *)nullptr, (u64 *)nullptr, (u32)n, km);
+        std::swap(*keys, *keys_alt);
+        if (has_pay) std::swap(*pay, *pay_alt);
+        return;
     }
     if (n <= RADIX_SMALL_N) {
         RadixPasses pl;
