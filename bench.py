@@ -310,7 +310,7 @@ def main():
     total_inst = n_inst * world
 
     # ---- roofline of the dominant kernel: one extra, untimed, profiled step ----
-    roofline, top = None, []
+    roofline, top, allk = None, [], []
     L.gg_ctx_set_profile(H, 1)   # every rank runs the step (it is collective for N > 1); rank 0 reports its own kernels
     gh = step_dev()
     L.gg_graph_free(gh)
@@ -337,7 +337,8 @@ def main():
         for name, cnt, ms in prof:
             a = agg.setdefault(name, [0, 0.0]); a[0] += cnt; a[1] += ms
         tot_ms = sum(v[1] for v in agg.values())
-        top = sorted(agg.items(), key=lambda kv: -kv[1][1])[:8]
+        allk = sorted(agg.items(), key=lambda kv: -kv[1][1])
+        top = allk[:8]
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -416,6 +417,7 @@ def main():
             "clocks": clocks,
             "roofline": roofline,
             "top_kernels_ms": [{"kernel": n_, "launches": v[0], "ms": round(v[1], 4)} for n_, v in top],
+            "all_kernels_ms": {n_: [v[0], round(v[1], 4)] for n_, v in allk},
             "cpu_baseline": cpu,
         }
         print(json.dumps(out), flush=True)

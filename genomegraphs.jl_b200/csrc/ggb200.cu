@@ -5,6 +5,7 @@
 #include "pack.cuh"
 #include "sort.cuh"
 #include "msdcount.cuh"
+#include "msdcountw.cuh"
 #include "dist.cuh"
 #include "graph.cuh"
 #include "umi.cuh"
@@ -240,6 +241,24 @@ static gg_counts *count_kmers_dev_impl(gg_ctx *ctx, const u8 *d_seq, const u64 *
             c->d_counts = counts.take();
             if (filtered) *filtered = true;
             return c;
+        }
+        if constexpr (W > 1) {
+            if (!getenv("GG_FORCE_LSD")) {
+                stage_begin(ctx, ST_PACK);
+                PackedReads pr;
+                pack_reads(ctx, d_seq, d_offs, nreads, nbytes, pr);
+                DBuf<u32> valid;
+                window_valid_mask(ctx, pr, k, valid);
+                stage_end(ctx, ST_PACK);
+                DBuf<u64> ukeys;
+                DBuf<u32> counts;
+                u32 mf = min_freq > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)min_freq;
+                c->n_unique = msdw_count<W>(ctx, pr, valid.p, k, canonical, mf < 1 ? 1 : mf, ukeys, counts, &c->n_instances);
+                c->d_keys = ukeys.take();
+                c->d_counts = counts.take();
+                if (filtered) *filtered = true;
+                return c;
+            }
         }
         DBuf<u64> keys;
         u64 n = extract_all<W>(ctx, d_seq, d_offs, nreads, nbytes, k, canonical, keys, 0);

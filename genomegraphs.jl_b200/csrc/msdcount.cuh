@@ -520,7 +520,8 @@ __global__ void __launch_bounds__(256) msd_gather_kernel(const u64 *__restrict__
 struct MsdTune {
     int b0_max = 8;          // preferred level-0 digit bits (grows up to MSD_HB when level 1 is full)
     int b1_max = MSD_MAX_B1; // level-1 digit bits
-    u32 dt = 3072;           // target DISTINCT keys per child (leaf table: 8192 slots)
+    u32 dt = 2048;           // target DISTINCT keys per child: 1/4 of the leaf table (8192 slots), which leaves room for the
+                             // ~1.75x skew of canonical k-mers towards small leading bases
     u32 it_log2 = 16;        // target instances per child (bounds the work of one CTA)
     int variant = 0;         // leaf geometry, see msd_launch_leaf
 };

@@ -1,0 +1,496 @@
+// msdcountw.cuh -- the MSD counting route of msdcount.cuh for 2- and 4-word keys (32 < k <= 128).
+//
+// Same passes (A histogram + distinct estimate, B level-0 scatter, C/D level 1, E one CTA per child,
+// F gather) and the same plan; what differs from the one-word kernels:
+//   * windows are extracted per position (kmer_at: funnel shift of W + 1 packed words, word-wise
+//     reverse complement) instead of rolled, and pass B extracts twice (count, then place) rather
+//     than holding 32 multi-word keys per thread in registers;
+//   * the leaf table (double hashing) claims a slot with a 32-bit tag (atomicCAS exists for one word only), the claimer
+//     stores the full key, and a second pass over the child's instances verifies key equality while
+//     it counts.  Two different keys with the same tag on the same probe path (astronomically rare)
+//     surface in that pass as "key not found" and the child is handed to the overflow path;
+//   * a child that overflows (table too full / tag clash) is finished from the host with the generic
+//     LSD radix sort + run-length count restricted to that child's segment.
+#pragma once
+#include "msdcount.cuh"
+
+template <int W>
+struct MsdW {
+    static constexpr int PPT = 32 / W;                  // window positions per thread in passes A / B
+    static constexpr int TILE_WORDS = 256 / W;          // packed words per CTA tile in pass B
+    static constexpr int TILE_KEYS = TILE_WORDS * 32;   // 4096 (W = 2), 2048 (W = 4): 64 KB of staging
+    static constexpr int KPT = 16 / W;                  // keys per thread in the level-1 tiles
+    static constexpr int T1 = 256 * KPT;
+    static constexpr int LOG_HT = W == 2 ? 12 : 11;     // leaf table slots: 64 KB of keys
+};
+#define MSDW_OVERFLOW 0xFFFFFFFFu
+__device__ unsigned long long g_msdw_dbg[4];
+
+// key bits [lowbit, lowbit + nbits), nbits <= 24
+template <int W>
+__device__ __forceinline__ u32 kw_bits(const Kmer<W> &x, int lowbit, int nbits) {
+    if (nbits == 0) return 0u;
+    const int wi = W - 1 - (lowbit >> 6), sh = lowbit & 63;
+    u64 lo = 0, hi = 0;
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        if (i == wi) lo = x.w[i];
+        if (i == wi - 1) hi = x.w[i];
+    }
+    u64 v = lo >> sh;
+    if (sh) v |= hi << (64 - sh);
+    return (u32)v & ((1u << nbits) - 1u);
+}
+// Full-avalanche hash (murmur3 finaliser over a multiplicative chain): the tag is its low half, so a
+// difference confined to the top bits of one word (a substitution in the first base of a word) must
+// still reach the low bits -- a plain multiply / short xorshift does not do that.
+template <int W>
+__device__ __forceinline__ u64 kw_hash(const Kmer<W> &x) {
+    u64 h = x.w[0];
+#pragma unroll
+    for (int i = 1; i < W; ++i) {
+        h ^= h >> 32;
+        h = (h * MSD_GOLD) ^ x.w[i];
+    }
+    h ^= h >> 33;
+    h *= 0xFF51AFD7ED558CCDULL;
+    h ^= h >> 33;
+    h *= 0xC4CEB9FE1A85EC53ULL;
+    h ^= h >> 33;
+    return h;
+}
+// valid-window bits of the PPT positions owned by sub-thread `sub` of packed word t (MSB = first position)
+template <int W>
+__device__ __forceinline__ u32 msdw_vm(const u32 *__restrict__ valid, u64 t, u32 sub) {
+    constexpr int PPT = MsdW<W>::PPT;
+    return (valid[t] >> (32 - (sub + 1) * PPT)) & ((1u << PPT) - 1u);
+}
+
+// Valid windows are sparse for long k (24 of 150 positions at k = 127) and come in runs, so a thread
+// that walked its own PPT positions would leave most lanes idle.  Each CTA tile therefore first
+// compacts the valid positions of its TILE_KEYS window starts into a shared list (block scan of
+// popcounts); every lane then extracts one listed window at a time.
+template <int W>
+__device__ __forceinline__ u32 msdw_compact_tile(const u32 *__restrict__ valid, u64 nwords, u64 tile, u16 *plist, u32 *ws) {
+    constexpr int PPT = MsdW<W>::PPT;
+    const u64 t = tile * MsdW<W>::TILE_WORDS + threadIdx.x / W;
+    const u32 sub = threadIdx.x % W;
+    u32 vm = t < nwords ? msdw_vm<W>(valid, t, sub) : 0u;
+    u32 total;
+    u32 base = block_excl_scan((u32)__popc(vm), ws, &total);
+    while (vm) {
+        const int b = 31 - __clz(vm);
+        vm &= ~(1u << b);
+        plist[base++] = (u16)(threadIdx.x * PPT + (PPT - 1 - b));
+    }
+    __syncthreads();
+    return total;
+}
+
+// ---- pass A ---------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(256) msdw_hist_kernel(const u64 *__restrict__ packed, const u32 *__restrict__ valid, u64 nwords, int k,
+                                                        int canonical, int hb, u32 *__restrict__ ghist, u32 est_max,
+                                                        u8 *__restrict__ est_map) {
+    __shared__ u32 h[1 << MSD_HB];
+    __shared__ u16 plist[MsdW<W>::TILE_KEYS];
+    __shared__ u32 ws[33];
+    const int nb = 1 << hb;
+    for (int i = threadIdx.x; i < nb; i += 256) h[i] = 0;
+    __syncthreads();
+    const u64 ntiles = (nwords + MsdW<W>::TILE_WORDS - 1) / MsdW<W>::TILE_WORDS;
+    for (u64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const u32 np = msdw_compact_tile<W>(valid, nwords, tile, plist, ws);
+        const u64 pbase = tile * MsdW<W>::TILE_KEYS;
+        for (u32 q = threadIdx.x; q < np; q += 256) {
+            const Kmer<W> key = kmer_at<W>(packed, pbase + plist[q], k, canonical, nullptr);
+            atomicAdd(&h[kw_bits<W>(key, 2 * k - hb, hb)], 1u);
+            if ((u32)key.w[W - 1] * 0x9E3779B1u <= est_max) est_map[(u32)(kw_hash<W>(key) >> (64 - EST_LOG))] = 1;
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < nb; i += 256)
+        if (h[i]) atomicAdd(&ghist[i], h[i]);
+}
+
+// ---- pass B ---------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(256, 2) msdw_scatter_kernel(const u64 *__restrict__ packed, const u32 *__restrict__ valid, u64 nwords,
+                                                              int k, int canonical, int b0, u32 *__restrict__ cursor,
+                                                              u64 *__restrict__ out) {
+    extern __shared__ __align__(16) u8 smem_raw[];
+    u64 *skeys = reinterpret_cast<u64 *>(smem_raw);                                  // TILE_KEYS * W
+    u32 *hist = reinterpret_cast<u32 *>(skeys + (size_t)MsdW<W>::TILE_KEYS * W);     // 2^MSD_HB
+    u32 *delta = hist + (1 << MSD_HB);                                               // 2^MSD_HB
+    u16 *plist = reinterpret_cast<u16 *>(delta + (1 << MSD_HB));                     // TILE_KEYS
+    __shared__ u32 ws[33];
+    const int nb = 1 << b0, lowbit = 2 * k - b0;
+    for (int i = threadIdx.x; i < nb; i += 256) hist[i] = 0;
+    const u32 np = msdw_compact_tile<W>(valid, nwords, blockIdx.x, plist, ws);  // ends with a barrier
+    const u64 pbase = (u64)blockIdx.x * MsdW<W>::TILE_KEYS;
+    for (u32 q = threadIdx.x; q < np; q += 256)
+        atomicAdd(&hist[kw_bits<W>(kmer_at<W>(packed, pbase + plist[q], k, canonical, nullptr), lowbit, b0)], 1u);
+    __syncthreads();
+    const u32 total = msd_reserve<(1 << MSD_HB) / 256>(hist, delta, nb, cursor, ws);
+    for (u32 q = threadIdx.x; q < np; q += 256) {
+        const Kmer<W> key = kmer_at<W>(packed, pbase + plist[q], k, canonical, nullptr);
+        km_store<W>(skeys, atomicAdd(&hist[kw_bits<W>(key, lowbit, b0)], 1u), key);
+    }
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < total; i += 256) {
+        const Kmer<W> key = km_load<W>(skeys, i);
+        km_store<W>(out, (u32)(delta[kw_bits<W>(key, lowbit, b0)] + i), key);
+    }
+}
+
+// ---- level 1 --------------------------------------------------------------------------------------
+template <int W>
+__global__ void msdw_tilecount_kernel(const u32 *__restrict__ vcnt, u32 nvb, u32 *__restrict__ tcount) {
+    u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b <= nvb) tcount[b] = b < nvb ? (vcnt[b] + MsdW<W>::T1 - 1) / MsdW<W>::T1 : 0;
+}
+template <int W>
+__device__ __forceinline__ bool msdw_tile_range(const u32 *__restrict__ tstart, const u32 *__restrict__ vbeg, const u32 *__restrict__ vcnt,
+                                                u32 nvb, u32 t, u32 &vb, u32 &s, u32 &e) {
+    if (t >= tstart[nvb]) return false;
+    u32 lo = 0, hi = nvb;
+    while (hi - lo > 1) {
+        u32 mid = (lo + hi) >> 1;
+        if (tstart[mid] <= t) lo = mid; else hi = mid;
+    }
+    vb = lo;
+    const u32 b0 = vbeg[vb];
+    s = b0 + (t - tstart[vb]) * MsdW<W>::T1;
+    e = min(b0 + vcnt[vb], s + MsdW<W>::T1);
+    return true;
+}
+template <int W>
+__global__ void __launch_bounds__(256) msdw_hist1_kernel(const u64 *__restrict__ A, const u32 *__restrict__ tstart, const u32 *__restrict__ vbeg,
+                                                         const u32 *__restrict__ vcnt, u32 nvb, int sh1, int b1, u32 *__restrict__ hist1) {
+    constexpr int KPT = MsdW<W>::KPT;
+    __shared__ u32 h[1 << MSD_MAX_B1];
+    u32 vb, s, e;
+    if (!msdw_tile_range<W>(tstart, vbeg, vcnt, nvb, blockIdx.x, vb, s, e)) return;
+    const int nb = 1 << b1;
+    for (int i = threadIdx.x; i < nb; i += 256) h[i] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < KPT; ++u) {
+        const u32 i = s + u * 256 + threadIdx.x;
+        if (i < e) atomicAdd(&h[kw_bits<W>(km_load<W>(A, i), sh1, b1)], 1u);
+    }
+    __syncthreads();
+    const u64 cb = (u64)vb << b1;
+    for (int i = threadIdx.x; i < nb; i += 256)
+        if (h[i]) atomicAdd(&hist1[cb + i], h[i]);
+}
+template <int W>
+__global__ void __launch_bounds__(256) msdw_scatter1_kernel(const u64 *__restrict__ A, const u32 *__restrict__ tstart,
+                                                            const u32 *__restrict__ vbeg, const u32 *__restrict__ vcnt, u32 nvb, int sh1,
+                                                            int b1, u32 *__restrict__ cursor1, u64 *__restrict__ B) {
+    constexpr int KPT = MsdW<W>::KPT;
+    __shared__ __align__(16) u64 skeys[MsdW<W>::T1 * W];
+    __shared__ u32 hist[1 << MSD_MAX_B1];
+    __shared__ u32 delta[1 << MSD_MAX_B1];
+    __shared__ u32 ws[33];
+    u32 vb, s, e;
+    if (!msdw_tile_range<W>(tstart, vbeg, vcnt, nvb, blockIdx.x, vb, s, e)) return;
+    const int nb = 1 << b1;
+    for (int i = threadIdx.x; i < nb; i += 256) hist[i] = 0;
+    __syncthreads();
+    Kmer<W> kk[KPT];
+#pragma unroll
+    for (int u = 0; u < KPT; ++u) {
+        const u32 i = s + u * 256 + threadIdx.x;
+        if (i < e) kk[u] = km_load<W>(A, i);
+    }
+#pragma unroll
+    for (int u = 0; u < KPT; ++u)
+        if (s + u * 256 + threadIdx.x < e) atomicAdd(&hist[kw_bits<W>(kk[u], sh1, b1)], 1u);
+    __syncthreads();
+    const u32 total = msd_reserve<(1 << MSD_MAX_B1) / 256>(hist, delta, nb, cursor1 + ((u64)vb << b1), ws);
+#pragma unroll
+    for (int u = 0; u < KPT; ++u)
+        if (s + u * 256 + threadIdx.x < e) km_store<W>(skeys, atomicAdd(&hist[kw_bits<W>(kk[u], sh1, b1)], 1u), kk[u]);
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < total; i += 256) {
+        const Kmer<W> key = km_load<W>(skeys, i);
+        km_store<W>(B, (u32)(delta[kw_bits<W>(key, sh1, b1)] + i), key);
+    }
+}
+
+// ---- pass E: one CTA per child ----------------------------------------------------------------------
+template <int W>
+struct LeafSmemW {
+    static constexpr int HT = 1 << MsdW<W>::LOG_HT;
+    u64 tab[HT * W];
+    u32 tcnt[HT];
+    u32 ttag[HT];  // 0 = empty, else the claimer's tag (odd)
+    u32 bins[LEAF_BINS + 1];
+    u32 bincur[LEAF_BINS];
+    u32 ws[33];
+    u32 s_task, s_ovf;
+};
+
+// child = X[start .. start + n): counted in place (unique keys + counts to X / OC[start ..)); SB is scratch.
+// Returns the number of kept distinct keys, or MSDW_OVERFLOW (nothing written).
+template <int W, int THREADS>
+__device__ u32 msdw_leaf(LeafSmemW<W> &S, u64 *X, u64 *SB, u32 *OC, u32 start, u32 n, int shift, u32 min_freq) {
+    constexpr int LOG_HT = MsdW<W>::LOG_HT;
+    constexpr int HT = 1 << LOG_HT;
+    constexpr u32 HM = HT - 1;
+    for (int i = threadIdx.x; i < HT; i += THREADS) { S.ttag[i] = 0; S.tcnt[i] = 0; }
+    if (threadIdx.x == 0) S.s_ovf = 0;
+    __syncthreads();
+    volatile u32 *ovf = &S.s_ovf;
+    // pass 1: claim one slot per distinct tag; the claimer stores the key
+    for (u32 i = threadIdx.x; i < n; i += THREADS) {
+        const Kmer<W> key = km_load<W>(X, (u64)start + i);
+        const u64 h = kw_hash<W>(key);
+        const u32 tag = (u32)h | 1u;
+        u32 slot = (u32)(h >> (64 - LOG_HT));
+        const u32 step = ((u32)(h >> 24) | 1u) & HM;  // double hashing: an odd stride visits every slot, no primary clustering
+        for (int probes = 0;; ++probes) {
+            u32 t = S.ttag[slot];
+            if (t == 0) {
+                t = atomicCAS(&S.ttag[slot], 0u, tag);
+                if (t == 0) { km_store<W>(S.tab, slot, key); break; }
+            }
+            if (t == tag) break;
+            slot = (slot + step) & HM;
+            if (probes > LEAF_MAX_PROBE) { *ovf = 1; atomicAdd(&g_msdw_dbg[0], 1ULL); break; }
+        }
+        if (*ovf) break;
+    }
+    __syncthreads();
+    if (S.s_ovf) return MSDW_OVERFLOW;
+    // pass 2: count, comparing the full key
+    for (u32 i = threadIdx.x; i < n; i += THREADS) {
+        const Kmer<W> key = km_load<W>(X, (u64)start + i);
+        const u64 h = kw_hash<W>(key);
+        const u32 tag = (u32)h | 1u;
+        u32 slot = (u32)(h >> (64 - LOG_HT));
+        const u32 step = ((u32)(h >> 24) | 1u) & HM;  // double hashing: an odd stride visits every slot, no primary clustering
+        for (int probes = 0;; ++probes) {
+            const u32 t = S.ttag[slot];
+            if (t == tag && km_eq<W>(km_load<W>(S.tab, slot), key)) { atomicAdd(&S.tcnt[slot], 1u); break; }
+            if (t == 0 || probes > LEAF_MAX_PROBE + 1) { *ovf = 1; atomicAdd(&g_msdw_dbg[t == 0 ? 1 : 2], 1ULL); break; }  // tag clash: this key never got a slot
+            slot = (slot + step) & HM;
+        }
+        if (*ovf) break;
+    }
+    for (int i = threadIdx.x; i <= LEAF_BINS; i += THREADS) S.bins[i] = 0;
+    __syncthreads();
+    if (S.s_ovf) return MSDW_OVERFLOW;
+    // order the kept keys: order-preserving bins over the top varying bits, rank by counting inside a bin
+    const int bb = shift < 10 ? shift : 10, blow = shift - bb;
+    const int nbins = 1 << bb;
+    for (int slot = threadIdx.x; slot < HT; slot += THREADS)
+        if (S.ttag[slot] && S.tcnt[slot] >= min_freq) atomicAdd(&S.bins[kw_bits<W>(km_load<W>(S.tab, slot), blow, bb)], 1u);
+    __syncthreads();
+    const u32 nd = block_scan_array<THREADS>(S.bins, nbins, S.ws);
+    for (int i = threadIdx.x; i < nbins; i += THREADS) S.bincur[i] = S.bins[i];
+    if (threadIdx.x == 0) S.bins[nbins] = nd;
+    __syncthreads();
+    for (int slot = threadIdx.x; slot < HT; slot += THREADS)
+        if (S.ttag[slot] && S.tcnt[slot] >= min_freq) {
+            const Kmer<W> key = km_load<W>(S.tab, slot);
+            km_store<W>(SB, (u64)start + atomicAdd(&S.bincur[kw_bits<W>(key, blow, bb)], 1u), key);
+        }
+    __syncthreads();
+    for (u32 j = threadIdx.x; j < nd; j += THREADS) {
+        const Kmer<W> key = km_load<W>(SB, (u64)start + j);
+        const u32 b = kw_bits<W>(key, blow, bb);
+        const u32 lo = S.bins[b], hi = S.bins[b + 1];
+        u32 rank = 0;
+        for (u32 q = lo; q < hi; ++q) rank += km_lt<W>(km_load<W>(SB, (u64)start + q), key) ? 1u : 0u;
+        const u64 h = kw_hash<W>(key);
+        const u32 tag = (u32)h | 1u;
+        u32 slot = (u32)(h >> (64 - LOG_HT));
+        const u32 step = ((u32)(h >> 24) | 1u) & HM;  // double hashing: an odd stride visits every slot, no primary clustering
+        while (!(S.ttag[slot] == tag && km_eq<W>(km_load<W>(S.tab, slot), key))) slot = (slot + step) & HM;
+        km_store<W>(X, (u64)start + lo + rank, key);
+        OC[start + lo + rank] = S.tcnt[slot];
+    }
+    __syncthreads();
+    return nd;
+}
+
+template <int W, int THREADS>
+__global__ void __launch_bounds__(THREADS) msdw_leaf_kernel(u64 *X, u64 *SB, u32 *OC, const u32 *__restrict__ off, u32 nchild, int shiftc,
+                                                            u32 *__restrict__ nu_out, u32 *ticket, u32 min_freq) {
+    extern __shared__ __align__(16) u8 smem_raw[];
+    LeafSmemW<W> &S = *reinterpret_cast<LeafSmemW<W> *>(smem_raw);
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) S.s_task = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const u32 c = S.s_task;
+        if (c >= nchild) break;
+        const u32 ob = off[c], n = off[c + 1] - ob;
+        if (n == 0) { if (threadIdx.x == 0) nu_out[c] = 0; continue; }
+        if (shiftc == 0) {  // no varying bits: the whole child is one k-mer (already at X[ob])
+            if (threadIdx.x == 0) {
+                const u32 keep = n >= min_freq;
+                if (keep) OC[ob] = n;
+                nu_out[c] = keep;
+            }
+            continue;
+        }
+        const u32 nd = msdw_leaf<W, THREADS>(S, X, SB, OC, ob, n, shiftc, min_freq);
+        if (threadIdx.x == 0) nu_out[c] = nd;
+    }
+}
+template <int W>
+__global__ void __launch_bounds__(256) msdw_gather_kernel(const u64 *__restrict__ X, const u32 *__restrict__ cnt, const u32 *__restrict__ off,
+                                                          const u32 *__restrict__ nu, const u32 *__restrict__ ustart, u32 nchild,
+                                                          u64 *__restrict__ okeys, u32 *__restrict__ ocnt) {
+    for (u32 t = blockIdx.x; t < nchild; t += gridDim.x) {
+        const u32 n = nu[t], s = off[t], d = ustart[t];
+        for (u32 i = threadIdx.x; i < n; i += 256) {
+            km_store<W>(okeys, (u64)d + i, km_load<W>(X, (u64)s + i));
+            ocnt[d + i] = cnt[s + i];
+        }
+    }
+}
+struct MsdwOverflowF {
+    const u32 *nu;
+    u32 *list;
+    __device__ bool pred(u64 c) const { return nu[c] == MSDW_OVERFLOW; }
+    __device__ void emit(u64 c, u64 dst) const { list[dst] = (u32)c; }
+};
+
+// ------------------------------------- host side -------------------------------------------------
+// packed reads -> sorted unique k-mers + counts (count >= min_freq only), 32 < k <= 128.
+template <int W>
+static u64 msdw_count(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int k, int canonical, u32 min_freq, DBuf<u64> &ukeys,
+                      DBuf<u32> &ucounts, u64 *n_instances) {
+    MsdTune tune = msd_tune();
+    tune.dt = tune.dt / W < 16 ? 16 : tune.dt / W;  // the leaf table holds 8192 / W slots
+    *n_instances = 0;
+    if (pr.nwords == 0) { ukeys.alloc(ctx, W); ucounts.alloc(ctx, 1); return 0; }
+    // ---- A ----
+    stage_begin(ctx, ST_EXTRACT);
+    const int hb = msd_hist_bits(k);
+    const u32 nbh = 1u << hb;
+    DBuf<u32> hist(ctx, nbh + 1);
+    DBuf<u8> est(ctx, 1ULL << EST_LOG);
+    CK(cudaMemsetAsync(hist.p, 0, (nbh + 1) * sizeof(u32), ctx->stream));
+    CK(cudaMemsetAsync(est.p, 0, 1ULL << EST_LOG, ctx->stream));
+    const int est_shift = msd_est_shift(pr.nbases);
+    u64 hgrid = ceil_div(pr.nwords, MsdW<W>::TILE_WORDS);
+    if (hgrid > (u64)ctx->num_sms * 8) hgrid = (u64)ctx->num_sms * 8;
+    LAUNCH(ctx, msdw_hist_kernel<W>, (unsigned)hgrid, 256, 0, pr.packed.p, valid, pr.nwords, k, canonical, hb, hist.p,
+           est_shift ? (0xFFFFFFFFu >> est_shift) : 0xFFFFFFFFu, est.p);
+    u64 N = 0, dest = 0;
+    msd_pass_a_read(ctx, hist.p, nbh, est.p, est_shift, &N, &dest);
+    est.release();
+    *n_instances = N;
+    if (N == 0) { stage_end(ctx, ST_EXTRACT); ukeys.alloc(ctx, W); ucounts.alloc(ctx, 1); return 0; }
+    if (N >= 0xFFFFFFFFull) GG_THROW(GG_ERR_LIMIT, "%llu k-mer instances exceed the 2^32-1 per-call limit", (unsigned long long)N);
+    const MsdPlan pl = msd_plan(dest, N, k, tune);
+    // ---- B ----
+    const u32 nb0 = 1u << pl.b0;
+    DBuf<u32> hist0(ctx, nb0 + 1), bstart(ctx, nb0 + 1), cursor(ctx, nb0);
+    LAUNCH(ctx, msd_collapse_kernel, (unsigned)ceil_div(nb0 + 1, 256), 256, 0, hist.p, pl.hb, pl.b0, hist0.p);
+    exclusive_scan_u32(ctx, hist0.p, bstart.p, nb0 + 1, nullptr);
+    LAUNCH(ctx, msd_copy_u32_kernel, (unsigned)ceil_div(nb0, 256), 256, 0, bstart.p, (u64)nb0, cursor.p);
+    DBuf<u64> A(ctx, N * W), B(ctx, N * W);
+    {
+        const size_t smemB = (size_t)MsdW<W>::TILE_KEYS * W * 8 + 2 * (size_t)(1 << MSD_HB) * 4 + (size_t)MsdW<W>::TILE_KEYS * 2;
+        static bool setB = false;
+        if (!setB) { CK(cudaFuncSetAttribute(msdw_scatter_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB)); setB = true; }
+        LAUNCH(ctx, msdw_scatter_kernel<W>, (unsigned)ceil_div(pr.nwords, MsdW<W>::TILE_WORDS), 256, smemB, pr.packed.p, valid, pr.nwords, k,
+               canonical, pl.b0, cursor.p, A.p);
+    }
+    stage_end(ctx, ST_EXTRACT);
+    // ---- C, D ----
+    stage_begin(ctx, ST_SORT);
+    const u64 nchild = (u64)nb0 << pl.b1;
+    DBuf<u32> off(ctx, nchild + 1), OC(ctx, N), ticket(ctx, 1), nu(ctx, nchild + 1), ustart(ctx, nchild + 1);
+    DBuf<u64> tot(ctx, 1);
+    u64 *X = A.p, *SB = B.p;
+    if (pl.b1 > 0) {
+        DBuf<u32> tcount(ctx, nb0 + 1), tstart(ctx, nb0 + 1), cursor1(ctx, nchild), hist1(ctx, nchild + 1);
+        CK(cudaMemsetAsync(hist1.p, 0, (nchild + 1) * sizeof(u32), ctx->stream));
+        LAUNCH(ctx, msdw_tilecount_kernel<W>, (unsigned)ceil_div(nb0 + 1, 256), 256, 0, hist0.p, nb0, tcount.p);
+        exclusive_scan_u32(ctx, tcount.p, tstart.p, nb0 + 1, nullptr);
+        const unsigned tgrid = (unsigned)(ceil_div(N, MsdW<W>::T1) + nb0);
+        LAUNCH(ctx, msdw_hist1_kernel<W>, tgrid, 256, 0, A.p, tstart.p, bstart.p, hist0.p, nb0, pl.shiftc, pl.b1, hist1.p);
+        exclusive_scan_u32(ctx, hist1.p, off.p, nchild + 1, nullptr);
+        LAUNCH(ctx, msd_copy_u32_kernel, (unsigned)ceil_div(nchild, 256), 256, 0, off.p, nchild, cursor1.p);
+        LAUNCH(ctx, msdw_scatter1_kernel<W>, tgrid, 256, 0, A.p, tstart.p, bstart.p, hist0.p, nb0, pl.shiftc, pl.b1, cursor1.p, B.p);
+        X = B.p; SB = A.p;
+    } else {
+        LAUNCH(ctx, msd_copy_u32_kernel, (unsigned)ceil_div(nchild + 1, 256), 256, 0, bstart.p, nchild + 1, off.p);
+    }
+    // ---- E ----
+    CK(cudaMemsetAsync(ticket.p, 0, sizeof(u32), ctx->stream));
+    {
+        const size_t smem = sizeof(LeafSmemW<W>);
+        static bool set = false;
+        if (!set) { CK(cudaFuncSetAttribute(msdw_leaf_kernel<W, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
+        u32 grid = (u32)ctx->num_sms * 2;
+        if (grid > nchild) grid = (u32)nchild;
+        LAUNCH(ctx, (msdw_leaf_kernel<W, 512>), grid, 512, smem, X, SB, OC.p, off.p, (u32)nchild, pl.shiftc, nu.p, ticket.p, min_freq);
+    }
+    // children the table could not hold: generic sort + run-length count of that segment
+    {
+        DBuf<u32> olist(ctx, nchild);
+        MsdwOverflowF of{nu.p, olist.p};
+        Compactor<MsdwOverflowF> oc(ctx, nchild, "msdw_overflow");
+        const u64 novf = oc.count(of);
+        if (getenv("GG_MSD_DEBUG")) {
+            unsigned long long hd[4];
+            cudaMemcpyFromSymbol(hd, g_msdw_dbg, sizeof(hd));
+            fprintf(stderr, "[msdw dbg] pass1 probe-limit %llu, pass2 empty-slot %llu, pass2 probe-limit %llu\n", hd[0], hd[1], hd[2]);
+        }
+        if (getenv("GG_MSD_DEBUG"))
+            fprintf(stderr, "[msdw W=%d] N=%llu distinct_est=%llu b0=%d b1=%d shiftc=%d children=%llu overflowed=%llu\n", W, (unsigned long long)N,
+                    (unsigned long long)dest, pl.b0, pl.b1, pl.shiftc, (unsigned long long)nchild, (unsigned long long)novf);
+        if (novf) {
+            oc.emit(of);
+            std::vector<u32> h_list(novf), h_off(nchild + 1);
+            CK(cudaMemcpyAsync(h_list.data(), olist.p, novf * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(h_off.data(), off.p, (nchild + 1) * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (getenv("GG_MSD_DEBUG")) {
+                u64 mx = 0, mn = ~0ULL, sum = 0, allmax = 0;
+                for (u32 c : h_list) { u64 n = h_off[c + 1] - h_off[c]; mx = n > mx ? n : mx; mn = n < mn ? n : mn; sum += n; }
+                for (u64 c = 0; c < nchild; ++c) { u64 n = h_off[c + 1] - h_off[c]; allmax = n > allmax ? n : allmax; }
+                fprintf(stderr, "[msdw] overflowed children: instances min %llu max %llu mean %.1f; largest child overall %llu; first few:", (unsigned long long)mn,
+                        (unsigned long long)mx, (double)sum / novf, (unsigned long long)allmax);
+                for (size_t q = 0; q < h_list.size() && q < 12; ++q) fprintf(stderr, " %u(%u)", h_list[q], h_off[h_list[q] + 1] - h_off[h_list[q]]);
+                fprintf(stderr, "\n");
+            }
+            for (u32 c : h_list) {
+                const u64 s = h_off[c], n = h_off[c + 1] - h_off[c];
+                u64 *a = X + s * W, *b = SB + s * W;
+                std::vector<BitRange> ranges = {{0, pl.shiftc}};
+                radix_sort<W>(ctx, &a, &b, nullptr, nullptr, n, ranges);
+                DBuf<u64> uk;
+                DBuf<u32> uc;
+                const u64 nuq = run_length_count<W>(ctx, a, n, uk, uc);
+                FilterF<W> ff{uk.p, uc.p, X + s * W, OC.p + s, min_freq, 0};
+                Compactor<FilterF<W>> fc(ctx, nuq, "filter");
+                const u32 kept = (u32)fc.count(ff);
+                fc.emit(ff);
+                CK(cudaMemcpyAsync(nu.p + c, &kept, sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+            }
+        }
+    }
+    stage_end(ctx, ST_SORT);
+    // ---- F ----
+    stage_begin(ctx, ST_COUNT);
+    exclusive_scan_u32(ctx, nu.p, ustart.p, nchild, tot.p);
+    const u64 U = read_scalar<u64>(ctx, tot.p);
+    ukeys.alloc(ctx, (U ? U : 1) * W);
+    ucounts.alloc(ctx, U ? U : 1);
+    if (U) {
+        u32 ggrid = nchild < (u64)ctx->num_sms * 16 ? (u32)nchild : (u32)ctx->num_sms * 16;
+        LAUNCH(ctx, msdw_gather_kernel<W>, ggrid, 256, 0, X, OC.p, off.p, nu.p, ustart.p, (u32)nchild, ukeys.p, ucounts.p);
+    }
+    stage_end(ctx, ST_COUNT);
+    return U;
+}
