@@ -439,7 +439,7 @@ template <int THREADS, int LOG_HT>
 __global__ void __launch_bounds__(THREADS) msd_leaf_kernel(const u64 *IN, u64 *SB, u64 *O, u32 *OC, const u32 *__restrict__ segbeg,
                                                            const u32 *__restrict__ segcnt, u32 nseg, const u32 *__restrict__ off,
                                                            u32 nchild, int shiftc, u32 *__restrict__ nu_out, u32 *ticket, u32 min_freq,
-                                                           u32 *fscr) {
+                                                           u32 *fscr, u32 test_ovf_mod) {
     extern __shared__ __align__(16) u8 smem_raw[];
     LeafSmem<THREADS, LOG_HT> &S = *reinterpret_cast<LeafSmem<THREADS, LOG_HT> *>(smem_raw);
     u32 *myscr = fscr + (size_t)blockIdx.x * MSD_MAXD * FSCR_STRIDE;
@@ -460,7 +460,8 @@ __global__ void __launch_bounds__(THREADS) msd_leaf_kernel(const u64 *IN, u64 *S
             continue;
         }
         u32 nd;
-        if (msd_leaf<THREADS, LOG_HT>(S, IN, segbeg + (size_t)c * nseg, segcnt + (size_t)c * nseg, nseg, SB, O, OC, ob, min_freq, &nd)) {
+        if (!(test_ovf_mod && c % test_ovf_mod == 0) &&  // tests: exercise the in-CTA partition fallback
+            msd_leaf<THREADS, LOG_HT>(S, IN, segbeg + (size_t)c * nseg, segcnt + (size_t)c * nseg, nseg, SB, O, OC, ob, min_freq, &nd)) {
             if (threadIdx.x == 0) nu_out[c] = nd;
             continue;
         }
@@ -524,6 +525,7 @@ struct MsdTune {
                              // ~1.75x skew of canonical k-mers towards small leading bases
     u32 it_log2 = 16;        // target instances per child (bounds the work of one CTA)
     int variant = 0;         // leaf geometry, see msd_launch_leaf
+    u32 test_ovf_mod = 0;    // tests only (GG_MSD_TEST_OVERFLOW=m): every child with index % m == 0 takes the overflow path
 };
 static MsdTune msd_tune() {
     MsdTune t;
@@ -532,6 +534,7 @@ static MsdTune msd_tune() {
     if (const char *e = getenv("GG_MSD_DT")) t.dt = (u32)atoi(e);
     if (const char *e = getenv("GG_MSD_IT")) t.it_log2 = (u32)atoi(e);
     if (const char *e = getenv("GG_MSD_VARIANT")) t.variant = atoi(e);
+    if (const char *e = getenv("GG_MSD_TEST_OVERFLOW")) t.test_ovf_mod = (u32)atoi(e);
     if (t.b0_max > MSD_HB) t.b0_max = MSD_HB;
     if (t.b0_max < 0) t.b0_max = 0;
     if (t.b1_max > MSD_MAX_B1) t.b1_max = MSD_MAX_B1;
@@ -631,7 +634,7 @@ __global__ void msd_child_total_kernel(const u32 *__restrict__ vcnt, u32 nsrc, u
 
 template <int THREADS, int LOG_HT>
 static void msd_launch_leaf(gg_ctx *ctx, int ctas_per_sm, const u64 *IN, u64 *SB, u64 *O, u32 *OC, const u32 *segbeg, const u32 *segcnt,
-                            u32 nseg, const u32 *off, u32 nchild, int shiftc, u32 *nu, u32 *ticket, u32 min_freq) {
+                            u32 nseg, const u32 *off, u32 nchild, int shiftc, u32 *nu, u32 *ticket, u32 min_freq, u32 test_ovf_mod) {
     size_t smem = sizeof(LeafSmem<THREADS, LOG_HT>);
     static bool set = false;
     if (!set) {
@@ -642,7 +645,7 @@ static void msd_launch_leaf(gg_ctx *ctx, int ctas_per_sm, const u64 *IN, u64 *SB
     if (grid > nchild) grid = nchild;
     DBuf<u32> fscr(ctx, (u64)grid * MSD_MAXD * FSCR_STRIDE);
     LAUNCH(ctx, (msd_leaf_kernel<THREADS, LOG_HT>), grid, THREADS, smem, IN, SB, O, OC, segbeg, segcnt, nseg, off, nchild, shiftc, nu, ticket,
-           min_freq, fscr.p);
+           min_freq, fscr.p, test_ovf_mod);
 }
 
 // Level-0 buckets -> sorted unique keys + counts (count >= min_freq).
@@ -688,11 +691,11 @@ static u64 msd_finish(gg_ctx *ctx, DBuf<u64> &IN, u64 n_in, const u32 *vbeg, con
     // ---- E: leaves ----
     CK(cudaMemsetAsync(ticket.p, 0, sizeof(u32), ctx->stream));
     if (tune.variant == 1)
-        msd_launch_leaf<1024, 14>(ctx, 1, leaf_in, leaf_sb, leaf_o, OC.p, segbeg, segcnt, nseg, off.p, (u32)nchild, pl.shiftc, nu.p, ticket.p, min_freq);
+        msd_launch_leaf<1024, 14>(ctx, 1, leaf_in, leaf_sb, leaf_o, OC.p, segbeg, segcnt, nseg, off.p, (u32)nchild, pl.shiftc, nu.p, ticket.p, min_freq, tune.test_ovf_mod);
     else if (tune.variant == 2)
-        msd_launch_leaf<256, 12>(ctx, 4, leaf_in, leaf_sb, leaf_o, OC.p, segbeg, segcnt, nseg, off.p, (u32)nchild, pl.shiftc, nu.p, ticket.p, min_freq);
+        msd_launch_leaf<256, 12>(ctx, 4, leaf_in, leaf_sb, leaf_o, OC.p, segbeg, segcnt, nseg, off.p, (u32)nchild, pl.shiftc, nu.p, ticket.p, min_freq, tune.test_ovf_mod);
     else
-        msd_launch_leaf<512, 13>(ctx, 2, leaf_in, leaf_sb, leaf_o, OC.p, segbeg, segcnt, nseg, off.p, (u32)nchild, pl.shiftc, nu.p, ticket.p, min_freq);
+        msd_launch_leaf<512, 13>(ctx, 2, leaf_in, leaf_sb, leaf_o, OC.p, segbeg, segcnt, nseg, off.p, (u32)nchild, pl.shiftc, nu.p, ticket.p, min_freq, tune.test_ovf_mod);
     stage_end(ctx, ST_SORT);
     // ---- F: gather ----
     stage_begin(ctx, ST_COUNT);

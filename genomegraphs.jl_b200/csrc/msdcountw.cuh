@@ -41,21 +41,20 @@ __device__ __forceinline__ u32 kw_bits(const Kmer<W> &x, int lowbit, int nbits) 
     if (sh) v |= hi << (64 - sh);
     return (u32)v & ((1u << nbits) - 1u);
 }
-// Full-avalanche hash (murmur3 finaliser over a multiplicative chain): the tag is its low half, so a
-// difference confined to the top bits of one word (a substitution in the first base of a word) must
-// still reach the low bits -- a plain multiply / short xorshift does not do that.
+// Hash of a multi-word key: folded 64x64 -> 128-bit multiplies (high ^ low half) chained over the
+// words, then a murmur3-style finaliser.  The tag is its low half, so every input difference must
+// reach the low bits: a plain multiply only diffuses upwards, and k-mers that differ by substitutions
+// in the top bases of two words (common among error variants of one genomic k-mer) then cancel each
+// other -- measured on real keys before this form was adopted.
+__device__ __forceinline__ u64 mum64(u64 a, u64 b) { return __umul64hi(a, b) ^ (a * b); }
 template <int W>
 __device__ __forceinline__ u64 kw_hash(const Kmer<W> &x) {
-    u64 h = x.w[0];
+    const u64 c[4] = {0x9E3779B97F4A7C15ULL, 0xBF58476D1CE4E5B9ULL, 0x94D049BB133111EBULL, 0xD6E8FEB86659FD93ULL};
+    u64 h = 0;
 #pragma unroll
-    for (int i = 1; i < W; ++i) {
-        h ^= h >> 32;
-        h = (h * MSD_GOLD) ^ x.w[i];
-    }
+    for (int i = 0; i < W; ++i) h = mum64(h ^ x.w[i], c[i]);
     h ^= h >> 33;
     h *= 0xFF51AFD7ED558CCDULL;
-    h ^= h >> 33;
-    h *= 0xC4CEB9FE1A85EC53ULL;
     h ^= h >> 33;
     return h;
 }
@@ -318,7 +317,7 @@ __device__ u32 msdw_leaf(LeafSmemW<W> &S, u64 *X, u64 *SB, u32 *OC, u32 start, u
 
 template <int W, int THREADS>
 __global__ void __launch_bounds__(THREADS) msdw_leaf_kernel(u64 *X, u64 *SB, u32 *OC, const u32 *__restrict__ off, u32 nchild, int shiftc,
-                                                            u32 *__restrict__ nu_out, u32 *ticket, u32 min_freq) {
+                                                            u32 *__restrict__ nu_out, u32 *ticket, u32 min_freq, u32 test_ovf_mod) {
     extern __shared__ __align__(16) u8 smem_raw[];
     LeafSmemW<W> &S = *reinterpret_cast<LeafSmemW<W> *>(smem_raw);
     for (;;) {
@@ -337,7 +336,8 @@ __global__ void __launch_bounds__(THREADS) msdw_leaf_kernel(u64 *X, u64 *SB, u32
             }
             continue;
         }
-        const u32 nd = msdw_leaf<W, THREADS>(S, X, SB, OC, ob, n, shiftc, min_freq);
+        const u32 nd = (test_ovf_mod && c % test_ovf_mod == 0) ? MSDW_OVERFLOW  // tests: exercise the overflow path
+                                                               : msdw_leaf<W, THREADS>(S, X, SB, OC, ob, n, shiftc, min_freq);
         if (threadIdx.x == 0) nu_out[c] = nd;
     }
 }
@@ -432,7 +432,7 @@ static u64 msdw_count(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int 
         if (!set) { CK(cudaFuncSetAttribute(msdw_leaf_kernel<W, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
         u32 grid = (u32)ctx->num_sms * 2;
         if (grid > nchild) grid = (u32)nchild;
-        LAUNCH(ctx, (msdw_leaf_kernel<W, 512>), grid, 512, smem, X, SB, OC.p, off.p, (u32)nchild, pl.shiftc, nu.p, ticket.p, min_freq);
+        LAUNCH(ctx, (msdw_leaf_kernel<W, 512>), grid, 512, smem, X, SB, OC.p, off.p, (u32)nchild, pl.shiftc, nu.p, ticket.p, min_freq, tune.test_ovf_mod);
     }
     // children the table could not hold: generic sort + run-length count of that segment
     {

@@ -221,3 +221,23 @@ def test_synth_device_matches_host(pkg, ctx):
     N.check(ctx.h, N.lib().gg_memcpy_d2h(ctx.h, back.ctypes.data_as(C.c_void_p), d, nreads * L))
     N.lib().gg_dev_free(ctx.h, d)
     assert np.array_equal(host, back)
+
+
+# ------------------------------ overflow paths of the counting leaves ------------------------
+@pytest.mark.parametrize("k", [15, 31, 32, 33, 63, 65, 127])
+@pytest.mark.parametrize("mod", [1, 3])
+def test_count_overflow_paths(pkg, ctx, k, mod, monkeypatch):
+    """GG_MSD_TEST_OVERFLOW=m sends every m-th child through the overflow path (k <= 32: in-CTA
+    re-partition; k > 32: host-driven radix sort + run-length count of the child's segment)."""
+    monkeypatch.setenv("GG_MSD_TEST_OVERFLOW", str(mod))
+    monkeypatch.setenv("GG_MSD_DT", "64")   # many small children even on a small input
+    seq, offs = pkg.synth_reads(seed=300 + k, genome_len=6000, nreads=1600, read_len=150, paired=True, frag_len=400, err_ppm=5000)
+    for min_freq in (1, 2):
+        okeys, ocnt = O.count_kmers(seq, offs, k)
+        counts = pkg.serial_mem(k, pkg.CANONICAL, ctx=ctx)((seq, offs))
+        keys, c32, _ = counts.export()
+        assert np.array_equal(keys, okeys) and np.array_equal(c32, ocnt), (k, mod)
+        ga = pkg.dbg_from_reads((seq, offs), k, min_freq, ctx=ctx)   # fused min-count filter inside the leaves
+        og = O.dbg(O.filter_counts(okeys, ocnt, k, min_freq), k)
+        assert ga.node_strings() == og.nodes() and ga.link_lists() == og.links(), (k, mod, min_freq)
+        counts.free()
