@@ -242,7 +242,8 @@ def main():
         return nn.value, nb.value, nl.value
 
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:   # one sampler per job: concurrent nvidia-smi pollers contend on the driver and stall CUDA calls
+        sampler.start()
 
     # ---- warm-up (also fills the memory pool) ----
     launches = 0

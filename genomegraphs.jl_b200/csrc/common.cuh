@@ -40,6 +40,7 @@ struct gg_ctx {
     std::string prof_text;
     // user events (gg_ctx_event_record / gg_ctx_event_elapsed_ms)
     cudaEvent_t user_ev[8];
+    struct GgArena *arena = nullptr;  // caching device allocator (below)
 };
 
 struct GgError {
@@ -82,18 +83,68 @@ static inline cudaEvent_t prof_event(gg_ctx *ctx) {
 
 static inline u64 ceil_div(u64 a, u64 b) { return (a + b - 1) / b; }
 
-// stream-ordered allocation from the device's default memory pool (cached: the release
-// threshold is raised in gg_ctx_create, so steady-state calls do not hit the driver)
+// Device memory: a per-context caching allocator.  Every pipeline call allocates the same sequence of
+// temporaries, so after the first call each request is served from the free list without touching
+// the driver (cudaMallocAsync pools re-map physical memory between differently sized requests, and
+// those driver calls serialise across the processes of a multi-GPU job: multi-millisecond stalls).
+// All work of a context runs on ONE stream, so a block freed by the host can be handed out again at
+// once: later kernels are ordered after the earlier users of the block.
+struct GgArena {
+    std::multimap<size_t, void *> free_blocks;   // size -> block
+    std::map<void *, size_t> live;               // block -> size (allocated and cached blocks alike)
+    size_t cached_bytes = 0, total_bytes = 0;
+};
+static inline GgArena &gg_arena(gg_ctx *ctx) {
+    if (!ctx->arena) ctx->arena = new GgArena();
+    return *ctx->arena;
+}
+static void arena_release_cached(gg_ctx *ctx) {
+    GgArena &a = gg_arena(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &kv : a.free_blocks) { cudaFree(kv.second); a.total_bytes -= kv.first; a.live.erase(kv.second); }
+    a.free_blocks.clear();
+    a.cached_bytes = 0;
+}
+static void *arena_alloc(gg_ctx *ctx, size_t bytes) {
+    GgArena &a = gg_arena(ctx);
+    bytes = (bytes + 511) & ~(size_t)511;
+    if (bytes == 0) bytes = 512;
+    auto it = a.free_blocks.lower_bound(bytes);
+    // reuse a cached block unless it is much larger than the request (keeps big blocks for big requests)
+    if (it != a.free_blocks.end() && it->first <= bytes + bytes / 4 + (1u << 20)) {
+        void *p = it->second;
+        a.cached_bytes -= it->first;
+        a.free_blocks.erase(it);
+        return p;
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaErrorMemoryAllocation) {  // give the cached blocks back and retry once
+        cudaGetLastError();
+        arena_release_cached(ctx);
+        e = cudaMalloc(&p, bytes);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        GG_THROW(e == cudaErrorMemoryAllocation ? GG_ERR_OOM : GG_ERR_CUDA, "cudaMalloc of %zu bytes: %s", bytes, cudaGetErrorString(e));
+    }
+    a.live[p] = bytes;
+    a.total_bytes += bytes;
+    return p;
+}
+static void arena_free(gg_ctx *ctx, void *p) {
+    GgArena &a = gg_arena(ctx);
+    auto it = a.live.find(p);
+    if (it == a.live.end()) { cudaFree(p); return; }  // not ours (never happens)
+    a.free_blocks.emplace(it->second, p);
+    a.cached_bytes += it->second;
+}
 template <class T>
 static T *dalloc(gg_ctx *ctx, u64 count) {
-    void *p = nullptr;
-    u64 bytes = count * sizeof(T);
-    if (bytes == 0) bytes = 16;
-    CK(cudaMallocAsync(&p, bytes, ctx->stream));
-    return (T *)p;
+    return (T *)arena_alloc(ctx, (size_t)(count * sizeof(T)));
 }
 static inline void dfree(gg_ctx *ctx, void *p) {
-    if (p) cudaFreeAsync(p, ctx->stream);
+    if (p) arena_free(ctx, p);
 }
 // RAII temp buffer
 template <class T>

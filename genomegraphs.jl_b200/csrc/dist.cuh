@@ -15,6 +15,7 @@
 #pragma once
 #include <dlfcn.h>
 #include <nccl.h>
+#include <chrono>
 #include "msdcount.cuh"
 
 struct NcclApi {
@@ -115,6 +116,13 @@ static u64 dist_msd_count(gg_comm *cm, const PackedReads &pr, const u32 *valid, 
     const MsdTune tune = msd_tune();
     const int hb = msd_hist_bits(k);
     const u32 nbh = 1u << hb;
+    // GG_DIST_DEBUG: host wall-clock of every phase on every rank (adds stream syncs; never set while timing)
+    const bool dbg = getenv("GG_DIST_DEBUG") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double tmark[8] = {0};
+    int nmark = 0;
+    auto mark = [&]() { if (dbg) { cudaStreamSynchronize(ctx->stream); if (nmark < 8) tmark[nmark++] = now(); } };
+    mark();
     stage_begin(ctx, ST_EXTRACT);
     // ---- global size -> sampling rate of the estimate (must agree on all ranks) ----
     DBuf<u64> sz(ctx, 1);
@@ -122,6 +130,7 @@ static u64 dist_msd_count(gg_comm *cm, const PackedReads &pr, const u32 *valid, 
     NCK(nc->AllReduce(sz.p, sz.p, 1, ncclUint64, ncclSum, cm->comm, ctx->stream));
     const u64 nbases_glob = read_scalar<u64>(ctx, sz.p);
     const int est_shift = msd_est_shift(nbases_glob);
+    mark();  // 1: size all-reduce done
     // ---- pass A on the local reads; histograms all-gathered, estimate maps merged ----
     DBuf<u32> hist, all_hist(ctx, (u64)P * nbh);
     DBuf<u8> est;
@@ -134,6 +143,7 @@ static u64 dist_msd_count(gg_comm *cm, const PackedReads &pr, const u32 *valid, 
     std::vector<u32> h_all((size_t)P * nbh);
     CK(cudaMemcpyAsync(h_all.data(), all_hist.p, h_all.size() * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    mark();  // 2: pass A + histogram all-gather + estimate merge done
     u64 N_glob = 0;
     for (u32 v : h_all) N_glob += v;
     *n_instances_local = N_loc;
@@ -154,6 +164,7 @@ static u64 dist_msd_count(gg_comm *cm, const PackedReads &pr, const u32 *valid, 
     DBuf<u64> A;
     msd_pass_b(ctx, pr, valid, k, canonical, pl, hist.p, N_loc, hist0, bstart, A);
     stage_end(ctx, ST_EXTRACT);
+    mark();  // 3: pass B done
     // ---- exchange ----
     stage_begin(ctx, ST_SORT);
     std::vector<u64> soff(P), scnt(P), roff(P), rcnt(P);
@@ -195,5 +206,12 @@ static u64 dist_msd_count(gg_comm *cm, const PackedReads &pr, const u32 *valid, 
     CK(cudaStreamSynchronize(ctx->stream));  // h_vbeg / h_vcnt are read by the copies above; A is released next
     A.release();
     stage_end(ctx, ST_SORT);
-    return msd_finish(ctx, R, N_recv, vbeg.p, vcnt.p, nb_local, (u32)P, pl, tune, min_freq, ukeys, ucounts);
+    mark();  // 4: exchange done
+    const u64 U = msd_finish(ctx, R, N_recv, vbeg.p, vcnt.p, nb_local, (u32)P, pl, tune, min_freq, ukeys, ucounts);
+    mark();  // 5: level 1 + leaves + gather done
+    if (dbg)
+        fprintf(stderr, "[dist rank %d] t0=%.3f size-allreduce %.2f | passA+allgather %.2f | passB %.2f | exchange %.2f (send %.1f MB, recv %.1f MB) | finish %.2f ms\n",
+                me, tmark[0], tmark[1] - tmark[0], tmark[2] - tmark[1], tmark[3] - tmark[2], tmark[4] - tmark[3],
+                (double)(N_loc - scnt[me]) * 8e-6, (double)(N_recv - rcnt[me]) * 8e-6, tmark[5] - tmark[4]);
+    return U;
 }

@@ -99,10 +99,6 @@ int gg_ctx_create(int device, gg_ctx **out) {
         for (int i = 0; i < 2 * GG_NSTAGE; ++i) CK(cudaEventCreate(&ctx->ev[i]));
         for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&ctx->user_ev[i]));
         CK(cudaHostAlloc((void **)&ctx->h_scalar, 64 * sizeof(u64), cudaHostAllocDefault));
-        cudaMemPool_t pool;
-        CK(cudaDeviceGetDefaultMemPool(&pool, device));
-        u64 thr = ~0ULL;  // keep freed blocks cached in the pool
-        CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
         timing_reset(ctx);
     } catch (const GgError &) {
         delete ctx;
@@ -121,6 +117,10 @@ void gg_ctx_destroy(gg_ctx *ctx) {
     for (auto &r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     cudaFreeHost(ctx->h_scalar);
+    if (ctx->arena) {  // handles still alive keep their blocks listed in `live`; everything is returned to the driver here
+        for (auto &kv : ctx->arena->live) cudaFree(kv.first);
+        delete ctx->arena;
+    }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -691,27 +691,46 @@ static gg_counts *dist_count_impl(gg_comm *cm, const u8 *d_seq, const u64 *d_off
         throw;
     }
 }
-// every rank's slice -> the whole table on every rank (slices are in key order by rank)
+// every rank's slice -> the whole table on every rank (slices are in key order by rank).
+// The slices are balanced, so they are padded to the largest one and moved with ONE ncclAllGather per
+// array (ring / NVLS inside NCCL) and then compacted; a mesh of sends costs several times more at 8 ranks.
+__global__ void allgather_compact_kernel(const u64 *__restrict__ pk, const u32 *__restrict__ pc, u64 maxn, int W, int P,
+                                         const u64 *__restrict__ n, const u64 *__restrict__ off, u64 *__restrict__ keys,
+                                         u32 *__restrict__ counts) {
+    for (int p = 0; p < P; ++p) {
+        const u64 np = n[p], o = off[p];
+        for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < np * W; i += (u64)gridDim.x * blockDim.x) keys[o * W + i] = pk[(u64)p * maxn * W + i];
+        for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < np; i += (u64)gridDim.x * blockDim.x) counts[o + i] = pc[(u64)p * maxn + i];
+    }
+}
 static gg_counts *counts_allgather_impl(gg_comm *cm, gg_counts *c) {
     NcclApi *nc = nccl_api();
     gg_ctx *ctx = cm->ctx;
     const int P = cm->world;
-    DBuf<u64> sz(ctx, P + 2);
-    u64 mine[2] = {c->n_unique, c->n_instances};
-    CK(cudaMemcpyAsync(sz.p + P, mine, sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
-    NCK(nc->AllGather(sz.p + P, sz.p, 1, ncclUint64, cm->comm, ctx->stream));
-    std::vector<u64> n(P), off(P), zero(P, 0), mycnt(P, c->n_unique);
+    DBuf<u64> sz(ctx, 2 * P + 2);
+    CK(cudaMemcpyAsync(sz.p + 2 * P, &c->n_unique, sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    NCK(nc->AllGather(sz.p + 2 * P, sz.p, 1, ncclUint64, cm->comm, ctx->stream));
+    std::vector<u64> n(P), off(P);
     CK(cudaMemcpyAsync(n.data(), sz.p, P * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    u64 total = 0;
-    for (int p = 0; p < P; ++p) { off[p] = total; total += n[p]; }
+    u64 total = 0, maxn = 1;
+    for (int p = 0; p < P; ++p) { off[p] = total; total += n[p]; maxn = n[p] > maxn ? n[p] : maxn; }
+    CK(cudaMemcpyAsync(sz.p + P, off.data(), P * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
     gg_counts *f = new gg_counts();
     f->ctx = ctx; f->k = c->k; f->W = c->W; f->n_unique = total; f->n_instances = c->n_instances;
     try {
-        f->d_keys = dalloc<u64>(ctx, total * c->W);
+        const int W = c->W;
+        f->d_keys = dalloc<u64>(ctx, total * W);
         f->d_counts = dalloc<u32>(ctx, total);
-        dist_alltoallv(cm, c->d_keys, zero.data(), mycnt.data(), f->d_keys, off.data(), n.data(), sizeof(u64) * c->W);
-        dist_alltoallv(cm, c->d_counts, zero.data(), mycnt.data(), f->d_counts, off.data(), n.data(), sizeof(u32));
+        DBuf<u64> mk(ctx, maxn * W), pk(ctx, (u64)P * maxn * W);
+        DBuf<u32> mc(ctx, maxn), pc(ctx, (u64)P * maxn);
+        if (c->n_unique) {
+            CK(cudaMemcpyAsync(mk.p, c->d_keys, c->n_unique * W * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(mc.p, c->d_counts, c->n_unique * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        NCK(nc->AllGather(mk.p, pk.p, maxn * W, ncclUint64, cm->comm, ctx->stream));
+        NCK(nc->AllGather(mc.p, pc.p, maxn, ncclUint32, cm->comm, ctx->stream));
+        LAUNCH(ctx, allgather_compact_kernel, (unsigned)(ctx->num_sms * 8), 256, 0, pk.p, pc.p, maxn, W, P, sz.p, sz.p + P, f->d_keys, f->d_counts);
         CK(cudaStreamSynchronize(ctx->stream));
     } catch (...) {
         dfree(ctx, f->d_keys); dfree(ctx, f->d_counts);

@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(256) radix_small_kernel(u64 *k0, u64 *k1, u64 
 // rank(i) = #{ j : key_j < key_i, or key_j == key_i and j < i } over the masked key bits: the same
 // permutation as a stable LSD radix sort over those bits, in O(n^2 / threads) compares instead of
 // ceil(bits / 8) dependent single-CTA passes.
-#define RANK_SORT_N 12288
+#define RANK_SORT_N 32768
 template <int KW>
 struct KeyMask {
     u64 m[KW];
