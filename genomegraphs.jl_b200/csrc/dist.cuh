@@ -107,6 +107,20 @@ static void dist_alltoallv(gg_comm *cm, const void *send, const u64 *soff, const
     NCK(nc->GroupEnd());
 }
 
+// instances per child of this rank's bucket range, summed over the ranks' pass-A histograms
+__global__ void dist_child_hist_kernel(const u32 *__restrict__ all_hist, int P, u32 nbh, int hb, int bits, u32 child0, u32 nchild,
+                                       u32 *__restrict__ out) {
+    u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > nchild) return;
+    u32 s = 0;
+    if (c < nchild) {
+        const u32 g = 1u << (hb - bits), base = (child0 + c) * g;
+        for (int p = 0; p < P; ++p)
+            for (u32 i = 0; i < g; ++i) s += all_hist[(size_t)p * nbh + base + i];
+    }
+    out[c] = s;
+}
+
 // reads of this rank -> this rank's key-range slice of the global sorted (k-mer, count) table
 static u64 dist_msd_count(gg_comm *cm, const PackedReads &pr, const u32 *valid, int k, int canonical, u32 min_freq, DBuf<u64> &ukeys,
                           DBuf<u32> &ucounts, u64 *n_instances_local, u64 *n_instances_global) {
@@ -149,7 +163,7 @@ static u64 dist_msd_count(gg_comm *cm, const PackedReads &pr, const u32 *valid, 
     *n_instances_local = N_loc;
     *n_instances_global = N_glob;
     if (N_loc >= 0xFFFFFFFFull) GG_THROW(GG_ERR_LIMIT, "%llu k-mer instances exceed the 2^32-1 per-GPU limit", (unsigned long long)N_loc);
-    const MsdPlan pl = msd_plan(dest, N_glob, k, tune);
+    const MsdPlan pl = msd_plan(dest, N_glob, k, tune, hb);
     const u32 nb0 = 1u << pl.b0, grp = 1u << (hb - pl.b0);
     // ---- per-rank histograms at level-0 resolution, owners of the buckets ----
     std::vector<u64> cnt((size_t)P * nb0, 0), gh(nb0, 0);
@@ -207,7 +221,14 @@ static u64 dist_msd_count(gg_comm *cm, const PackedReads &pr, const u32 *valid, 
     A.release();
     stage_end(ctx, ST_SORT);
     mark();  // 4: exchange done
-    const u64 U = msd_finish(ctx, R, N_recv, vbeg.p, vcnt.p, nb_local, (u32)P, pl, tune, min_freq, ukeys, ucounts);
+    DBuf<u32> child_hist;
+    if (pl.b1 > 0 && pl.b0 + pl.b1 <= hb && nb_local) {  // pass C for free (see msd_count)
+        const u32 nchild = nb_local << pl.b1;
+        child_hist.alloc(ctx, nchild + 1);
+        LAUNCH(ctx, dist_child_hist_kernel, (unsigned)ceil_div(nchild + 1, 256), 256, 0, all_hist.p, P, nbh, hb, pl.b0 + pl.b1,
+               first[me] << pl.b1, nchild, child_hist.p);
+    }
+    const u64 U = msd_finish(ctx, R, N_recv, vbeg.p, vcnt.p, nb_local, (u32)P, pl, tune, min_freq, ukeys, ucounts, child_hist.p);
     mark();  // 5: level 1 + leaves + gather done
     if (dbg)
         fprintf(stderr, "[dist rank %d] t0=%.3f size-allreduce %.2f | passA+allgather %.2f | passB %.2f | exchange %.2f (send %.1f MB, recv %.1f MB) | finish %.2f ms\n",

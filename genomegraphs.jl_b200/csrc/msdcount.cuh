@@ -29,7 +29,9 @@
 #include "sort.cuh"
 #include <math.h>
 
-#define MSD_HB 12      // resolution of the pass-A histogram (bits) = largest level-0 digit
+#define MSD_HB 14      // resolution of the pass-A histogram (bits): covers b0 + b1 of mid-size inputs, so that the
+                       // level-1 histogram (pass C) falls out of pass A for free
+#define MSD_B0_MAX 12  // largest level-0 digit (bins of the pass-B tile)
 #define MSD_MAX_B1 10
 #define MSD_UNROLL 8   // independent global loads in flight per thread in the leaf kernel
 #define MSD_EMPTY 0xFFFFFFFFFFFFFFFFULL  // never a valid key: all-T k-mers are not canonical, 2k < 64 otherwise (see msd_supported)
@@ -65,21 +67,23 @@ __device__ __forceinline__ u32 msd_digit0(u64 key, int sh, int b0) { return b0 ?
 // Estimate (linear counting): keys whose sampler hash falls into a 2^-est_shift slice set one byte
 // of a 2^EST_LOG-byte map; with Z zero bytes left, distinct ~= 2^EST_LOG * ln(2^EST_LOG / Z) << est_shift.
 // The map of several GPUs merges with an elementwise max (dist.cuh).
-__global__ void __launch_bounds__(256) msd_hist_kernel(const u64 *__restrict__ packed, const u32 *__restrict__ valid, u64 nwords,
-                                                       int k, int canonical, int hb, u32 *__restrict__ ghist, u32 est_max,
-                                                       u8 *__restrict__ est_map) {
-    __shared__ u32 h[1 << MSD_HB];
+#define MSD_HIST_THREADS 512
+__global__ void __launch_bounds__(MSD_HIST_THREADS) msd_hist_kernel(const u64 *__restrict__ packed, const u32 *__restrict__ valid, u64 nwords,
+                                                                    int k, int canonical, int hb, u32 *__restrict__ ghist, u32 est_max,
+                                                                    u8 *__restrict__ est_map) {
+    extern __shared__ __align__(16) u8 smem_raw[];
+    u32 *h = reinterpret_cast<u32 *>(smem_raw);  // 2^hb bins
     const int nb = 1 << hb, sh = 2 * k - hb;
-    for (int i = threadIdx.x; i < nb; i += 256) h[i] = 0;
+    for (int i = threadIdx.x; i < nb; i += MSD_HIST_THREADS) h[i] = 0;
     __syncthreads();
-    for (u64 t = (u64)blockIdx.x * 256 + threadIdx.x; t < nwords; t += (u64)gridDim.x * 256)
+    for (u64 t = (u64)blockIdx.x * MSD_HIST_THREADS + threadIdx.x; t < nwords; t += (u64)gridDim.x * MSD_HIST_THREADS)
         roll32(packed, valid, t, k, canonical, [&](u64 key, int) {
             atomicAdd(&h[msd_digit0(key, sh, hb)], 1u);
             const u32 p = (u32)key * 0x9E3779B1u;  // hash of the last 16 bases: a sampler, not an identity
             if (p <= est_max) est_map[(u32)((key * MSD_GOLD) >> (64 - EST_LOG))] = 1;
         });
     __syncthreads();
-    for (int i = threadIdx.x; i < nb; i += 256)
+    for (int i = threadIdx.x; i < nb; i += MSD_HIST_THREADS)
         if (h[i]) atomicAdd(&ghist[i], h[i]);
 }
 // out[0] += number of set map bytes; out[1] += sum of the histogram (N)
@@ -139,8 +143,8 @@ __global__ void __launch_bounds__(256, 2) msd_scatter_kernel(const u64 *__restri
                                                              int k, int canonical, int b0, u32 *__restrict__ cursor, u64 *__restrict__ out) {
     extern __shared__ __align__(16) u8 smem_raw[];
     u64 *skeys = reinterpret_cast<u64 *>(smem_raw);                      // MSD_TILE_KEYS
-    u32 *hist = reinterpret_cast<u32 *>(skeys + MSD_TILE_KEYS);          // 2^MSD_HB
-    u32 *delta = hist + (1 << MSD_HB);                                   // 2^MSD_HB
+    u32 *hist = reinterpret_cast<u32 *>(skeys + MSD_TILE_KEYS);          // 2^MSD_B0_MAX
+    u32 *delta = hist + (1 << MSD_B0_MAX);                               // 2^MSD_B0_MAX
     __shared__ u32 ws[33];
     const int nb = 1 << b0, sh = 2 * k - b0;
     const u64 t = (u64)blockIdx.x * 256 + threadIdx.x;
@@ -154,7 +158,7 @@ __global__ void __launch_bounds__(256, 2) msd_scatter_kernel(const u64 *__restri
         roll32(packed, valid, t, k, canonical, [&](u64 key, int j) { keys[j] = key; atomicAdd(&hist[msd_digit0(key, sh, b0)], 1u); });
     }
     __syncthreads();
-    const u32 total = msd_reserve<(1 << MSD_HB) / 256>(hist, delta, nb, cursor, ws);
+    const u32 total = msd_reserve<(1 << MSD_B0_MAX) / 256>(hist, delta, nb, cursor, ws);
 #pragma unroll
     for (int j = 0; j < 32; ++j)
         if ((vm >> (31 - j)) & 1u) skeys[atomicAdd(&hist[msd_digit0(keys[j], sh, b0)], 1u)] = keys[j];
@@ -519,7 +523,7 @@ __global__ void __launch_bounds__(256) msd_gather_kernel(const u64 *__restrict__
 
 // ------------------------------------- host side -------------------------------------------------
 struct MsdTune {
-    int b0_max = 8;          // preferred level-0 digit bits (grows up to MSD_HB when level 1 is full)
+    int b0_max = 8;          // preferred level-0 digit bits (grows up to MSD_B0_MAX when level 1 is full)
     int b1_max = MSD_MAX_B1; // level-1 digit bits
     u32 dt = 2048;           // target DISTINCT keys per child: 1/4 of the leaf table (8192 slots), which leaves room for the
                              // ~1.75x skew of canonical k-mers towards small leading bases
@@ -535,7 +539,7 @@ static MsdTune msd_tune() {
     if (const char *e = getenv("GG_MSD_IT")) t.it_log2 = (u32)atoi(e);
     if (const char *e = getenv("GG_MSD_VARIANT")) t.variant = atoi(e);
     if (const char *e = getenv("GG_MSD_TEST_OVERFLOW")) t.test_ovf_mod = (u32)atoi(e);
-    if (t.b0_max > MSD_HB) t.b0_max = MSD_HB;
+    if (t.b0_max > MSD_B0_MAX) t.b0_max = MSD_B0_MAX;
     if (t.b0_max < 0) t.b0_max = 0;
     if (t.b1_max > MSD_MAX_B1) t.b1_max = MSD_MAX_B1;
     if (t.b1_max < 0) t.b1_max = 0;
@@ -549,10 +553,10 @@ struct MsdPlan {
     int shiftc = 0;  // key bits below the child digits
 };
 static inline int msd_hist_bits(int k) { return 2 * k < MSD_HB ? 2 * k : MSD_HB; }
-// children of ~dt distinct keys and <= 2^it_log2 instances
-static MsdPlan msd_plan(u64 distinct_est, u64 n_instances, int k, const MsdTune &t) {
+// children of ~dt distinct keys and <= 2^it_log2 instances; hb = bits of the pass-A histogram
+static MsdPlan msd_plan(u64 distinct_est, u64 n_instances, int k, const MsdTune &t, int hb) {
     MsdPlan p;
-    p.hb = msd_hist_bits(k);
+    p.hb = hb;
     int bits = 0;
     while (bits < 22 && (distinct_est >> bits) > t.dt) ++bits;
     while (bits < 22 && (n_instances >> bits) > (1ULL << t.it_log2)) ++bits;
@@ -561,7 +565,7 @@ static MsdPlan msd_plan(u64 distinct_est, u64 n_instances, int k, const MsdTune 
     p.b0 = bits < t.b0_max ? bits : t.b0_max;
     p.b1 = bits - p.b0;
     if (p.b1 > t.b1_max) { p.b0 += p.b1 - t.b1_max; p.b1 = t.b1_max; }
-    if (p.b0 > MSD_HB) p.b0 = MSD_HB;
+    if (p.b0 > MSD_B0_MAX) p.b0 = MSD_B0_MAX;
     if (p.b0 > p.hb) p.b0 = p.hb;
     if (p.b1 > 2 * k - p.b0) p.b1 = 2 * k - p.b0;
     p.shiftc = 2 * k - p.b0 - p.b1;
@@ -590,9 +594,12 @@ static void msd_pass_a_launch(gg_ctx *ctx, const PackedReads &pr, const u32 *val
     CK(cudaMemsetAsync(hist.p, 0, (nb + 1) * sizeof(u32), ctx->stream));
     CK(cudaMemsetAsync(est.p, 0, 1ULL << EST_LOG, ctx->stream));
     if (pr.nwords == 0) return;
-    u64 hgrid = ceil_div(pr.nwords, 256);
-    if (hgrid > (u64)ctx->num_sms * 8) hgrid = (u64)ctx->num_sms * 8;
-    LAUNCH(ctx, msd_hist_kernel, (unsigned)hgrid, 256, 0, pr.packed.p, valid, pr.nwords, k, canonical, hb, hist.p,
+    u64 hgrid = ceil_div(pr.nwords, MSD_HIST_THREADS);
+    if (hgrid > (u64)ctx->num_sms * 3) hgrid = (u64)ctx->num_sms * 3;
+    const size_t smemA = sizeof(u32) << MSD_HB;
+    static bool setA = false;
+    if (!setA) { CK(cudaFuncSetAttribute(msd_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA)); setA = true; }
+    LAUNCH(ctx, msd_hist_kernel, (unsigned)hgrid, MSD_HIST_THREADS, smemA, pr.packed.p, valid, pr.nwords, k, canonical, hb, hist.p,
            est_shift ? (0xFFFFFFFFu >> est_shift) : 0xFFFFFFFFu, est.p);
 }
 // pass A, read back: N = sum of hist, distinct estimate from the map
@@ -618,7 +625,7 @@ static void msd_pass_b(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int
     LAUNCH(ctx, msd_copy_u32_kernel, (unsigned)ceil_div(nb0, 256), 256, 0, bstart.p, (u64)nb0, cursor.p);
     A.alloc(ctx, N ? N : 1);
     if (N == 0) return;
-    size_t smemB = (size_t)MSD_TILE_KEYS * 8 + 2 * (size_t)(1 << MSD_HB) * 4;
+    size_t smemB = (size_t)MSD_TILE_KEYS * 8 + 2 * (size_t)(1 << MSD_B0_MAX) * 4;
     static bool setB = false;
     if (!setB) { CK(cudaFuncSetAttribute(msd_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB)); setB = true; }
     LAUNCH(ctx, msd_scatter_kernel, (unsigned)ceil_div(pr.nwords, 256), 256, smemB, pr.packed.p, valid, pr.nwords, k, canonical, pl.b0, cursor.p, A.p);
@@ -651,8 +658,9 @@ static void msd_launch_leaf(gg_ctx *ctx, int ctas_per_sm, const u64 *IN, u64 *SB
 // Level-0 buckets -> sorted unique keys + counts (count >= min_freq).
 // IN holds n_in keys; local bucket bl (0 .. nb_local) consists of the nsrc virtual buckets
 // vb = bl * nsrc + s: IN[vbeg[vb] .. + vcnt[vb]).  IN is consumed (used as scratch).
+// child_hist (optional, nchild + 1 entries, last 0): instances per child when pass A already knows them.
 static u64 msd_finish(gg_ctx *ctx, DBuf<u64> &IN, u64 n_in, const u32 *vbeg, const u32 *vcnt, u32 nb_local, u32 nsrc, const MsdPlan &pl,
-                      const MsdTune &tune, u32 min_freq, DBuf<u64> &ukeys, DBuf<u32> &ucounts) {
+                      const MsdTune &tune, u32 min_freq, DBuf<u64> &ukeys, DBuf<u32> &ucounts, const u32 *child_hist = nullptr) {
     if (n_in == 0) { ukeys.alloc(ctx, 1); ucounts.alloc(ctx, 1); return 0; }
     const u32 nvb = nb_local * nsrc;
     const u64 nchild = (u64)nb_local << pl.b1;
@@ -668,17 +676,21 @@ static u64 msd_finish(gg_ctx *ctx, DBuf<u64> &IN, u64 n_in, const u32 *vbeg, con
     if (pl.b1 > 0) {
         // ---- C, D: level-1 partition into S1 ----
         DBuf<u32> tcount(ctx, nvb + 1), tstart(ctx, nvb + 1), cursor1(ctx, nchild);
-        hist1.alloc(ctx, nchild + 1);
-        CK(cudaMemsetAsync(hist1.p, 0, (nchild + 1) * sizeof(u32), ctx->stream));
         LAUNCH(ctx, msd_tilecount_kernel, (unsigned)ceil_div(nvb + 1, 256), 256, 0, vcnt, nvb, tcount.p);
         exclusive_scan_u32(ctx, tcount.p, tstart.p, nvb + 1, nullptr);
         const unsigned tgrid = (unsigned)(ceil_div(n_in, MSD_T1) + nvb);
-        LAUNCH(ctx, msd_hist1_kernel, tgrid, 256, 0, IN.p, tstart.p, vbeg, vcnt, nvb, nsrc, pl.shiftc, pl.b1, hist1.p);
-        exclusive_scan_u32(ctx, hist1.p, off.p, nchild + 1, nullptr);
+        const u32 *h1 = child_hist;
+        if (!h1) {  // pass C: the pass-A histogram is too coarse for b0 + b1 bits
+            hist1.alloc(ctx, nchild + 1);
+            CK(cudaMemsetAsync(hist1.p, 0, (nchild + 1) * sizeof(u32), ctx->stream));
+            LAUNCH(ctx, msd_hist1_kernel, tgrid, 256, 0, IN.p, tstart.p, vbeg, vcnt, nvb, nsrc, pl.shiftc, pl.b1, hist1.p);
+            h1 = hist1.p;
+        }
+        exclusive_scan_u32(ctx, h1, off.p, nchild + 1, nullptr);
         LAUNCH(ctx, msd_copy_u32_kernel, (unsigned)ceil_div(nchild, 256), 256, 0, off.p, nchild, cursor1.p);
         LAUNCH(ctx, msd_scatter1_kernel, tgrid, 256, 0, IN.p, tstart.p, vbeg, vcnt, nvb, nsrc, pl.shiftc, pl.b1, cursor1.p, S1.p);
         leaf_in = S1.p; leaf_o = S1.p; leaf_sb = IN.p;
-        segbeg = off.p; segcnt = hist1.p; nseg = 1;
+        segbeg = off.p; segcnt = h1; nseg = 1;
     } else {
         ctot.alloc(ctx, nchild + 1);
         LAUNCH(ctx, msd_child_total_kernel, (unsigned)ceil_div(nchild + 1, 256), 256, 0, vcnt, nsrc, (u32)nchild, ctot.p);
@@ -730,8 +742,14 @@ static u64 msd_count(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int k
     *n_instances = N;
     if (N == 0) { stage_end(ctx, ST_EXTRACT); ukeys.alloc(ctx, 1); ucounts.alloc(ctx, 1); return 0; }
     if (N >= 0xFFFFFFFFull) GG_THROW(GG_ERR_LIMIT, "%llu k-mer instances exceed the 2^32-1 per-call limit", (unsigned long long)N);
-    const MsdPlan pl = msd_plan(dest, N, k, tune);
+    const MsdPlan pl = msd_plan(dest, N, k, tune, msd_hist_bits(k));
     msd_pass_b(ctx, pr, valid, k, canonical, pl, hist.p, N, hist0, bstart, A);
+    DBuf<u32> child_hist;
+    if (pl.b1 > 0 && pl.b0 + pl.b1 <= pl.hb) {  // pass C for free: collapse the pass-A histogram to b0 + b1 bits
+        const u32 nchild = 1u << (pl.b0 + pl.b1);
+        child_hist.alloc(ctx, nchild + 1);
+        LAUNCH(ctx, msd_collapse_kernel, (unsigned)ceil_div(nchild + 1, 256), 256, 0, hist.p, pl.hb, pl.b0 + pl.b1, child_hist.p);
+    }
     stage_end(ctx, ST_EXTRACT);
-    return msd_finish(ctx, A, N, bstart.p, hist0.p, 1u << pl.b0, 1, pl, tune, min_freq, ukeys, ucounts);
+    return msd_finish(ctx, A, N, bstart.p, hist0.p, 1u << pl.b0, 1, pl, tune, min_freq, ukeys, ucounts, child_hist.p);
 }

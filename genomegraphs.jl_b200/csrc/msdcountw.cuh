@@ -24,6 +24,8 @@ struct MsdW {
     static constexpr int LOG_HT = W == 2 ? 12 : 11;     // leaf table slots: 64 KB of keys
 };
 #define MSDW_OVERFLOW 0xFFFFFFFFu
+#define MSDW_HB 12  // pass-A histogram bits of the multi-word path = largest level-0 digit
+static inline int msdw_hist_bits(int k) { return 2 * k < MSDW_HB ? 2 * k : MSDW_HB; }
 __device__ unsigned long long g_msdw_dbg[4];
 
 // key bits [lowbit, lowbit + nbits), nbits <= 24
@@ -91,7 +93,7 @@ template <int W>
 __global__ void __launch_bounds__(256) msdw_hist_kernel(const u64 *__restrict__ packed, const u32 *__restrict__ valid, u64 nwords, int k,
                                                         int canonical, int hb, u32 *__restrict__ ghist, u32 est_max,
                                                         u8 *__restrict__ est_map) {
-    __shared__ u32 h[1 << MSD_HB];
+    __shared__ u32 h[1 << MSDW_HB];
     __shared__ u16 plist[MsdW<W>::TILE_KEYS];
     __shared__ u32 ws[33];
     const int nb = 1 << hb;
@@ -119,9 +121,9 @@ __global__ void __launch_bounds__(256, 2) msdw_scatter_kernel(const u64 *__restr
                                                               u64 *__restrict__ out) {
     extern __shared__ __align__(16) u8 smem_raw[];
     u64 *skeys = reinterpret_cast<u64 *>(smem_raw);                                  // TILE_KEYS * W
-    u32 *hist = reinterpret_cast<u32 *>(skeys + (size_t)MsdW<W>::TILE_KEYS * W);     // 2^MSD_HB
-    u32 *delta = hist + (1 << MSD_HB);                                               // 2^MSD_HB
-    u16 *plist = reinterpret_cast<u16 *>(delta + (1 << MSD_HB));                     // TILE_KEYS
+    u32 *hist = reinterpret_cast<u32 *>(skeys + (size_t)MsdW<W>::TILE_KEYS * W);     // 2^MSDW_HB
+    u32 *delta = hist + (1 << MSDW_HB);                                               // 2^MSDW_HB
+    u16 *plist = reinterpret_cast<u16 *>(delta + (1 << MSDW_HB));                     // TILE_KEYS
     __shared__ u32 ws[33];
     const int nb = 1 << b0, lowbit = 2 * k - b0;
     for (int i = threadIdx.x; i < nb; i += 256) hist[i] = 0;
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__(256, 2) msdw_scatter_kernel(const u64 *__restr
     for (u32 q = threadIdx.x; q < np; q += 256)
         atomicAdd(&hist[kw_bits<W>(kmer_at<W>(packed, pbase + plist[q], k, canonical, nullptr), lowbit, b0)], 1u);
     __syncthreads();
-    const u32 total = msd_reserve<(1 << MSD_HB) / 256>(hist, delta, nb, cursor, ws);
+    const u32 total = msd_reserve<(1 << MSDW_HB) / 256>(hist, delta, nb, cursor, ws);
     for (u32 q = threadIdx.x; q < np; q += 256) {
         const Kmer<W> key = kmer_at<W>(packed, pbase + plist[q], k, canonical, nullptr);
         km_store<W>(skeys, atomicAdd(&hist[kw_bits<W>(key, lowbit, b0)], 1u), key);
@@ -371,7 +373,7 @@ static u64 msdw_count(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int 
     if (pr.nwords == 0) { ukeys.alloc(ctx, W); ucounts.alloc(ctx, 1); return 0; }
     // ---- A ----
     stage_begin(ctx, ST_EXTRACT);
-    const int hb = msd_hist_bits(k);
+    const int hb = msdw_hist_bits(k);
     const u32 nbh = 1u << hb;
     DBuf<u32> hist(ctx, nbh + 1);
     DBuf<u8> est(ctx, 1ULL << EST_LOG);
@@ -388,7 +390,9 @@ static u64 msdw_count(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int 
     *n_instances = N;
     if (N == 0) { stage_end(ctx, ST_EXTRACT); ukeys.alloc(ctx, W); ucounts.alloc(ctx, 1); return 0; }
     if (N >= 0xFFFFFFFFull) GG_THROW(GG_ERR_LIMIT, "%llu k-mer instances exceed the 2^32-1 per-call limit", (unsigned long long)N);
-    const MsdPlan pl = msd_plan(dest, N, k, tune);
+    MsdTune t2 = tune;
+    if (t2.b0_max > MSDW_HB) t2.b0_max = MSDW_HB;
+    const MsdPlan pl = msd_plan(dest, N, k, t2, hb);
     // ---- B ----
     const u32 nb0 = 1u << pl.b0;
     DBuf<u32> hist0(ctx, nb0 + 1), bstart(ctx, nb0 + 1), cursor(ctx, nb0);
@@ -397,7 +401,7 @@ static u64 msdw_count(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int 
     LAUNCH(ctx, msd_copy_u32_kernel, (unsigned)ceil_div(nb0, 256), 256, 0, bstart.p, (u64)nb0, cursor.p);
     DBuf<u64> A(ctx, N * W), B(ctx, N * W);
     {
-        const size_t smemB = (size_t)MsdW<W>::TILE_KEYS * W * 8 + 2 * (size_t)(1 << MSD_HB) * 4 + (size_t)MsdW<W>::TILE_KEYS * 2;
+        const size_t smemB = (size_t)MsdW<W>::TILE_KEYS * W * 8 + 2 * (size_t)(1 << MSDW_HB) * 4 + (size_t)MsdW<W>::TILE_KEYS * 2;
         static bool setB = false;
         if (!setB) { CK(cudaFuncSetAttribute(msdw_scatter_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB)); setB = true; }
         LAUNCH(ctx, msdw_scatter_kernel<W>, (unsigned)ceil_div(pr.nwords, MsdW<W>::TILE_WORDS), 256, smemB, pr.packed.p, valid, pr.nwords, k,
