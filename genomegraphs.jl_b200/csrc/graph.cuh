@@ -159,7 +159,7 @@ __global__ void split_list_kernel(const u32 *__restrict__ sflag, const u32 *__re
 // one thread per splitter (dense: every lane of a warp walks).  A walk can only run into a
 // hash-sampled splitter: heads have no predecessor, so no memory lookup is needed for the test.
 __global__ void split_walk_kernel(const u32 *__restrict__ succ, const u32 *__restrict__ red_vertex, const u32 *__restrict__ sidx, u64 ns,
-                                  int sl, u32 *__restrict__ owner, u32 *__restrict__ local, u64 *__restrict__ red_rec,
+                                  int sl, u64 *__restrict__ ownloc, u64 *__restrict__ red_rec,
                                   u32 *__restrict__ red_tail) {
     u64 ii = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (ii >= ns) return;
@@ -170,14 +170,12 @@ __global__ void split_walk_kernel(const u32 *__restrict__ succ, const u32 *__res
         if (n == V_NONE) { red_rec[i] = ((u64)d << 32) | (i | V_TERM); red_tail[i] = u; break; }
         if (hash_splitter(n, sl)) { red_rec[i] = ((u64)(d + 1) << 32) | sidx[n]; red_tail[i] = V_NONE; break; }
         ++d;
-        owner[n] = i;
-        local[n] = d;
+        ownloc[n] = ((u64)i << 32) | d;  // owner splitter and distance from it, one store
         u = n;
     }
 }
 __global__ void split_expand_kernel(const u64 *__restrict__ red_rec, const u32 *__restrict__ red_tail, const u32 *__restrict__ sflag,
-                                    const u32 *__restrict__ sidx, const u32 *__restrict__ owner, const u32 *__restrict__ local, u64 nv,
-                                    u64 *__restrict__ rec) {
+                                    const u32 *__restrict__ sidx, const u64 *__restrict__ ownloc, u64 nv, u64 *__restrict__ rec) {
     u64 vv = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (vv >= nv) return;
     u32 v = (u32)vv;
@@ -185,9 +183,10 @@ __global__ void split_expand_kernel(const u64 *__restrict__ red_rec, const u32 *
     u32 i, back = 0;
     if (sflag[v]) i = sidx[v];
     else {
-        i = owner[v];
+        const u64 ol = ownloc[v];
+        i = (u32)(ol >> 32);
         if (i == V_NONE) return;  // on a cycle that holds no splitter: record stays non-terminal
-        back = local[v];
+        back = (u32)ol;
     }
     u64 r = red_rec[i];
     u32 ptr = (u32)r;
@@ -252,8 +251,7 @@ template <int W>
 __global__ void __launch_bounds__(256) resolve_kernel(const u64 *__restrict__ keys, const u8 *__restrict__ flags,
                                                       const u64 *__restrict__ rec, const u32 *__restrict__ cyc_head, u64 nv, int k,
                                                       u32 *__restrict__ vhead, u32 *__restrict__ vrank,
-                                                      u32 *__restrict__ key_head, u32 *__restrict__ key_ranke,
-                                                      u32 *__restrict__ key_cnt, u32 *__restrict__ pflag, u32 *__restrict__ cflag) {
+                                                      uint4 *__restrict__ prec, u32 *__restrict__ pflag, u32 *__restrict__ cflag) {
     u64 vv = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (vv >= nv) return;
     u32 v = (u32)vv;
@@ -269,7 +267,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(const u64 *__restrict__ ke
         vrank[v] = rank;
         if (rank == 0) {
             u32 key = v >> 1;
-            key_head[key] = v; key_ranke[key] = 0; key_cnt[key] = n; cflag[key] = 1;
+            prec[key] = make_uint4(v, 0u, n, V_NONE); cflag[key] = 1;
         }
         return;
     }
@@ -287,7 +285,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(const u64 *__restrict__ ke
             Kmer<W> a = vertex_kmer<W>(keys, v, k), b = vertex_kmer<W>(keys, mirror_of(flags, tail), k);
             if (km_lt<W>(a, b)) {
                 u32 key = min(v >> 1, tail >> 1);
-                key_head[key] = v; key_ranke[key] = 0; key_cnt[key] = n; pflag[key] = 1;
+                prec[key] = make_uint4(v, 0u, n, V_NONE); pflag[key] = 1;
             }
         }
     } else {
@@ -297,32 +295,31 @@ __global__ void __launch_bounds__(256) resolve_kernel(const u64 *__restrict__ ke
         if (rank == n - h) {
             Kmer<W> a = vertex_kmer<W>(keys, head, k), b = vertex_kmer<W>(keys, v, k);
             u32 key = head >> 1;
-            key_head[key] = head;
-            key_ranke[key] = km_cmp<W>(a, b) <= 0 ? 0 : (n - h);
-            key_cnt[key] = h;
+            prec[key] = make_uint4(head, km_cmp<W>(a, b) <= 0 ? 0u : (n - h), h, V_NONE);
             pflag[key] = 1;
         }
     }
 }
 // node ids from the scanned flags; node lengths
 __global__ void node_len_kernel(const u32 *__restrict__ pflag, const u32 *__restrict__ pscan, const u32 *__restrict__ cflag,
-                                const u32 *__restrict__ cscan, u64 n, u32 n_path, int k, const u32 *__restrict__ key_cnt,
-                                u32 *__restrict__ key_node, u32 *__restrict__ node_len) {
+                                const u32 *__restrict__ cscan, u64 n, u32 n_path, int k, uint4 *__restrict__ prec,
+                                u32 *__restrict__ node_len) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     u32 id = V_NONE;
     if (pflag[i]) id = pscan[i];
     else if (cflag && cflag[i]) id = n_path + cscan[i];
-    key_node[i] = id;
-    if (id != V_NONE) node_len[id] = (u32)k + key_cnt[i] - 1;
+    if (id != V_NONE) {
+        prec[i].w = id;
+        node_len[id] = (u32)k + prec[i].z - 1;
+    }
 }
 // every vertex of an emitted range writes its base(s)
 template <int W>
 __global__ void __launch_bounds__(256) emit_kernel(const u64 *__restrict__ keys, const u64 *__restrict__ rec,
                                                    const u32 *__restrict__ cyc_head, const u32 *__restrict__ vhead,
-                                                   const u32 *__restrict__ vrank, u64 nv, int k, const u32 *__restrict__ key_head,
-                                                   const u32 *__restrict__ key_ranke, const u32 *__restrict__ key_cnt,
-                                                   const u32 *__restrict__ key_node, const u32 *__restrict__ node_off,
+                                                   const u32 *__restrict__ vrank, u64 nv, int k, const uint4 *__restrict__ prec,
+                                                   const u32 *__restrict__ node_off,
                                                    u8 *__restrict__ bases, u32 *__restrict__ node_first, u32 *__restrict__ node_last) {
     u64 vv = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (vv >= nv) return;
@@ -332,9 +329,10 @@ __global__ void __launch_bounds__(256) emit_kernel(const u64 *__restrict__ keys,
     u32 tail = ((u32)rec[v]) & ~V_TERM;
     bool cyc = cyc_head && cyc_head[v] != V_NONE;
     u32 key = cyc ? (head >> 1) : min(head >> 1, tail >> 1);
-    if (key_head[key] != head) return;  // the mirror orientation is the emitted one
-    u32 id = key_node[key];
-    u32 rank = vrank[v], re = key_ranke[key], cnt = key_cnt[key];
+    const uint4 pr = prec[key];  // (head, first emitted rank, emitted count, node id) of the path keyed here
+    if (pr.x != head) return;    // the mirror orientation is the emitted one
+    u32 id = pr.w;
+    u32 rank = vrank[v], re = pr.y, cnt = pr.z;
     if (rank < re || rank - re >= cnt) return;
     u32 j = rank - re;
     u64 off = node_off[id];
@@ -581,17 +579,18 @@ static gg_graph *build_graph(gg_ctx *ctx, const u64 *keys, u64 U, int k) {
         if (getenv("GG_PLAIN_WYLLIE")) {
             run_wyllie();
         } else {
-            DBuf<u32> sflag(ctx, nv), sidx(ctx, nv), owner(ctx, nv), local(ctx, nv);
+            DBuf<u32> sflag(ctx, nv), sidx(ctx, nv);
+            DBuf<u64> ownloc(ctx, nv);
             DBuf<u64> stot(ctx, 1);
             const int sl = getenv("GG_SPLIT_LOG") ? atoi(getenv("GG_SPLIT_LOG")) : 4;  // splitters: heads + a 2^-sl hash sample
             LAUNCH(ctx, split_flag_kernel, (unsigned)ceil_div(nv, 256), 256, 0, succ.p, flags.p, rin, nv, sl, sflag.p);
             exclusive_scan_u32(ctx, sflag.p, sidx.p, nv, stot.p);
             const u64 ns = read_scalar<u64>(ctx, stot.p);
-            CK(cudaMemsetAsync(owner.p, 0xFF, nv * sizeof(u32), ctx->stream));
+            CK(cudaMemsetAsync(ownloc.p, 0xFF, nv * sizeof(u64), ctx->stream));
             DBuf<u64> redA(ctx, ns + 1), redB(ctx, ns + 1);
             DBuf<u32> red_tail(ctx, ns + 1), red_vertex(ctx, ns + 1);
             LAUNCH(ctx, split_list_kernel, (unsigned)ceil_div(nv, 256), 256, 0, sflag.p, sidx.p, nv, red_vertex.p);
-            if (ns) LAUNCH(ctx, split_walk_kernel, (unsigned)ceil_div(ns, 128), 128, 0, succ.p, red_vertex.p, sidx.p, ns, sl, owner.p, local.p, redA.p, red_tail.p);
+            if (ns) LAUNCH(ctx, split_walk_kernel, (unsigned)ceil_div(ns, 128), 128, 0, succ.p, red_vertex.p, sidx.p, ns, sl, ownloc.p, redA.p, red_tail.p);
             u64 *ra = redA.p, *rb = redB.p;
             if (ns) {
                 const int rounds = ilog2_ceil(ns) + 2;  // fixed count: no host round trips
@@ -600,7 +599,7 @@ static gg_graph *build_graph(gg_ctx *ctx, const u64 *keys, u64 U, int k) {
                     std::swap(ra, rb);
                 }
             }
-            LAUNCH(ctx, split_expand_kernel, (unsigned)ceil_div(nv, 256), 256, 0, ra, red_tail.p, sflag.p, sidx.p, owner.p, local.p, nv, rin);
+            LAUNCH(ctx, split_expand_kernel, (unsigned)ceil_div(nv, 256), 256, 0, ra, red_tail.p, sflag.p, sidx.p, ownloc.p, nv, rin);
         }
         CK(cudaMemsetAsync(d_flag.p, 0, sizeof(u32), ctx->stream));
         LAUNCH(ctx, count_cyclic_kernel, (unsigned)ceil_div(nv, 256), 256, 0, rin, nv, d_flag.p);
@@ -622,15 +621,16 @@ static gg_graph *build_graph(gg_ctx *ctx, const u64 *keys, u64 U, int k) {
         }
         const u64 *rec = rin;
         DBuf<u32> vhead(ctx, nv), vrank(ctx, nv);
-        DBuf<u32> key_head(ctx, U), key_ranke(ctx, U), key_cnt(ctx, U), key_node(ctx, U), pflag(ctx, U), cflag;
-        CK(cudaMemsetAsync(key_head.p, 0xFF, U * sizeof(u32), ctx->stream));
+        DBuf<uint4> prec(ctx, U);
+        DBuf<u32> pflag(ctx, U), cflag;
+        CK(cudaMemsetAsync(prec.p, 0xFF, U * sizeof(uint4), ctx->stream));
         CK(cudaMemsetAsync(pflag.p, 0, U * sizeof(u32), ctx->stream));
         if (has_cycles) {
             cflag.alloc(ctx, U);
             CK(cudaMemsetAsync(cflag.p, 0, U * sizeof(u32), ctx->stream));
         }
         LAUNCH(ctx, resolve_kernel<W>, (unsigned)ceil_div(nv, 256), 256, 0, keys, flags.p, rec, cyc_head.p, nv, k, vhead.p, vrank.p,
-               key_head.p, key_ranke.p, key_cnt.p, pflag.p, cflag.p);
+               prec.p, pflag.p, cflag.p);
         DBuf<u32> pscan(ctx, U), cscan;
         DBuf<u64> tot(ctx, 2);
         exclusive_scan_u32(ctx, pflag.p, pscan.p, U, tot.p);
@@ -649,7 +649,7 @@ static gg_graph *build_graph(gg_ctx *ctx, const u64 *keys, u64 U, int k) {
         g->n_nodes = nn;
         DBuf<u32> node_len(ctx, nn + 1), node_off32(ctx, nn + 1), node_first(ctx, nn + 1), node_last(ctx, nn + 1);
         LAUNCH(ctx, node_len_kernel, (unsigned)ceil_div(U, 256), 256, 0, pflag.p, pscan.p, cflag.p, cscan.p, U, (u32)n_path, k,
-               key_cnt.p, key_node.p, node_len.p);
+               prec.p, node_len.p);
         exclusive_scan_u32(ctx, node_len.p, node_off32.p, nn, tot.p);
         u64 total_bases = read_scalar<u64>(ctx, tot.p);
         if (total_bases >= 0xFFFFFFFFull) GG_THROW(GG_ERR_LIMIT, "node sequences exceed 2^32 bases (%llu)", (unsigned long long)total_bases);
@@ -657,8 +657,8 @@ static gg_graph *build_graph(gg_ctx *ctx, const u64 *keys, u64 U, int k) {
         g->d_bases = dalloc<u8>(ctx, total_bases ? total_bases : 1);
         g->d_node_off = dalloc<u64>(ctx, nn + 1);
         LAUNCH(ctx, widen_offsets_kernel, (unsigned)ceil_div(nn + 1, 256), 256, 0, node_off32.p, nn, total_bases, g->d_node_off);
-        LAUNCH(ctx, emit_kernel<W>, (unsigned)ceil_div(nv, 256), 256, 0, keys, rec, cyc_head.p, vhead.p, vrank.p, nv, k, key_head.p,
-               key_ranke.p, key_cnt.p, key_node.p, node_off32.p, g->d_bases, node_first.p, node_last.p);
+        LAUNCH(ctx, emit_kernel<W>, (unsigned)ceil_div(nv, 256), 256, 0, keys, rec, cyc_head.p, vhead.p, vrank.p, nv, k, prec.p,
+               node_off32.p, g->d_bases, node_first.p, node_last.p);
         stage_end(ctx, ST_UNITIG);
         // ---- K8 ----
         stage_begin(ctx, ST_LINKS);
