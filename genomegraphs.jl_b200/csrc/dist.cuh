@@ -71,7 +71,69 @@ struct gg_comm {
     gg_ctx *ctx = nullptr;
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
+    // receive buffer of the fused scatter + exchange, mapped into every peer with CUDA IPC
+    u64 *R = nullptr;
+    u64 cap = 0;                       // keys
+    u64 *peerR[MSD_MAX_PEERS] = {};    // peerR[rank] == R
+    int ipc_state = 0;                 // 0 untried, 1 usable, -1 unavailable (NCCL send/recv is used instead)
 };
+
+static void dist_close_peers(gg_comm *cm) {
+    for (int p = 0; p < cm->world && p < MSD_MAX_PEERS; ++p) {
+        if (p != cm->rank && cm->peerR[p]) cudaIpcCloseMemHandle(cm->peerR[p]);
+        cm->peerR[p] = nullptr;
+    }
+}
+// Collective: every rank calls it with the same `need` (keys).  (Re)allocates the receive buffers and
+// exchanges the IPC handles with an all-gather.  Returns false when peer mapping is not available.
+static bool dist_ensure_recv(gg_comm *cm, u64 need) {
+    NcclApi *nc = nccl_api();
+    gg_ctx *ctx = cm->ctx;
+    if (cm->ipc_state < 0 || cm->world > MSD_MAX_PEERS || getenv("GG_DIST_NO_IPC")) { cm->ipc_state = -1; return false; }
+    if (cm->ipc_state == 1 && need <= cm->cap) return true;
+    // every rank reaches this point with the same arguments, so the collective sequence below is consistent
+    DBuf<u64> tok(ctx, 1);
+    CK(cudaMemsetAsync(tok.p, 0, sizeof(u64), ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    dist_close_peers(cm);
+    NCK(nc->AllReduce(tok.p, tok.p, 1, ncclUint64, ncclSum, cm->comm, ctx->stream));  // barrier: nobody maps the old buffers any more
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (cm->R) { cudaFree(cm->R); cm->R = nullptr; cm->cap = 0; }
+    const u64 cap = need + need / 8 + 1024;
+    u64 ok = 1;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    if (cudaMalloc((void **)&cm->R, cap * sizeof(u64)) != cudaSuccess || cudaIpcGetMemHandle(&mine, cm->R) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DBuf<u8> hd(ctx, 64 * (u64)(cm->world + 1));
+    CK(cudaMemcpyAsync(hd.p + 64 * (u64)cm->world, &mine, 64, cudaMemcpyHostToDevice, ctx->stream));
+    NCK(nc->AllGather(hd.p + 64 * (u64)cm->world, hd.p, 64, ncclUint8, cm->comm, ctx->stream));
+    std::vector<cudaIpcMemHandle_t> all(cm->world);
+    CK(cudaMemcpyAsync(all.data(), hd.p, 64 * (u64)cm->world, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ok) {
+        for (int p = 0; p < cm->world; ++p) {
+            if (p == cm->rank) { cm->peerR[p] = cm->R; continue; }
+            void *q = nullptr;
+            if (cudaIpcOpenMemHandle(&q, all[p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+            cm->peerR[p] = (u64 *)q;
+        }
+    }
+    // all ranks must agree: one failure anywhere switches everybody to NCCL send/recv
+    CK(cudaMemcpyAsync(tok.p, &ok, sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    NCK(nc->AllReduce(tok.p, tok.p, 1, ncclUint64, ncclMin, cm->comm, ctx->stream));
+    const u64 all_ok = read_scalar<u64>(ctx, tok.p);
+    if (!all_ok) {
+        dist_close_peers(cm);
+        if (cm->R) { cudaFree(cm->R); cm->R = nullptr; }
+        cm->cap = 0;
+        cm->ipc_state = -1;
+        return false;
+    }
+    cm->cap = cap;
+    cm->ipc_state = 1;
+    return true;
+}
 
 // Contiguous bucket ranges balanced on the global histogram: rank q owns buckets
 // [first[q], first[q + 1]).  Pure host code (also exported for tests: gg_dist_splitters).
@@ -173,14 +235,18 @@ static u64 dist_msd_count(gg_comm *cm, const PackedReads &pr, const u32 *valid, 
         for (u32 b = 0; b < nb0; ++b) gh[b] += cnt[(size_t)p * nb0 + b];
     std::vector<u32> first(P + 1);
     dist_splitters(gh.data(), nb0, P, first.data());
-    // ---- pass B: local scatter (its output doubles as the send buffer) ----
-    DBuf<u32> hist0, bstart;
-    DBuf<u64> A;
-    msd_pass_b(ctx, pr, valid, k, canonical, pl, hist.p, N_loc, hist0, bstart, A);
-    stage_end(ctx, ST_EXTRACT);
-    mark();  // 3: pass B done
-    // ---- exchange ----
-    stage_begin(ctx, ST_SORT);
+    // ---- who sends what to whom (every rank can compute the whole matrix from the all-gathered histograms) ----
+    const u32 nb_local = first[me + 1] - first[me];
+    std::vector<u64> nrecv(P, 0);
+    for (int q = 0; q < P; ++q)
+        for (int p = 0; p < P; ++p)
+            for (u32 b = first[q]; b < first[q + 1]; ++b) nrecv[q] += cnt[(size_t)p * nb0 + b];
+    u64 need = 1;
+    for (int q = 0; q < P; ++q) need = nrecv[q] > need ? nrecv[q] : need;
+    if (need >= 0xFFFFFFFFull) GG_THROW(GG_ERR_LIMIT, "%llu received k-mer instances exceed the 2^32-1 per-GPU limit", (unsigned long long)need);
+    const u64 N_recv = nrecv[me];
+    // layout of rank q's receive buffer: source-major, buckets of q's range in order inside every source segment
+    auto seg_off = [&](int q, int p) { u64 o = 0; for (int pp = 0; pp < p; ++pp) for (u32 b = first[q]; b < first[q + 1]; ++b) o += cnt[(size_t)pp * nb0 + b]; return o; };
     std::vector<u64> soff(P), scnt(P), roff(P), rcnt(P);
     {
         u64 run = 0;
@@ -189,19 +255,12 @@ static u64 dist_msd_count(gg_comm *cm, const PackedReads &pr, const u32 *valid, 
             soff[p] = run;
             for (; b < first[p + 1]; ++b) run += cnt[(size_t)me * nb0 + b];
             scnt[p] = run - soff[p];
+            roff[p] = seg_off(me, p);
+            rcnt[p] = 0;
+            for (u32 bb = first[me]; bb < first[me + 1]; ++bb) rcnt[p] += cnt[(size_t)p * nb0 + bb];
         }
     }
-    const u32 nb_local = first[me + 1] - first[me];
-    u64 N_recv = 0;
-    for (int p = 0; p < P; ++p) {
-        roff[p] = N_recv;
-        u64 c = 0;
-        for (u32 b = first[me]; b < first[me + 1]; ++b) c += cnt[(size_t)p * nb0 + b];
-        rcnt[p] = c;
-        N_recv += c;
-    }
-    if (N_recv >= 0xFFFFFFFFull) GG_THROW(GG_ERR_LIMIT, "%llu received k-mer instances exceed the 2^32-1 per-GPU limit", (unsigned long long)N_recv);
-    // virtual buckets of the receive buffer: vb = (b - first[me]) * P + p
+    // virtual buckets of MY receive buffer: vb = (b - first[me]) * P + p
     std::vector<u32> h_vbeg((size_t)nb_local * P + 1, 0), h_vcnt((size_t)nb_local * P + 1, 0);
     for (int p = 0; p < P; ++p) {
         u64 run = roff[p];
@@ -215,10 +274,45 @@ static u64 dist_msd_count(gg_comm *cm, const PackedReads &pr, const u32 *valid, 
     DBuf<u32> vbeg(ctx, h_vbeg.size()), vcnt(ctx, h_vcnt.size());
     CK(cudaMemcpyAsync(vbeg.p, h_vbeg.data(), h_vbeg.size() * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(vcnt.p, h_vcnt.data(), h_vcnt.size() * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
-    DBuf<u64> R(ctx, N_recv ? N_recv : 1);
-    dist_alltoallv(cm, A.p, soff.data(), scnt.data(), R.p, roff.data(), rcnt.data(), sizeof(u64));
-    CK(cudaStreamSynchronize(ctx->stream));  // h_vbeg / h_vcnt are read by the copies above; A is released next
-    A.release();
+    DBuf<u32> hist0, bstart;
+    DBuf<u64> A, Rtmp;
+    u64 *R = nullptr;
+    if (dist_ensure_recv(cm, need)) {
+        // ---- pass B fused with the exchange: tiles are written into the owners' buffers over NVLink ----
+        MsdPeers pt;
+        memset(&pt, 0, sizeof(pt));
+        pt.n = P;
+        for (int q = 0; q < P; ++q) { pt.ptr[q] = cm->peerR[q]; pt.first[q] = first[q]; }
+        pt.first[P] = first[P];
+        std::vector<u32> h_cur(nb0);  // where my keys of bucket b start inside the owner's buffer
+        for (int q = 0; q < P; ++q) {
+            u64 run = seg_off(q, me);
+            for (u32 b = first[q]; b < first[q + 1]; ++b) { h_cur[b] = (u32)run; run += cnt[(size_t)me * nb0 + b]; }
+        }
+        DBuf<u32> pcur(ctx, nb0);
+        DBuf<u64> tok(ctx, 1);
+        CK(cudaMemcpyAsync(pcur.p, h_cur.data(), nb0 * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+        // the collectives of pass A ran after every rank's previous call on its stream: nobody still reads its buffer
+        msd_pass_b(ctx, pr, valid, k, canonical, pl, hist.p, N_loc, hist0, bstart, A, &pt, pcur.p);
+        stage_end(ctx, ST_EXTRACT);
+        mark();  // 3: pass B (scatter into the peers) done locally
+        stage_begin(ctx, ST_SORT);
+        CK(cudaMemsetAsync(tok.p, 0, sizeof(u64), ctx->stream));
+        NCK(nc->AllReduce(tok.p, tok.p, 1, ncclUint64, ncclSum, cm->comm, ctx->stream));  // barrier: every rank's stores have landed
+        CK(cudaStreamSynchronize(ctx->stream));  // h_vbeg / h_vcnt / h_cur are read by the copies above
+        R = cm->R;
+    } else {
+        // ---- pass B locally (its output doubles as the send buffer), then one grouped ncclSend / ncclRecv exchange ----
+        msd_pass_b(ctx, pr, valid, k, canonical, pl, hist.p, N_loc, hist0, bstart, A);
+        stage_end(ctx, ST_EXTRACT);
+        mark();  // 3: pass B done
+        stage_begin(ctx, ST_SORT);
+        Rtmp.alloc(ctx, N_recv ? N_recv : 1);
+        dist_alltoallv(cm, A.p, soff.data(), scnt.data(), Rtmp.p, roff.data(), rcnt.data(), sizeof(u64));
+        CK(cudaStreamSynchronize(ctx->stream));  // h_vbeg / h_vcnt are read by the copies above; A is released next
+        A.release();
+        R = Rtmp.p;
+    }
     stage_end(ctx, ST_SORT);
     mark();  // 4: exchange done
     DBuf<u32> child_hist;

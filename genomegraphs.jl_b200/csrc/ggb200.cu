@@ -653,6 +653,8 @@ void gg_comm_destroy(gg_comm *cm) {
     if (!cm) return;
     cudaSetDevice(cm->ctx->device);
     cudaStreamSynchronize(cm->ctx->stream);
+    dist_close_peers(cm);
+    if (cm->R) cudaFree(cm->R);
     if (cm->comm) nccl_api()->CommDestroy(cm->comm);
     delete cm;
 }

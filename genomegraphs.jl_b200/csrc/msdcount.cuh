@@ -139,8 +139,25 @@ __device__ __forceinline__ u32 msd_reserve(u32 *hist, u32 *delta, int nb, u32 *_
 
 // ---- pass B: tile = 256 words = 8192 window positions ------------------------------------------
 #define MSD_TILE_KEYS 8192
+// Multi-GPU: the buckets are owned by ranks (contiguous ranges first[q] .. first[q + 1]); with PEER the
+// tile is written straight into the owner's receive buffer over NVLink (peer pointers from CUDA IPC),
+// so the level-0 scatter IS the exchange.  The cursors then hold offsets inside the owners' buffers.
+#define MSD_MAX_PEERS 8
+struct MsdPeers {
+    u64 *ptr[MSD_MAX_PEERS];
+    u32 first[MSD_MAX_PEERS + 1];
+    int n;
+};
+__device__ __forceinline__ int msd_owner(const MsdPeers &pt, u32 d) {
+    int o = 0;
+#pragma unroll
+    for (int q = 1; q < MSD_MAX_PEERS; ++q) o += (q < pt.n && d >= pt.first[q]) ? 1 : 0;
+    return o;
+}
+template <bool PEER>
 __global__ void __launch_bounds__(256, 2) msd_scatter_kernel(const u64 *__restrict__ packed, const u32 *__restrict__ valid, u64 nwords,
-                                                             int k, int canonical, int b0, u32 *__restrict__ cursor, u64 *__restrict__ out) {
+                                                             int k, int canonical, int b0, u32 *__restrict__ cursor, u64 *__restrict__ out,
+                                                             MsdPeers pt) {
     extern __shared__ __align__(16) u8 smem_raw[];
     u64 *skeys = reinterpret_cast<u64 *>(smem_raw);                      // MSD_TILE_KEYS
     u32 *hist = reinterpret_cast<u32 *>(skeys + MSD_TILE_KEYS);          // 2^MSD_B0_MAX
@@ -164,8 +181,10 @@ __global__ void __launch_bounds__(256, 2) msd_scatter_kernel(const u64 *__restri
         if ((vm >> (31 - j)) & 1u) skeys[atomicAdd(&hist[msd_digit0(keys[j], sh, b0)], 1u)] = keys[j];
     __syncthreads();
     for (u32 i = threadIdx.x; i < total; i += 256) {
-        u64 key = skeys[i];
-        out[delta[msd_digit0(key, sh, b0)] + i] = key;
+        const u64 key = skeys[i];
+        const u32 d = msd_digit0(key, sh, b0);
+        if (PEER) pt.ptr[msd_owner(pt, d)][(u32)(delta[d] + i)] = key;
+        else out[delta[d] + i] = key;
     }
 }
 
@@ -614,8 +633,10 @@ static void msd_pass_a_read(gg_ctx *ctx, const u32 *hist, u32 nb, const u8 *est,
 }
 
 // pass B: keys scattered into 2^b0 buckets; hist0 (nb0 + 1, last 0) and bstart (nb0 + 1) describe them
+// With `peers` (multi-GPU, dist.cuh) the keys go to the owners' receive buffers at the offsets in
+// peer_cursor (one per bucket, device) and A stays empty.
 static void msd_pass_b(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int k, int canonical, const MsdPlan &pl, const u32 *hist,
-                       u64 N, DBuf<u32> &hist0, DBuf<u32> &bstart, DBuf<u64> &A) {
+                       u64 N, DBuf<u32> &hist0, DBuf<u32> &bstart, DBuf<u64> &A, const MsdPeers *peers = nullptr, u32 *peer_cursor = nullptr) {
     const u32 nb0 = 1u << pl.b0;
     hist0.alloc(ctx, nb0 + 1);
     bstart.alloc(ctx, nb0 + 1);
@@ -623,12 +644,23 @@ static void msd_pass_b(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int
     LAUNCH(ctx, msd_collapse_kernel, (unsigned)ceil_div(nb0 + 1, 256), 256, 0, hist, pl.hb, pl.b0, hist0.p);
     exclusive_scan_u32(ctx, hist0.p, bstart.p, nb0 + 1, nullptr);
     LAUNCH(ctx, msd_copy_u32_kernel, (unsigned)ceil_div(nb0, 256), 256, 0, bstart.p, (u64)nb0, cursor.p);
-    A.alloc(ctx, N ? N : 1);
+    A.alloc(ctx, (N && !peers) ? N : 1);
     if (N == 0) return;
     size_t smemB = (size_t)MSD_TILE_KEYS * 8 + 2 * (size_t)(1 << MSD_B0_MAX) * 4;
     static bool setB = false;
-    if (!setB) { CK(cudaFuncSetAttribute(msd_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB)); setB = true; }
-    LAUNCH(ctx, msd_scatter_kernel, (unsigned)ceil_div(pr.nwords, 256), 256, smemB, pr.packed.p, valid, pr.nwords, k, canonical, pl.b0, cursor.p, A.p);
+    if (!setB) {
+        CK(cudaFuncSetAttribute(msd_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
+        CK(cudaFuncSetAttribute(msd_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
+        setB = true;
+    }
+    MsdPeers none;
+    memset(&none, 0, sizeof(none));
+    if (peers)
+        LAUNCH(ctx, msd_scatter_kernel<true>, (unsigned)ceil_div(pr.nwords, 256), 256, smemB, pr.packed.p, valid, pr.nwords, k, canonical, pl.b0,
+               peer_cursor, (u64 *)nullptr, *peers);
+    else
+        LAUNCH(ctx, msd_scatter_kernel<false>, (unsigned)ceil_div(pr.nwords, 256), 256, smemB, pr.packed.p, valid, pr.nwords, k, canonical, pl.b0,
+               cursor.p, A.p, none);
 }
 
 __global__ void msd_child_total_kernel(const u32 *__restrict__ vcnt, u32 nsrc, u32 nchild, u32 *__restrict__ ctot) {
@@ -659,7 +691,7 @@ static void msd_launch_leaf(gg_ctx *ctx, int ctas_per_sm, const u64 *IN, u64 *SB
 // IN holds n_in keys; local bucket bl (0 .. nb_local) consists of the nsrc virtual buckets
 // vb = bl * nsrc + s: IN[vbeg[vb] .. + vcnt[vb]).  IN is consumed (used as scratch).
 // child_hist (optional, nchild + 1 entries, last 0): instances per child when pass A already knows them.
-static u64 msd_finish(gg_ctx *ctx, DBuf<u64> &IN, u64 n_in, const u32 *vbeg, const u32 *vcnt, u32 nb_local, u32 nsrc, const MsdPlan &pl,
+static u64 msd_finish(gg_ctx *ctx, u64 *IN, u64 n_in, const u32 *vbeg, const u32 *vcnt, u32 nb_local, u32 nsrc, const MsdPlan &pl,
                       const MsdTune &tune, u32 min_freq, DBuf<u64> &ukeys, DBuf<u32> &ucounts, const u32 *child_hist = nullptr) {
     if (n_in == 0) { ukeys.alloc(ctx, 1); ucounts.alloc(ctx, 1); return 0; }
     const u32 nvb = nb_local * nsrc;
@@ -683,21 +715,21 @@ static u64 msd_finish(gg_ctx *ctx, DBuf<u64> &IN, u64 n_in, const u32 *vbeg, con
         if (!h1) {  // pass C: the pass-A histogram is too coarse for b0 + b1 bits
             hist1.alloc(ctx, nchild + 1);
             CK(cudaMemsetAsync(hist1.p, 0, (nchild + 1) * sizeof(u32), ctx->stream));
-            LAUNCH(ctx, msd_hist1_kernel, tgrid, 256, 0, IN.p, tstart.p, vbeg, vcnt, nvb, nsrc, pl.shiftc, pl.b1, hist1.p);
+            LAUNCH(ctx, msd_hist1_kernel, tgrid, 256, 0, IN, tstart.p, vbeg, vcnt, nvb, nsrc, pl.shiftc, pl.b1, hist1.p);
             h1 = hist1.p;
         }
         exclusive_scan_u32(ctx, h1, off.p, nchild + 1, nullptr);
         LAUNCH(ctx, msd_copy_u32_kernel, (unsigned)ceil_div(nchild, 256), 256, 0, off.p, nchild, cursor1.p);
-        LAUNCH(ctx, msd_scatter1_kernel, tgrid, 256, 0, IN.p, tstart.p, vbeg, vcnt, nvb, nsrc, pl.shiftc, pl.b1, cursor1.p, S1.p);
-        leaf_in = S1.p; leaf_o = S1.p; leaf_sb = IN.p;
+        LAUNCH(ctx, msd_scatter1_kernel, tgrid, 256, 0, IN, tstart.p, vbeg, vcnt, nvb, nsrc, pl.shiftc, pl.b1, cursor1.p, S1.p);
+        leaf_in = S1.p; leaf_o = S1.p; leaf_sb = IN;
         segbeg = off.p; segcnt = h1; nseg = 1;
     } else {
         ctot.alloc(ctx, nchild + 1);
         LAUNCH(ctx, msd_child_total_kernel, (unsigned)ceil_div(nchild + 1, 256), 256, 0, vcnt, nsrc, (u32)nchild, ctot.p);
         exclusive_scan_u32(ctx, ctot.p, off.p, nchild + 1, nullptr);
-        leaf_in = IN.p; leaf_sb = S1.p;
+        leaf_in = IN; leaf_sb = S1.p;
         segbeg = vbeg; segcnt = vcnt; nseg = nsrc;
-        if (nsrc == 1) leaf_o = IN.p;  // contiguous buckets: off == vbeg, counted in place
+        if (nsrc == 1) leaf_o = IN;  // contiguous buckets: off == vbeg, counted in place
         else { S2.alloc(ctx, n_in); leaf_o = S2.p; }
     }
     // ---- E: leaves ----
@@ -751,5 +783,5 @@ static u64 msd_count(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int k
         LAUNCH(ctx, msd_collapse_kernel, (unsigned)ceil_div(nchild + 1, 256), 256, 0, hist.p, pl.hb, pl.b0 + pl.b1, child_hist.p);
     }
     stage_end(ctx, ST_EXTRACT);
-    return msd_finish(ctx, A, N, bstart.p, hist0.p, 1u << pl.b0, 1, pl, tune, min_freq, ukeys, ucounts, child_hist.p);
+    return msd_finish(ctx, A.p, N, bstart.p, hist0.p, 1u << pl.b0, 1, pl, tune, min_freq, ukeys, ucounts, child_hist.p);
 }
