@@ -62,7 +62,11 @@ ALG_BYTES = {
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
 # captures of the default workload (profiles/README.md); null where no capture exists
-NCU_TRAFFIC = {}
+NCU_TRAFFIC = {  # profiles/r1_e_ncu_full_<kernel>.txt, workload c2_ecoli50x_k31 on one GPU
+    "msd_leaf_kernel": 1.486635e9 + 91.601664e6,
+    "msd_scatter_kernel": 87.484672e6 + 1.428851e9,
+    "msd_scatter1_kernel": 1.485387e9 + 1.438692e9,
+}
 
 
 def nreads_for(w):
@@ -360,7 +364,7 @@ def main():
         m = model(name, cnt, ms)
         if m is not None:
             roofline = {"bound": "hbm", "kernel": name, "achieved": m[1], "peak": peak, "unit": "GB/s", "frac": m[1] / peak,
-                        "traffic": NCU_TRAFFIC.get(name), "launches_per_step": cnt, "avg_launch_ms": ms / cnt, "share_of_kernel_time": ms / tot_ms,
+                        "traffic": NCU_TRAFFIC.get(name) if (args.workload == "c2_ecoli50x_k31" and world == 1) else None, "launches_per_step": cnt, "avg_launch_ms": ms / cnt, "share_of_kernel_time": ms / tot_ms,
                         "alg_bytes_per_launch": m[0], "peak_source": peak_src}
         else:
             roofline = {"bound": "hbm", "kernel": name, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
