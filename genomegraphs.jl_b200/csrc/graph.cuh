@@ -12,6 +12,7 @@
 //   started at the smallest stored k-mer.  Node creation order = ascending smallest stored
 //   index of the two path ends (paths first, then cycles by smallest stored index).
 #pragma once
+#include <cooperative_groups.h>
 #include "sort.cuh"
 
 #define V_NONE 0xFFFFFFFFu  // no vertex / dead vertex
@@ -135,6 +136,25 @@ __global__ void wyllie_kernel(const u64 *__restrict__ in, u64 *__restrict__ out,
     u32 np = (u32)q;
     out[v] = ((u64)d << 32) | np;
     if (!(np & V_TERM)) *active = 1;
+}
+// all pointer-jumping rounds of a list in ONE cooperative launch (grid-wide barrier between rounds): the
+// reduced splitter list is small, so separate launches would cost more than the rounds themselves
+__global__ void __launch_bounds__(256) wyllie_fused_kernel(u64 *a, u64 *b, u64 nv, int rounds) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    u64 *in = a, *out = b;
+    for (int r = 0; r < rounds; ++r) {
+        for (u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += (u64)gridDim.x * blockDim.x) {
+            u64 rec = in[v];
+            const u32 ptr = (u32)rec;
+            if (ptr != V_NONE && !(ptr & V_TERM)) {
+                const u64 q = in[ptr];
+                rec = ((u64)((u32)(rec >> 32) + (u32)(q >> 32)) << 32) | (u32)q;
+            }
+            out[v] = rec;
+        }
+        grid.sync();
+        u64 *t = in; in = out; out = t;
+    }
 }
 // ---- splitter-based list ranking (work-efficient front end of the Wyllie rounds) -----------
 // Splitters = path heads + a 2^-sl hash sample.  Every splitter walks to the next splitter (or
@@ -593,10 +613,30 @@ static gg_graph *build_graph(gg_ctx *ctx, const u64 *keys, u64 U, int k) {
             if (ns) LAUNCH(ctx, split_walk_kernel, (unsigned)ceil_div(ns, 128), 128, 0, succ.p, red_vertex.p, sidx.p, ns, sl, ownloc.p, redA.p, red_tail.p);
             u64 *ra = redA.p, *rb = redB.p;
             if (ns) {
-                const int rounds = ilog2_ceil(ns) + 2;  // fixed count: no host round trips
-                for (int r = 0; r < rounds; ++r) {
-                    LAUNCH(ctx, wyllie_kernel, (unsigned)ceil_div(ns, 256), 256, 0, ra, rb, ns, d_flag.p);
-                    std::swap(ra, rb);
+                int rounds = ilog2_ceil(ns) + 2;  // fixed count: no host round trips
+                static int coop_blocks = -1;      // co-resident CTAs per SM of the fused kernel (0: not supported)
+                if (coop_blocks < 0) {
+                    int supported = 0, nb = 0;
+                    cudaDeviceGetAttribute(&supported, cudaDevAttrCooperativeLaunch, ctx->device);
+                    if (supported) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wyllie_fused_kernel, 256, 0);
+                    coop_blocks = supported ? nb : 0;
+                }
+                if (coop_blocks > 0 && !getenv("GG_NO_COOP")) {
+                    u64 grid = ceil_div(ns, 256);
+                    if (grid > (u64)coop_blocks * ctx->num_sms) grid = (u64)coop_blocks * ctx->num_sms;
+                    u64 nsv = ns;
+                    void *args[] = {&ra, &rb, &nsv, &rounds};
+                    cudaEvent_t pa = nullptr, pb = nullptr;
+                    if (ctx->profile) { pa = prof_event(ctx); pb = prof_event(ctx); cudaEventRecord(pa, ctx->stream); }
+                    CK(cudaLaunchCooperativeKernel((void *)wyllie_fused_kernel, dim3((unsigned)grid), dim3(256), args, 0, ctx->stream));
+                    ctx->launches++;
+                    if (ctx->profile) { cudaEventRecord(pb, ctx->stream); ctx->prof.push_back({std::string("wyllie_fused_kernel"), pa, pb}); }
+                    if (rounds & 1) std::swap(ra, rb);
+                } else {
+                    for (int r = 0; r < rounds; ++r) {
+                        LAUNCH(ctx, wyllie_kernel, (unsigned)ceil_div(ns, 256), 256, 0, ra, rb, ns, d_flag.p);
+                        std::swap(ra, rb);
+                    }
                 }
             }
             LAUNCH(ctx, split_expand_kernel, (unsigned)ceil_div(nv, 256), 256, 0, ra, red_tail.p, sflag.p, sidx.p, ownloc.p, nv, rin);

@@ -26,7 +26,6 @@ struct MsdW {
 #define MSDW_OVERFLOW 0xFFFFFFFFu
 #define MSDW_HB 12  // pass-A histogram bits of the multi-word path = largest level-0 digit
 static inline int msdw_hist_bits(int k) { return 2 * k < MSDW_HB ? 2 * k : MSDW_HB; }
-__device__ unsigned long long g_msdw_dbg[4];
 
 // key bits [lowbit, lowbit + nbits), nbits <= 24
 template <int W>
@@ -259,7 +258,7 @@ __device__ u32 msdw_leaf(LeafSmemW<W> &S, u64 *X, u64 *SB, u32 *OC, u32 start, u
             }
             if (t == tag) break;
             slot = (slot + step) & HM;
-            if (probes > LEAF_MAX_PROBE) { *ovf = 1; atomicAdd(&g_msdw_dbg[0], 1ULL); break; }
+            if (probes > LEAF_MAX_PROBE) { *ovf = 1; break; }
         }
         if (*ovf) break;
     }
@@ -275,7 +274,7 @@ __device__ u32 msdw_leaf(LeafSmemW<W> &S, u64 *X, u64 *SB, u32 *OC, u32 start, u
         for (int probes = 0;; ++probes) {
             const u32 t = S.ttag[slot];
             if (t == tag && km_eq<W>(km_load<W>(S.tab, slot), key)) { atomicAdd(&S.tcnt[slot], 1u); break; }
-            if (t == 0 || probes > LEAF_MAX_PROBE + 1) { *ovf = 1; atomicAdd(&g_msdw_dbg[t == 0 ? 1 : 2], 1ULL); break; }  // tag clash: this key never got a slot
+            if (t == 0 || probes > LEAF_MAX_PROBE + 1) { *ovf = 1; break; }  // empty slot: this key never got one (tag clash)  // tag clash: this key never got a slot
             slot = (slot + step) & HM;
         }
         if (*ovf) break;
@@ -444,11 +443,6 @@ static u64 msdw_count(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int 
         MsdwOverflowF of{nu.p, olist.p};
         Compactor<MsdwOverflowF> oc(ctx, nchild, "msdw_overflow");
         const u64 novf = oc.count(of);
-        if (getenv("GG_MSD_DEBUG")) {
-            unsigned long long hd[4];
-            cudaMemcpyFromSymbol(hd, g_msdw_dbg, sizeof(hd));
-            fprintf(stderr, "[msdw dbg] pass1 probe-limit %llu, pass2 empty-slot %llu, pass2 probe-limit %llu\n", hd[0], hd[1], hd[2]);
-        }
         if (getenv("GG_MSD_DEBUG"))
             fprintf(stderr, "[msdw W=%d] N=%llu distinct_est=%llu b0=%d b1=%d shiftc=%d children=%llu overflowed=%llu\n", W, (unsigned long long)N,
                     (unsigned long long)dest, pl.b0, pl.b1, pl.shiftc, (unsigned long long)nchild, (unsigned long long)novf);
