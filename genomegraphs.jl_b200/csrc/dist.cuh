@@ -17,6 +17,7 @@
 #include <nccl.h>
 #include <chrono>
 #include "msdcount.cuh"
+#include "msdcountw.cuh"
 
 struct NcclApi {
     void *h = nullptr;
@@ -184,13 +185,14 @@ __global__ void dist_child_hist_kernel(const u32 *__restrict__ all_hist, int P, 
 }
 
 // reads of this rank -> this rank's key-range slice of the global sorted (k-mer, count) table
+template <int W>
 static u64 dist_msd_count(gg_comm *cm, const PackedReads &pr, const u32 *valid, int k, int canonical, u32 min_freq, DBuf<u64> &ukeys,
                           DBuf<u32> &ucounts, u64 *n_instances_local, u64 *n_instances_global) {
     NcclApi *nc = nccl_api();
     gg_ctx *ctx = cm->ctx;
     const int P = cm->world, me = cm->rank;
-    const MsdTune tune = msd_tune();
-    const int hb = msd_hist_bits(k);
+    const MsdTune tune = W == 1 ? msd_tune() : msdw_tune<W>();
+    const int hb = W == 1 ? msd_hist_bits(k) : msdw_hist_bits(k);
     const u32 nbh = 1u << hb;
     // GG_DIST_DEBUG: host wall-clock of every phase on every rank (adds stream syncs; never set while timing)
     const bool dbg = getenv("GG_DIST_DEBUG") != nullptr;
@@ -210,7 +212,8 @@ static u64 dist_msd_count(gg_comm *cm, const PackedReads &pr, const u32 *valid, 
     // ---- pass A on the local reads; histograms all-gathered, estimate maps merged ----
     DBuf<u32> hist, all_hist(ctx, (u64)P * nbh);
     DBuf<u8> est;
-    msd_pass_a_launch(ctx, pr, valid, k, canonical, est_shift, hist, est);
+    if constexpr (W == 1) msd_pass_a_launch(ctx, pr, valid, k, canonical, est_shift, hist, est);
+    else msdw_pass_a_launch<W>(ctx, pr, valid, k, canonical, est_shift, hist, est);
     NCK(nc->AllGather(hist.p, all_hist.p, nbh, ncclUint32, cm->comm, ctx->stream));
     NCK(nc->AllReduce(est.p, est.p, 1ULL << EST_LOG, ncclUint8, ncclMax, cm->comm, ctx->stream));
     u64 N_loc = 0, dest = 0;
@@ -271,13 +274,14 @@ static u64 dist_msd_count(gg_comm *cm, const PackedReads &pr, const u32 *valid, 
             run += c;
         }
     }
+    h_vbeg.back() = (u32)N_recv;  // with a single source the virtual buckets are contiguous and vbeg doubles as an offset array
     DBuf<u32> vbeg(ctx, h_vbeg.size()), vcnt(ctx, h_vcnt.size());
     CK(cudaMemcpyAsync(vbeg.p, h_vbeg.data(), h_vbeg.size() * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(vcnt.p, h_vcnt.data(), h_vcnt.size() * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
     DBuf<u32> hist0, bstart;
     DBuf<u64> A, Rtmp;
     u64 *R = nullptr;
-    if (dist_ensure_recv(cm, need)) {
+    if (W == 1 && dist_ensure_recv(cm, need)) {
         // ---- pass B fused with the exchange: tiles are written into the owners' buffers over NVLink ----
         MsdPeers pt;
         memset(&pt, 0, sizeof(pt));
@@ -303,12 +307,13 @@ static u64 dist_msd_count(gg_comm *cm, const PackedReads &pr, const u32 *valid, 
         R = cm->R;
     } else {
         // ---- pass B locally (its output doubles as the send buffer), then one grouped ncclSend / ncclRecv exchange ----
-        msd_pass_b(ctx, pr, valid, k, canonical, pl, hist.p, N_loc, hist0, bstart, A);
+        if constexpr (W == 1) msd_pass_b(ctx, pr, valid, k, canonical, pl, hist.p, N_loc, hist0, bstart, A);
+        else msdw_pass_b<W>(ctx, pr, valid, k, canonical, pl, hist.p, N_loc, hist0, bstart, A);
         stage_end(ctx, ST_EXTRACT);
         mark();  // 3: pass B done
         stage_begin(ctx, ST_SORT);
-        Rtmp.alloc(ctx, N_recv ? N_recv : 1);
-        dist_alltoallv(cm, A.p, soff.data(), scnt.data(), Rtmp.p, roff.data(), rcnt.data(), sizeof(u64));
+        Rtmp.alloc(ctx, (N_recv ? N_recv : 1) * W);
+        dist_alltoallv(cm, A.p, soff.data(), scnt.data(), Rtmp.p, roff.data(), rcnt.data(), sizeof(u64) * W);
         CK(cudaStreamSynchronize(ctx->stream));  // h_vbeg / h_vcnt are read by the copies above; A is released next
         A.release();
         R = Rtmp.p;
@@ -316,17 +321,19 @@ static u64 dist_msd_count(gg_comm *cm, const PackedReads &pr, const u32 *valid, 
     stage_end(ctx, ST_SORT);
     mark();  // 4: exchange done
     DBuf<u32> child_hist;
-    if (pl.b1 > 0 && pl.b0 + pl.b1 <= hb && nb_local) {  // pass C for free (see msd_count)
+    if (W == 1 && pl.b1 > 0 && pl.b0 + pl.b1 <= hb && nb_local) {  // pass C for free (see msd_count)
         const u32 nchild = nb_local << pl.b1;
         child_hist.alloc(ctx, nchild + 1);
         LAUNCH(ctx, dist_child_hist_kernel, (unsigned)ceil_div(nchild + 1, 256), 256, 0, all_hist.p, P, nbh, hb, pl.b0 + pl.b1,
                first[me] << pl.b1, nchild, child_hist.p);
     }
-    const u64 U = msd_finish(ctx, R, N_recv, vbeg.p, vcnt.p, nb_local, (u32)P, pl, tune, min_freq, ukeys, ucounts, child_hist.p);
+    u64 U = 0;
+    if constexpr (W == 1) U = msd_finish(ctx, R, N_recv, vbeg.p, vcnt.p, nb_local, (u32)P, pl, tune, min_freq, ukeys, ucounts, child_hist.p);
+    else U = msdw_finish<W>(ctx, R, N_recv, vbeg.p, vcnt.p, nb_local, (u32)P, pl, tune, min_freq, ukeys, ucounts);
     mark();  // 5: level 1 + leaves + gather done
     if (dbg)
         fprintf(stderr, "[dist rank %d] t0=%.3f size-allreduce %.2f | passA+allgather %.2f | passB %.2f | exchange %.2f (send %.1f MB, recv %.1f MB) | finish %.2f ms\n",
                 me, tmark[0], tmark[1] - tmark[0], tmark[2] - tmark[1], tmark[3] - tmark[2], tmark[4] - tmark[3],
-                (double)(N_loc - scnt[me]) * 8e-6, (double)(N_recv - rcnt[me]) * 8e-6, tmark[5] - tmark[4]);
+                (double)(N_loc - scnt[me]) * 8e-6 * W, (double)(N_recv - rcnt[me]) * 8e-6 * W, tmark[5] - tmark[4]);
     return U;
 }

@@ -665,12 +665,13 @@ int gg_dist_splitters(const uint64_t *hist, uint32_t nb, int world, uint32_t *fi
 }
 }  // extern "C"
 
+template <int W>
 static gg_counts *dist_count_impl(gg_comm *cm, const u8 *d_seq, const u64 *d_offs, u64 nreads, u64 nbytes, int k, int canonical, u64 min_freq,
                                   u64 *n_glob) {
     gg_ctx *ctx = cm->ctx;
-    if (!msd_supported(k, canonical)) GG_THROW(GG_ERR_LIMIT, "the multi-GPU path covers k <= 32 (k = 32 canonical only) in this version");
+    if (W == 1 && !msd_supported(k, canonical)) GG_THROW(GG_ERR_LIMIT, "non-canonical counting at k = 32 is not covered by the multi-GPU path");
     gg_counts *c = new gg_counts();
-    c->ctx = ctx; c->k = k; c->W = 1;
+    c->ctx = ctx; c->k = k; c->W = W;
     try {
         stage_begin(ctx, ST_PACK);
         PackedReads pr;
@@ -682,7 +683,7 @@ static gg_counts *dist_count_impl(gg_comm *cm, const u8 *d_seq, const u64 *d_off
         DBuf<u32> counts;
         u32 mf = min_freq > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)min_freq;
         u64 ng = 0;
-        c->n_unique = dist_msd_count(cm, pr, valid.p, k, canonical, mf < 1 ? 1 : mf, ukeys, counts, &c->n_instances, &ng);
+        c->n_unique = dist_msd_count<W>(cm, pr, valid.p, k, canonical, mf < 1 ? 1 : mf, ukeys, counts, &c->n_instances, &ng);
         if (n_glob) *n_glob = ng;
         c->d_keys = ukeys.take();
         c->d_counts = counts.take();
@@ -753,7 +754,7 @@ int gg_dist_count_kmers_dev(gg_comm *cm, const uint8_t *d_seq, const uint64_t *d
     CK(cudaSetDevice(_c->device));
     timing_reset(_c);
     stage_begin(_c, ST_TOTAL);
-    *out = dist_count_impl(cm, d_seq, d_offs, nreads, nbytes, k, canonical, min_freq, n_instances_global);
+    DISPATCH_W(kmer_words(k), *out = dist_count_impl<W>(cm, d_seq, d_offs, nreads, nbytes, k, canonical, min_freq, n_instances_global));
     stage_end(_c, ST_TOTAL);
     timing_collect(_c);
     API_END
@@ -777,7 +778,8 @@ int gg_dist_dbg_from_reads_dev(gg_comm *cm, const uint8_t *d_seq, const uint64_t
     CK(cudaSetDevice(_c->device));
     timing_reset(_c);
     stage_begin(_c, ST_TOTAL);
-    gg_counts *c = dist_count_impl(cm, d_seq, d_offs, nreads, nbytes, k, 1, min_freq, n_instances_global), *f = nullptr;
+    gg_counts *c = nullptr, *f = nullptr;
+    DISPATCH_W(kmer_words(k), c = dist_count_impl<W>(cm, d_seq, d_offs, nreads, nbytes, k, 1, min_freq, n_instances_global));
     try {
         stage_begin(_c, ST_FILTER);  // the all-gather of the kept k-mers is booked under "filter"
         f = counts_allgather_impl(cm, c);

@@ -166,7 +166,8 @@ __device__ __forceinline__ bool msdw_tile_range(const u32 *__restrict__ tstart, 
 }
 template <int W>
 __global__ void __launch_bounds__(256) msdw_hist1_kernel(const u64 *__restrict__ A, const u32 *__restrict__ tstart, const u32 *__restrict__ vbeg,
-                                                         const u32 *__restrict__ vcnt, u32 nvb, int sh1, int b1, u32 *__restrict__ hist1) {
+                                                         const u32 *__restrict__ vcnt, u32 nvb, u32 nsrc, int sh1, int b1,
+                                                         u32 *__restrict__ hist1) {
     constexpr int KPT = MsdW<W>::KPT;
     __shared__ u32 h[1 << MSD_MAX_B1];
     u32 vb, s, e;
@@ -180,14 +181,14 @@ __global__ void __launch_bounds__(256) msdw_hist1_kernel(const u64 *__restrict__
         if (i < e) atomicAdd(&h[kw_bits<W>(km_load<W>(A, i), sh1, b1)], 1u);
     }
     __syncthreads();
-    const u64 cb = (u64)vb << b1;
+    const u64 cb = (u64)(vb / nsrc) << b1;
     for (int i = threadIdx.x; i < nb; i += 256)
         if (h[i]) atomicAdd(&hist1[cb + i], h[i]);
 }
 template <int W>
 __global__ void __launch_bounds__(256) msdw_scatter1_kernel(const u64 *__restrict__ A, const u32 *__restrict__ tstart,
-                                                            const u32 *__restrict__ vbeg, const u32 *__restrict__ vcnt, u32 nvb, int sh1,
-                                                            int b1, u32 *__restrict__ cursor1, u64 *__restrict__ B) {
+                                                            const u32 *__restrict__ vbeg, const u32 *__restrict__ vcnt, u32 nvb, u32 nsrc,
+                                                            int sh1, int b1, u32 *__restrict__ cursor1, u64 *__restrict__ B) {
     constexpr int KPT = MsdW<W>::KPT;
     __shared__ __align__(16) u64 skeys[MsdW<W>::T1 * W];
     __shared__ u32 hist[1 << MSD_MAX_B1];
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(256) msdw_scatter1_kernel(const u64 *__restric
     for (int u = 0; u < KPT; ++u)
         if (s + u * 256 + threadIdx.x < e) atomicAdd(&hist[kw_bits<W>(kk[u], sh1, b1)], 1u);
     __syncthreads();
-    const u32 total = msd_reserve<(1 << MSD_MAX_B1) / 256>(hist, delta, nb, cursor1 + ((u64)vb << b1), ws);
+    const u32 total = msd_reserve<(1 << MSD_MAX_B1) / 256>(hist, delta, nb, cursor1 + ((u64)(vb / nsrc) << b1), ws);
 #pragma unroll
     for (int u = 0; u < KPT; ++u)
         if (s + u * 256 + threadIdx.x < e) km_store<W>(skeys, atomicAdd(&hist[kw_bits<W>(kk[u], sh1, b1)], 1u), kk[u]);
@@ -362,70 +363,73 @@ struct MsdwOverflowF {
 };
 
 // ------------------------------------- host side -------------------------------------------------
-// packed reads -> sorted unique k-mers + counts (count >= min_freq only), 32 < k <= 128.
 template <int W>
-static u64 msdw_count(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int k, int canonical, u32 min_freq, DBuf<u64> &ukeys,
-                      DBuf<u32> &ucounts, u64 *n_instances) {
+static MsdTune msdw_tune() {
     MsdTune tune = msd_tune();
     tune.dt = tune.dt / W < 16 ? 16 : tune.dt / W;  // the leaf table holds 8192 / W slots
-    *n_instances = 0;
-    if (pr.nwords == 0) { ukeys.alloc(ctx, W); ucounts.alloc(ctx, 1); return 0; }
-    // ---- A ----
-    stage_begin(ctx, ST_EXTRACT);
+    if (tune.b0_max > MSDW_HB) tune.b0_max = MSDW_HB;
+    return tune;
+}
+// pass A, launch (see msd_pass_a_launch)
+template <int W>
+static void msdw_pass_a_launch(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int k, int canonical, int est_shift, DBuf<u32> &hist,
+                               DBuf<u8> &est) {
     const int hb = msdw_hist_bits(k);
     const u32 nbh = 1u << hb;
-    DBuf<u32> hist(ctx, nbh + 1);
-    DBuf<u8> est(ctx, 1ULL << EST_LOG);
+    hist.alloc(ctx, nbh + 1);
+    est.alloc(ctx, 1ULL << EST_LOG);
     CK(cudaMemsetAsync(hist.p, 0, (nbh + 1) * sizeof(u32), ctx->stream));
     CK(cudaMemsetAsync(est.p, 0, 1ULL << EST_LOG, ctx->stream));
-    const int est_shift = msd_est_shift(pr.nbases);
+    if (pr.nwords == 0) return;
     u64 hgrid = ceil_div(pr.nwords, MsdW<W>::TILE_WORDS);
     if (hgrid > (u64)ctx->num_sms * 8) hgrid = (u64)ctx->num_sms * 8;
     LAUNCH(ctx, msdw_hist_kernel<W>, (unsigned)hgrid, 256, 0, pr.packed.p, valid, pr.nwords, k, canonical, hb, hist.p,
            est_shift ? (0xFFFFFFFFu >> est_shift) : 0xFFFFFFFFu, est.p);
-    u64 N = 0, dest = 0;
-    msd_pass_a_read(ctx, hist.p, nbh, est.p, est_shift, &N, &dest);
-    est.release();
-    *n_instances = N;
-    if (N == 0) { stage_end(ctx, ST_EXTRACT); ukeys.alloc(ctx, W); ucounts.alloc(ctx, 1); return 0; }
-    if (N >= 0xFFFFFFFFull) GG_THROW(GG_ERR_LIMIT, "%llu k-mer instances exceed the 2^32-1 per-call limit", (unsigned long long)N);
-    MsdTune t2 = tune;
-    if (t2.b0_max > MSDW_HB) t2.b0_max = MSDW_HB;
-    const MsdPlan pl = msd_plan(dest, N, k, t2, hb);
-    // ---- B ----
+}
+// pass B: keys scattered into 2^b0 buckets of A (N * W words)
+template <int W>
+static void msdw_pass_b(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int k, int canonical, const MsdPlan &pl, const u32 *hist, u64 N,
+                        DBuf<u32> &hist0, DBuf<u32> &bstart, DBuf<u64> &A) {
     const u32 nb0 = 1u << pl.b0;
-    DBuf<u32> hist0(ctx, nb0 + 1), bstart(ctx, nb0 + 1), cursor(ctx, nb0);
-    LAUNCH(ctx, msd_collapse_kernel, (unsigned)ceil_div(nb0 + 1, 256), 256, 0, hist.p, pl.hb, pl.b0, hist0.p);
+    hist0.alloc(ctx, nb0 + 1);
+    bstart.alloc(ctx, nb0 + 1);
+    DBuf<u32> cursor(ctx, nb0);
+    LAUNCH(ctx, msd_collapse_kernel, (unsigned)ceil_div(nb0 + 1, 256), 256, 0, hist, pl.hb, pl.b0, hist0.p);
     exclusive_scan_u32(ctx, hist0.p, bstart.p, nb0 + 1, nullptr);
     LAUNCH(ctx, msd_copy_u32_kernel, (unsigned)ceil_div(nb0, 256), 256, 0, bstart.p, (u64)nb0, cursor.p);
-    DBuf<u64> A(ctx, N * W), B(ctx, N * W);
-    {
-        const size_t smemB = (size_t)MsdW<W>::TILE_KEYS * W * 8 + 2 * (size_t)(1 << MSDW_HB) * 4 + (size_t)MsdW<W>::TILE_KEYS * 2;
-        static bool setB = false;
-        if (!setB) { CK(cudaFuncSetAttribute(msdw_scatter_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB)); setB = true; }
-        LAUNCH(ctx, msdw_scatter_kernel<W>, (unsigned)ceil_div(pr.nwords, MsdW<W>::TILE_WORDS), 256, smemB, pr.packed.p, valid, pr.nwords, k,
-               canonical, pl.b0, cursor.p, A.p);
-    }
-    stage_end(ctx, ST_EXTRACT);
-    // ---- C, D ----
+    A.alloc(ctx, (N ? N : 1) * W);
+    if (N == 0) return;
+    const size_t smemB = (size_t)MsdW<W>::TILE_KEYS * W * 8 + 2 * (size_t)(1 << MSDW_HB) * 4 + (size_t)MsdW<W>::TILE_KEYS * 2;
+    static bool setB = false;
+    if (!setB) { CK(cudaFuncSetAttribute(msdw_scatter_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB)); setB = true; }
+    LAUNCH(ctx, msdw_scatter_kernel<W>, (unsigned)ceil_div(pr.nwords, MsdW<W>::TILE_WORDS), 256, smemB, pr.packed.p, valid, pr.nwords, k,
+           canonical, pl.b0, cursor.p, A.p);
+}
+// Level-0 buckets -> sorted unique keys + counts (see msd_finish).  With nsrc > 1 (multi-GPU) level 1 always
+// runs (with b1 = 0 bits if need be): it merges the pieces of a bucket into one contiguous child.
+template <int W>
+static u64 msdw_finish(gg_ctx *ctx, u64 *IN, u64 n_in, const u32 *vbeg, const u32 *vcnt, u32 nb_local, u32 nsrc, const MsdPlan &pl,
+                       const MsdTune &tune, u32 min_freq, DBuf<u64> &ukeys, DBuf<u32> &ucounts) {
+    if (n_in == 0) { ukeys.alloc(ctx, W); ucounts.alloc(ctx, 1); return 0; }
+    const u32 nvb = nb_local * nsrc;
+    const u64 nchild = (u64)nb_local << pl.b1;
     stage_begin(ctx, ST_SORT);
-    const u64 nchild = (u64)nb0 << pl.b1;
-    DBuf<u32> off(ctx, nchild + 1), OC(ctx, N), ticket(ctx, 1), nu(ctx, nchild + 1), ustart(ctx, nchild + 1);
-    DBuf<u64> tot(ctx, 1);
-    u64 *X = A.p, *SB = B.p;
-    if (pl.b1 > 0) {
-        DBuf<u32> tcount(ctx, nb0 + 1), tstart(ctx, nb0 + 1), cursor1(ctx, nchild), hist1(ctx, nchild + 1);
+    DBuf<u32> off(ctx, nchild + 1), OC(ctx, n_in), ticket(ctx, 1), nu(ctx, nchild + 1), ustart(ctx, nchild + 1);
+    DBuf<u64> tot(ctx, 1), B(ctx, n_in * W);
+    u64 *X = IN, *SB = B.p;
+    if (pl.b1 > 0 || nsrc > 1) {
+        DBuf<u32> tcount(ctx, nvb + 1), tstart(ctx, nvb + 1), cursor1(ctx, nchild), hist1(ctx, nchild + 1);
         CK(cudaMemsetAsync(hist1.p, 0, (nchild + 1) * sizeof(u32), ctx->stream));
-        LAUNCH(ctx, msdw_tilecount_kernel<W>, (unsigned)ceil_div(nb0 + 1, 256), 256, 0, hist0.p, nb0, tcount.p);
-        exclusive_scan_u32(ctx, tcount.p, tstart.p, nb0 + 1, nullptr);
-        const unsigned tgrid = (unsigned)(ceil_div(N, MsdW<W>::T1) + nb0);
-        LAUNCH(ctx, msdw_hist1_kernel<W>, tgrid, 256, 0, A.p, tstart.p, bstart.p, hist0.p, nb0, pl.shiftc, pl.b1, hist1.p);
+        LAUNCH(ctx, msdw_tilecount_kernel<W>, (unsigned)ceil_div(nvb + 1, 256), 256, 0, vcnt, nvb, tcount.p);
+        exclusive_scan_u32(ctx, tcount.p, tstart.p, nvb + 1, nullptr);
+        const unsigned tgrid = (unsigned)(ceil_div(n_in, MsdW<W>::T1) + nvb);
+        LAUNCH(ctx, msdw_hist1_kernel<W>, tgrid, 256, 0, IN, tstart.p, vbeg, vcnt, nvb, nsrc, pl.shiftc, pl.b1, hist1.p);
         exclusive_scan_u32(ctx, hist1.p, off.p, nchild + 1, nullptr);
         LAUNCH(ctx, msd_copy_u32_kernel, (unsigned)ceil_div(nchild, 256), 256, 0, off.p, nchild, cursor1.p);
-        LAUNCH(ctx, msdw_scatter1_kernel<W>, tgrid, 256, 0, A.p, tstart.p, bstart.p, hist0.p, nb0, pl.shiftc, pl.b1, cursor1.p, B.p);
-        X = B.p; SB = A.p;
+        LAUNCH(ctx, msdw_scatter1_kernel<W>, tgrid, 256, 0, IN, tstart.p, vbeg, vcnt, nvb, nsrc, pl.shiftc, pl.b1, cursor1.p, B.p);
+        X = B.p; SB = IN;
     } else {
-        LAUNCH(ctx, msd_copy_u32_kernel, (unsigned)ceil_div(nchild + 1, 256), 256, 0, bstart.p, nchild + 1, off.p);
+        LAUNCH(ctx, msd_copy_u32_kernel, (unsigned)ceil_div(nchild + 1, 256), 256, 0, vbeg, nchild + 1, off.p);  // contiguous buckets: off == vbeg
     }
     // ---- E ----
     CK(cudaMemsetAsync(ticket.p, 0, sizeof(u32), ctx->stream));
@@ -444,23 +448,14 @@ static u64 msdw_count(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int 
         Compactor<MsdwOverflowF> oc(ctx, nchild, "msdw_overflow");
         const u64 novf = oc.count(of);
         if (getenv("GG_MSD_DEBUG"))
-            fprintf(stderr, "[msdw W=%d] N=%llu distinct_est=%llu b0=%d b1=%d shiftc=%d children=%llu overflowed=%llu\n", W, (unsigned long long)N,
-                    (unsigned long long)dest, pl.b0, pl.b1, pl.shiftc, (unsigned long long)nchild, (unsigned long long)novf);
+            fprintf(stderr, "[msdw W=%d] n_in=%llu b0=%d b1=%d shiftc=%d children=%llu overflowed=%llu\n", W, (unsigned long long)n_in, pl.b0, pl.b1,
+                    pl.shiftc, (unsigned long long)nchild, (unsigned long long)novf);
         if (novf) {
             oc.emit(of);
             std::vector<u32> h_list(novf), h_off(nchild + 1);
             CK(cudaMemcpyAsync(h_list.data(), olist.p, novf * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaMemcpyAsync(h_off.data(), off.p, (nchild + 1) * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
-            if (getenv("GG_MSD_DEBUG")) {
-                u64 mx = 0, mn = ~0ULL, sum = 0, allmax = 0;
-                for (u32 c : h_list) { u64 n = h_off[c + 1] - h_off[c]; mx = n > mx ? n : mx; mn = n < mn ? n : mn; sum += n; }
-                for (u64 c = 0; c < nchild; ++c) { u64 n = h_off[c + 1] - h_off[c]; allmax = n > allmax ? n : allmax; }
-                fprintf(stderr, "[msdw] overflowed children: instances min %llu max %llu mean %.1f; largest child overall %llu; first few:", (unsigned long long)mn,
-                        (unsigned long long)mx, (double)sum / novf, (unsigned long long)allmax);
-                for (size_t q = 0; q < h_list.size() && q < 12; ++q) fprintf(stderr, " %u(%u)", h_list[q], h_off[h_list[q] + 1] - h_off[h_list[q]]);
-                fprintf(stderr, "\n");
-            }
             for (u32 c : h_list) {
                 const u64 s = h_off[c], n = h_off[c + 1] - h_off[c];
                 u64 *a = X + s * W, *b = SB + s * W;
@@ -491,4 +486,30 @@ static u64 msdw_count(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int 
     }
     stage_end(ctx, ST_COUNT);
     return U;
+}
+
+// packed reads -> sorted unique k-mers + counts (count >= min_freq only), 32 < k <= 128.
+template <int W>
+static u64 msdw_count(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int k, int canonical, u32 min_freq, DBuf<u64> &ukeys,
+                      DBuf<u32> &ucounts, u64 *n_instances) {
+    const MsdTune tune = msdw_tune<W>();
+    *n_instances = 0;
+    if (pr.nwords == 0) { ukeys.alloc(ctx, W); ucounts.alloc(ctx, 1); return 0; }
+    stage_begin(ctx, ST_EXTRACT);
+    const int hb = msdw_hist_bits(k);
+    DBuf<u32> hist, hist0, bstart;
+    DBuf<u8> est;
+    DBuf<u64> A;
+    const int est_shift = msd_est_shift(pr.nbases);
+    msdw_pass_a_launch<W>(ctx, pr, valid, k, canonical, est_shift, hist, est);
+    u64 N = 0, dest = 0;
+    msd_pass_a_read(ctx, hist.p, 1u << hb, est.p, est_shift, &N, &dest);
+    est.release();
+    *n_instances = N;
+    if (N == 0) { stage_end(ctx, ST_EXTRACT); ukeys.alloc(ctx, W); ucounts.alloc(ctx, 1); return 0; }
+    if (N >= 0xFFFFFFFFull) GG_THROW(GG_ERR_LIMIT, "%llu k-mer instances exceed the 2^32-1 per-call limit", (unsigned long long)N);
+    const MsdPlan pl = msd_plan(dest, N, k, tune, hb);
+    msdw_pass_b<W>(ctx, pr, valid, k, canonical, pl, hist.p, N, hist0, bstart, A);
+    stage_end(ctx, ST_EXTRACT);
+    return msdw_finish<W>(ctx, A.p, N, bstart.p, hist0.p, 1u << pl.b0, 1, pl, tune, min_freq, ukeys, ucounts);
 }

@@ -149,8 +149,9 @@ void gg_umi_free(gg_umi *u);
  * merged).  Every rank passes ITS shard of the reads; k-mers are range-partitioned over the
  * ranks on the all-gathered level-0 histogram and exchanged once (NCCL send/recv over
  * NVLink); rank r returns the r-th contiguous slice of the global sorted table, so the
- * concatenation over ranks equals the single-GPU gg_count_kmers result.  k <= 32 in this
- * version (GG_ERR_LIMIT otherwise).
+ * concatenation over ranks equals the single-GPU gg_count_kmers result.  All k <= 128
+ * (k <= 32 scatters straight into the peers' buffers over NVLink; longer k-mers use
+ * ncclSend / ncclRecv); non-canonical counting at k = 32 is not covered (GG_ERR_LIMIT).
  * Bootstrap: rank 0 calls gg_comm_unique_id and ships the bytes to the other ranks by any
  * host channel (the Python host uses torch.distributed, Julia would use Distributed / MPI);
  * every rank then calls gg_comm_create on its own context.  Collective calls must be made
