@@ -30,6 +30,20 @@ __device__ __forceinline__ void pack_byte(u32 c, u32 &code, u32 &isbad) {
     isbad = !(up == 'A' || up == 'C' || up == 'G' || up == 'T');
 }
 
+// four ASCII bases (byte 0 = first base) at once: 8 code bits (first base in the top 2 bits) and 4 bad bits
+// (first base in bit 3).  Codes come from bits 1-2 of the upper-cased letter; validity by comparing with the
+// letter that code stands for (PRMT table lookup), all four bytes in one 32-bit word.
+__device__ __forceinline__ void pack4(u32 w, u32 &code8, u32 &bad4) {
+    const u32 up = w & 0xDFDFDFDFu;
+    const u32 t = (up >> 1) & 0x03030303u;                   // A0 C1 T2 G3
+    const u32 c = t ^ ((t >> 1) & 0x01010101u);              // A0 C1 G2 T3
+    code8 = (c * 0x40100401u) >> 24;
+    const u32 expect = __byte_perm(0x47544341u, 0u, t | (t >> 12));  // "ACTG"[t] for bases 0, 2, 1, 3
+    const u32 x = __byte_perm(up, 0u, 0x3120u) ^ expect;
+    const u32 nz = ((((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u) >> 7;  // 1 per mismatching byte (bases 0, 2, 1, 3)
+    bad4 = ((nz * 0x08020401u) >> 24) & 0xFu;
+}
+
 // one thread = 16 bases (one 128-bit load when aligned and fully inside the buffer)
 __global__ void __launch_bounds__(256) pack_kernel(const u8 *__restrict__ seq, u64 nbytes, int aligned16,
                                                    u32 *__restrict__ packed32, u32 *__restrict__ bad, u64 ngroups) {
@@ -51,11 +65,11 @@ __global__ void __launch_bounds__(256) pack_kernel(const u8 *__restrict__ seq, u
         }
         bd = 0;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            u32 c = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu, code, isbad;
-            pack_byte(c, code, isbad);
-            pk |= code << (30 - 2 * i);
-            bd |= isbad << (15 - i);
+        for (int q = 0; q < 4; ++q) {
+            u32 code8, bad4;
+            pack4(w[q], code8, bad4);
+            pk |= code8 << (24 - 8 * q);
+            bd |= bad4 << (12 - 4 * q);
         }
     }
     // packed u64 word j = [group 2j | group 2j+1]; little-endian halves: u32 index 2j+1 is the high half

@@ -93,11 +93,34 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_final_kernel(const u32 *__r
         ex += v[i];
     }
 }
+// small arrays (bucket / child / tile tables): one CTA, one launch
+#define SCAN_SMALL_N 65536
+__global__ void __launch_bounds__(1024) scan_small_kernel(const u32 *__restrict__ in, u32 *__restrict__ out, u32 n, u64 *total) {
+    __shared__ u32 ws[33];
+    u64 run = 0;
+    for (u32 base = 0; base < n; base += 4096) {  // 4 consecutive items per thread
+        const u32 i0 = base + threadIdx.x * 4;
+        u32 v[4], s = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { v[j] = (i0 + j < n) ? in[i0 + j] : 0; s += v[j]; }
+        u32 tot;
+        u32 ex = block_excl_scan(s, ws, &tot) + (u32)run;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { if (i0 + j < n) out[i0 + j] = ex; ex += v[j]; }
+        run += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total) *total = run;
+}
 // out may alias in. d_total (device u64, optional) receives the grand total (exact in u64 as
 // long as each tile sum fits u32; offsets themselves are u32 -> callers keep totals < 2^32).
 static void exclusive_scan_u32(gg_ctx *ctx, const u32 *in, u32 *out, u64 n, u64 *d_total) {
     if (n == 0) {
         if (d_total) CK(cudaMemsetAsync(d_total, 0, sizeof(u64), ctx->stream));
+        return;
+    }
+    if (n <= SCAN_SMALL_N) {
+        LAUNCH(ctx, scan_small_kernel, 1, 1024, 0, in, out, (u32)n, d_total);
         return;
     }
     u64 nb = ceil_div(n, SCAN_TILE);
