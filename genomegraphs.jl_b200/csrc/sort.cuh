@@ -246,12 +246,12 @@ template <int KW>
 struct KeyMask {
     u64 m[KW];
 };
-// 32 records per CTA, 8 lanes per record: lane `sub` compares against the tile entries q = sub (mod 8)
+// 8 records per CTA, one warp per record: lane `sub` compares against the tile entries q = sub (mod 32)
 template <int KW, bool PAY>
 __global__ void __launch_bounds__(256) rank_sort_kernel(const u64 *__restrict__ kin, u64 *__restrict__ kout, const u64 *__restrict__ pin,
                                                         u64 *__restrict__ pout, u32 n, KeyMask<KW> km) {
     __shared__ u64 tile[256 * KW];
-    const u32 i = blockIdx.x * 32 + (threadIdx.x >> 3), sub = threadIdx.x & 7u;
+    const u32 i = blockIdx.x * 8 + (threadIdx.x >> 5), sub = threadIdx.x & 31u;
     const bool live = i < n;
     Kmer<KW> x, xm;
 #pragma unroll
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(256) rank_sort_kernel(const u64 *__restrict__ 
         const u32 cnt = n - t0 < 256u ? n - t0 : 256u;
         if (live) {
 #pragma unroll 4
-            for (u32 q = sub; q < cnt; q += 8) {
+            for (u32 q = sub; q < cnt; q += 32) {
                 Kmer<KW> y;
 #pragma unroll
                 for (int j = 0; j < KW; ++j) y.w[j] = tile[q * KW + j];
@@ -281,9 +281,7 @@ __global__ void __launch_bounds__(256) rank_sort_kernel(const u64 *__restrict__ 
             }
         }
     }
-    rank += __shfl_xor_sync(FULL_MASK, rank, 1);
-    rank += __shfl_xor_sync(FULL_MASK, rank, 2);
-    rank += __shfl_xor_sync(FULL_MASK, rank, 4);
+    rank = warp_sum(rank);
     if (live && sub == 0) {
         km_store<KW>(kout, rank, x);
         if (PAY) pout[rank] = pin[i];
@@ -320,8 +318,8 @@ static void radix_sort(gg_ctx *ctx, u64 **keys, u64 **keys_alt, u64 **pay, u64 *
             for (int bit = r.lo; bit < r.hi; ++bit) km.m[KW - 1 - (bit >> 6)] |= 1ULL << (bit & 63);
         // ranges are given least significant first and must not interleave within a word in a way that changes
         // the lexicographic order: every caller passes disjoint ranges in ascending significance
-        if (has_pay) LAUNCH(ctx, (rank_sort_kernel<KW, true>), (unsigned)ceil_div(n, 32), 256, 0, *keys, *keys_alt, *pay, *pay_alt, (u32)n, km);
-        else LAUNCH(ctx, (rank_sort_kernel<KW, false>), (unsigned)ceil_div(n, 32), 256, 0, *keys, *keys_alt, (const u64 *)nullptr, (u64 *)nullptr, (u32)n, km);
+        if (has_pay) LAUNCH(ctx, (rank_sort_kernel<KW, true>), (unsigned)ceil_div(n, 8), 256, 0, *keys, *keys_alt, *pay, *pay_alt, (u32)n, km);
+        else LAUNCH(ctx, (rank_sort_kernel<KW, false>), (unsigned)ceil_div(n, 8), 256, 0, *keys, *keys_alt, (const u64 *)nullptr, (u64 *)nullptr, (u32)n, km);
         std::swap(*keys, *keys_alt);
         if (has_pay) std::swap(*pay, *pay_alt);
         return;
