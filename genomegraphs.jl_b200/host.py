@@ -63,6 +63,34 @@ def pack_reads(reads):
     return seq, offs
 
 
+def read_sequences(path):
+    """Sequence lines of a FASTA or FASTQ file -> (seq_bytes, read_offsets): the host side of
+    `read_datastore` / `FASTQ.Reader` (src/GenomeGraphs.jl:79-83, examples/construct_dbg.jl:15-21).
+    Only the sequence lines matter for this path; headers and qualities are dropped on the host."""
+    import gzip
+    op = gzip.open if str(path).endswith(".gz") else open
+    seqs = []
+    with op(path, "rb") as f:
+        first = f.read(1)
+        f.seek(0)
+        if first == b"@":     # FASTQ: 4-line records
+            for i, line in enumerate(f):
+                if i % 4 == 1:
+                    seqs.append(line.strip())
+        else:                 # FASTA: a record's sequence may span lines
+            cur = []
+            for line in f:
+                if line.startswith(b">"):
+                    if cur:
+                        seqs.append(b"".join(cur))
+                    cur = []
+                else:
+                    cur.append(line.strip())
+            if cur:
+                seqs.append(b"".join(cur))
+    return pack_reads(seqs)
+
+
 def _as_reads(reads):
     if isinstance(reads, tuple) and len(reads) == 2:
         seq = np.ascontiguousarray(reads[0], dtype=np.uint8)

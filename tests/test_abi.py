@@ -79,3 +79,30 @@ def test_synth_reads_host_semantics(pkg):
     assert 0.03 < float(np.mean(n == ord("N"))) < 0.07
     with pytest.raises(ValueError):
         pkg.synth_reads(7, 10, 4, 60)
+
+
+def test_read_sequences(pkg, tmp_path):
+    """FASTQ (4-line records) and multi-line FASTA -> concatenated sequence bytes + offsets."""
+    fq = tmp_path / "a.fastq"
+    fq.write_text("@r1\nACGTN\n+\nIIIII\n@r2\nGGCC\n+\nIIII\n")
+    fa = tmp_path / "b.fasta"
+    fa.write_text(">x desc\nACGT\nAC\n>y\nTTTT\n")
+    s, o = pkg.read_sequences(str(fq))
+    assert bytes(s) == b"ACGTNGGCC" and o.tolist() == [0, 5, 9]
+    s, o = pkg.read_sequences(str(fa))
+    assert bytes(s) == b"ACGTACTTTT" and o.tolist() == [0, 6, 10]
+
+
+def test_gfa_writer(pkg, tmp_path):
+    """write_to_gfa1 (src/Graphs.jl:892-926): one S line per node, each link once."""
+    g = pkg.empty_graph()
+    for s in ("AATC", "AATG", "ACGAAT"):
+        g.add_node_(s)
+    g.add_link_(1, -3, -3)
+    g.add_link_(2, -3, -3)
+    g.write_to_gfa1(str(tmp_path / "g"))
+    lines = (tmp_path / "g.gfa").read_text().splitlines()
+    assert lines[0] == "H\tVN:Z:1.0" and sum(l.startswith("S\t") for l in lines) == 3
+    assert sum(l.startswith("L\t") for l in lines) == 2
+    assert (tmp_path / "g.fasta").read_text() == ">seq1\nAATC\n>seq2\nAATG\n>seq3\nACGAAT\n"
+    assert g.sequence(-1) == "GATT"
