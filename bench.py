@@ -220,7 +220,18 @@ def main():
     N.check(H, L.gg_dev_alloc(H, nbytes + 64, C.byref(d_seq)))
     N.check(H, L.gg_dev_alloc(H, 8 * (nreads + 1), C.byref(d_offs)))
     N.check(H, L.gg_synth_reads_range_dev(H, seed, genome_total, rank * nreads, nreads, rl, 1, w["frag_len"], w["err_ppm"], 0, d_seq))
-    offs = np.arange(nreads + 1, dtype=np.uint64) * np.uint64(rl)
+    pinned = []
+
+    def pinned_array(count, dtype):
+        """numpy view of page-locked host memory (gg_host_alloc): every host buffer of the e2e leg is pinned"""
+        p = C.c_void_p()
+        nbytes_ = max(int(count), 1) * np.dtype(dtype).itemsize
+        N.check(H, L.gg_host_alloc(H, nbytes_, C.byref(p)))
+        pinned.append(p)
+        return np.frombuffer((C.c_uint8 * nbytes_).from_address(p.value), dtype=dtype, count=max(int(count), 1))
+
+    offs = pinned_array(nreads + 1, np.uint64)
+    offs[:] = np.arange(nreads + 1, dtype=np.uint64) * np.uint64(rl)
     N.check(H, L.gg_memcpy_h2d(H, d_offs, offs.ctypes.data_as(C.c_void_p), offs.nbytes))
     N.check(H, L.gg_host_alloc(H, nbytes + 64, C.byref(h_seq)))
     N.check(H, L.gg_memcpy_d2h(H, h_seq, d_seq, nbytes))
@@ -277,8 +288,8 @@ def main():
 
     # ---- e2e: host buffers in, full graph out, every step ----
     nn, nb, nl = sizes
-    out_off = np.zeros(nn + 1, dtype=np.uint64); out_bases = np.zeros(max(nb, 1), dtype=np.uint8)
-    out_row = np.zeros(nn + 1, dtype=np.uint64); out_tri = np.zeros(max(3 * nl, 1), dtype=np.int64)
+    out_off = pinned_array(nn + 1, np.uint64); out_bases = pinned_array(max(nb, 1), np.uint8)
+    out_row = pinned_array(nn + 1, np.uint64); out_tri = pinned_array(max(3 * nl, 1), np.int64)
 
     d_seq2, d_offs2 = C.c_void_p(), C.c_void_p()
     if comm is not None:
@@ -428,6 +439,9 @@ def main():
         print(json.dumps(out), flush=True)
 
     L.gg_dev_free(H, d_seq); L.gg_dev_free(H, d_offs); L.gg_host_free(H, h_seq)
+    del offs, out_off, out_bases, out_row, out_tri
+    for p in pinned:
+        L.gg_host_free(H, p)
     if comm is not None:
         L.gg_dev_free(H, d_seq2); L.gg_dev_free(H, d_offs2)
         comm.close()

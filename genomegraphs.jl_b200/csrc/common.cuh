@@ -24,6 +24,8 @@ struct gg_ctx {
     int device = 0;
     int num_sms = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t aux = nullptr;       // second copy stream: read offsets travel beside the read bytes
+    cudaEvent_t aux_ev = nullptr;
     std::string err;
     // timing of the last pipeline call
     cudaEvent_t ev[2 * GG_NSTAGE];

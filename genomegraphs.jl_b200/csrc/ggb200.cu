@@ -96,6 +96,8 @@ int gg_ctx_create(int device, gg_ctx **out) {
         CK(cudaGetDeviceProperties(&prop, device));
         ctx->num_sms = prop.multiProcessorCount;
         CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->aux_ev, cudaEventDisableTiming));
         for (int i = 0; i < 2 * GG_NSTAGE; ++i) CK(cudaEventCreate(&ctx->ev[i]));
         for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&ctx->user_ev[i]));
         CK(cudaHostAlloc((void **)&ctx->h_scalar, 64 * sizeof(u64), cudaHostAllocDefault));
@@ -122,6 +124,8 @@ void gg_ctx_destroy(gg_ctx *ctx) {
         delete ctx->arena;
     }
     cudaStreamDestroy(ctx->stream);
+    if (ctx->aux) cudaStreamDestroy(ctx->aux);
+    if (ctx->aux_ev) cudaEventDestroy(ctx->aux_ev);
     delete ctx;
 }
 const char *gg_last_error(gg_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
@@ -318,13 +322,25 @@ struct StagedReads {
 static void stage_reads(gg_ctx *ctx, const u8 *seq, const u64 *offs, u64 nreads, StagedReads &s) {
     if (!offs) GG_THROW(GG_ERR_ARG, "read_offsets is null");
     s.nbytes = offs[nreads];
-    for (u64 i = 0; i < nreads; ++i)
-        if (offs[i] > offs[i + 1]) GG_THROW(GG_ERR_ARG, "read_offsets must be non-decreasing (read %llu)", (unsigned long long)i);
     if (s.nbytes && !seq) GG_THROW(GG_ERR_ARG, "seq_bytes is null");
     s.seq.alloc(ctx, s.nbytes + 32);
     s.offs.alloc(ctx, nreads + 1);
+    // the bytes go first (asynchronous from pinned memory); the offsets travel on the second copy stream and the
+    // host checks them meanwhile, so neither the check nor the small copy adds to the transfer time
+    CK(cudaEventRecord(ctx->aux_ev, ctx->stream));        // the blocks may still be in use by earlier work of this context
+    CK(cudaStreamWaitEvent(ctx->aux, ctx->aux_ev, 0));
     if (s.nbytes) CK(cudaMemcpyAsync(s.seq.p, seq, s.nbytes, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(s.offs.p, offs, (nreads + 1) * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(s.offs.p, offs, (nreads + 1) * sizeof(u64), cudaMemcpyHostToDevice, ctx->aux));
+    bool ok = true;
+    u64 bad = 0;
+    for (u64 i = 0; i < nreads; ++i)
+        if (offs[i] > offs[i + 1]) { ok = false; bad = i; break; }
+    CK(cudaEventRecord(ctx->aux_ev, ctx->aux));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->aux_ev, 0));
+    if (!ok) {
+        cudaStreamSynchronize(ctx->stream);  // the buffers go back to the allocator when this frame unwinds
+        GG_THROW(GG_ERR_ARG, "read_offsets must be non-decreasing (read %llu)", (unsigned long long)bad);
+    }
 }
 
 extern "C" {
