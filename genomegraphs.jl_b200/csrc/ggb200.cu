@@ -800,7 +800,7 @@ int gg_dist_dbg_from_reads_dev(gg_comm *cm, const uint8_t *d_seq, const uint64_t
         stage_begin(_c, ST_FILTER);  // the all-gather of the kept k-mers is booked under "filter"
         f = counts_allgather_impl(cm, c);
         stage_end(_c, ST_FILTER);
-        DISPATCH_W(f->W, *out = build_graph<W>(_c, f->d_keys, f->n_unique, f->k));
+        DISPATCH_W(f->W, *out = build_graph<W>(_c, f->d_keys, f->n_unique, f->k, cm));
     } catch (...) {
         gg_counts_free(c);
         gg_counts_free(f);

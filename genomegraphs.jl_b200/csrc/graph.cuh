@@ -52,13 +52,14 @@ __device__ __forceinline__ u32 find_key(const u64 *__restrict__ keys, const u32 
 // 8 lanes per stored k-mer: lanes 0-3 the forward neighbours (src/dbg.jl:30-34, 81-90),
 // lanes 4-7 the backward ones (:36-42, :70-79).  flags = cf | cb << 3 | palindrome << 6.
 template <int W>
-__global__ void __launch_bounds__(256) lookup_kernel(const u64 *__restrict__ keys, u64 n, int k, int pbits,
+// Stored k-mers [i0, i1) are looked up (the multi-GPU graph stage gives every rank one index range).
+__global__ void __launch_bounds__(256) lookup_kernel(const u64 *__restrict__ keys, u64 i0, u64 i1, int k, int pbits,
                                                      const u32 *__restrict__ start, u8 *__restrict__ flags,
                                                      u32 *__restrict__ nbF, u32 *__restrict__ nbB) {
     u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    u64 i = gid >> 3;
+    u64 i = i0 + (gid >> 3);
     u32 sub = (u32)gid & 7u, b = sub & 3u;
-    bool live = i < n;
+    bool live = i < i1;
     u32 v = V_NONE;
     bool pal = false;
     if (live) {
@@ -546,8 +547,10 @@ static void build_links(gg_ctx *ctx, gg_graph *g, const u64 *keys, const u32 *no
 }
 
 // keys: U sorted unique canonical k-mers (device). Builds the graph handle.
+// cm (optional): communicator of a multi-GPU job in which every rank holds the same table; the neighbour
+// lookups are then split over the ranks by index range and their results all-gathered.
 template <int W>
-static gg_graph *build_graph(gg_ctx *ctx, const u64 *keys, u64 U, int k) {
+static gg_graph *build_graph(gg_ctx *ctx, const u64 *keys, u64 U, int k, gg_comm *cm = nullptr) {
     gg_graph *g = new gg_graph();
     g->ctx = ctx;
     g->k = k;
@@ -571,9 +574,20 @@ static gg_graph *build_graph(gg_ctx *ctx, const u64 *keys, u64 U, int k) {
         if (pbits < 0) pbits = 0;
         DBuf<u32> start(ctx, (1ULL << pbits) + 1);
         LAUNCH(ctx, prefix_index_kernel<W>, (unsigned)ceil_div(U + 1, 256), 256, 0, keys, U, k, pbits, start.p);
-        DBuf<u8> flags(ctx, U);
-        DBuf<u32> nbF(ctx, U), nbB(ctx, U);
-        LAUNCH(ctx, lookup_kernel<W>, (unsigned)ceil_div(8 * U, 256), 256, 0, keys, U, k, pbits, start.p, flags.p, nbF.p, nbB.p);
+        const int P = (cm && cm->world > 1 && !getenv("GG_DIST_NO_SHARDED_LOOKUP")) ? cm->world : 1;
+        const u64 chunk = (ceil_div(U, (u64)P) + 15) & ~15ULL;  // keys per rank (16-aligned pieces for the all-gathers)
+        DBuf<u8> flags(ctx, chunk * P);
+        DBuf<u32> nbF(ctx, chunk * P), nbB(ctx, chunk * P);
+        if (P == 1) {
+            LAUNCH(ctx, lookup_kernel<W>, (unsigned)ceil_div(8 * U, 256), 256, 0, keys, 0ULL, U, k, pbits, start.p, flags.p, nbF.p, nbB.p);
+        } else {
+            NcclApi *nc = nccl_api();
+            const u64 i0 = chunk * cm->rank < U ? chunk * cm->rank : U, i1 = i0 + chunk < U ? i0 + chunk : U;
+            if (i1 > i0) LAUNCH(ctx, lookup_kernel<W>, (unsigned)ceil_div(8 * (i1 - i0), 256), 256, 0, keys, i0, i1, k, pbits, start.p, flags.p, nbF.p, nbB.p);
+            NCK(nc->AllGather(flags.p + chunk * cm->rank, flags.p, chunk, ncclUint8, cm->comm, ctx->stream));
+            NCK(nc->AllGather(nbF.p + chunk * cm->rank, nbF.p, chunk, ncclUint32, cm->comm, ctx->stream));
+            NCK(nc->AllGather(nbB.p + chunk * cm->rank, nbB.p, chunk, ncclUint32, cm->comm, ctx->stream));
+        }
         stage_end(ctx, ST_LOOKUP);
         // ---- K6/K7 ----
         stage_begin(ctx, ST_UNITIG);
