@@ -61,6 +61,27 @@ __device__ __forceinline__ void roll32(const u64 *__restrict__ packed, const u32
     }
 }
 
+// Pass-A form of the roll: only what the histogram needs.  The top bits of the canonical k-mer are the
+// smaller of the two strands' top bits (equal tops give the same digit either way), and the sampler of the
+// distinct estimate is a symmetric function of the two strands' high words -- both without the 64-bit
+// compare / select / shift of the full key, which is built only for the sampled keys.
+template <class F>
+__device__ __forceinline__ void roll32_tops(const u64 *__restrict__ packed, const u32 *__restrict__ valid, u64 t, int k, F &&f) {
+    const u32 vm = valid[t];
+    if (vm == 0) return;
+    const u64 a0 = packed[t], a1 = packed[t + 1];
+    const int s = 64 - 2 * k;
+    const u64 topmask = ~0ULL << s;
+    const u64 nbc = ~(k == 32 ? a1 : ((a0 << (2 * k)) | (a1 >> s)));
+    u64 rl = rev2_u64(~a0) << s;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const u64 fl = (j == 0 ? a0 : ((a0 << (2 * j)) | (a1 >> (64 - 2 * j)))) & topmask;
+        if ((vm >> (31 - j)) & 1u) f(fl, rl);
+        if (j < 31) rl = ((rl >> 2) & topmask) | ((nbc << (2 * j)) & 0xC000000000000000ULL);
+    }
+}
+
 __device__ __forceinline__ u32 msd_digit0(u64 key, int sh, int b0) { return b0 ? (u32)(key >> sh) : 0u; }
 
 // ---- pass A: 12-bit histogram + distinct estimate -------------------------------------------
@@ -73,14 +94,20 @@ __global__ void __launch_bounds__(MSD_HIST_THREADS) msd_hist_kernel(const u64 *_
                                                                     u8 *__restrict__ est_map) {
     extern __shared__ __align__(16) u8 smem_raw[];
     u32 *h = reinterpret_cast<u32 *>(smem_raw);  // 2^hb bins
-    const int nb = 1 << hb, sh = 2 * k - hb;
+    const int nb = 1 << hb;
     for (int i = threadIdx.x; i < nb; i += MSD_HIST_THREADS) h[i] = 0;
     __syncthreads();
+    const int s = 64 - 2 * k;
     for (u64 t = (u64)blockIdx.x * MSD_HIST_THREADS + threadIdx.x; t < nwords; t += (u64)gridDim.x * MSD_HIST_THREADS)
-        roll32(packed, valid, t, k, canonical, [&](u64 key, int) {
-            atomicAdd(&h[msd_digit0(key, sh, hb)], 1u);
-            const u32 p = (u32)key * 0x9E3779B1u;  // hash of the last 16 bases: a sampler, not an identity
-            if (p <= est_max) est_map[(u32)((key * MSD_GOLD) >> (64 - EST_LOG))] = 1;
+        roll32_tops(packed, valid, t, k, [&](u64 fl, u64 rl) {
+            const u32 fh = (u32)(fl >> 32), rh = (u32)(rl >> 32);
+            const u32 top = canonical ? min(fh, rh) : fh;   // left-aligned: the digit is its top hb bits
+            atomicAdd(&h[hb ? (top >> (32 - hb)) : 0u], 1u);
+            const u32 p = (canonical ? fh + rh : fh) * 0x9E3779B1u;  // a sampler of the canonical k-mer, not an identity
+            if (p <= est_max) {
+                const u64 key = ((canonical && rl < fl) ? rl : fl) >> s;
+                est_map[(u32)((key * MSD_GOLD) >> (64 - EST_LOG))] = 1;
+            }
         });
     __syncthreads();
     for (int i = threadIdx.x; i < nb; i += MSD_HIST_THREADS)
@@ -289,6 +316,12 @@ struct LeafSmem {
     u64 s_min, s_max;
 };
 
+// table slot of a key: folded 32-bit multiplicative hash (one IMUL instead of a 64-bit multiply chain)
+template <int LOG_HT>
+__device__ __forceinline__ u32 leaf_slot(u64 key) {
+    return (((u32)key ^ (u32)(key >> 32)) * 0x9E3779B1u) >> (32 - LOG_HT);
+}
+
 template <int THREADS>
 __device__ __forceinline__ u32 block_scan_array(u32 *arr, int n, u32 *ws) {
     // exclusive scan of arr[0..n) in place (n <= 8 * THREADS); returns the total
@@ -335,7 +368,7 @@ __device__ bool msd_leaf(LeafSmem<THREADS, LOG_HT> &S, const u64 *IN, const u32 
             for (int u = 0; u < MSD_UNROLL; ++u) {
                 const u64 key = cur[u];
                 if (key == MSD_EMPTY) continue;
-                u32 slot = (u32)((key * MSD_GOLD) >> (64 - LOG_HT));
+                u32 slot = leaf_slot<LOG_HT>(key);
                 int probes = 0;
                 for (;;) {
                     u64 c = S.tab[slot];
@@ -404,7 +437,7 @@ __device__ bool msd_leaf(LeafSmem<THREADS, LOG_HT> &S, const u64 *IN, const u32 
         const u32 lo = S.bins[b], hi2 = S.bins[b + 1];
         u32 rank = 0;
         for (u32 q = lo; q < hi2; ++q) rank += sk[q] < key;
-        u32 slot = (u32)((key * MSD_GOLD) >> (64 - LOG_HT));
+        u32 slot = leaf_slot<LOG_HT>(key);
         while (S.tab[slot] != key) slot = (slot + 1) & HM;
         OK[obase + lo + rank] = key;
         OC[obase + lo + rank] = S.tcnt[slot];
