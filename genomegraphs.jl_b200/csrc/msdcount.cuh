@@ -5,12 +5,15 @@
 // run-length collapse (docs/src/man/assembly.md:126-128).  Output is identical (sorted unique
 // k-mers + counts); the route is an MSD formulation sized for HBM traffic:
 //
-//   A  msd_hist_kernel      roll over the packed reads: histogram of the top 12 key bits and a
-//                           distinct-count estimate (hash-sampled slice of the key space)
-//      plan                 children of ~3072 DISTINCT keys: b0 (<= 12) + b1 (<= 10) digit bits
+//   A  msd_hist_kernel      roll over the packed reads: histogram of the top 14 key bits and a
+//                           distinct-count estimate (linear counting over a hash-sampled slice of
+//                           the key space)
+//      plan                 children of ~2048 DISTINCT keys: b0 (8 preferred, <= 12) + b1 (<= 10) bits
 //   B  msd_scatter_kernel   one roll per 32 windows (keys stay in registers), tile staged in
-//                           shared memory grouped by bucket, one reservation per (tile, bucket)
-//   C  msd_hist1_kernel     (only when b1 > 0) per level-0 bucket, histogram of the next b1 bits
+//                           shared memory grouped by bucket, one reservation per (tile, bucket);
+//                           multi-GPU: written straight into the owner GPU's buffer (PEER)
+//   C  msd_hist1_kernel     (only when b0 + b1 > 14; otherwise pass A's histogram is collapsed)
+//                           per level-0 bucket, histogram of the next b1 bits
 //   D  msd_scatter1_kernel  same staging scheme, keys -> 2^(b0+b1) ordered children
 //   E  msd_leaf_kernel      one CTA per child: all instances streamed through a shared-memory
 //                           hash table (capacity bounds DISTINCT keys, not instances), distinct
@@ -36,7 +39,7 @@
 #define MSD_UNROLL 8   // independent global loads in flight per thread in the leaf kernel
 #define MSD_EMPTY 0xFFFFFFFFFFFFFFFFULL  // never a valid key: all-T k-mers are not canonical, 2k < 64 otherwise (see msd_supported)
 #define MSD_GOLD 0x9E3779B97F4A7C15ULL
-#define EST_LOG 20     // slots of the distinct-estimate table
+#define EST_LOG 20     // log2 of the bytes of the distinct-estimate map
 
 static inline bool msd_supported(int k, int canonical) { return k <= 32 && (canonical || k < 32); }
 
