@@ -26,6 +26,7 @@ struct gg_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t aux = nullptr;       // second copy stream: read offsets travel beside the read bytes
     cudaEvent_t aux_ev = nullptr;
+    std::vector<cudaEvent_t> chunk_ev;  // one per in-flight chunk of the pipelined host front end
     std::string err;
     // timing of the last pipeline call
     cudaEvent_t ev[2 * GG_NSTAGE];
@@ -85,6 +86,13 @@ static inline cudaEvent_t prof_event(gg_ctx *ctx) {
 
 static inline u64 ceil_div(u64 a, u64 b) { return (a + b - 1) / b; }
 
+// Fill with a kernel instead of cudaMemsetAsync, so that the main stream carries no copy-engine style work in the
+// part of the host path that overlaps with the host-to-device transfer (see count_kmers_host_pipelined).
+__global__ void gg_fill_kernel(uint4 *p, u64 n16, u32 v) {
+    const uint4 x = make_uint4(v, v, v, v);
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (u64)gridDim.x * blockDim.x) p[i] = x;
+}
+
 // Device memory: a per-context caching allocator.  Every pipeline call allocates the same sequence of
 // temporaries, so after the first call each request is served from the free list without touching
 // the driver (cudaMallocAsync pools re-map physical memory between differently sized requests, and
@@ -95,6 +103,7 @@ struct GgArena {
     std::multimap<size_t, void *> free_blocks;   // size -> block
     std::map<void *, size_t> live;               // block -> size (allocated and cached blocks alike)
     size_t cached_bytes = 0, total_bytes = 0;
+    u64 driver_allocs = 0;  // cudaMalloc calls so far (0 per call in steady state)
 };
 static inline GgArena &gg_arena(gg_ctx *ctx) {
     if (!ctx->arena) ctx->arena = new GgArena();
@@ -120,6 +129,7 @@ static void *arena_alloc(gg_ctx *ctx, size_t bytes) {
         return p;
     }
     void *p = nullptr;
+    a.driver_allocs++;
     cudaError_t e = cudaMalloc(&p, bytes);
     if (e == cudaErrorMemoryAllocation) {  // give the cached blocks back and retry once
         cudaGetLastError();
@@ -169,6 +179,14 @@ struct DBuf {
     ~DBuf() { release(); }
 };
 
+// device fill of `bytes` (rounded up to 16; every arena block is a multiple of 512 bytes) with a 32-bit pattern
+static inline void dfill(gg_ctx *ctx, void *p, u64 bytes, u32 pattern) {
+    const u64 n16 = ceil_div(bytes, 16);
+    if (n16 == 0) return;
+    u64 grid = ceil_div(n16, 256);
+    if (grid > (u64)ctx->num_sms * 16) grid = (u64)ctx->num_sms * 16;
+    LAUNCH(ctx, gg_fill_kernel, (unsigned)grid, 256, 0, (uint4 *)p, n16, pattern);
+}
 static inline void stage_begin(gg_ctx *ctx, int s) {
     if (!ctx->ev_used[s]) { cudaEventRecord(ctx->ev[2 * s], ctx->stream); ctx->ev_used[s] = true; }
 }

@@ -126,6 +126,7 @@ void gg_ctx_destroy(gg_ctx *ctx) {
     cudaStreamDestroy(ctx->stream);
     if (ctx->aux) cudaStreamDestroy(ctx->aux);
     if (ctx->aux_ev) cudaEventDestroy(ctx->aux_ev);
+    for (auto e : ctx->chunk_ev) cudaEventDestroy(e);
     delete ctx;
 }
 const char *gg_last_error(gg_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
@@ -343,6 +344,95 @@ static void stage_reads(gg_ctx *ctx, const u8 *seq, const u64 *offs, u64 nreads,
     }
 }
 
+// Host buffers -> counts with the transfer pipelined against the front of the path (k <= 32 MSD route):
+// the read bytes travel in chunks on the copy stream; as soon as chunk c has landed it is packed, and the
+// window masks + pass A (histogram, distinct estimate) of chunk c - 1 run (they look one word ahead, hence the
+// lag).  When the last byte arrives only pass B onwards remains.
+#define GG_H2D_CHUNK (32ULL << 20)  // bytes; a multiple of 8192 (whole packed words and pack-thread pairs)
+static gg_counts *count_kmers_host_pipelined(gg_ctx *ctx, const u8 *seq, const u64 *offs, u64 nreads, int k, int canonical, u64 min_freq,
+                                             bool *filtered) {
+    if (!offs) GG_THROW(GG_ERR_ARG, "read_offsets is null");
+    const u64 nbytes = offs[nreads];
+    if (nbytes && !seq) GG_THROW(GG_ERR_ARG, "seq_bytes is null");
+    gg_counts *c = new gg_counts();
+    c->ctx = ctx; c->k = k; c->W = 1;
+    if (filtered) *filtered = true;
+    try {
+        DBuf<u8> dseq(ctx, nbytes + 32);
+        DBuf<u64> doffs(ctx, nreads + 1);
+        const u64 nch = ceil_div(nbytes, GG_H2D_CHUNK);
+        while (ctx->chunk_ev.size() < nch) {
+            cudaEvent_t e;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->chunk_ev.push_back(e);
+        }
+        // EVERY copy goes to the copy stream (offsets first, then the chunks) and the main stream only waits on events.
+        // Measured: one host-to-device copy issued on the main stream itself is enough to hold all its later kernels
+        // back until the copy stream has drained -- no overlap at all.
+        CK(cudaEventRecord(ctx->aux_ev, ctx->stream));      // the copy stream starts after the earlier work of this context
+        CK(cudaStreamWaitEvent(ctx->aux, ctx->aux_ev, 0));
+        CK(cudaMemcpyAsync(doffs.p, offs, (nreads + 1) * sizeof(u64), cudaMemcpyHostToDevice, ctx->aux));
+        CK(cudaEventRecord(ctx->aux_ev, ctx->aux));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->aux_ev, 0));
+        for (u64 ch = 0; ch < nch; ++ch) {
+            const u64 b0 = ch * GG_H2D_CHUNK, b1 = b0 + GG_H2D_CHUNK < nbytes ? b0 + GG_H2D_CHUNK : nbytes;
+            CK(cudaMemcpyAsync(dseq.p + b0, seq + b0, b1 - b0, cudaMemcpyHostToDevice, ctx->aux));
+            CK(cudaEventRecord(ctx->chunk_ev[ch], ctx->aux));
+        }
+        for (u64 i = 0; i < nreads; ++i)   // checked while the bytes are in flight
+            if (offs[i] > offs[i + 1]) {
+                cudaStreamSynchronize(ctx->aux);
+                cudaStreamSynchronize(ctx->stream);
+                GG_THROW(GG_ERR_ARG, "read_offsets must be non-decreasing (read %llu)", (unsigned long long)i);
+            }
+        stage_begin(ctx, ST_PACK);
+        PackedReads pr;
+        pack_prepare(ctx, doffs.p, nreads, nbytes, pr);
+        DBuf<u32> valid(ctx, pr.nwords ? pr.nwords : 1), hist;
+        DBuf<u8> est;
+        msd_pass_a_alloc(ctx, k, hist, est);
+        const int est_shift = msd_est_shift(nbytes);
+        const u32 nbh = 1u << msd_hist_bits(k);
+        const u32 nrows = 3u * (u32)ctx->num_sms;
+        DBuf<u32> rows(ctx, (u64)nrows * nbh);  // per-CTA histogram rows of the chunked pass A
+        dfill(ctx, rows.p, (u64)nrows * nbh * sizeof(u32), 0u);
+        stage_begin(ctx, ST_EXTRACT);
+        for (u64 ch = 0; ch <= nch; ++ch) {
+            if (ch < nch) {
+                const u64 b0 = ch * GG_H2D_CHUNK, b1 = b0 + GG_H2D_CHUNK < nbytes ? b0 + GG_H2D_CHUNK : nbytes;
+                CK(cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[ch], 0));
+                pack_range(ctx, dseq.p, nbytes, pr, b0 / 16, ceil_div(b1, 16));
+            }
+            if (ch > 0) {  // chunk ch - 1: its look-ahead word is packed now (or it is the last chunk)
+                const u64 w0 = (ch - 1) * (GG_H2D_CHUNK / 32), w1 = ch < nch ? ch * (GG_H2D_CHUNK / 32) : pr.nwords;
+                if (w1 > w0) {
+                    LAUNCH(ctx, valid32_kernel, (unsigned)ceil_div(w1 - w0, 256), 256, 0, pr.bad.p, pr.brk.p, w0, w1, k, valid.p);
+                    msd_pass_a_range(ctx, pr, valid.p, k, canonical, est_shift, hist.p, est.p, w0, w1, rows.p);
+                }
+            }
+        }
+        LAUNCH(ctx, msd_hist_rows_reduce_kernel, (unsigned)ceil_div(nbh, 256), 256, 0, rows.p, nrows, nbh, hist.p);
+        rows.release();
+        stage_end(ctx, ST_PACK);
+        DBuf<u64> ukeys;
+        DBuf<u32> counts;
+        u32 mf = min_freq > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)min_freq;
+        if (pr.nwords == 0) { ukeys.alloc(ctx, 1); counts.alloc(ctx, 1); stage_end(ctx, ST_EXTRACT); }
+        else c->n_unique = msd_count_after_a(ctx, pr, valid.p, k, canonical, mf < 1 ? 1 : mf, hist, est, est_shift, ukeys, counts, &c->n_instances);
+        c->d_keys = ukeys.take();
+        c->d_counts = counts.take();
+        return c;
+    } catch (...) {
+        cudaStreamSynchronize(ctx->aux);  // no copy may still be writing into a block that goes back to the allocator
+        dfree(ctx, c->d_keys); dfree(ctx, c->d_counts);
+        delete c;
+        throw;
+    }
+}
+static inline bool host_pipeline_ok(int k, int canonical) {
+    return kmer_words(k) == 1 && msd_supported(k, canonical) && !getenv("GG_FORCE_LSD") && !getenv("GG_NO_PIPELINE");
+}
+
 extern "C" {
 
 int gg_count_kmers_dev(gg_ctx *ctx, const uint8_t *d_seq, const uint64_t *d_offs, uint64_t nreads, uint64_t nbytes, int k,
@@ -366,6 +456,13 @@ int gg_count_kmers(gg_ctx *ctx, const uint8_t *seq, const uint64_t *offs, uint64
     check_k(k);
     CK(cudaSetDevice(_c->device));
     timing_reset(_c);
+    if (host_pipeline_ok(k, canonical)) {
+        stage_begin(_c, ST_TOTAL);
+        *out = count_kmers_host_pipelined(_c, seq, offs, nreads, k, canonical, 1, nullptr);
+        stage_end(_c, ST_TOTAL);
+        timing_collect(_c);
+        return GG_OK;
+    }
     StagedReads s;
     stage_reads(_c, seq, offs, nreads, s);
     stage_begin(_c, ST_TOTAL);
@@ -540,6 +637,20 @@ int gg_dbg_from_reads(gg_ctx *ctx, const uint8_t *seq, const uint64_t *offs, uin
     check_k(k);
     CK(cudaSetDevice(_c->device));
     timing_reset(_c);
+    if (host_pipeline_ok(k, 1)) {
+        stage_begin(_c, ST_TOTAL);
+        gg_counts *c = count_kmers_host_pipelined(_c, seq, offs, nreads, k, 1, min_freq, nullptr);
+        try {
+            DISPATCH_W(c->W, *out = build_graph<W>(_c, c->d_keys, c->n_unique, c->k));
+        } catch (...) {
+            gg_counts_free(c);
+            throw;
+        }
+        gg_counts_free(c);
+        stage_end(_c, ST_TOTAL);
+        timing_collect(_c);
+        return GG_OK;
+    }
     StagedReads s;
     stage_reads(_c, seq, offs, nreads, s);
     dbg_from_reads_dev(_c, s.seq.p, s.offs.p, nreads, s.nbytes, k, min_freq, out);

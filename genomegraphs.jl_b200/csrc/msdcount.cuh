@@ -92,16 +92,17 @@ __device__ __forceinline__ u32 msd_digit0(u64 key, int sh, int b0) { return b0 ?
 // of a 2^EST_LOG-byte map; with Z zero bytes left, distinct ~= 2^EST_LOG * ln(2^EST_LOG / Z) << est_shift.
 // The map of several GPUs merges with an elementwise max (dist.cuh).
 #define MSD_HIST_THREADS 512
-__global__ void __launch_bounds__(MSD_HIST_THREADS) msd_hist_kernel(const u64 *__restrict__ packed, const u32 *__restrict__ valid, u64 nwords,
+// words [w0, nwords) of the packed stream (the pipelined host path calls it once per arrived chunk)
+__global__ void __launch_bounds__(MSD_HIST_THREADS) msd_hist_kernel(const u64 *__restrict__ packed, const u32 *__restrict__ valid, u64 w0, u64 nwords,
                                                                     int k, int canonical, int hb, u32 *__restrict__ ghist, u32 est_max,
-                                                                    u8 *__restrict__ est_map) {
+                                                                    u8 *__restrict__ est_map, u32 *__restrict__ rows) {
     extern __shared__ __align__(16) u8 smem_raw[];
     u32 *h = reinterpret_cast<u32 *>(smem_raw);  // 2^hb bins
     const int nb = 1 << hb;
     for (int i = threadIdx.x; i < nb; i += MSD_HIST_THREADS) h[i] = 0;
     __syncthreads();
     const int s = 64 - 2 * k;
-    for (u64 t = (u64)blockIdx.x * MSD_HIST_THREADS + threadIdx.x; t < nwords; t += (u64)gridDim.x * MSD_HIST_THREADS)
+    for (u64 t = w0 + (u64)blockIdx.x * MSD_HIST_THREADS + threadIdx.x; t < nwords; t += (u64)gridDim.x * MSD_HIST_THREADS)
         roll32_tops(packed, valid, t, k, [&](u64 fl, u64 rl) {
             const u32 fh = (u32)(fl >> 32), rh = (u32)(rl >> 32);
             const u32 top = canonical ? min(fh, rh) : fh;   // left-aligned: the digit is its top hb bits
@@ -113,8 +114,21 @@ __global__ void __launch_bounds__(MSD_HIST_THREADS) msd_hist_kernel(const u64 *_
             }
         });
     __syncthreads();
-    for (int i = threadIdx.x; i < nb; i += MSD_HIST_THREADS)
-        if (h[i]) atomicAdd(&ghist[i], h[i]);
+    if (rows) {  // chunked launches: every CTA owns one row (plain adds, launches are stream ordered); reduced once at the end
+        u32 *row = rows + (size_t)blockIdx.x * nb;
+        for (int i = threadIdx.x; i < nb; i += MSD_HIST_THREADS)
+            if (h[i]) row[i] += h[i];
+    } else {
+        for (int i = threadIdx.x; i < nb; i += MSD_HIST_THREADS)
+            if (h[i]) atomicAdd(&ghist[i], h[i]);
+    }
+}
+__global__ void msd_hist_rows_reduce_kernel(const u32 *__restrict__ rows, u32 nrows, u32 nb, u32 *__restrict__ ghist) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nb) return;
+    u32 s = 0;
+    for (u32 r = 0; r < nrows; ++r) s += rows[(size_t)r * nb + i];
+    ghist[i] += s;
 }
 // out[0] += number of set map bytes; out[1] += sum of the histogram (N)
 __global__ void __launch_bounds__(256) msd_est_count_kernel(const u8 *__restrict__ est_map, const u32 *__restrict__ hist,
@@ -640,22 +654,31 @@ static inline u64 msd_est_value(u64 set_bytes, int est_shift) {
 }
 // pass A, launch: hist (2^hb + 1 entries, last 0) and the estimate map (2^EST_LOG bytes); est_shift
 // must be the same on every GPU whose maps are merged
-static void msd_pass_a_launch(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int k, int canonical, int est_shift, DBuf<u32> &hist,
-                              DBuf<u8> &est) {
-    const int hb = msd_hist_bits(k);
-    const u32 nb = 1u << hb;
+static void msd_pass_a_alloc(gg_ctx *ctx, int k, DBuf<u32> &hist, DBuf<u8> &est) {
+    const u32 nb = 1u << msd_hist_bits(k);
     hist.alloc(ctx, nb + 1);
     est.alloc(ctx, 1ULL << EST_LOG);
-    CK(cudaMemsetAsync(hist.p, 0, (nb + 1) * sizeof(u32), ctx->stream));
-    CK(cudaMemsetAsync(est.p, 0, 1ULL << EST_LOG, ctx->stream));
-    if (pr.nwords == 0) return;
-    u64 hgrid = ceil_div(pr.nwords, MSD_HIST_THREADS);
-    if (hgrid > (u64)ctx->num_sms * 3) hgrid = (u64)ctx->num_sms * 3;
+    dfill(ctx, hist.p, (nb + 1) * sizeof(u32), 0u);
+    dfill(ctx, est.p, 1ULL << EST_LOG, 0u);
+}
+// histogram + estimate over the packed words [w0, w1), accumulated into hist / est
+// rows (optional): 3 * num_sms per-CTA histogram rows for chunked launches (see msd_hist_kernel)
+static void msd_pass_a_range(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int k, int canonical, int est_shift, u32 *hist, u8 *est, u64 w0,
+                             u64 w1, u32 *rows = nullptr) {
+    if (w1 <= w0) return;
+    u64 hgrid = ceil_div(w1 - w0, MSD_HIST_THREADS);
+    const u64 gmax = (u64)ctx->num_sms * 3;  // rows, when given, hold one row per CTA of this grid
+    if (hgrid > gmax) hgrid = gmax;
     const size_t smemA = sizeof(u32) << MSD_HB;
     static bool setA = false;
     if (!setA) { CK(cudaFuncSetAttribute(msd_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA)); setA = true; }
-    LAUNCH(ctx, msd_hist_kernel, (unsigned)hgrid, MSD_HIST_THREADS, smemA, pr.packed.p, valid, pr.nwords, k, canonical, hb, hist.p,
-           est_shift ? (0xFFFFFFFFu >> est_shift) : 0xFFFFFFFFu, est.p);
+    LAUNCH(ctx, msd_hist_kernel, (unsigned)hgrid, MSD_HIST_THREADS, smemA, pr.packed.p, valid, w0, w1, k, canonical, msd_hist_bits(k), hist,
+           est_shift ? (0xFFFFFFFFu >> est_shift) : 0xFFFFFFFFu, est, rows);
+}
+static void msd_pass_a_launch(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int k, int canonical, int est_shift, DBuf<u32> &hist,
+                              DBuf<u8> &est) {
+    msd_pass_a_alloc(ctx, k, hist, est);
+    msd_pass_a_range(ctx, pr, valid, k, canonical, est_shift, hist.p, est.p, 0, pr.nwords);
 }
 // pass A, read back: N = sum of hist, distinct estimate from the map
 static void msd_pass_a_read(gg_ctx *ctx, const u32 *hist, u32 nb, const u8 *est, int est_shift, u64 *N, u64 *distinct_est) {
@@ -791,20 +814,13 @@ static u64 msd_finish(gg_ctx *ctx, u64 *IN, u64 n_in, const u32 *vbeg, const u32
     return U;
 }
 
-// packed reads -> sorted unique k-mers + counts (count >= min_freq only).  msd_supported(k, canonical).
-// Returns U; *n_instances = number of k-mer windows.
-static u64 msd_count(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int k, int canonical, u32 min_freq,
-                     DBuf<u64> &ukeys, DBuf<u32> &ucounts, u64 *n_instances) {
+// everything after pass A: hist / est hold the accumulated 14-bit histogram and estimate map
+static u64 msd_count_after_a(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int k, int canonical, u32 min_freq, DBuf<u32> &hist,
+                             DBuf<u8> &est, int est_shift, DBuf<u64> &ukeys, DBuf<u32> &ucounts, u64 *n_instances) {
     const MsdTune tune = msd_tune();
-    *n_instances = 0;
-    if (pr.nwords == 0) { ukeys.alloc(ctx, 1); ucounts.alloc(ctx, 1); return 0; }
-    stage_begin(ctx, ST_EXTRACT);
-    DBuf<u32> hist, hist0, bstart;
+    DBuf<u32> hist0, bstart;
     DBuf<u64> A;
     u64 N = 0, dest = 0;
-    DBuf<u8> est;
-    const int est_shift = msd_est_shift(pr.nbases);
-    msd_pass_a_launch(ctx, pr, valid, k, canonical, est_shift, hist, est);
     msd_pass_a_read(ctx, hist.p, 1u << msd_hist_bits(k), est.p, est_shift, &N, &dest);
     est.release();
     *n_instances = N;
@@ -820,4 +836,18 @@ static u64 msd_count(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int k
     }
     stage_end(ctx, ST_EXTRACT);
     return msd_finish(ctx, A.p, N, bstart.p, hist0.p, 1u << pl.b0, 1, pl, tune, min_freq, ukeys, ucounts, child_hist.p);
+}
+
+// packed reads -> sorted unique k-mers + counts (count >= min_freq only).  msd_supported(k, canonical).
+// Returns U; *n_instances = number of k-mer windows.
+static u64 msd_count(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int k, int canonical, u32 min_freq,
+                     DBuf<u64> &ukeys, DBuf<u32> &ucounts, u64 *n_instances) {
+    *n_instances = 0;
+    if (pr.nwords == 0) { ukeys.alloc(ctx, 1); ucounts.alloc(ctx, 1); return 0; }
+    stage_begin(ctx, ST_EXTRACT);
+    DBuf<u32> hist;
+    DBuf<u8> est;
+    const int est_shift = msd_est_shift(pr.nbases);
+    msd_pass_a_launch(ctx, pr, valid, k, canonical, est_shift, hist, est);
+    return msd_count_after_a(ctx, pr, valid, k, canonical, min_freq, hist, est, est_shift, ukeys, ucounts, n_instances);
 }

@@ -45,9 +45,10 @@ __device__ __forceinline__ void pack4(u32 w, u32 &code8, u32 &bad4) {
 }
 
 // one thread = 16 bases (one 128-bit load when aligned and fully inside the buffer)
+// groups [g0, ngroups) are packed by this launch (g0 even): the pipelined host path packs chunk by chunk
 __global__ void __launch_bounds__(256) pack_kernel(const u8 *__restrict__ seq, u64 nbytes, int aligned16,
-                                                   u32 *__restrict__ packed32, u32 *__restrict__ bad, u64 ngroups) {
-    u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;  // 16-base group index
+                                                   u32 *__restrict__ packed32, u32 *__restrict__ bad, u64 g0, u64 ngroups) {
+    u64 g = g0 + (u64)blockIdx.x * blockDim.x + threadIdx.x;  // 16-base group index
     u32 pk = 0, bd = 0xFFFFu;
     if (g < ngroups) {
         u64 b0 = g * 16;
@@ -147,9 +148,9 @@ __global__ void __launch_bounds__(256) valid_kernel(const u32 *__restrict__ bad,
 }
 
 // k <= 32: every window lies inside two mask words, so the sliding OR runs on one u64
-__global__ void __launch_bounds__(256) valid32_kernel(const u32 *__restrict__ bad, const u32 *__restrict__ brk, u64 nwords, int k,
+__global__ void __launch_bounds__(256) valid32_kernel(const u32 *__restrict__ bad, const u32 *__restrict__ brk, u64 w0, u64 nwords, int k,
                                                       u32 *__restrict__ valid) {
-    u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 j = w0 + (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nwords) return;
     const u64 B = ((u64)bad[j] << 32) | bad[j + 1], R = ((u64)brk[j] << 32) | brk[j + 1];  // MSB-first positions 0 .. 63
     const int m = k - 1;
@@ -164,29 +165,36 @@ __global__ void __launch_bounds__(256) valid32_kernel(const u32 *__restrict__ ba
     valid[j] = ~(u32)(inv >> 32);
 }
 
-static void pack_reads(gg_ctx *ctx, const u8 *d_seq, const u64 *d_offs, u64 nreads, u64 nbytes, PackedReads &pr) {
+// buffers of the packed form, cleared / padded; read starts marked (needs only the offsets)
+static void pack_prepare(gg_ctx *ctx, const u64 *d_offs, u64 nreads, u64 nbytes, PackedReads &pr) {
     pr.nbases = nbytes;
     pr.nwords = ceil_div(nbytes, 32);
     u64 tot = pr.nwords + PACK_PAD_WORDS;
     pr.packed.alloc(ctx, tot);
     pr.bad.alloc(ctx, tot);
     pr.brk.alloc(ctx, tot);
-    CK(cudaMemsetAsync(pr.packed.p, 0, tot * sizeof(u64), ctx->stream));
-    CK(cudaMemsetAsync(pr.bad.p, 0xFF, tot * sizeof(u32), ctx->stream));
-    CK(cudaMemsetAsync(pr.brk.p, 0, tot * sizeof(u32), ctx->stream));
-    if (nbytes == 0) return;
-    u64 ngroups = ceil_div(nbytes, 16);
-    int aligned = (((uintptr_t)d_seq) & 15) == 0;
-    // grid covers an even number of groups so that the shuffle partner always exists
-    u64 nthreads = ngroups + (ngroups & 1);
-    LAUNCH(ctx, pack_kernel, (unsigned)ceil_div(nthreads, 256), 256, 0, d_seq, nbytes, aligned, (u32 *)pr.packed.p, pr.bad.p, ngroups);
-    if (nreads) LAUNCH(ctx, brk_kernel, (unsigned)ceil_div(nreads, 256), 256, 0, d_offs, nreads, nbytes, pr.brk.p);
+    dfill(ctx, pr.packed.p, tot * sizeof(u64), 0u);
+    dfill(ctx, pr.bad.p, tot * sizeof(u32), 0xFFFFFFFFu);
+    dfill(ctx, pr.brk.p, tot * sizeof(u32), 0u);
+    if (nbytes && nreads) LAUNCH(ctx, brk_kernel, (unsigned)ceil_div(nreads, 256), 256, 0, d_offs, nreads, nbytes, pr.brk.p);
+}
+// pack the 16-base groups [g0, g1) (g0 even; g1 = number of groups when it is the last piece)
+static void pack_range(gg_ctx *ctx, const u8 *d_seq, u64 nbytes, PackedReads &pr, u64 g0, u64 g1) {
+    if (g1 <= g0) return;
+    const int aligned = (((uintptr_t)d_seq) & 15) == 0;
+    // an even number of threads so that the shuffle partner of every even group exists
+    const u64 nthreads = (g1 - g0) + ((g1 - g0) & 1);
+    LAUNCH(ctx, pack_kernel, (unsigned)ceil_div(nthreads, 256), 256, 0, d_seq, nbytes, aligned, (u32 *)pr.packed.p, pr.bad.p, g0, g1);
+}
+static void pack_reads(gg_ctx *ctx, const u8 *d_seq, const u64 *d_offs, u64 nreads, u64 nbytes, PackedReads &pr) {
+    pack_prepare(ctx, d_offs, nreads, nbytes, pr);
+    pack_range(ctx, d_seq, nbytes, pr, 0, ceil_div(nbytes, 16));
 }
 
 // valid-window mask for a given k (nwords u32)
 static void window_valid_mask(gg_ctx *ctx, const PackedReads &pr, int k, DBuf<u32> &valid) {
     valid.alloc(ctx, pr.nwords ? pr.nwords : 1);
-    if (pr.nwords && k <= 32) LAUNCH(ctx, valid32_kernel, (unsigned)ceil_div(pr.nwords, 256), 256, 0, pr.bad.p, pr.brk.p, pr.nwords, k, valid.p);
+    if (pr.nwords && k <= 32) LAUNCH(ctx, valid32_kernel, (unsigned)ceil_div(pr.nwords, 256), 256, 0, pr.bad.p, pr.brk.p, 0ULL, pr.nwords, k, valid.p);
     else if (pr.nwords) LAUNCH(ctx, valid_kernel, (unsigned)ceil_div(pr.nwords, 256), 256, 0, pr.bad.p, pr.brk.p, pr.nwords, k, valid.p);
 }
 

@@ -9,7 +9,10 @@ nreads = 2 * int(round(50 * glen / (2.0 * rl))); nbytes = nreads * rl
 d_seq, d_offs, h_seq = C.c_void_p(), C.c_void_p(), C.c_void_p()
 N.check(H, L.gg_dev_alloc(H, nbytes + 64, C.byref(d_seq))); N.check(H, L.gg_dev_alloc(H, 8 * (nreads + 1), C.byref(d_offs)))
 N.check(H, L.gg_synth_reads_dev(H, 1, glen, nreads, rl, 1, 700, 1000, 0, d_seq))
-offs = np.arange(nreads + 1, dtype=np.uint64) * np.uint64(rl)
+h_offs = C.c_void_p()
+N.check(H, L.gg_host_alloc(H, 8 * (nreads + 1), C.byref(h_offs)))   # pinned, as bench.py does
+offs = np.frombuffer((C.c_uint8 * (8 * (nreads + 1))).from_address(h_offs.value), dtype=np.uint64)
+offs[:] = np.arange(nreads + 1, dtype=np.uint64) * np.uint64(rl)
 N.check(H, L.gg_memcpy_h2d(H, d_offs, offs.ctypes.data_as(C.c_void_p), offs.nbytes))
 N.check(H, L.gg_host_alloc(H, nbytes + 64, C.byref(h_seq))); N.check(H, L.gg_memcpy_d2h(H, h_seq, d_seq, nbytes))
 def T(f, n=5):
@@ -17,7 +20,7 @@ def T(f, n=5):
     for _ in range(n): f()
     return (time.perf_counter() - t) / n * 1e3
 print("H2D reads (pinned, %d MB): %.2f ms" % (nbytes >> 20, T(lambda: L.gg_memcpy_h2d(H, d_seq, h_seq, nbytes))))
-print("H2D offsets (pageable numpy, %d MB): %.2f ms" % (offs.nbytes >> 20, T(lambda: L.gg_memcpy_h2d(H, d_offs, offs.ctypes.data_as(C.c_void_p), offs.nbytes))))
+print("H2D offsets (pinned, %d MB): %.2f ms" % (offs.nbytes >> 20, T(lambda: L.gg_memcpy_h2d(H, d_offs, offs.ctypes.data_as(C.c_void_p), offs.nbytes))))
 def dev():
     gh = C.c_void_p(); N.check(H, L.gg_dbg_from_reads_dev(H, d_seq, d_offs, nreads, nbytes, k, 2, C.byref(gh))); L.gg_graph_free(gh)
 print("device pipeline: %.2f ms" % T(dev))
