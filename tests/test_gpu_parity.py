@@ -1,6 +1,7 @@
 """Parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same
 inputs.  Bit-exact for every k-mer word, count, node sequence, node id and link entry
 (including per-node link order).  All tests need a B200 (`-m gpu`)."""
+import ctypes as C
 import random
 
 import numpy as np
@@ -241,3 +242,31 @@ def test_count_overflow_paths(pkg, ctx, k, mod, monkeypatch):
         og = O.dbg(O.filter_counts(okeys, ocnt, k, min_freq), k)
         assert ga.node_strings() == og.nodes() and ga.link_lists() == og.links(), (k, mod, min_freq)
         counts.free()
+
+
+# ------------------------------ error behaviour at the boundary -------------------------------
+def test_error_behaviour(pkg, ctx):
+    """Bad arguments come back as status codes (ValueError = the reference's ArgumentError), never as crashes,
+    and the context stays usable afterwards."""
+    N, L = pkg._native, pkg._native.lib()
+    seq = np.frombuffer(b"ACGTACGTACGT", dtype=np.uint8)
+    h = C.c_void_p()
+    bad_offs = np.array([0, 8, 4, 12], dtype=np.uint64)  # decreasing
+    assert L.gg_count_kmers(ctx.h, seq.ctypes.data_as(C.c_void_p), bad_offs.ctypes.data_as(C.c_void_p), 3, 4, 1, C.byref(h)) == N.GG_ERR_ARG
+    assert b"non-decreasing" in L.gg_last_error(ctx.h)
+    offs = np.array([0, 12], dtype=np.uint64)
+    for k in (0, -3, 129):
+        assert L.gg_count_kmers(ctx.h, seq.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(C.c_void_p), 1, k, 1, C.byref(h)) == N.GG_ERR_ARG
+    assert L.gg_count_kmers(ctx.h, None, offs.ctypes.data_as(C.c_void_p), 1, 4, 1, C.byref(h)) == N.GG_ERR_ARG      # null bytes, non-empty reads
+    assert L.gg_count_kmers(ctx.h, seq.ctypes.data_as(C.c_void_p), None, 1, 4, 1, C.byref(h)) == N.GG_ERR_ARG       # null offsets
+    assert L.gg_count_kmers(ctx.h, seq.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(C.c_void_p), 1, 4, 1, None) == N.GG_ERR_ARG
+    assert L.gg_dbg_build(ctx.h, None, C.byref(h)) == N.GG_ERR_ARG
+    with pytest.raises(ValueError):
+        pkg.serial_mem(200)
+    with pytest.raises(ValueError):   # counts given with unsorted k-mers
+        km = O.kmers_from_strings(["CCCC", "AAAA"])
+        cnt = np.array([1, 1], dtype=np.uint32)
+        N.check(ctx.h, L.gg_counts_from_kmers(ctx.h, km.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p), 2, 4, C.byref(h)))
+    # still healthy
+    c = pkg.serial_mem(4, ctx=ctx)(["ACGTACGTACGT"])
+    assert c.export()[1].tolist() == [3, 4, 2]   # ACGT, CGTA (= TACG), GTAC
