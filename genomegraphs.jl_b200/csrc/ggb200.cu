@@ -348,7 +348,13 @@ static void stage_reads(gg_ctx *ctx, const u8 *seq, const u64 *offs, u64 nreads,
 // the read bytes travel in chunks on the copy stream; as soon as chunk c has landed it is packed, and the
 // window masks + pass A (histogram, distinct estimate) of chunk c - 1 run (they look one word ahead, hence the
 // lag).  When the last byte arrives only pass B onwards remains.
-#define GG_H2D_CHUNK (32ULL << 20)  // bytes; a multiple of 8192 (whole packed words and pack-thread pairs)
+static u64 h2d_chunk_bytes() {  // a multiple of 8192 (whole packed words and pack-thread pairs); GG_H2D_CHUNK_KB for tests
+    if (const char *e = getenv("GG_H2D_CHUNK_KB")) {
+        u64 kb = (u64)atoll(e);
+        if (kb >= 8) return (kb / 8) * 8192;
+    }
+    return 32ULL << 20;
+}
 static gg_counts *count_kmers_host_pipelined(gg_ctx *ctx, const u8 *seq, const u64 *offs, u64 nreads, int k, int canonical, u64 min_freq,
                                              bool *filtered) {
     if (!offs) GG_THROW(GG_ERR_ARG, "read_offsets is null");
@@ -360,6 +366,7 @@ static gg_counts *count_kmers_host_pipelined(gg_ctx *ctx, const u8 *seq, const u
     try {
         DBuf<u8> dseq(ctx, nbytes + 32);
         DBuf<u64> doffs(ctx, nreads + 1);
+        const u64 GG_H2D_CHUNK = h2d_chunk_bytes();
         const u64 nch = ceil_div(nbytes, GG_H2D_CHUNK);
         while (ctx->chunk_ev.size() < nch) {
             cudaEvent_t e;
@@ -396,6 +403,20 @@ static gg_counts *count_kmers_host_pipelined(gg_ctx *ctx, const u8 *seq, const u
         const u32 nrows = 3u * (u32)ctx->num_sms;
         DBuf<u32> rows(ctx, (u64)nrows * nbh);  // per-CTA histogram rows of the chunked pass A
         dfill(ctx, rows.p, (u64)nrows * nbh * sizeof(u32), 0u);
+        // Speculative pass B: with at least three chunks, the first chunk's histogram predicts the bucket shares (reads
+        // arrive in no particular order), every bucket gets its share of nbytes * 1.1 key slots (the number of windows
+        // is below nbytes), and chunk c - 1 is scattered as soon as its masks exist.  An overflowing bucket (input
+        // sorted by position, say) only costs a repeat of pass B with exact offsets.
+        MsdSpec spec;
+        const int spec_b0 = msd_tune().b0_max;
+        const bool speculate = nch >= 3 && spec_b0 <= msd_hist_bits(k) && spec_b0 <= MSD_B0_MAX && !getenv("GG_NO_SPEC");
+        if (speculate) {
+            const u32 nb0 = 1u << spec_b0;
+            spec.b0 = spec_b0;
+            spec.A.alloc(ctx, nbytes + nbytes / 10 + 4096);
+            spec.start.alloc(ctx, nb0 + 1); spec.cursor.alloc(ctx, nb0); spec.bend.alloc(ctx, nb0); spec.ovf.alloc(ctx, 1);
+            dfill(ctx, spec.ovf.p, sizeof(u32), 0u);
+        }
         stage_begin(ctx, ST_EXTRACT);
         for (u64 ch = 0; ch <= nch; ++ch) {
             if (ch < nch) {
@@ -408,6 +429,17 @@ static gg_counts *count_kmers_host_pipelined(gg_ctx *ctx, const u8 *seq, const u
                 if (w1 > w0) {
                     LAUNCH(ctx, valid32_kernel, (unsigned)ceil_div(w1 - w0, 256), 256, 0, pr.bad.p, pr.brk.p, w0, w1, k, valid.p);
                     msd_pass_a_range(ctx, pr, valid.p, k, canonical, est_shift, hist.p, est.p, w0, w1, rows.p);
+                    if (speculate) {
+                        if (ch == 1) {  // capacities from the first chunk's histogram
+                            DBuf<u32> h0(ctx, nbh);
+                            dfill(ctx, h0.p, (u64)nbh * sizeof(u32), 0u);
+                            LAUNCH(ctx, msd_hist_rows_reduce_kernel, (unsigned)ceil_div(nbh, 256), 256, 0, rows.p, nrows, nbh, h0.p);
+                            LAUNCH(ctx, msd_spec_caps_kernel, 1, 1024, 0, h0.p, msd_hist_bits(k), spec_b0, (u64)spec.A.n, spec.start.p, spec.cursor.p,
+                                   spec.bend.p);
+                            spec.used = true;
+                        }
+                        msd_pass_b_spec(ctx, pr, valid.p, k, canonical, spec_b0, spec.cursor.p, spec.bend.p, spec.ovf.p, spec.A.p, w0, w1);
+                    }
                 }
             }
         }
@@ -418,7 +450,8 @@ static gg_counts *count_kmers_host_pipelined(gg_ctx *ctx, const u8 *seq, const u
         DBuf<u32> counts;
         u32 mf = min_freq > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)min_freq;
         if (pr.nwords == 0) { ukeys.alloc(ctx, 1); counts.alloc(ctx, 1); stage_end(ctx, ST_EXTRACT); }
-        else c->n_unique = msd_count_after_a(ctx, pr, valid.p, k, canonical, mf < 1 ? 1 : mf, hist, est, est_shift, ukeys, counts, &c->n_instances);
+        else c->n_unique = msd_count_after_a(ctx, pr, valid.p, k, canonical, mf < 1 ? 1 : mf, hist, est, est_shift, ukeys, counts, &c->n_instances,
+                                             speculate ? &spec : nullptr);
         c->d_keys = ukeys.take();
         c->d_counts = counts.take();
         return c;

@@ -198,17 +198,21 @@ __device__ __forceinline__ int msd_owner(const MsdPeers &pt, u32 d) {
     for (int q = 1; q < MSD_MAX_PEERS; ++q) o += (q < pt.n && d >= pt.first[q]) ? 1 : 0;
     return o;
 }
-template <bool PEER>
+// SPEC (speculative bucket capacities, pipelined host path): the launch covers the packed words [w0, nwords), a
+// bucket ends at bend[d], and a key that would land beyond it is dropped and raises *ovf (the caller then repeats
+// pass B with exact offsets).
+template <bool PEER, bool SPEC = false>
 __global__ void __launch_bounds__(256, 2) msd_scatter_kernel(const u64 *__restrict__ packed, const u32 *__restrict__ valid, u64 nwords,
                                                              int k, int canonical, int b0, u32 *__restrict__ cursor, u64 *__restrict__ out,
-                                                             MsdPeers pt) {
+                                                             MsdPeers pt, u64 w0 = 0, const u32 *__restrict__ bend = nullptr,
+                                                             u32 *__restrict__ ovf = nullptr) {
     extern __shared__ __align__(16) u8 smem_raw[];
     u64 *skeys = reinterpret_cast<u64 *>(smem_raw);                      // MSD_TILE_KEYS
     u32 *hist = reinterpret_cast<u32 *>(skeys + MSD_TILE_KEYS);          // 2^MSD_B0_MAX
     u32 *delta = hist + (1 << MSD_B0_MAX);                               // 2^MSD_B0_MAX
     __shared__ u32 ws[33];
     const int nb = 1 << b0, sh = 2 * k - b0;
-    const u64 t = (u64)blockIdx.x * 256 + threadIdx.x;
+    const u64 t = (SPEC ? w0 : 0) + (u64)blockIdx.x * 256 + threadIdx.x;
     for (int i = threadIdx.x; i < nb; i += 256) hist[i] = 0;
     __syncthreads();
     // one roll: the 32 keys of the thread stay in registers between the count and the placement
@@ -228,8 +232,43 @@ __global__ void __launch_bounds__(256, 2) msd_scatter_kernel(const u64 *__restri
         const u64 key = skeys[i];
         const u32 d = msd_digit0(key, sh, b0);
         if (PEER) pt.ptr[msd_owner(pt, d)][(u32)(delta[d] + i)] = key;
-        else out[delta[d] + i] = key;
+        else if (SPEC) {
+            const u32 pos = delta[d] + i;
+            if (pos < bend[d]) out[pos] = key;
+            else *ovf = 1u;
+        } else out[delta[d] + i] = key;
     }
+}
+// Speculative capacities from the histogram of the first chunk: bucket shares of `total_cap` key slots in
+// proportion to (count + 64).  One CTA; h14 = 2^hb-bin histogram of the sample.  start has nb + 1 entries.
+__global__ void __launch_bounds__(1024) msd_spec_caps_kernel(const u32 *__restrict__ h14, int hb, int b0, u64 total_cap, u32 *__restrict__ start,
+                                                             u32 *__restrict__ cursor, u32 *__restrict__ bend) {
+    __shared__ u32 bin[1 << MSD_B0_MAX];
+    __shared__ u32 ws[33];
+    __shared__ double s_scale;
+    const u32 nb = 1u << b0, g = 1u << (hb - b0);
+    u32 mysum = 0;
+    for (u32 b = threadIdx.x; b < nb; b += 1024) {
+        u32 c = 64;
+        for (u32 i = 0; i < g; ++i) c += h14[b * g + i];
+        bin[b] = c;
+        mysum += c;
+    }
+    u32 tot;
+    block_excl_scan(mysum, ws, &tot);
+    if (threadIdx.x == 0) s_scale = (double)total_cap / (double)(tot ? tot : 1);
+    __syncthreads();
+    for (u32 b = threadIdx.x; b < nb; b += 1024) bin[b] = (u32)((double)bin[b] * s_scale);
+    __syncthreads();
+    if (threadIdx.x == 0) {  // nb <= 4096: a serial scan is fine here
+        u32 run = 0;
+        for (u32 b = 0; b < nb; ++b) { start[b] = run; cursor[b] = run; run += bin[b]; bend[b] = run; }
+        start[nb] = run;
+    }
+}
+__global__ void msd_spec_counts_kernel(const u32 *__restrict__ start, const u32 *__restrict__ cursor, u32 nb, u32 *__restrict__ vcnt) {
+    u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b <= nb) vcnt[b] = b < nb ? cursor[b] - start[b] : 0;
 }
 
 // ---- level 1 over virtual buckets ---------------------------------------------------------------
@@ -722,6 +761,19 @@ static void msd_pass_b(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int
                cursor.p, A.p, none);
 }
 
+// speculative pass B over the packed words [w0, w1) (see msd_scatter_kernel<.., SPEC>)
+static void msd_pass_b_spec(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int k, int canonical, int b0, u32 *cursor, const u32 *bend,
+                            u32 *ovf, u64 *A, u64 w0, u64 w1) {
+    if (w1 <= w0) return;
+    const size_t smemB = (size_t)MSD_TILE_KEYS * 8 + 2 * (size_t)(1 << MSD_B0_MAX) * 4;
+    static bool set = false;
+    if (!set) { CK(cudaFuncSetAttribute((msd_scatter_kernel<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB)); set = true; }
+    MsdPeers none;
+    memset(&none, 0, sizeof(none));
+    LAUNCH(ctx, (msd_scatter_kernel<false, true>), (unsigned)ceil_div(w1 - w0, 256), 256, smemB, pr.packed.p, valid, w1, k, canonical, b0, cursor,
+           A, none, w0, bend, ovf);
+}
+
 __global__ void msd_child_total_kernel(const u32 *__restrict__ vcnt, u32 nsrc, u32 nchild, u32 *__restrict__ ctot) {
     u32 c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c > nchild) return;
@@ -751,7 +803,8 @@ static void msd_launch_leaf(gg_ctx *ctx, int ctas_per_sm, const u64 *IN, u64 *SB
 // vb = bl * nsrc + s: IN[vbeg[vb] .. + vcnt[vb]).  IN is consumed (used as scratch).
 // child_hist (optional, nchild + 1 entries, last 0): instances per child when pass A already knows them.
 static u64 msd_finish(gg_ctx *ctx, u64 *IN, u64 n_in, const u32 *vbeg, const u32 *vcnt, u32 nb_local, u32 nsrc, const MsdPlan &pl,
-                      const MsdTune &tune, u32 min_freq, DBuf<u64> &ukeys, DBuf<u32> &ucounts, const u32 *child_hist = nullptr) {
+                      const MsdTune &tune, u32 min_freq, DBuf<u64> &ukeys, DBuf<u32> &ucounts, const u32 *child_hist = nullptr,
+                      bool contiguous = true) {
     if (n_in == 0) { ukeys.alloc(ctx, 1); ucounts.alloc(ctx, 1); return 0; }
     const u32 nvb = nb_local * nsrc;
     const u64 nchild = (u64)nb_local << pl.b1;
@@ -788,7 +841,7 @@ static u64 msd_finish(gg_ctx *ctx, u64 *IN, u64 n_in, const u32 *vbeg, const u32
         exclusive_scan_u32(ctx, ctot.p, off.p, nchild + 1, nullptr);
         leaf_in = IN; leaf_sb = S1.p;
         segbeg = vbeg; segcnt = vcnt; nseg = nsrc;
-        if (nsrc == 1) leaf_o = IN;  // contiguous buckets: off == vbeg, counted in place
+        if (nsrc == 1 && contiguous) leaf_o = IN;  // contiguous buckets: off == vbeg, counted in place
         else { S2.alloc(ctx, n_in); leaf_o = S2.p; }
     }
     // ---- E: leaves ----
@@ -814,9 +867,18 @@ static u64 msd_finish(gg_ctx *ctx, u64 *IN, u64 n_in, const u32 *vbeg, const u32
     return U;
 }
 
-// everything after pass A: hist / est hold the accumulated 14-bit histogram and estimate map
+// state of a speculative pass B that ran while the reads were still arriving (pipelined host path)
+struct MsdSpec {
+    int b0 = 0;
+    DBuf<u64> A;                          // total_cap key slots
+    DBuf<u32> start, cursor, bend, ovf;   // nb + 1, nb, nb, 1
+    bool used = false;
+};
+// everything after pass A: hist / est hold the accumulated 14-bit histogram and estimate map.  With `spec`,
+// pass B has already happened into speculative bucket regions; it is kept if nothing overflowed and the plan
+// agrees with its digit width, and repeated exactly otherwise.
 static u64 msd_count_after_a(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int k, int canonical, u32 min_freq, DBuf<u32> &hist,
-                             DBuf<u8> &est, int est_shift, DBuf<u64> &ukeys, DBuf<u32> &ucounts, u64 *n_instances) {
+                             DBuf<u8> &est, int est_shift, DBuf<u64> &ukeys, DBuf<u32> &ucounts, u64 *n_instances, MsdSpec *spec = nullptr) {
     const MsdTune tune = msd_tune();
     DBuf<u32> hist0, bstart;
     DBuf<u64> A;
@@ -827,13 +889,23 @@ static u64 msd_count_after_a(gg_ctx *ctx, const PackedReads &pr, const u32 *vali
     if (N == 0) { stage_end(ctx, ST_EXTRACT); ukeys.alloc(ctx, 1); ucounts.alloc(ctx, 1); return 0; }
     if (N >= 0xFFFFFFFFull) GG_THROW(GG_ERR_LIMIT, "%llu k-mer instances exceed the 2^32-1 per-call limit", (unsigned long long)N);
     const MsdPlan pl = msd_plan(dest, N, k, tune, msd_hist_bits(k));
-    msd_pass_b(ctx, pr, valid, k, canonical, pl, hist.p, N, hist0, bstart, A);
+    bool keep_spec = spec && spec->used && spec->b0 == pl.b0 && !getenv("GG_PIPE_TEST_OVERFLOW");
+    if (keep_spec) keep_spec = read_scalar<u32>(ctx, spec->ovf.p) == 0;
     DBuf<u32> child_hist;
     if (pl.b1 > 0 && pl.b0 + pl.b1 <= pl.hb) {  // pass C for free: collapse the pass-A histogram to b0 + b1 bits
         const u32 nchild = 1u << (pl.b0 + pl.b1);
         child_hist.alloc(ctx, nchild + 1);
         LAUNCH(ctx, msd_collapse_kernel, (unsigned)ceil_div(nchild + 1, 256), 256, 0, hist.p, pl.hb, pl.b0 + pl.b1, child_hist.p);
     }
+    if (keep_spec) {
+        const u32 nb0 = 1u << pl.b0;
+        DBuf<u32> vcnt(ctx, nb0 + 1);
+        LAUNCH(ctx, msd_spec_counts_kernel, (unsigned)ceil_div(nb0 + 1, 256), 256, 0, spec->start.p, spec->cursor.p, nb0, vcnt.p);
+        stage_end(ctx, ST_EXTRACT);
+        return msd_finish(ctx, spec->A.p, spec->A.n, spec->start.p, vcnt.p, nb0, 1, pl, tune, min_freq, ukeys, ucounts, child_hist.p, false);
+    }
+    if (spec) { spec->A.release(); }
+    msd_pass_b(ctx, pr, valid, k, canonical, pl, hist.p, N, hist0, bstart, A);
     stage_end(ctx, ST_EXTRACT);
     return msd_finish(ctx, A.p, N, bstart.p, hist0.p, 1u << pl.b0, 1, pl, tune, min_freq, ukeys, ucounts, child_hist.p);
 }

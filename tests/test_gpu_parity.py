@@ -270,3 +270,27 @@ def test_error_behaviour(pkg, ctx):
     # still healthy
     c = pkg.serial_mem(4, ctx=ctx)(["ACGTACGTACGT"])
     assert c.export()[1].tolist() == [3, 4, 2]   # ACGT, CGTA (= TACG), GTAC
+
+
+# ------------------------------ pipelined host path --------------------------------------------
+@pytest.mark.parametrize("case", ["random", "sorted", "forced"])
+def test_host_pipeline_chunks(pkg, ctx, case, monkeypatch):
+    """gg_count_kmers / gg_dbg_from_reads copy the reads in chunks and run pack, masks, pass A and a speculative
+    pass B behind the transfer.  8 KB chunks make a small input take that route; reads sorted by content make the
+    first chunk unrepresentative (bucket overflow -> exact pass B); 'forced' discards the speculation."""
+    monkeypatch.setenv("GG_H2D_CHUNK_KB", "8")
+    if case == "forced":
+        monkeypatch.setenv("GG_PIPE_TEST_OVERFLOW", "1")
+    seq, offs = pkg.synth_reads(seed=77, genome_len=30000, nreads=6000, read_len=150, paired=True, frag_len=400, err_ppm=3000, n_ppm=200)
+    if case == "sorted":
+        reads = sorted(bytes(seq[i * 150:(i + 1) * 150]) for i in range(6000))
+        seq = np.frombuffer(b"".join(reads), dtype=np.uint8)
+    for k in (31, 15):
+        okeys, ocnt = O.count_kmers(seq, offs, k)
+        counts = pkg.serial_mem(k, pkg.CANONICAL, ctx=ctx)((seq, offs))
+        keys, c32, _ = counts.export()
+        assert np.array_equal(keys, okeys) and np.array_equal(c32, ocnt), (case, k)
+        counts.free()
+        ga = pkg.dbg_from_reads((seq, offs), k, 2, ctx=ctx)
+        og = O.dbg(O.filter_counts(okeys, ocnt, k, 2), k)
+        assert ga.node_strings() == og.nodes() and ga.link_lists() == og.links(), (case, k)
