@@ -353,7 +353,7 @@ static u64 h2d_chunk_bytes() {  // a multiple of 8192 (whole packed words and pa
         u64 kb = (u64)atoll(e);
         if (kb >= 8) return (kb / 8) * 8192;
     }
-    return 32ULL << 20;
+    return 16ULL << 20;
 }
 static gg_counts *count_kmers_host_pipelined(gg_ctx *ctx, const u8 *seq, const u64 *offs, u64 nreads, int k, int canonical, u64 min_freq,
                                              bool *filtered) {
