@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(256) radix_scatter_kernel(const u64 *__restric
 
 // Small inputs (graph link records, tiny k-mer sets): ONE launch, one CTA, all digit passes inside
 // (a pass of the tiled path costs five launches, which dominates below ~64 K keys).
-#define RADIX_SMALL_N 65536
+#define RADIX_SMALL_N 32768
 #define RADIX_MAX_PASSES 40
 struct RadixPasses {
     int n;
