@@ -6,6 +6,7 @@
 #include <string.h>
 #include <new>
 #include <map>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -44,6 +45,7 @@ struct gg_ctx {
     // user events (gg_ctx_event_record / gg_ctx_event_elapsed_ms)
     cudaEvent_t user_ev[8];
     struct GgArena *arena = nullptr;  // caching device allocator (below)
+    std::set<const void *> smem_attr_done;  // kernels whose dynamic shared-memory limit was raised on THIS device
 };
 
 struct GgError {
@@ -85,6 +87,21 @@ static inline cudaEvent_t prof_event(gg_ctx *ctx) {
     } while (0)
 
 static inline u64 ceil_div(u64 a, u64 b) { return (a + b - 1) / b; }
+
+// Raise a kernel's dynamic shared-memory limit once per context: the attribute belongs to the device, so a process
+// that drives several GPUs must set it on each of them.
+template <class K>
+static inline void set_max_smem(gg_ctx *ctx, K kernel, size_t bytes) {
+    const void *key = (const void *)kernel;
+    if (ctx->smem_attr_done.count(key)) return;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) {
+        char b[256];
+        snprintf(b, sizeof(b), "cudaFuncSetAttribute(%zu bytes of shared memory): %s", bytes, cudaGetErrorString(e));
+        throw GgError{GG_ERR_CUDA, std::string(b)};
+    }
+    ctx->smem_attr_done.insert(key);
+}
 
 // Fill with a kernel instead of cudaMemsetAsync, so that the main stream carries no copy-engine style work in the
 // part of the host path that overlaps with the host-to-device transfer (see count_kmers_host_pipelined).

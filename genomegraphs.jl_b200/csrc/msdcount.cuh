@@ -709,8 +709,7 @@ static void msd_pass_a_range(gg_ctx *ctx, const PackedReads &pr, const u32 *vali
     const u64 gmax = (u64)ctx->num_sms * 3;  // rows, when given, hold one row per CTA of this grid
     if (hgrid > gmax) hgrid = gmax;
     const size_t smemA = sizeof(u32) << MSD_HB;
-    static bool setA = false;
-    if (!setA) { CK(cudaFuncSetAttribute(msd_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA)); setA = true; }
+    set_max_smem(ctx, msd_hist_kernel, smemA);
     LAUNCH(ctx, msd_hist_kernel, (unsigned)hgrid, MSD_HIST_THREADS, smemA, pr.packed.p, valid, w0, w1, k, canonical, msd_hist_bits(k), hist,
            est_shift ? (0xFFFFFFFFu >> est_shift) : 0xFFFFFFFFu, est, rows);
 }
@@ -745,12 +744,8 @@ static void msd_pass_b(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int
     A.alloc(ctx, (N && !peers) ? N : 1);
     if (N == 0) return;
     size_t smemB = (size_t)MSD_TILE_KEYS * 8 + 2 * (size_t)(1 << MSD_B0_MAX) * 4;
-    static bool setB = false;
-    if (!setB) {
-        CK(cudaFuncSetAttribute(msd_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
-        CK(cudaFuncSetAttribute(msd_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
-        setB = true;
-    }
+    set_max_smem(ctx, msd_scatter_kernel<false>, smemB);
+    set_max_smem(ctx, msd_scatter_kernel<true>, smemB);
     MsdPeers none;
     memset(&none, 0, sizeof(none));
     if (peers)
@@ -766,8 +761,7 @@ static void msd_pass_b_spec(gg_ctx *ctx, const PackedReads &pr, const u32 *valid
                             u32 *ovf, u64 *A, u64 w0, u64 w1) {
     if (w1 <= w0) return;
     const size_t smemB = (size_t)MSD_TILE_KEYS * 8 + 2 * (size_t)(1 << MSD_B0_MAX) * 4;
-    static bool set = false;
-    if (!set) { CK(cudaFuncSetAttribute((msd_scatter_kernel<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB)); set = true; }
+    set_max_smem(ctx, msd_scatter_kernel<false, true>, smemB);
     MsdPeers none;
     memset(&none, 0, sizeof(none));
     LAUNCH(ctx, (msd_scatter_kernel<false, true>), (unsigned)ceil_div(w1 - w0, 256), 256, smemB, pr.packed.p, valid, w1, k, canonical, b0, cursor,
@@ -786,11 +780,7 @@ template <int THREADS, int LOG_HT>
 static void msd_launch_leaf(gg_ctx *ctx, int ctas_per_sm, const u64 *IN, u64 *SB, u64 *O, u32 *OC, const u32 *segbeg, const u32 *segcnt,
                             u32 nseg, const u32 *off, u32 nchild, int shiftc, u32 *nu, u32 *ticket, u32 min_freq, u32 test_ovf_mod) {
     size_t smem = sizeof(LeafSmem<THREADS, LOG_HT>);
-    static bool set = false;
-    if (!set) {
-        CK(cudaFuncSetAttribute(msd_leaf_kernel<THREADS, LOG_HT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        set = true;
-    }
+    set_max_smem(ctx, msd_leaf_kernel<THREADS, LOG_HT>, smem);
     u32 grid = (u32)ctx->num_sms * ctas_per_sm;
     if (grid > nchild) grid = nchild;
     DBuf<u32> fscr(ctx, (u64)grid * MSD_MAXD * FSCR_STRIDE);

@@ -400,8 +400,7 @@ static void msdw_pass_b(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, in
     A.alloc(ctx, (N ? N : 1) * W);
     if (N == 0) return;
     const size_t smemB = (size_t)MsdW<W>::TILE_KEYS * W * 8 + 2 * (size_t)(1 << MSDW_HB) * 4 + (size_t)MsdW<W>::TILE_KEYS * 2;
-    static bool setB = false;
-    if (!setB) { CK(cudaFuncSetAttribute(msdw_scatter_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB)); setB = true; }
+    set_max_smem(ctx, msdw_scatter_kernel<W>, smemB);
     LAUNCH(ctx, msdw_scatter_kernel<W>, (unsigned)ceil_div(pr.nwords, MsdW<W>::TILE_WORDS), 256, smemB, pr.packed.p, valid, pr.nwords, k,
            canonical, pl.b0, cursor.p, A.p);
 }
@@ -435,8 +434,7 @@ static u64 msdw_finish(gg_ctx *ctx, u64 *IN, u64 n_in, const u32 *vbeg, const u3
     CK(cudaMemsetAsync(ticket.p, 0, sizeof(u32), ctx->stream));
     {
         const size_t smem = sizeof(LeafSmemW<W>);
-        static bool set = false;
-        if (!set) { CK(cudaFuncSetAttribute(msdw_leaf_kernel<W, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
+        set_max_smem(ctx, msdw_leaf_kernel<W, 512>, smem);
         u32 grid = (u32)ctx->num_sms * 2;
         if (grid > nchild) grid = (u32)nchild;
         LAUNCH(ctx, (msdw_leaf_kernel<W, 512>), grid, 512, smem, X, SB, OC.p, off.p, (u32)nchild, pl.shiftc, nu.p, ticket.p, min_freq, tune.test_ovf_mod);

@@ -300,16 +300,12 @@ static void radix_sort(gg_ctx *ctx, u64 **keys, u64 **keys_alt, u64 **pay, u64 *
     u64 ntiles = ceil_div(n, TILE);
     DBuf<u32> hist(ctx, 256 * ntiles);
     size_t smem = (size_t)TILE * KW * 8 + (has_pay ? (size_t)TILE * 8 : 0);
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[has_pay]) {
-        if (has_pay) {
-            CK(cudaFuncSetAttribute(radix_scatter_kernel<KW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CK(cudaFuncSetAttribute(radix_small_kernel<KW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        } else {
-            CK(cudaFuncSetAttribute(radix_scatter_kernel<KW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CK(cudaFuncSetAttribute(radix_small_kernel<KW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        }
-        attr_set[has_pay] = true;
+    if (has_pay) {
+        set_max_smem(ctx, radix_scatter_kernel<KW, true>, smem);
+        set_max_smem(ctx, radix_small_kernel<KW, true>, smem);
+    } else {
+        set_max_smem(ctx, radix_scatter_kernel<KW, false>, smem);
+        set_max_smem(ctx, radix_small_kernel<KW, false>, smem);
     }
     if (n <= RANK_SORT_N) {
         KeyMask<KW> km;
