@@ -3,8 +3,9 @@
 // Same passes (A histogram + distinct estimate, B level-0 scatter, C/D level 1, E one CTA per child,
 // F gather) and the same plan; what differs from the one-word kernels:
 //   * windows are extracted per position (kmer_at: funnel shift of W + 1 packed words, word-wise
-//     reverse complement) instead of rolled, and pass B extracts twice (count, then place) rather
-//     than holding 32 multi-word keys per thread in registers;
+//     reverse complement) instead of rolled, and pass B keeps the extracted keys of its tile in a
+//     second shared-memory buffer between the count and the placement (two-word keys) or extracts
+//     them a second time (four-word keys: the buffer would halve the tile, which costs more there);
 //   * the leaf table (double hashing) claims a slot with a 32-bit tag (atomicCAS exists for one word only), the claimer
 //     stores the full key, and a second pass over the child's instances verifies key equality while
 //     it counts.  Two different keys with the same tag on the same probe path (astronomically rare)
@@ -16,9 +17,11 @@
 
 template <int W>
 struct MsdW {
-    static constexpr int PPT = 32 / W;                  // window positions per thread in passes A / B
-    static constexpr int TILE_WORDS = 256 / W;          // packed words per CTA tile in pass B
-    static constexpr int TILE_KEYS = TILE_WORDS * 32;   // 4096 (W = 2), 2048 (W = 4): 64 KB of staging
+    static constexpr int TILE_WORDS = 64;               // packed words per CTA tile in passes A / B
+    static constexpr bool STASH = W == 2;               // pass B keeps the extracted keys in a second buffer (else re-extracts)
+    static constexpr int TPW = 256 / TILE_WORDS;        // threads per packed word when the valid bits are compacted
+    static constexpr int PPT = 32 / TPW;                // window positions per thread in that step
+    static constexpr int TILE_KEYS = TILE_WORDS * 32;   // 2048 window starts: 32 KB (W = 2) / 64 KB (W = 4) per key buffer
     static constexpr int KPT = 16 / W;                  // keys per thread in the level-1 tiles
     static constexpr int T1 = 256 * KPT;
     static constexpr int LOG_HT = W == 2 ? 12 : 11;     // leaf table slots: 64 KB of keys
@@ -73,8 +76,8 @@ __device__ __forceinline__ u32 msdw_vm(const u32 *__restrict__ valid, u64 t, u32
 template <int W>
 __device__ __forceinline__ u32 msdw_compact_tile(const u32 *__restrict__ valid, u64 nwords, u64 tile, u16 *plist, u32 *ws) {
     constexpr int PPT = MsdW<W>::PPT;
-    const u64 t = tile * MsdW<W>::TILE_WORDS + threadIdx.x / W;
-    const u32 sub = threadIdx.x % W;
+    const u64 t = tile * MsdW<W>::TILE_WORDS + threadIdx.x / MsdW<W>::TPW;
+    const u32 sub = threadIdx.x % MsdW<W>::TPW;
     u32 vm = t < nwords ? msdw_vm<W>(valid, t, sub) : 0u;
     u32 total;
     u32 base = block_excl_scan((u32)__popc(vm), ws, &total);
@@ -119,21 +122,25 @@ __global__ void __launch_bounds__(256, 2) msdw_scatter_kernel(const u64 *__restr
                                                               int k, int canonical, int b0, u32 *__restrict__ cursor,
                                                               u64 *__restrict__ out) {
     extern __shared__ __align__(16) u8 smem_raw[];
-    u64 *skeys = reinterpret_cast<u64 *>(smem_raw);                                  // TILE_KEYS * W
-    u32 *hist = reinterpret_cast<u32 *>(skeys + (size_t)MsdW<W>::TILE_KEYS * W);     // 2^MSDW_HB
-    u32 *delta = hist + (1 << MSDW_HB);                                               // 2^MSDW_HB
-    u16 *plist = reinterpret_cast<u16 *>(delta + (1 << MSDW_HB));                     // TILE_KEYS
+    u64 *skeys = reinterpret_cast<u64 *>(smem_raw);                                  // TILE_KEYS * W: keys grouped by bucket
+    u64 *akeys = skeys + (size_t)MsdW<W>::TILE_KEYS * W;                             // STASH: TILE_KEYS * W keys as extracted
+    u32 *hist = reinterpret_cast<u32 *>(akeys + (MsdW<W>::STASH ? (size_t)MsdW<W>::TILE_KEYS * W : 0));  // 2^MSDW_HB
+    u32 *delta = hist + (1 << MSDW_HB);                                              // 2^MSDW_HB
+    u16 *plist = reinterpret_cast<u16 *>(delta + (1 << MSDW_HB));                    // TILE_KEYS
     __shared__ u32 ws[33];
     const int nb = 1 << b0, lowbit = 2 * k - b0;
     for (int i = threadIdx.x; i < nb; i += 256) hist[i] = 0;
     const u32 np = msdw_compact_tile<W>(valid, nwords, blockIdx.x, plist, ws);  // ends with a barrier
     const u64 pbase = (u64)blockIdx.x * MsdW<W>::TILE_KEYS;
-    for (u32 q = threadIdx.x; q < np; q += 256)
-        atomicAdd(&hist[kw_bits<W>(kmer_at<W>(packed, pbase + plist[q], k, canonical, nullptr), lowbit, b0)], 1u);
+    for (u32 q = threadIdx.x; q < np; q += 256) {
+        const Kmer<W> key = kmer_at<W>(packed, pbase + plist[q], k, canonical, nullptr);
+        if (MsdW<W>::STASH) km_store<W>(akeys, q, key);  // extracted once, kept in shared memory until it is placed
+        atomicAdd(&hist[kw_bits<W>(key, lowbit, b0)], 1u);
+    }
     __syncthreads();
     const u32 total = msd_reserve<(1 << MSDW_HB) / 256>(hist, delta, nb, cursor, ws);
     for (u32 q = threadIdx.x; q < np; q += 256) {
-        const Kmer<W> key = kmer_at<W>(packed, pbase + plist[q], k, canonical, nullptr);
+        const Kmer<W> key = MsdW<W>::STASH ? km_load<W>(akeys, q) : kmer_at<W>(packed, pbase + plist[q], k, canonical, nullptr);
         km_store<W>(skeys, atomicAdd(&hist[kw_bits<W>(key, lowbit, b0)], 1u), key);
     }
     __syncthreads();
@@ -399,7 +406,7 @@ static void msdw_pass_b(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, in
     LAUNCH(ctx, msd_copy_u32_kernel, (unsigned)ceil_div(nb0, 256), 256, 0, bstart.p, (u64)nb0, cursor.p);
     A.alloc(ctx, (N ? N : 1) * W);
     if (N == 0) return;
-    const size_t smemB = (size_t)MsdW<W>::TILE_KEYS * W * 8 + 2 * (size_t)(1 << MSDW_HB) * 4 + (size_t)MsdW<W>::TILE_KEYS * 2;
+    const size_t smemB = (MsdW<W>::STASH ? 2 : 1) * (size_t)MsdW<W>::TILE_KEYS * W * 8 + 2 * (size_t)(1 << MSDW_HB) * 4 + (size_t)MsdW<W>::TILE_KEYS * 2;
     set_max_smem(ctx, msdw_scatter_kernel<W>, smemB);
     LAUNCH(ctx, msdw_scatter_kernel<W>, (unsigned)ceil_div(pr.nwords, MsdW<W>::TILE_WORDS), 256, smemB, pr.packed.p, valid, pr.nwords, k,
            canonical, pl.b0, cursor.p, A.p);
