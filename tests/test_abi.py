@@ -106,3 +106,18 @@ def test_gfa_writer(pkg, tmp_path):
     assert sum(l.startswith("L\t") for l in lines) == 2
     assert (tmp_path / "g.fasta").read_text() == ">seq1\nAATC\n>seq2\nAATG\n>seq3\nACGAAT\n"
     assert g.sequence(-1) == "GATT"
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (CPU port of the reference algorithm) prints one JSON line with the contract keys."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--cpu-sample-frac", "0.004"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["unit"] == "k-mers/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert d["config"]["workload"] == "c2_ecoli50x_k31"
