@@ -321,7 +321,7 @@ static u64 dist_msd_count(gg_comm *cm, const PackedReads &pr, const u32 *valid, 
     stage_end(ctx, ST_SORT);
     mark();  // 4: exchange done
     DBuf<u32> child_hist;
-    if (W == 1 && pl.b1 > 0 && pl.b0 + pl.b1 <= hb && nb_local) {  // pass C for free (see msd_count)
+    if (pl.b1 > 0 && pl.b0 + pl.b1 <= hb && nb_local) {  // pass C for free (see msd_count)
         const u32 nchild = nb_local << pl.b1;
         child_hist.alloc(ctx, nchild + 1);
         LAUNCH(ctx, dist_child_hist_kernel, (unsigned)ceil_div(nchild + 1, 256), 256, 0, all_hist.p, P, nbh, hb, pl.b0 + pl.b1,
@@ -329,7 +329,7 @@ static u64 dist_msd_count(gg_comm *cm, const PackedReads &pr, const u32 *valid, 
     }
     u64 U = 0;
     if constexpr (W == 1) U = msd_finish(ctx, R, N_recv, vbeg.p, vcnt.p, nb_local, (u32)P, pl, tune, min_freq, ukeys, ucounts, child_hist.p);
-    else U = msdw_finish<W>(ctx, R, N_recv, vbeg.p, vcnt.p, nb_local, (u32)P, pl, tune, min_freq, ukeys, ucounts);
+    else U = msdw_finish<W>(ctx, R, N_recv, vbeg.p, vcnt.p, nb_local, (u32)P, pl, tune, min_freq, ukeys, ucounts, child_hist.p);
     mark();  // 5: level 1 + leaves + gather done
     if (dbg)
         fprintf(stderr, "[dist rank %d] t0=%.3f size-allreduce %.2f | passA+allgather %.2f | passB %.2f | exchange %.2f (send %.1f MB, recv %.1f MB) | finish %.2f ms\n",

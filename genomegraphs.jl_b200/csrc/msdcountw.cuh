@@ -27,7 +27,8 @@ struct MsdW {
     static constexpr int LOG_HT = W == 2 ? 12 : 11;     // leaf table slots: 64 KB of keys
 };
 #define MSDW_OVERFLOW 0xFFFFFFFFu
-#define MSDW_HB 12  // pass-A histogram bits of the multi-word path = largest level-0 digit
+#define MSDW_HB 14      // pass-A histogram bits of the multi-word path (doubles as the level-1 histogram when b0 + b1 <= 14)
+#define MSDW_B0_MAX 12  // largest level-0 digit (bins of the pass-B tile)
 static inline int msdw_hist_bits(int k) { return 2 * k < MSDW_HB ? 2 * k : MSDW_HB; }
 
 // key bits [lowbit, lowbit + nbits), nbits <= 24
@@ -95,7 +96,8 @@ template <int W>
 __global__ void __launch_bounds__(256) msdw_hist_kernel(const u64 *__restrict__ packed, const u32 *__restrict__ valid, u64 nwords, int k,
                                                         int canonical, int hb, u32 *__restrict__ ghist, u32 est_max,
                                                         u8 *__restrict__ est_map) {
-    __shared__ u32 h[1 << MSDW_HB];
+    extern __shared__ __align__(16) u8 smem_raw[];
+    u32 *h = reinterpret_cast<u32 *>(smem_raw);  // 2^hb bins
     __shared__ u16 plist[MsdW<W>::TILE_KEYS];
     __shared__ u32 ws[33];
     const int nb = 1 << hb;
@@ -124,9 +126,9 @@ __global__ void __launch_bounds__(256, 2) msdw_scatter_kernel(const u64 *__restr
     extern __shared__ __align__(16) u8 smem_raw[];
     u64 *skeys = reinterpret_cast<u64 *>(smem_raw);                                  // TILE_KEYS * W: keys grouped by bucket
     u64 *akeys = skeys + (size_t)MsdW<W>::TILE_KEYS * W;                             // STASH: TILE_KEYS * W keys as extracted
-    u32 *hist = reinterpret_cast<u32 *>(akeys + (MsdW<W>::STASH ? (size_t)MsdW<W>::TILE_KEYS * W : 0));  // 2^MSDW_HB
-    u32 *delta = hist + (1 << MSDW_HB);                                              // 2^MSDW_HB
-    u16 *plist = reinterpret_cast<u16 *>(delta + (1 << MSDW_HB));                    // TILE_KEYS
+    u32 *hist = reinterpret_cast<u32 *>(akeys + (MsdW<W>::STASH ? (size_t)MsdW<W>::TILE_KEYS * W : 0));  // 2^MSDW_B0_MAX
+    u32 *delta = hist + (1 << MSDW_B0_MAX);                                          // 2^MSDW_B0_MAX
+    u16 *plist = reinterpret_cast<u16 *>(delta + (1 << MSDW_B0_MAX));                // TILE_KEYS
     __shared__ u32 ws[33];
     const int nb = 1 << b0, lowbit = 2 * k - b0;
     for (int i = threadIdx.x; i < nb; i += 256) hist[i] = 0;
@@ -138,7 +140,7 @@ __global__ void __launch_bounds__(256, 2) msdw_scatter_kernel(const u64 *__restr
         atomicAdd(&hist[kw_bits<W>(key, lowbit, b0)], 1u);
     }
     __syncthreads();
-    const u32 total = msd_reserve<(1 << MSDW_HB) / 256>(hist, delta, nb, cursor, ws);
+    const u32 total = msd_reserve<(1 << MSDW_B0_MAX) / 256>(hist, delta, nb, cursor, ws);
     for (u32 q = threadIdx.x; q < np; q += 256) {
         const Kmer<W> key = MsdW<W>::STASH ? km_load<W>(akeys, q) : kmer_at<W>(packed, pbase + plist[q], k, canonical, nullptr);
         km_store<W>(skeys, atomicAdd(&hist[kw_bits<W>(key, lowbit, b0)], 1u), key);
@@ -374,7 +376,7 @@ template <int W>
 static MsdTune msdw_tune() {
     MsdTune tune = msd_tune();
     tune.dt = tune.dt / W < 16 ? 16 : tune.dt / W;  // the leaf table holds 8192 / W slots
-    if (tune.b0_max > MSDW_HB) tune.b0_max = MSDW_HB;
+    if (tune.b0_max > MSDW_B0_MAX) tune.b0_max = MSDW_B0_MAX;
     return tune;
 }
 // pass A, launch (see msd_pass_a_launch)
@@ -389,8 +391,10 @@ static void msdw_pass_a_launch(gg_ctx *ctx, const PackedReads &pr, const u32 *va
     CK(cudaMemsetAsync(est.p, 0, 1ULL << EST_LOG, ctx->stream));
     if (pr.nwords == 0) return;
     u64 hgrid = ceil_div(pr.nwords, MsdW<W>::TILE_WORDS);
-    if (hgrid > (u64)ctx->num_sms * 8) hgrid = (u64)ctx->num_sms * 8;
-    LAUNCH(ctx, msdw_hist_kernel<W>, (unsigned)hgrid, 256, 0, pr.packed.p, valid, pr.nwords, k, canonical, hb, hist.p,
+    if (hgrid > (u64)ctx->num_sms * 3) hgrid = (u64)ctx->num_sms * 3;  // 64 KB of histogram per CTA
+    const size_t smemA = sizeof(u32) << MSDW_HB;
+    set_max_smem(ctx, msdw_hist_kernel<W>, smemA);
+    LAUNCH(ctx, msdw_hist_kernel<W>, (unsigned)hgrid, 256, smemA, pr.packed.p, valid, pr.nwords, k, canonical, hb, hist.p,
            est_shift ? (0xFFFFFFFFu >> est_shift) : 0xFFFFFFFFu, est.p);
 }
 // pass B: keys scattered into 2^b0 buckets of A (N * W words)
@@ -406,7 +410,7 @@ static void msdw_pass_b(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, in
     LAUNCH(ctx, msd_copy_u32_kernel, (unsigned)ceil_div(nb0, 256), 256, 0, bstart.p, (u64)nb0, cursor.p);
     A.alloc(ctx, (N ? N : 1) * W);
     if (N == 0) return;
-    const size_t smemB = (MsdW<W>::STASH ? 2 : 1) * (size_t)MsdW<W>::TILE_KEYS * W * 8 + 2 * (size_t)(1 << MSDW_HB) * 4 + (size_t)MsdW<W>::TILE_KEYS * 2;
+    const size_t smemB = (MsdW<W>::STASH ? 2 : 1) * (size_t)MsdW<W>::TILE_KEYS * W * 8 + 2 * (size_t)(1 << MSDW_B0_MAX) * 4 + (size_t)MsdW<W>::TILE_KEYS * 2;
     set_max_smem(ctx, msdw_scatter_kernel<W>, smemB);
     LAUNCH(ctx, msdw_scatter_kernel<W>, (unsigned)ceil_div(pr.nwords, MsdW<W>::TILE_WORDS), 256, smemB, pr.packed.p, valid, pr.nwords, k,
            canonical, pl.b0, cursor.p, A.p);
@@ -415,7 +419,7 @@ static void msdw_pass_b(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, in
 // runs (with b1 = 0 bits if need be): it merges the pieces of a bucket into one contiguous child.
 template <int W>
 static u64 msdw_finish(gg_ctx *ctx, u64 *IN, u64 n_in, const u32 *vbeg, const u32 *vcnt, u32 nb_local, u32 nsrc, const MsdPlan &pl,
-                       const MsdTune &tune, u32 min_freq, DBuf<u64> &ukeys, DBuf<u32> &ucounts) {
+                       const MsdTune &tune, u32 min_freq, DBuf<u64> &ukeys, DBuf<u32> &ucounts, const u32 *child_hist = nullptr) {
     if (n_in == 0) { ukeys.alloc(ctx, W); ucounts.alloc(ctx, 1); return 0; }
     const u32 nvb = nb_local * nsrc;
     const u64 nchild = (u64)nb_local << pl.b1;
@@ -424,13 +428,18 @@ static u64 msdw_finish(gg_ctx *ctx, u64 *IN, u64 n_in, const u32 *vbeg, const u3
     DBuf<u64> tot(ctx, 1), B(ctx, n_in * W);
     u64 *X = IN, *SB = B.p;
     if (pl.b1 > 0 || nsrc > 1) {
-        DBuf<u32> tcount(ctx, nvb + 1), tstart(ctx, nvb + 1), cursor1(ctx, nchild), hist1(ctx, nchild + 1);
-        CK(cudaMemsetAsync(hist1.p, 0, (nchild + 1) * sizeof(u32), ctx->stream));
+        DBuf<u32> tcount(ctx, nvb + 1), tstart(ctx, nvb + 1), cursor1(ctx, nchild), hist1;
         LAUNCH(ctx, msdw_tilecount_kernel<W>, (unsigned)ceil_div(nvb + 1, 256), 256, 0, vcnt, nvb, tcount.p);
         exclusive_scan_u32(ctx, tcount.p, tstart.p, nvb + 1, nullptr);
         const unsigned tgrid = (unsigned)(ceil_div(n_in, MsdW<W>::T1) + nvb);
-        LAUNCH(ctx, msdw_hist1_kernel<W>, tgrid, 256, 0, IN, tstart.p, vbeg, vcnt, nvb, nsrc, pl.shiftc, pl.b1, hist1.p);
-        exclusive_scan_u32(ctx, hist1.p, off.p, nchild + 1, nullptr);
+        const u32 *h1 = child_hist;
+        if (!h1) {  // pass C: pass A's histogram is too coarse for b0 + b1 bits
+            hist1.alloc(ctx, nchild + 1);
+            CK(cudaMemsetAsync(hist1.p, 0, (nchild + 1) * sizeof(u32), ctx->stream));
+            LAUNCH(ctx, msdw_hist1_kernel<W>, tgrid, 256, 0, IN, tstart.p, vbeg, vcnt, nvb, nsrc, pl.shiftc, pl.b1, hist1.p);
+            h1 = hist1.p;
+        }
+        exclusive_scan_u32(ctx, h1, off.p, nchild + 1, nullptr);
         LAUNCH(ctx, msd_copy_u32_kernel, (unsigned)ceil_div(nchild, 256), 256, 0, off.p, nchild, cursor1.p);
         LAUNCH(ctx, msdw_scatter1_kernel<W>, tgrid, 256, 0, IN, tstart.p, vbeg, vcnt, nvb, nsrc, pl.shiftc, pl.b1, cursor1.p, B.p);
         X = B.p; SB = IN;
@@ -515,6 +524,12 @@ static u64 msdw_count(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int 
     if (N >= 0xFFFFFFFFull) GG_THROW(GG_ERR_LIMIT, "%llu k-mer instances exceed the 2^32-1 per-call limit", (unsigned long long)N);
     const MsdPlan pl = msd_plan(dest, N, k, tune, hb);
     msdw_pass_b<W>(ctx, pr, valid, k, canonical, pl, hist.p, N, hist0, bstart, A);
+    DBuf<u32> child_hist;
+    if (pl.b1 > 0 && pl.b0 + pl.b1 <= pl.hb) {  // pass C for free: collapse the pass-A histogram to b0 + b1 bits
+        const u32 nchild = 1u << (pl.b0 + pl.b1);
+        child_hist.alloc(ctx, nchild + 1);
+        LAUNCH(ctx, msd_collapse_kernel, (unsigned)ceil_div(nchild + 1, 256), 256, 0, hist.p, pl.hb, pl.b0 + pl.b1, child_hist.p);
+    }
     stage_end(ctx, ST_EXTRACT);
-    return msdw_finish<W>(ctx, A.p, N, bstart.p, hist0.p, 1u << pl.b0, 1, pl, tune, min_freq, ukeys, ucounts);
+    return msdw_finish<W>(ctx, A.p, N, bstart.p, hist0.p, 1u << pl.b0, 1, pl, tune, min_freq, ukeys, ucounts, child_hist.p);
 }

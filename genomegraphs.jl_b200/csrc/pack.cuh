@@ -166,6 +166,23 @@ __global__ void __launch_bounds__(256) valid32_kernel(const u32 *__restrict__ ba
 }
 
 // buffers of the packed form, cleared / padded; read starts marked (needs only the offsets)
+// 32 < k <= 64: three mask words (96 positions) in one 128-bit value
+__global__ void __launch_bounds__(256) valid64_kernel(const u32 *__restrict__ bad, const u32 *__restrict__ brk, u64 nwords, int k,
+                                                      u32 *__restrict__ valid) {
+    typedef unsigned __int128 u128;
+    u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nwords) return;
+    const u128 B = ((u128)bad[j] << 96) | ((u128)bad[j + 1] << 64) | ((u128)bad[j + 2] << 32);  // MSB-first positions 0 .. 95
+    const u128 R = ((u128)brk[j] << 96) | ((u128)brk[j + 1] << 64) | ((u128)brk[j + 2] << 32);
+    const int m = k - 1;
+    u128 acc = B | (R << 1);
+    int sz = 1;
+    while (2 * sz <= m) { acc |= acc << sz; sz *= 2; }
+    if (sz < m) acc |= acc << (m - sz);
+    const u128 inv = acc | (B << m);
+    valid[j] = ~(u32)(inv >> 96);
+}
+
 static void pack_prepare(gg_ctx *ctx, const u64 *d_offs, u64 nreads, u64 nbytes, PackedReads &pr) {
     pr.nbases = nbytes;
     pr.nwords = ceil_div(nbytes, 32);
@@ -195,6 +212,7 @@ static void pack_reads(gg_ctx *ctx, const u8 *d_seq, const u64 *d_offs, u64 nrea
 static void window_valid_mask(gg_ctx *ctx, const PackedReads &pr, int k, DBuf<u32> &valid) {
     valid.alloc(ctx, pr.nwords ? pr.nwords : 1);
     if (pr.nwords && k <= 32) LAUNCH(ctx, valid32_kernel, (unsigned)ceil_div(pr.nwords, 256), 256, 0, pr.bad.p, pr.brk.p, 0ULL, pr.nwords, k, valid.p);
+    else if (pr.nwords && k <= 64) LAUNCH(ctx, valid64_kernel, (unsigned)ceil_div(pr.nwords, 256), 256, 0, pr.bad.p, pr.brk.p, pr.nwords, k, valid.p);
     else if (pr.nwords) LAUNCH(ctx, valid_kernel, (unsigned)ceil_div(pr.nwords, 256), 256, 0, pr.bad.p, pr.brk.p, pr.nwords, k, valid.p);
 }
 
