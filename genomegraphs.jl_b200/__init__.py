@@ -9,5 +9,5 @@ from . import _native  # noqa: F401
 from . import dist  # noqa: F401
 from .host import *  # noqa: F401,F403
 from .host import (CANONICAL, NONCANONICAL, Context, GraphArrays, GraphStrandPosition, MerCounts, SDGLink, SDGNode,  # noqa: F401
-                   SequenceDistanceGraph, UniqueMerIndex, dbg_, dbg_arrays, dbg_from_reads, empty_graph, extract_kmers, freq,
+                   SequenceDistanceGraph, UniqueMerIndex, WorkSpace, dbg_, dbg_arrays, dbg_from_reads, empty_graph, extract_kmers, freq,
                    mer, pack_reads, read_sequences, serial_mem, spectra, synth_genome, synth_reads)

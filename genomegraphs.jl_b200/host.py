@@ -387,6 +387,42 @@ def dbg_from_reads(reads, k, min_freq, ctx=None):
         N.lib().gg_graph_free(gh)
 
 
+class WorkSpace:
+    """A live WorkSpace for the construction path: a graph plus named, device-resident k-mer count stores.
+    In the reference v0.2.0 the type is dead code (src/workspace/WorkSpace.jl is not included and names types
+    that exist nowhere); only its field / accessor names are kept (sdg, mer_count_stores, add_mer_counts!,
+    mer_counts)."""
+
+    def __init__(self, ctx=None):
+        self.ctx = ctx or Context.default()
+        self.sdg = SequenceDistanceGraph()
+        self.mer_count_stores = {}
+
+    def graph(self):
+        return self.sdg
+
+    def add_mer_counts_(self, k, mode, name, reads):
+        """add_mer_counts!(ws, DNAMer{k}, mode, name): count the k-mers of `reads` on the GPU, keep the table"""
+        self.mer_count_stores[name] = serial_mem(k, mode, ctx=self.ctx)(reads)
+        return self
+
+    def mer_counts(self, name):
+        if name not in self.mer_count_stores:
+            raise KeyError("WorkSpace has no mer count datastore datastore called %s" % name)
+        return self.mer_count_stores[name]
+
+    def dbg_(self, name, min_freq):
+        """dbg!(ws, counted_kmers, min_freq): build the workspace graph from a stored count table"""
+        self.sdg = dbg_(SequenceDistanceGraph(), self.mer_counts(name), min_freq, ctx=self.ctx)
+        return self
+
+    def __repr__(self):
+        lines = ["Graph Genome workspace", " Sequence distance graph (%d nodes)" % self.sdg.n_nodes(),
+                 " Mer count stores: %d" % len(self.mer_count_stores)]
+        lines += ["  %s: %d distinct %d-mers" % (n, len(c), c.k) for n, c in self.mer_count_stores.items()]
+        return "\n".join(lines)
+
+
 class GraphStrandPosition:
     """src/GraphIndexes.jl:14-17"""
     __slots__ = ("node", "position")

@@ -294,3 +294,18 @@ def test_host_pipeline_chunks(pkg, ctx, case, monkeypatch):
         ga = pkg.dbg_from_reads((seq, offs), k, 2, ctx=ctx)
         og = O.dbg(O.filter_counts(okeys, ocnt, k, 2), k)
         assert ga.node_strings() == og.nodes() and ga.link_lists() == og.links(), (case, k)
+
+
+def test_workspace(pkg, ctx):
+    """WorkSpace entry points (names of src/workspace/WorkSpace.jl): counts stored by name, dbg! from a store."""
+    seq, offs = pkg.synth_reads(seed=5, genome_len=4000, nreads=800, read_len=100, paired=True, frag_len=300, err_ppm=2000)
+    ws = pkg.WorkSpace(ctx=ctx)
+    ws.add_mer_counts_(21, pkg.CANONICAL, "reads", (seq, offs))
+    okeys, ocnt = O.count_kmers(seq, offs, 21)
+    assert np.array_equal(ws.mer_counts("reads").export()[0], okeys)
+    with pytest.raises(KeyError):
+        ws.mer_counts("nope")
+    ws.dbg_("reads", 2)
+    og = O.dbg(O.filter_counts(okeys, ocnt, 21, 2), 21)
+    assert [n.seq for n in ws.graph().nodes] == og.nodes() and ws.graph().link_tuples() == og.links()
+    assert "1 " not in repr(ws)[:5] and "workspace" in repr(ws)
