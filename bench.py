@@ -53,6 +53,13 @@ ALG_BYTES = {
     "msd_scatter1_kernel": lambda N, nb, U, W: 2.0 * W * N,
     "msd_leaf_kernel": lambda N, nb, U, W: W * N + (W + 4.0) * U,
     "msd_gather_kernel": lambda N, nb, U, W: 2.0 * (W + 4.0) * U,
+    # multi-word keys (k > 32): same formulas with W = 16 / 32 bytes
+    "msdw_hist_kernel": lambda N, nb, U, W: _stream_bytes(nb),
+    "msdw_scatter_kernel": lambda N, nb, U, W: _stream_bytes(nb) + W * N,
+    "msdw_hist1_kernel": lambda N, nb, U, W: W * N,
+    "msdw_scatter1_kernel": lambda N, nb, U, W: 2.0 * W * N,
+    "msdw_leaf_kernel": lambda N, nb, U, W: W * N + (W + 4.0) * U,
+    "msdw_gather_kernel": lambda N, nb, U, W: 2.0 * (W + 4.0) * U,
     "radix_scatter_kernel": lambda N, nb, U, W: 2.0 * W * N,   # per pass
     "radix_hist_kernel": lambda N, nb, U, W: 1.0 * W * N,
     "extract_emit_kernel": lambda N, nb, U, W: _stream_bytes(nb) + W * N,
