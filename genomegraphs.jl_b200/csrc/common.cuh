@@ -273,6 +273,15 @@ __host__ __device__ __forceinline__ Kmer<W> km_shr(const Kmer<W> &x, int s) {
     }
     return r;
 }
+// two-word values: one 128-bit shift instead of the generic word-select form
+template <>
+__host__ __device__ __forceinline__ Kmer<2> km_shr<2>(const Kmer<2> &x, int s) {
+    const unsigned __int128 v = (((unsigned __int128)x.w[0] << 64) | x.w[1]) >> s;
+    Kmer<2> r;
+    r.w[0] = (u64)(v >> 64);
+    r.w[1] = (u64)v;
+    return r;
+}
 // low 2k bits mask applied in place
 template <int W>
 __host__ __device__ __forceinline__ Kmer<W> km_mask(const Kmer<W> &x, int k) {
