@@ -282,6 +282,22 @@ __host__ __device__ __forceinline__ Kmer<2> km_shr<2>(const Kmer<2> &x, int s) {
     r.w[1] = (u64)v;
     return r;
 }
+// four-word values: branch on the word part of the shift (uniform within a kernel: it only depends on k), so that
+// every word index below is a compile-time constant
+template <>
+__host__ __device__ __forceinline__ Kmer<4> km_shr<4>(const Kmer<4> &x, int s) {
+    const int ws = s >> 6, bs = s & 63;
+    Kmer<4> r;
+#define GG_SHR4(i, lo, hi) r.w[i] = bs ? (((lo) >> bs) | ((hi) << (64 - bs))) : (lo)
+    switch (ws) {
+        case 0: GG_SHR4(3, x.w[3], x.w[2]); GG_SHR4(2, x.w[2], x.w[1]); GG_SHR4(1, x.w[1], x.w[0]); GG_SHR4(0, x.w[0], 0ULL); break;
+        case 1: GG_SHR4(3, x.w[2], x.w[1]); GG_SHR4(2, x.w[1], x.w[0]); GG_SHR4(1, x.w[0], 0ULL); r.w[0] = 0; break;
+        case 2: GG_SHR4(3, x.w[1], x.w[0]); GG_SHR4(2, x.w[0], 0ULL); r.w[1] = 0; r.w[0] = 0; break;
+        default: GG_SHR4(3, x.w[0], 0ULL); r.w[2] = 0; r.w[1] = 0; r.w[0] = 0; break;
+    }
+#undef GG_SHR4
+    return r;
+}
 // low 2k bits mask applied in place
 template <int W>
 __host__ __device__ __forceinline__ Kmer<W> km_mask(const Kmer<W> &x, int k) {
