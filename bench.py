@@ -2,21 +2,25 @@
 """bench.py -- DBG build throughput (input k-mers/sec) on B200, contract per the task brief.
 
 A "step" is one pass of the whole hot path over one batch of synthetic reads:
-reads (ASCII) -> 2-bit pack -> canonical k-mers -> sort + run-length counts -> min-count
-filter -> unitig nodes -> (k-1)-overlap links.  Workload = BASELINE.json configs[1]
-(C2): 4,641,652 bp uniform genome, 50x 150 bp paired reads (fragment
-700, 0.1 % substitutions), k = 31, min-count 2.
+reads (ASCII) -> 2-bit pack -> canonical k-mers -> counts -> min-count filter -> unitig nodes ->
+(k-1)-overlap links.  Default workload = BASELINE.json configs[2] (C3), the
+largest configuration that fits one GPU: 100 Mbp uniform genome, 30x 150 bp paired reads with 1 %
+substitutions, k = 31, min-count 2 (2.4e9 k-mer instances).  `--gpus N` runs the SAME job on N GPUs
+(reads sharded by index: strong scaling, as config 3 is written); `--scaling weak` grows the genome
+with N instead.
 
   value  : whole-job input k-mers/s with the read buffers already resident in HBM
   e2e    : same metric through the host-buffer C-ABI call (gg_dbg_from_reads) + full export of
            the graph to host memory, H2D / D2H inside the timed region
-  roofline / cpu_baseline : see DESIGN.md, "Measurement"
+  roofline / cpu_baseline / parity_checked : see DESIGN.md, "Measurement"
 
-`--impl reference` times the CPU restatement of the reference algorithm (oracle/, kind "port":
-the Julia reference cannot run here) on a bounded sample of the same workload.
+`--impl reference` times the CPU restatement of the reference algorithm (oracle/, kind "port": the
+Julia reference cannot run here) on a bounded sample of the same workload; it loads nothing but
+oracle/ (the read generator included).
 """
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
 import subprocess
@@ -28,60 +32,57 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-import __graft_entry__ as G  # noqa: E402
 
 WORKLOADS = {
-    # name: genome_len, coverage, read_len, frag_len, err_ppm, k, min_freq
-    "c2_ecoli50x_k31": dict(genome_len=4641652, cov=50, read_len=150, frag_len=700, err_ppm=1000, k=31, min_freq=2),
-    "c2_ecoli50x_k63": dict(genome_len=4641652, cov=50, read_len=150, frag_len=700, err_ppm=1000, k=63, min_freq=2),
-    "c3_100mbp30x_k31": dict(genome_len=100000000, cov=30, read_len=150, frag_len=700, err_ppm=10000, k=31, min_freq=2),
-    "c5_100mbp30x_k127": dict(genome_len=100000000, cov=30, read_len=150, frag_len=700, err_ppm=10000, k=127, min_freq=2),
-    "tiny": dict(genome_len=200000, cov=30, read_len=150, frag_len=500, err_ppm=2000, k=31, min_freq=2),
+    # name: genome_len, coverage, read_len, frag_len, err_ppm, k, min_freq, seed, cpu_frac (share of the genome the CPU legs build)
+    "c2_ecoli50x_k31": dict(genome_len=4641652, cov=50, read_len=150, frag_len=700, err_ppm=1000, k=31, min_freq=2, seed=1, cpu_frac=0.25),
+    "c2_ecoli50x_k63": dict(genome_len=4641652, cov=50, read_len=150, frag_len=700, err_ppm=1000, k=63, min_freq=2, seed=1, cpu_frac=0.25),
+    "c3_100mbp30x_k31": dict(genome_len=100000000, cov=30, read_len=150, frag_len=700, err_ppm=10000, k=31, min_freq=2, seed=2, cpu_frac=0.03),
+    "c5_100mbp30x_k127": dict(genome_len=100000000, cov=30, read_len=150, frag_len=700, err_ppm=10000, k=127, min_freq=2, seed=2, cpu_frac=0.03),
+    "tiny": dict(genome_len=200000, cov=30, read_len=150, frag_len=500, err_ppm=2000, k=31, min_freq=2, seed=1, cpu_frac=1.0),
 }
-
-# algorithmic (compulsory) bytes per LAUNCH of the kernels that can dominate ("Kernels"):
-# every input element read once, every output element written once.  N = k-mer instances,
-# nb = input bases, U = distinct k-mers kept by the min-count filter, W = key bytes.
-def _stream_bytes(nb):  # packed words (8 B / 32 bases) + window-valid masks (4 B / 32 bases)
-    return 12.0 * ((nb + 31) // 32)
+DEFAULT_WORKLOAD = "c3_100mbp30x_k31"
 
 
-ALG_BYTES = {
-    "msd_hist_kernel": lambda N, nb, U, W: _stream_bytes(nb),
-    "msd_scatter_kernel": lambda N, nb, U, W: _stream_bytes(nb) + W * N,
-    "msd_hist1_kernel": lambda N, nb, U, W: W * N,
-    "msd_scatter1_kernel": lambda N, nb, U, W: 2.0 * W * N,
-    "msd_leaf_kernel": lambda N, nb, U, W: W * N + (W + 4.0) * U,
-    "msd_gather_kernel": lambda N, nb, U, W: 2.0 * (W + 4.0) * U,
-    # multi-word keys (k > 32): same formulas with W = 16 / 32 bytes
-    "msdw_hist_kernel": lambda N, nb, U, W: _stream_bytes(nb),
-    "msdw_scatter_kernel": lambda N, nb, U, W: _stream_bytes(nb) + W * N,
-    "msdw_hist1_kernel": lambda N, nb, U, W: W * N,
-    "msdw_scatter1_kernel": lambda N, nb, U, W: 2.0 * W * N,
-    "msdw_leaf_kernel": lambda N, nb, U, W: W * N + (W + 4.0) * U,
-    "msdw_gather_kernel": lambda N, nb, U, W: 2.0 * (W + 4.0) * U,
-    "radix_scatter_kernel": lambda N, nb, U, W: 2.0 * W * N,   # per pass
-    "radix_hist_kernel": lambda N, nb, U, W: 1.0 * W * N,
-    "extract_emit_kernel": lambda N, nb, U, W: _stream_bytes(nb) + W * N,
-    "pack_kernel": lambda N, nb, U, W: 1.375 * nb,             # 1 B ASCII in, 2 bits + 1 bad bit out
-}
-
-
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
-# captures of the default workload (profiles/README.md); null where no capture exists
-NCU_TRAFFIC = {  # profiles/r1_e_ncu_full_<kernel>.txt, workload c2_ecoli50x_k31 on one GPU
-    "msd_leaf_kernel": 1.486635e9 + 91.601664e6,
-    "msd_scatter_kernel": 87.484672e6 + 1.428851e9,
-    "msd_scatter1_kernel": 1.485387e9 + 1.438692e9,
-}
-
-
-def nreads_for(w):
-    return 2 * int(round(w["cov"] * w["genome_len"] / (2.0 * w["read_len"])))
+def nreads_for(w, genome_len=None):
+    return 2 * int(round(w["cov"] * (genome_len or w["genome_len"]) / (2.0 * w["read_len"])))
 
 
 def kmers_per_read(w):
     return max(0, w["read_len"] - w["k"] + 1)
+
+
+def shard_range(n, rank, world, mult=2):
+    """reads [first, first + count) of rank `rank` (pairs stay together); same rule as genomegraphs.jl_b200/dist.py"""
+    units = n // mult
+    lo = (units * rank // world) * mult
+    hi = (units * (rank + 1) // world) * mult if rank + 1 < world else n
+    return lo, hi - lo
+
+
+def dtype_of(k):
+    return "u64" if k <= 32 else "u128" if k <= 64 else "u256"
+
+
+def base_config(args, w, world):
+    """identical in both arms (ours / reference): the workload and how it is spread over the GPUs"""
+    weak = args.scaling == "weak"
+    genome_total = w["genome_len"] * (world if weak else 1)
+    nreads_total = nreads_for(w) * (world if weak else 1)
+    wl = {k: v for k, v in w.items() if k != "cpu_frac"}
+    return {"workload": args.workload, **wl, "n_gpus": world, "scaling": args.scaling if world > 1 else "single",
+            "genome_len_total": genome_total, "reads_total": nreads_total, "kmer_instances_total": nreads_total * kmers_per_read(w),
+            "input_bytes_total": nreads_total * w["read_len"],
+            "l2_policy": "inputs (%.0f MB of reads per GPU per step) larger than the 126 MB L2; no flush needed" % (nreads_total * w["read_len"] / world / 1e6),
+            "parallelism": ("1 GPU" if world == 1 else
+                            "1 process per GPU; reads sharded by index; super-k-mers partitioned by minimizer hash and stored into the owner "
+                            "GPU's buffer over NVLink; kept k-mers range-partitioned in a second exchange; graph stage on the gathered table")}
+
+
+def cpu_sample(w):
+    """the bounded sample of the workload the CPU legs build: the same generator parameters on a shorter genome"""
+    glen = max(int(w["genome_len"] * w["cpu_frac"]), 4 * w["frag_len"])
+    return glen, nreads_for(w, glen)
 
 
 class ClockSampler:
@@ -136,23 +137,27 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def run_reference(args, w, rank, world):
-    """CPU arm: the oracle (C restatement of the reference algorithm) on a bounded sample."""
+    """CPU arm: the oracle (C restatement of the reference algorithm) on a bounded sample.  Loads oracle/ only."""
     if rank != 0:
         return
     from oracle import oracle as O
-    pkg = G.load_package()
-    frac = args.cpu_sample_frac
-    glen = max(int(w["genome_len"] * frac), 4 * w["frag_len"])
-    ws = dict(w, genome_len=glen)
-    nreads = nreads_for(ws)
-    seq, offs = pkg.synth_reads(1, glen, nreads, w["read_len"], True, w["frag_len"], w["err_ppm"])
+    threads = host_threads()   # stated explicitly: torch.distributed.run exports OMP_NUM_THREADS=1
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    glen, nreads = cpu_sample(w)
+    seq, offs = O.synth_reads(w["seed"], glen, nreads, w["read_len"], True, w["frag_len"], w["err_ppm"], threads=threads)
     n_inst = nreads * kmers_per_read(w)
-    threads = O.lib().ggo_max_threads()
 
     def step():
         keys, cnt = O.count_kmers(seq, offs, w["k"], threads=threads)
-        g = O.dbg(O.filter_counts(keys, cnt, w["k"], w["min_freq"]), w["k"])
+        g = O.dbg(O.filter_counts(keys, cnt, w["k"], w["min_freq"], u8=True), w["k"])
         return g.n_nodes
 
     for _ in range(args.warmup):
@@ -162,18 +167,40 @@ def run_reference(args, w, rank, world):
         step()
     dt = time.perf_counter() - t0
     v = n_inst * args.steps / dt
-    sample = "genome %d bp (%.3g of the workload's), %d reads, %d k-mer instances per step; counting with %d OpenMP threads, unitig walk sequential" % (
-        glen, frac, nreads, n_inst, threads)
+    sample = ("each step = the workload's generator on a %d bp genome (%.3g of the workload's %d bp), %d reads, %d k-mer instances; "
+              "counting with %d OpenMP threads (set explicitly), unitig walk sequential as in the reference" % (
+                  glen, glen / w["genome_len"], w["genome_len"], nreads, n_inst, threads))
     out = {
         "impl": "reference", "metric": "DBG build: input k-mers/sec", "value": v, "unit": "k-mers/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u64" if w["k"] <= 32 else "u128" if w["k"] <= 64 else "u256", "data": "synthetic",
-        "config": {"workload": args.workload, **w, "sample": sample},
+        "scaling": "weak" if args.scaling == "weak" else "strong", "vs_baseline": None, "dtype": dtype_of(w["k"]), "data": "synthetic",
+        "config": base_config(args, w, world),
         "cpu_baseline": {"value": v, "unit": "k-mers/s", "cores": threads, "kind": "port", "sample": sample,
                          "note": "C restatement of the Julia algorithm (oracle/), not Julia itself; JULIA_NUM_THREADS n/a (the reference is single-threaded)"},
         "e2e": {"value": v, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out), flush=True)
+
+
+def csrc_sha():
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "genomegraphs.jl_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def ncu_traffic(kernel, workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from an `ncu --set full` capture of THIS build
+    (profiles/ncu_traffic.json, written by scripts/ncu_summary.py --traffic with the csrc hash of the build it saw); else None"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        return None
+    if t.get("csrc_sha") != csrc_sha() or t.get("workload") != workload:
+        return None
+    return t.get("kernels", {}).get(kernel)
 
 
 def main():
@@ -182,9 +209,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2_ecoli50x_k31", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-sample-frac", type=float, default=0.25)
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the one-GPU rebuild of the whole job that checks the N-GPU result")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     rank = int(os.environ.get("RANK", "0"))
@@ -197,6 +225,7 @@ def main():
         run_reference(args, w, rank, world)
         return
 
+    import __graft_entry__ as G
     pkg = G.build() if rank == 0 or world == 1 else None
     dist = None
     if world > 1:
@@ -211,22 +240,20 @@ def main():
     L = N.lib()
     ctx = pkg.Context(local_rank)
     H = ctx.h
-    k, min_freq, rl = w["k"], w["min_freq"], w["read_len"]
-    W = 8 * L.gg_kmer_words(k)
-    nreads = nreads_for(w)
+    k, min_freq, rl, seed = w["k"], w["min_freq"], w["read_len"], w["seed"]
+    weak = args.scaling == "weak" and world > 1
+    genome_total = w["genome_len"] * (world if weak else 1)
+    nreads_total = nreads_for(w) * (world if weak else 1)
+    first_read, nreads = shard_range(nreads_total, rank, world, 2)
     nbytes = nreads * rl
-    n_inst = nreads * kmers_per_read(w)
-    # Weak scaling: ONE job whose size grows with the GPU count -- genome world x genome_len, world x nreads
-    # reads; rank r owns reads [r * nreads, (r + 1) * nreads) and (after the exchange) one key range.
-    seed = 1
-    genome_total = w["genome_len"] * world
+    n_inst_total = nreads_total * kmers_per_read(w)
     comm = pkg.dist.Comm.from_torch(ctx) if world > 1 else None
 
     # ---- inputs: generated on the device, kept resident in HBM; pinned host copy for the e2e leg
     d_seq, d_offs, h_seq = C.c_void_p(), C.c_void_p(), C.c_void_p()
     N.check(H, L.gg_dev_alloc(H, nbytes + 64, C.byref(d_seq)))
     N.check(H, L.gg_dev_alloc(H, 8 * (nreads + 1), C.byref(d_offs)))
-    N.check(H, L.gg_synth_reads_range_dev(H, seed, genome_total, rank * nreads, nreads, rl, 1, w["frag_len"], w["err_ppm"], 0, d_seq))
+    N.check(H, L.gg_synth_reads_range_dev(H, seed, genome_total, first_read, nreads, rl, 1, w["frag_len"], w["err_ppm"], 0, d_seq))
     pinned = []
 
     def pinned_array(count, dtype):
@@ -254,7 +281,7 @@ def main():
         gh = C.c_void_p()
         if comm is None:
             N.check(H, L.gg_dbg_from_reads_dev(H, d_seq, d_offs, nreads, nbytes, k, min_freq, C.byref(gh)))
-        else:  # distributed count (one NCCL exchange) + all-gather of the kept k-mers + graph stage
+        else:
             N.check(H, L.gg_dist_dbg_from_reads_dev(comm.h, d_seq, d_offs, nreads, nbytes, k, min_freq, C.byref(gh), None))
         return gh
 
@@ -263,25 +290,29 @@ def main():
         N.check(H, L.gg_graph_sizes(gh, C.byref(nn), C.byref(nb), C.byref(nl), C.byref(kk)))
         return nn.value, nb.value, nl.value
 
+    def graph_checksum(gh):
+        cs = C.c_uint64()
+        N.check(H, L.gg_graph_checksum(gh, C.byref(cs)))
+        return cs.value
+
     sampler = ClockSampler(local_rank)
     if rank == 0:   # one sampler per job: concurrent nvidia-smi pollers contend on the driver and stall CUDA calls
         sampler.start()
 
     # ---- warm-up (also fills the memory pool) ----
     launches = 0
-    sizes = None
+    sizes = checksum = None
     for _ in range(args.warmup):
         gh = step_dev()
-        sizes = graph_sizes(gh)
+        sizes, checksum = graph_sizes(gh), graph_checksum(gh)
         L.gg_graph_free(gh)
         launches = ctx.last_timings()[1]
 
-    # ---- timed: K steps, inputs resident in HBM (232 MB of reads > 126 MB L2) ----
+    # ---- timed: K steps, inputs resident in HBM ----
     barrier()
     s_first = sampler.mark()
     N.check(H, L.gg_ctx_event_record(H, 0))
     t0 = time.perf_counter()
-    stage_ms = None
     for _ in range(args.steps):
         gh = step_dev()
         L.gg_graph_free(gh)
@@ -330,7 +361,6 @@ def main():
         t = torch.tensor([dev_s, e2e_s, wall], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_s, e2e_s, wall = (float(x) for x in t.tolist())
-    total_inst = n_inst * world
 
     # ---- roofline of the dominant kernel: one extra, untimed, profiled step ----
     roofline, top, allk = None, [], []
@@ -339,26 +369,13 @@ def main():
     L.gg_graph_free(gh)
     L.gg_ctx_set_profile(H, 0)
     prof_text = L.gg_ctx_kernel_profile(H).decode()
-    # distinct k-mers (all / kept by the filter) of this rank's key range: the writes of the counting kernels
-    ch = C.c_void_p()
-    if comm is None:
-        N.check(H, L.gg_count_kmers_dev(H, d_seq, d_offs, nreads, nbytes, k, 1, C.byref(ch)))
-    else:
-        N.check(H, L.gg_dist_count_kmers_dev(comm.h, d_seq, d_offs, nreads, nbytes, k, 1, 1, C.byref(ch), None))
-    nu_all = C.c_uint64()
-    N.check(H, L.gg_counts_sizes(ch, C.byref(nu_all), None, None, None))
-    N.check(H, L.gg_counts_filter(ch, min_freq, 0))
-    nu_kept = C.c_uint64()
-    N.check(H, L.gg_counts_sizes(ch, C.byref(nu_kept), None, None, None))
-    L.gg_counts_free(ch)
     if rank == 0:
-        prof = []
-        for ln in prof_text.splitlines():
-            name, cnt, ms = ln.split("\t")
-            prof.append((name.split("<")[0].strip("( "), int(cnt), float(ms)))
         agg = {}
-        for name, cnt, ms in prof:
-            a = agg.setdefault(name, [0, 0.0]); a[0] += cnt; a[1] += ms
+        for ln in prof_text.splitlines():
+            f = ln.split("\t")
+            name = f[0].split("<")[0].strip("( ")
+            a = agg.setdefault(name, [0, 0.0, 0.0])
+            a[0] += int(f[1]); a[1] += float(f[2]); a[2] += float(f[3]) if len(f) > 3 else 0.0
         tot_ms = sum(v[1] for v in agg.values())
         allk = sorted(agg.items(), key=lambda kv: -kv[1][1])
         top = allk[:8]
@@ -368,73 +385,86 @@ def main():
         except Exception:
             pass
         peak, peak_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json hbm_gbs)") if peaks.get("hbm_gbs") else (6650.0, "fallback (B200_PROFILING.md)")
-        distinct = {"all": nu_all.value, "kept": nu_kept.value}
 
-        def model(kname, kcnt, kms):
-            f = ALG_BYTES.get(kname)
-            if f is None:
-                return None
-            by = f(float(n_inst), float(nbytes), float(nu_kept.value), float(W))
-            gbs = by / (kms / kcnt / 1e3) / 1e9
-            return by, gbs
+        def line(kname, kcnt, kms, kby):
+            d = {"kernel": kname, "launches_per_step": kcnt, "avg_launch_ms": kms / kcnt, "share_of_kernel_time": kms / tot_ms}
+            if kby > 0:   # algorithmic bytes of the launches themselves (library-side model)
+                gbs = kby / (kms / 1e3) / 1e9
+                d.update({"alg_bytes_per_launch": kby / kcnt, "achieved": gbs, "frac": gbs / peak})
+            else:
+                d.update({"alg_bytes_per_launch": None, "achieved": None, "frac": None,
+                          "note": "latency-bound (random access / pointer chasing) or bookkeeping: no streaming byte model"})
+            return d
 
-        name, (cnt, ms) = top[0]
-        m = model(name, cnt, ms)
-        if m is not None:
-            roofline = {"bound": "hbm", "kernel": name, "achieved": m[1], "peak": peak, "unit": "GB/s", "frac": m[1] / peak,
-                        "traffic": NCU_TRAFFIC.get(name) if (args.workload == "c2_ecoli50x_k31" and world == 1) else None, "launches_per_step": cnt, "avg_launch_ms": ms / cnt, "share_of_kernel_time": ms / tot_ms,
-                        "alg_bytes_per_launch": m[0], "peak_source": peak_src}
-        else:
-            roofline = {"bound": "hbm", "kernel": name, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
-                        "launches_per_step": cnt, "avg_launch_ms": ms / cnt, "share_of_kernel_time": ms / tot_ms, "peak_source": peak_src,
-                        "note": "latency-bound pointer chasing; no streaming byte model"}
-        kernel_rooflines = []
-        for kname, (kcnt, kms) in top:
-            m = model(kname, kcnt, kms)
-            if m is not None:
-                kernel_rooflines.append({"kernel": kname, "alg_bytes_per_launch": m[0], "avg_launch_ms": kms / kcnt,
-                                         "achieved_gbs": round(m[1], 1), "frac": round(m[1] / peak, 4)})
-        roofline["distinct_kmers"] = distinct
-        roofline["other_kernels"] = kernel_rooflines
+        name, (cnt, ms, by) = top[0]
+        roofline = {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src, **line(name, cnt, ms, by),
+                    "traffic": ncu_traffic(name, args.workload) if world == 1 else None,
+                    "other_kernels": [line(n_, *v) for n_, v in top[1:] if v[2] > 0]}
+        # the whole path against the pipeline-independent floor of SURVEY 8(d): ASCII bases in, kept (k-mer, count) out
+        Wb = 8 * L.gg_kmer_words(k)
+        roofline["path"] = {"floor_bytes_per_step_per_gpu": 1.0 * nbytes, "note": "floor = every input base read once as ASCII (SURVEY 8d, + (W+4) per kept k-mer)",
+                            "floor_gbs_at_value": nbytes / (dev_s / args.steps) / 1e9, "key_bytes": Wb}
 
-    # ---- CPU baseline beside it (rank 0, N = 1 only) ----
+    # ---- parity of the benchmarked result + CPU baseline beside it ----
+    parity = {"ok": True}
     cpu = None
+    if world > 1 and not args.no_parity:
+        # the same job once more on ONE GPU (rank 0, outside every timed region): checksum + sizes must equal the N-GPU result
+        if rank == 0:
+            da, do = C.c_void_p(), C.c_void_p()
+            nb_all = nreads_total * rl
+            N.check(H, L.gg_dev_alloc(H, nb_all + 64, C.byref(da)))
+            N.check(H, L.gg_dev_alloc(H, 8 * (nreads_total + 1), C.byref(do)))
+            N.check(H, L.gg_synth_reads_range_dev(H, seed, genome_total, 0, nreads_total, rl, 1, w["frag_len"], w["err_ppm"], 0, da))
+            oa = np.arange(nreads_total + 1, dtype=np.uint64) * np.uint64(rl)
+            N.check(H, L.gg_memcpy_h2d(H, do, oa.ctypes.data_as(C.c_void_p), oa.nbytes))
+            g1 = C.c_void_p()
+            N.check(H, L.gg_dbg_from_reads_dev(H, da, do, nreads_total, nb_all, k, min_freq, C.byref(g1)))
+            s1, c1 = graph_sizes(g1), graph_checksum(g1)
+            L.gg_graph_free(g1); L.gg_dev_free(H, da); L.gg_dev_free(H, do)
+            parity.update({"n_gpu_vs_1_gpu": {"sizes_equal": s1 == sizes, "checksum_equal": c1 == checksum, "sizes": list(sizes), "checksum": "%016x" % checksum}})
+            parity["ok"] = parity["ok"] and s1 == sizes and c1 == checksum
+        barrier()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O
-        frac = args.cpu_sample_frac
-        glen = int(w["genome_len"] * frac)
-        ws = dict(w, genome_len=glen)
-        nr = nreads_for(ws)
-        sseq, soffs = pkg.synth_reads(1, glen, nr, rl, True, w["frag_len"], w["err_ppm"])
+        glen, nr = cpu_sample(w)
+        sseq, soffs = O.synth_reads(seed, glen, nr, rl, True, w["frag_len"], w["err_ppm"], threads=host_threads())
         tc = time.perf_counter()
-        keys, cnt = O.count_kmers(sseq, soffs, k, threads=1)
-        og = O.dbg(O.filter_counts(keys, cnt, k, min_freq), k)
+        okeys, ocnt = O.count_kmers(sseq, soffs, k, threads=1)
+        okept = O.filter_counts(okeys, ocnt, k, min_freq, u8=True)
+        og = O.dbg(okept, k)
         tc = time.perf_counter() - tc
         cpu = {"value": nr * kmers_per_read(w) / tc, "unit": "k-mers/s", "cores": 1, "kind": "port",
-               "sample": "same workload at %.3g of the genome length (%d bp, %d reads, %d k-mer instances), 1 thread as the reference runs; %.1f s" % (
-                   frac, glen, nr, nr * kmers_per_read(w), tc),
+               "sample": "the workload's generator on a %d bp genome (%.3g of the workload's), %d reads, %d k-mer instances, 1 thread as the reference runs; %.1f s" % (
+                   glen, glen / w["genome_len"], nr, nr * kmers_per_read(w), tc),
                "host_cpus": os.cpu_count(), "nodes": og.n_nodes,
                "note": "C restatement of the Julia algorithm (oracle/), not Julia itself; JULIA_NUM_THREADS n/a"}
+        # the GPU path on the SAME bytes, through the host-buffer C-ABI calls: everything must be bit-equal
+        counts = pkg.serial_mem(k, pkg.CANONICAL, ctx=ctx)((sseq, soffs))
+        gk, gc, _ = counts.export()
+        ga = pkg.dbg_from_reads((sseq, soffs), k, min_freq, ctx=ctx)
+        counts.free()
+        chk = {"kmers": bool(np.array_equal(gk, okeys)), "counts": bool(np.array_equal(gc, ocnt)),
+               "nodes": bool(np.array_equal(ga.bases, og.bases) and np.array_equal(ga.node_offsets.astype(np.int64), og.node_off)),
+               "links": bool(np.array_equal(ga.link_triples, og.link_tri) and np.array_equal(ga.link_row_offsets.astype(np.int64), og.link_row))}
+        parity.update({"gpu_vs_oracle_on_cpu_sample": chk, "distinct_kmers": int(len(okeys)), "kept_kmers": int(len(okept)), "nodes": int(og.n_nodes),
+                       "link_entries": int(len(og.link_tri) // 3)})
+        parity["ok"] = parity["ok"] and all(chk.values())
 
     if rank == 0:
         h2d = nbytes + offs.nbytes
         d2h = out_off.nbytes + nb + out_row.nbytes + 3 * nl * 8
         out = {
-            "metric": "DBG build: input k-mers/sec", "value": total_inst * args.steps / dev_s, "unit": "k-mers/s",
+            "metric": "DBG build: input k-mers/sec", "value": n_inst_total * args.steps / dev_s, "unit": "k-mers/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u64" if k <= 32 else "u128" if k <= 64 else "u256", "data": "synthetic",
-            "config": {"workload": args.workload, **w, "reads_per_gpu": nreads, "kmer_instances_per_gpu": n_inst,
-                       "input_bytes_per_gpu": nbytes, "l2_policy": "inputs (%.0f MB of reads + %.0f MB of k-mers per step) larger than the 126 MB L2" % (nbytes / 1e6, n_inst * W / 1e6),
-                       "genome_len_total": genome_total,
-                       "parallelism": ("1 GPU" if world == 1 else "1 process per GPU; reads sharded by index, k-mers range-partitioned over the ranks "
-                                       "with one NCCL send/recv exchange, kept k-mers all-gathered, graph stage replicated"),
-                       "graph": {"nodes": nn, "bases": nb, "link_entries": nl}},
+            "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None,
+            "dtype": dtype_of(k), "data": "synthetic",
+            "config": base_config(args, w, world),
+            "graph": {"nodes": nn, "bases": nb, "link_entries": nl, "checksum": "%016x" % checksum},
             "wall_ms_per_step": 1e3 * wall / args.steps,
             "stage_ms_last_step": stage_ms,
-            "hbm_gbs_effective": None,
-            "e2e": {"value": total_inst * args.steps / e2e_s, "unit": "k-mers/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * e2e_s / args.steps},
+            "e2e": {"value": n_inst_total * args.steps / e2e_s, "unit": "k-mers/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * e2e_s / args.steps, "per": "rank 0's shard (every rank copies its own shard in and the graph out)"},
             "gpu_launches": launches * args.steps,
             "gpu_launches_per_step": launches,
             "clocks": clocks,
@@ -442,6 +472,7 @@ def main():
             "top_kernels_ms": [{"kernel": n_, "launches": v[0], "ms": round(v[1], 4)} for n_, v in top],
             "all_kernels_ms": {n_: [v[0], round(v[1], 4)] for n_, v in allk},
             "cpu_baseline": cpu,
+            "parity_checked": parity,
         }
         print(json.dumps(out), flush=True)
 
@@ -456,6 +487,9 @@ def main():
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    if not parity["ok"]:
+        sys.stderr.write("PARITY FAILURE: %s\n" % json.dumps(parity))
+        sys.exit(3)
 
 
 if __name__ == "__main__":

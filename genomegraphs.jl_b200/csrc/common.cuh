@@ -38,7 +38,8 @@ struct gg_ctx {
     u64 *h_scalar = nullptr;  // 64 x u64
     // optional per-kernel profiling (gg_ctx_set_profile): events around every launch
     bool profile = false;
-    struct ProfRec { std::string name; cudaEvent_t a, b; };
+    struct ProfRec { std::string name; cudaEvent_t a, b; double bytes; };
+    double next_bytes = 0.0;  // algorithmic bytes of the next launch (prof_bytes); consumed by LAUNCH
     std::vector<ProfRec> prof;
     std::vector<cudaEvent_t> ev_pool;
     std::string prof_text;
@@ -82,9 +83,20 @@ static inline cudaEvent_t prof_event(gg_ctx *ctx) {
         if ((ctx)->profile) { _pa = prof_event(ctx); _pb = prof_event(ctx); cudaEventRecord(_pa, (ctx)->stream); } \
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);             \
         (ctx)->launches++;                                                           \
-        if ((ctx)->profile) { cudaEventRecord(_pb, (ctx)->stream); (ctx)->prof.push_back({std::string(kname), _pa, _pb}); } \
+        if ((ctx)->profile) { cudaEventRecord(_pb, (ctx)->stream); (ctx)->prof.push_back({std::string(kname), _pa, _pb, (ctx)->next_bytes}); } \
+        (ctx)->next_bytes = 0.0;                                                     \
         CK(cudaGetLastError());                                                      \
     } while (0)
+
+// Algorithmic (compulsory) bytes of the NEXT launch, for the per-kernel roofline of the profile: every input element
+// read once + every output element written once, evaluated with the launch's own element counts.
+static inline void prof_bytes(gg_ctx *ctx, double bytes) { ctx->next_bytes = bytes; }
+// bytes that are only known after the launch (output sizes): added to the latest profiled launch whose name contains `name`
+static inline void prof_add_bytes(gg_ctx *ctx, const char *name, double bytes) {
+    if (!ctx->profile) return;
+    for (size_t i = ctx->prof.size(); i-- > 0;)
+        if (ctx->prof[i].name.find(name) != std::string::npos) { ctx->prof[i].bytes += bytes; return; }
+}
 
 static inline u64 ceil_div(u64 a, u64 b) { return (a + b - 1) / b; }
 

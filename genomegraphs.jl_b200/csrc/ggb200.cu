@@ -6,6 +6,7 @@
 #include "sort.cuh"
 #include "msdcount.cuh"
 #include "msdcountw.cuh"
+#include "skm.cuh"
 #include "dist.cuh"
 #include "graph.cuh"
 #include "umi.cuh"
@@ -45,14 +46,15 @@ static void timing_reset(gg_ctx *ctx) {
 }
 static void profile_collect(gg_ctx *ctx) {
     if (ctx->prof.empty()) return;
-    std::map<std::string, std::pair<u64, double>> acc;
+    struct Acc { u64 n; double ms, bytes; };
+    std::map<std::string, Acc> acc;
     std::vector<std::string> order;
     for (auto &r : ctx->prof) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, r.a, r.b);
         auto it = acc.find(r.name);
-        if (it == acc.end()) { acc[r.name] = {1, ms}; order.push_back(r.name); }
-        else { it->second.first++; it->second.second += ms; }
+        if (it == acc.end()) { acc[r.name] = {1, ms, r.bytes}; order.push_back(r.name); }
+        else { it->second.n++; it->second.ms += ms; it->second.bytes += r.bytes; }
         ctx->ev_pool.push_back(r.a);
         ctx->ev_pool.push_back(r.b);
     }
@@ -60,7 +62,7 @@ static void profile_collect(gg_ctx *ctx) {
     ctx->prof_text.clear();
     char line[512];
     for (auto &n : order) {
-        snprintf(line, sizeof(line), "%s\t%llu\t%.6f\n", n.c_str(), (unsigned long long)acc[n].first, acc[n].second);
+        snprintf(line, sizeof(line), "%s\t%llu\t%.6f\t%.0f\n", n.c_str(), (unsigned long long)acc[n].n, acc[n].ms, acc[n].bytes);
         ctx->prof_text += line;
     }
 }
@@ -222,6 +224,13 @@ static u64 extract_all(gg_ctx *ctx, const u8 *d_seq, const u64 *d_offs, u64 nrea
     return n;
 }
 
+static inline u32 eff_min_freq(u64 min_freq) {
+    u32 mf = min_freq > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)min_freq;
+    return mf < 1 ? 1 : mf;
+}
+// dbg!(sg, counted_kmers, min_freq) compares freq(x), the UInt8-saturated count of a MerCount (KmerAnalysis, recalled):
+// min(count, 255) >= min_freq.  For min_freq <= 255 that equals count >= min_freq; above it nothing is kept.
+static inline u64 dbg_min_freq(u64 min_freq) { return min_freq > 255 ? 0xFFFFFFFFull : min_freq; }
 // min_freq > 1 drops rarer k-mers inside the counting kernels (fused filter of the reads -> graph
 // pipeline); *filtered tells the caller whether that happened.
 template <int W>
@@ -231,6 +240,21 @@ static gg_counts *count_kmers_dev_impl(gg_ctx *ctx, const u8 *d_seq, const u64 *
     c->ctx = ctx; c->k = k; c->W = W;
     if (filtered) *filtered = false;
     try {
+        if (W == 1 && skm_supported(k, canonical) && !getenv("GG_FORCE_LSD") && !getenv("GG_FORCE_MSD")) {
+            stage_begin(ctx, ST_PACK);
+            PackedReads pr;
+            pack_reads(ctx, d_seq, d_offs, nreads, nbytes, pr);
+            DBuf<u32> valid;
+            window_valid_mask(ctx, pr, k, valid);
+            stage_end(ctx, ST_PACK);
+            DBuf<u64> ukeys;
+            DBuf<u32> counts;
+            c->n_unique = skm_count(ctx, pr, valid.p, k, canonical, eff_min_freq(min_freq), ukeys, counts, &c->n_instances);
+            c->d_keys = ukeys.take();
+            c->d_counts = counts.take();
+            if (filtered) *filtered = true;
+            return c;
+        }
         if (W == 1 && msd_supported(k, canonical) && !getenv("GG_FORCE_LSD")) {
             stage_begin(ctx, ST_PACK);
             PackedReads pr;
@@ -314,6 +338,34 @@ __global__ void is_sorted_kernel(const u64 *__restrict__ keys, u64 n, u32 *__res
     if (km_cmp<W>(km_load<W>(keys, i), km_load<W>(keys, i + 1)) > 0) *flag = 1;
 }
 
+// read_offsets (host): offs[0] == 0 and non-decreasing (the reference's per-read sequences cannot overlap or leave gaps)
+static void check_offsets_host(gg_ctx *ctx, const u64 *offs, u64 nreads) {
+    bool ok = offs[0] == 0;
+    u64 bad = 0;
+    for (u64 i = 0; ok && i < nreads; ++i)
+        if (offs[i] > offs[i + 1]) { ok = false; bad = i; }
+    if (!ok) {
+        cudaStreamSynchronize(ctx->aux);  // the buffers go back to the allocator when the caller's frame unwinds
+        cudaStreamSynchronize(ctx->stream);
+        if (offs[0] != 0) GG_THROW(GG_ERR_ARG, "read_offsets[0] must be 0 (it is %llu)", (unsigned long long)offs[0]);
+        GG_THROW(GG_ERR_ARG, "read_offsets must be non-decreasing (read %llu)", (unsigned long long)bad);
+    }
+}
+// read_offsets (device, the *_dev entry points): offs[0] == 0, non-decreasing, offs[nreads] == nbytes
+__global__ void check_offsets_kernel(const u64 *__restrict__ offs, u64 nreads, u64 nbytes, u32 *__restrict__ bad) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > nreads) return;
+    if (i == 0 && offs[0] != 0) *bad = 1u;
+    if (i == nreads) { if (offs[nreads] != nbytes) *bad = 1u; }
+    else if (offs[i] > offs[i + 1]) *bad = 1u;
+}
+static void check_offsets_dev(gg_ctx *ctx, const u64 *d_offs, u64 nreads, u64 nbytes) {
+    if (!d_offs) GG_THROW(GG_ERR_ARG, "read_offsets is null");
+    DBuf<u32> bad(ctx, 1);
+    dfill(ctx, bad.p, sizeof(u32), 0u);
+    LAUNCH(ctx, check_offsets_kernel, (unsigned)ceil_div(nreads + 1, 256), 256, 0, d_offs, nreads, nbytes, bad.p);
+    if (read_scalar<u32>(ctx, bad.p)) GG_THROW(GG_ERR_ARG, "device read_offsets must start at 0, be non-decreasing and end at nbytes");
+}
 // stage device input from host buffers (padded so that 128-bit loads stay in bounds)
 struct StagedReads {
     DBuf<u8> seq;
@@ -330,18 +382,11 @@ static void stage_reads(gg_ctx *ctx, const u8 *seq, const u64 *offs, u64 nreads,
     // host checks them meanwhile, so neither the check nor the small copy adds to the transfer time
     CK(cudaEventRecord(ctx->aux_ev, ctx->stream));        // the blocks may still be in use by earlier work of this context
     CK(cudaStreamWaitEvent(ctx->aux, ctx->aux_ev, 0));
-    if (s.nbytes) CK(cudaMemcpyAsync(s.seq.p, seq, s.nbytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (s.nbytes) CK(cudaMemcpyAsync(s.seq.p, seq, s.nbytes, cudaMemcpyHostToDevice, ctx->aux));
     CK(cudaMemcpyAsync(s.offs.p, offs, (nreads + 1) * sizeof(u64), cudaMemcpyHostToDevice, ctx->aux));
-    bool ok = true;
-    u64 bad = 0;
-    for (u64 i = 0; i < nreads; ++i)
-        if (offs[i] > offs[i + 1]) { ok = false; bad = i; break; }
     CK(cudaEventRecord(ctx->aux_ev, ctx->aux));
     CK(cudaStreamWaitEvent(ctx->stream, ctx->aux_ev, 0));
-    if (!ok) {
-        cudaStreamSynchronize(ctx->stream);  // the buffers go back to the allocator when this frame unwinds
-        GG_THROW(GG_ERR_ARG, "read_offsets must be non-decreasing (read %llu)", (unsigned long long)bad);
-    }
+    check_offsets_host(ctx, offs, nreads);
 }
 
 // Host buffers -> counts with the transfer pipelined against the front of the path (k <= 32 MSD route):
@@ -355,6 +400,56 @@ static u64 h2d_chunk_bytes() {  // a multiple of 8192 (whole packed words and pa
     }
     return 16ULL << 20;
 }
+// Front of the pipelined host path, shared by the two counting routes: copies on the copy stream, chunk c packed as
+// soon as it has landed, window masks of chunk c - 1 right after (they look one word ahead), then
+// on_range(ci, w0, w1) for the packed words of chunk ci = c - 1.
+template <class OnRange>
+static void host_pipeline_front(gg_ctx *ctx, const u8 *seq, const u64 *offs, u64 nreads, u64 nbytes, int k, DBuf<u8> &dseq, DBuf<u64> &doffs,
+                                PackedReads &pr, DBuf<u32> &valid, u64 chunk_bytes, OnRange on_range) {
+    const u64 nch = ceil_div(nbytes, chunk_bytes);
+    while (ctx->chunk_ev.size() < nch) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->chunk_ev.push_back(e);
+    }
+    // EVERY copy goes to the copy stream (offsets first, then the chunks) and the main stream only waits on events.
+    // Measured: one host-to-device copy issued on the main stream itself is enough to hold all its later kernels
+    // back until the copy stream has drained -- no overlap at all.
+    CK(cudaEventRecord(ctx->aux_ev, ctx->stream));      // the copy stream starts after the earlier work of this context
+    CK(cudaStreamWaitEvent(ctx->aux, ctx->aux_ev, 0));
+    CK(cudaMemcpyAsync(doffs.p, offs, (nreads + 1) * sizeof(u64), cudaMemcpyHostToDevice, ctx->aux));
+    CK(cudaEventRecord(ctx->aux_ev, ctx->aux));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->aux_ev, 0));
+    for (u64 ch = 0; ch < nch; ++ch) {
+        const u64 b0 = ch * chunk_bytes, b1 = b0 + chunk_bytes < nbytes ? b0 + chunk_bytes : nbytes;
+        CK(cudaMemcpyAsync(dseq.p + b0, seq + b0, b1 - b0, cudaMemcpyHostToDevice, ctx->aux));
+        CK(cudaEventRecord(ctx->chunk_ev[ch], ctx->aux));
+    }
+    check_offsets_host(ctx, offs, nreads);  // while the bytes are in flight
+    stage_begin(ctx, ST_PACK);
+    pack_prepare(ctx, doffs.p, nreads, nbytes, pr);
+    valid.alloc(ctx, pr.nwords ? pr.nwords : 1);
+    stage_begin(ctx, ST_EXTRACT);
+    for (u64 ch = 0; ch <= nch; ++ch) {
+        if (ch < nch) {
+            const u64 b0 = ch * chunk_bytes, b1 = b0 + chunk_bytes < nbytes ? b0 + chunk_bytes : nbytes;
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[ch], 0));
+            pack_range(ctx, dseq.p, nbytes, pr, b0 / 16, ceil_div(b1, 16));
+        }
+        if (ch > 0) {  // chunk ch - 1: its look-ahead word is packed now (or it is the last chunk)
+            const u64 w0 = (ch - 1) * (chunk_bytes / 32), w1 = ch < nch ? ch * (chunk_bytes / 32) : pr.nwords;
+            if (w1 > w0) {
+                LAUNCH(ctx, valid32_kernel, (unsigned)ceil_div(w1 - w0, 256), 256, 0, pr.bad.p, pr.brk.p, w0, w1, k, valid.p);
+                on_range(ch - 1, w0, w1);
+            }
+        }
+    }
+}
+
+// Host buffers -> counts with the transfer pipelined against the front of the path (one-word keys):
+// the read bytes travel in chunks on the copy stream; as soon as chunk c has landed it is packed, the window masks of
+// chunk c - 1 follow, and the chunk is scattered at once (super-k-mer route: level-0 capacities from the first chunk's
+// exact record histogram; MSD route: pass A + speculative pass B).  When the last byte arrives only the tail remains.
 static gg_counts *count_kmers_host_pipelined(gg_ctx *ctx, const u8 *seq, const u64 *offs, u64 nreads, int k, int canonical, u64 min_freq,
                                              bool *filtered) {
     if (!offs) GG_THROW(GG_ERR_ARG, "read_offsets is null");
@@ -368,34 +463,51 @@ static gg_counts *count_kmers_host_pipelined(gg_ctx *ctx, const u8 *seq, const u
         DBuf<u64> doffs(ctx, nreads + 1);
         const u64 GG_H2D_CHUNK = h2d_chunk_bytes();
         const u64 nch = ceil_div(nbytes, GG_H2D_CHUNK);
-        while (ctx->chunk_ev.size() < nch) {
-            cudaEvent_t e;
-            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            ctx->chunk_ev.push_back(e);
-        }
-        // EVERY copy goes to the copy stream (offsets first, then the chunks) and the main stream only waits on events.
-        // Measured: one host-to-device copy issued on the main stream itself is enough to hold all its later kernels
-        // back until the copy stream has drained -- no overlap at all.
-        CK(cudaEventRecord(ctx->aux_ev, ctx->stream));      // the copy stream starts after the earlier work of this context
-        CK(cudaStreamWaitEvent(ctx->aux, ctx->aux_ev, 0));
-        CK(cudaMemcpyAsync(doffs.p, offs, (nreads + 1) * sizeof(u64), cudaMemcpyHostToDevice, ctx->aux));
-        CK(cudaEventRecord(ctx->aux_ev, ctx->aux));
-        CK(cudaStreamWaitEvent(ctx->stream, ctx->aux_ev, 0));
-        for (u64 ch = 0; ch < nch; ++ch) {
-            const u64 b0 = ch * GG_H2D_CHUNK, b1 = b0 + GG_H2D_CHUNK < nbytes ? b0 + GG_H2D_CHUNK : nbytes;
-            CK(cudaMemcpyAsync(dseq.p + b0, seq + b0, b1 - b0, cudaMemcpyHostToDevice, ctx->aux));
-            CK(cudaEventRecord(ctx->chunk_ev[ch], ctx->aux));
-        }
-        for (u64 i = 0; i < nreads; ++i)   // checked while the bytes are in flight
-            if (offs[i] > offs[i + 1]) {
-                cudaStreamSynchronize(ctx->aux);
-                cudaStreamSynchronize(ctx->stream);
-                GG_THROW(GG_ERR_ARG, "read_offsets must be non-decreasing (read %llu)", (unsigned long long)i);
-            }
-        stage_begin(ctx, ST_PACK);
         PackedReads pr;
-        pack_prepare(ctx, doffs.p, nreads, nbytes, pr);
-        DBuf<u32> valid(ctx, pr.nwords ? pr.nwords : 1), hist;
+        DBuf<u32> valid;
+        DBuf<u64> ukeys;
+        DBuf<u32> counts;
+        const u32 mf = eff_min_freq(min_freq);
+        if (skm_supported(k, canonical) && !getenv("GG_FORCE_MSD")) {
+            const SkmTune tune = skm_tune();
+            SkmL0 L;
+            SkmGeom g0;
+            g0.k = k; g0.canonical = canonical; g0.b0 = SKM_MAX_B0; g0.b1 = 0;
+            const bool speculate = nch >= 3 && !getenv("GG_NO_SPEC");
+            bool scattered = false;
+            host_pipeline_front(ctx, seq, offs, nreads, nbytes, k, dseq, doffs, pr, valid, GG_H2D_CHUNK, [&](u64 ci, u64 w0, u64 w1) {
+                if (!speculate) return;
+                if (ci == 0) {  // geometry and capacities from the first chunk's records, scaled to the whole input
+                    L.alloc_sample(ctx);
+                    skm_scan_launch<0, false>(ctx, pr, valid.p, w0, w1, 1, g0, L.hist0.p, nullptr, nullptr, nullptr, nullptr, nullptr, L.totals.p, nullptr,
+                                              nullptr);
+                    skm_l0_prepare(ctx, L, k, canonical, (double)pr.nwords / (double)(w1 - w0), false, tune);
+                    scattered = true;
+                }
+                skm_scan_launch<1, false>(ctx, pr, valid.p, w0, w1, 1, L.g, nullptr, L.cur0.p, L.base0.p, L.cap0.p, L.rec0.p, L.hist1.p, L.totals.p,
+                                          L.ovf.p, nullptr);
+            });
+            stage_end(ctx, ST_PACK);
+            bool done = false;
+            if (scattered) {
+                CK(cudaMemcpyAsync(ctx->h_scalar, L.totals.p, 2 * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaMemcpyAsync(ctx->h_scalar + 2, L.ovf.p, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+                if ((u32)ctx->h_scalar[2] == 0 && !getenv("GG_PIPE_TEST_OVERFLOW")) {
+                    const u64 n_inst = ctx->h_scalar[0], n_rec = ctx->h_scalar[1];
+                    c->n_instances = n_inst;
+                    stage_end(ctx, ST_EXTRACT);
+                    c->n_unique = skm_finish(ctx, L.rec0.p, L.base0.p, L.cur0.p, SKM_CUR_STRIDE, 1u << L.g.b0, 1, L.cap_total, L.g, L.hist1.p, n_inst, n_rec,
+                                             mf, tune, ukeys, counts);
+                    done = true;
+                } else L.rec0.release();  // a bin outgrew the share the first chunk predicted (reads sorted by content, say): exact repeat
+            }
+            if (!done) c->n_unique = skm_count(ctx, pr, valid.p, k, canonical, mf, ukeys, counts, &c->n_instances);
+            c->d_keys = ukeys.take();
+            c->d_counts = counts.take();
+            return c;
+        }
+        DBuf<u32> hist;
         DBuf<u8> est;
         msd_pass_a_alloc(ctx, k, hist, est);
         const int est_shift = msd_est_shift(nbytes);
@@ -409,7 +521,8 @@ static gg_counts *count_kmers_host_pipelined(gg_ctx *ctx, const u8 *seq, const u
         // sorted by position, say) only costs a repeat of pass B with exact offsets.
         MsdSpec spec;
         const int spec_b0 = msd_tune().b0_max;
-        const bool speculate = nch >= 3 && spec_b0 <= msd_hist_bits(k) && spec_b0 <= MSD_B0_MAX && !getenv("GG_NO_SPEC");
+        const bool speculate = nch >= 3 && spec_b0 <= msd_hist_bits(k) && spec_b0 <= MSD_B0_MAX && !getenv("GG_NO_SPEC") &&
+                               nbytes + nbytes / 10 + 4096 < 0xFFFFFFFFull;  // the speculative bucket offsets are 32-bit
         if (speculate) {
             const u32 nb0 = 1u << spec_b0;
             spec.b0 = spec_b0;
@@ -417,40 +530,24 @@ static gg_counts *count_kmers_host_pipelined(gg_ctx *ctx, const u8 *seq, const u
             spec.start.alloc(ctx, nb0 + 1); spec.cursor.alloc(ctx, nb0); spec.bend.alloc(ctx, nb0); spec.ovf.alloc(ctx, 1);
             dfill(ctx, spec.ovf.p, sizeof(u32), 0u);
         }
-        stage_begin(ctx, ST_EXTRACT);
-        for (u64 ch = 0; ch <= nch; ++ch) {
-            if (ch < nch) {
-                const u64 b0 = ch * GG_H2D_CHUNK, b1 = b0 + GG_H2D_CHUNK < nbytes ? b0 + GG_H2D_CHUNK : nbytes;
-                CK(cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[ch], 0));
-                pack_range(ctx, dseq.p, nbytes, pr, b0 / 16, ceil_div(b1, 16));
-            }
-            if (ch > 0) {  // chunk ch - 1: its look-ahead word is packed now (or it is the last chunk)
-                const u64 w0 = (ch - 1) * (GG_H2D_CHUNK / 32), w1 = ch < nch ? ch * (GG_H2D_CHUNK / 32) : pr.nwords;
-                if (w1 > w0) {
-                    LAUNCH(ctx, valid32_kernel, (unsigned)ceil_div(w1 - w0, 256), 256, 0, pr.bad.p, pr.brk.p, w0, w1, k, valid.p);
-                    msd_pass_a_range(ctx, pr, valid.p, k, canonical, est_shift, hist.p, est.p, w0, w1, rows.p);
-                    if (speculate) {
-                        if (ch == 1) {  // capacities from the first chunk's histogram
-                            DBuf<u32> h0(ctx, nbh);
-                            dfill(ctx, h0.p, (u64)nbh * sizeof(u32), 0u);
-                            LAUNCH(ctx, msd_hist_rows_reduce_kernel, (unsigned)ceil_div(nbh, 256), 256, 0, rows.p, nrows, nbh, h0.p);
-                            LAUNCH(ctx, msd_spec_caps_kernel, 1, 1024, 0, h0.p, msd_hist_bits(k), spec_b0, (u64)spec.A.n, spec.start.p, spec.cursor.p,
-                                   spec.bend.p);
-                            spec.used = true;
-                        }
-                        msd_pass_b_spec(ctx, pr, valid.p, k, canonical, spec_b0, spec.cursor.p, spec.bend.p, spec.ovf.p, spec.A.p, w0, w1);
-                    }
+        host_pipeline_front(ctx, seq, offs, nreads, nbytes, k, dseq, doffs, pr, valid, GG_H2D_CHUNK, [&](u64 ci, u64 w0, u64 w1) {
+            msd_pass_a_range(ctx, pr, valid.p, k, canonical, est_shift, hist.p, est.p, w0, w1, rows.p);
+            if (speculate) {
+                if (ci == 0) {  // capacities from the first chunk's histogram
+                    DBuf<u32> h0(ctx, nbh);
+                    dfill(ctx, h0.p, (u64)nbh * sizeof(u32), 0u);
+                    LAUNCH(ctx, msd_hist_rows_reduce_kernel, (unsigned)ceil_div(nbh, 256), 256, 0, rows.p, nrows, nbh, h0.p);
+                    LAUNCH(ctx, msd_spec_caps_kernel, 1, 1024, 0, h0.p, msd_hist_bits(k), spec_b0, (u64)spec.A.n, spec.start.p, spec.cursor.p, spec.bend.p);
+                    spec.used = true;
                 }
+                msd_pass_b_spec(ctx, pr, valid.p, k, canonical, spec_b0, spec.cursor.p, spec.bend.p, spec.ovf.p, spec.A.p, w0, w1);
             }
-        }
+        });
         LAUNCH(ctx, msd_hist_rows_reduce_kernel, (unsigned)ceil_div(nbh, 256), 256, 0, rows.p, nrows, nbh, hist.p);
         rows.release();
         stage_end(ctx, ST_PACK);
-        DBuf<u64> ukeys;
-        DBuf<u32> counts;
-        u32 mf = min_freq > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)min_freq;
         if (pr.nwords == 0) { ukeys.alloc(ctx, 1); counts.alloc(ctx, 1); stage_end(ctx, ST_EXTRACT); }
-        else c->n_unique = msd_count_after_a(ctx, pr, valid.p, k, canonical, mf < 1 ? 1 : mf, hist, est, est_shift, ukeys, counts, &c->n_instances,
+        else c->n_unique = msd_count_after_a(ctx, pr, valid.p, k, canonical, mf, hist, est, est_shift, ukeys, counts, &c->n_instances,
                                              speculate ? &spec : nullptr);
         c->d_keys = ukeys.take();
         c->d_counts = counts.take();
@@ -476,6 +573,7 @@ int gg_count_kmers_dev(gg_ctx *ctx, const uint8_t *d_seq, const uint64_t *d_offs
     check_k(k);
     CK(cudaSetDevice(_c->device));
     timing_reset(_c);
+    check_offsets_dev(_c, d_offs, nreads, nbytes);
     stage_begin(_c, ST_TOTAL);
     DISPATCH_W(kmer_words(k), *out = count_kmers_dev_impl<W>(_c, d_seq, d_offs, nreads, nbytes, k, canonical));
     stage_end(_c, ST_TOTAL);
@@ -638,11 +736,12 @@ int gg_dbg_build(gg_ctx *ctx, gg_counts *counts, gg_graph **out) {
 }
 static void dbg_from_reads_dev(gg_ctx *ctx, const u8 *d_seq, const u64 *d_offs, u64 nreads, u64 nbytes, int k, u64 min_freq, gg_graph **out) {
     gg_counts *c = nullptr;
+    min_freq = dbg_min_freq(min_freq);
     stage_begin(ctx, ST_TOTAL);
     bool filtered = false;
     DISPATCH_W(kmer_words(k), c = count_kmers_dev_impl<W>(ctx, d_seq, d_offs, nreads, nbytes, k, 1, min_freq, &filtered));
     try {
-        if (!filtered) { DISPATCH_W(c->W, filter_impl<W>(c, min_freq, 0)); }
+        if (!filtered) { DISPATCH_W(c->W, filter_impl<W>(c, min_freq, 1)); }
         DISPATCH_W(c->W, *out = build_graph<W>(ctx, c->d_keys, c->n_unique, c->k));
     } catch (...) {
         gg_counts_free(c);
@@ -660,6 +759,7 @@ int gg_dbg_from_reads_dev(gg_ctx *ctx, const uint8_t *d_seq, const uint64_t *d_o
     check_k(k);
     CK(cudaSetDevice(_c->device));
     timing_reset(_c);
+    check_offsets_dev(_c, d_offs, nreads, nbytes);
     dbg_from_reads_dev(_c, d_seq, d_offs, nreads, nbytes, k, min_freq, out);
     API_END
 }
@@ -672,7 +772,7 @@ int gg_dbg_from_reads(gg_ctx *ctx, const uint8_t *seq, const uint64_t *offs, uin
     timing_reset(_c);
     if (host_pipeline_ok(k, 1)) {
         stage_begin(_c, ST_TOTAL);
-        gg_counts *c = count_kmers_host_pipelined(_c, seq, offs, nreads, k, 1, min_freq, nullptr);
+        gg_counts *c = count_kmers_host_pipelined(_c, seq, offs, nreads, k, 1, dbg_min_freq(min_freq), nullptr);
         try {
             DISPATCH_W(c->W, *out = build_graph<W>(_c, c->d_keys, c->n_unique, c->k));
         } catch (...) {
@@ -939,7 +1039,7 @@ int gg_dist_dbg_from_reads_dev(gg_comm *cm, const uint8_t *d_seq, const uint64_t
     timing_reset(_c);
     stage_begin(_c, ST_TOTAL);
     gg_counts *c = nullptr, *f = nullptr;
-    DISPATCH_W(kmer_words(k), c = dist_count_impl<W>(cm, d_seq, d_offs, nreads, nbytes, k, 1, min_freq, n_instances_global));
+    DISPATCH_W(kmer_words(k), c = dist_count_impl<W>(cm, d_seq, d_offs, nreads, nbytes, k, 1, dbg_min_freq(min_freq), n_instances_global));
     try {
         stage_begin(_c, ST_FILTER);  // the all-gather of the kept k-mers is booked under "filter"
         f = counts_allgather_impl(cm, c);

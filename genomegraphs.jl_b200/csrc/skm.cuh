@@ -1,0 +1,806 @@
+// skm.cuh -- K2+K3+K4 for 17 <= k <= 32: counting by MINIMIZER-partitioned super-k-mers.
+//
+// Replaces (reference) KmerAnalysis serial_mem: collect every canonical k-mer -> sort! ->
+// run-length collapse (docs/src/man/assembly.md:126-128), followed by the min-count filter of
+// dbg!(sg, counted_kmers, min_freq) (src/dbg.jl:275-276).  Output is identical (sorted unique
+// k-mers + counts); the route never materialises the 8-byte k-mer instances in HBM:
+//
+//   S  skm_scan_kernel<COUNT>   (sample) records per level-0 bin -> speculative bin capacities
+//   0  skm_scan_kernel<SCATTER> roll over the packed reads; every window gets the minimum, over its
+//                               k-m+1 m-mers, of a strand-symmetric m-mer hash (its minimizer);
+//                               consecutive windows with one minimizer form a SUPER-K-MER, stored as
+//                               one 16-byte record (<= 48 bases + length + level-1 digit) in the
+//                               level-0 bin its minimizer hashes to: ~1.9 B per k-mer instead of 8.
+//                               A k-mer and its reverse complement have the same m-mer set, so all
+//                               instances of a canonical k-mer meet in one bin.  Multi-GPU: the bins
+//                               are owned by ranks and the records are stored straight into the
+//                               owner's buffer over NVLink (dist.cuh).
+//   1  skm_l1_kernel            records -> 2^(b0+b1) leaf bins (exact sizes from pass 0's histogram)
+//   E  skm_leaf_kernel          one CTA per leaf bin: records expanded to canonical k-mers in
+//                               registers, counted in a shared-memory hash table; keys with
+//                               count >= min_freq appended (unordered) to the kept list
+//   F  skm_sort_*               kept (k-mer, count) pairs -> ascending k-mer order: one partition by
+//                               the top key bits + one shared-memory ordering pass per bucket
+//
+// Algorithmic bytes per k-mer instance (R = records per instance ~ 2 / (WIN + 1), U' = kept keys):
+// S+0: 0.375 B/base read + 16 R written; 1: 32 R; E: 16 R read + 12 U'/N written; F: 48 U'/N.
+#pragma once
+#include "msdcount.cuh"
+
+#define SKM_THREADS 256
+#define SKM_STAGE_CAP 4096    // records a CTA stages in shared memory before it reserves space in the bins
+#define SKM_CUR_STRIDE 64     // the level-0 cursors sit 256 bytes apart: neighbours would serialise in one L2 slice
+#define SKM_MAX_B0 9
+#define SKM_MAX_B1 12
+#define SKM_ALIGN 1024        // level-0 regions are multiples of this many records (tiles of pass 1 never straddle a region)
+#define SKM_MAXPROBE 64
+
+static inline bool skm_supported(int k, int canonical) { return k >= 17 && k <= 32 && (canonical || k < 32); }
+static inline int skm_logw(int k) { return k >= 25 ? 4 : 3; }   // WIN = 2^logw + 1 = k - m + 1 m-mer positions per window
+// consecutive packed words (32 windows each) per thread: a CTA tile yields ~3 K records in both geometries
+static inline int skm_twords(int k) { return skm_logw(k) == 4 ? 4 : 2; }
+static inline u64 skm_tile_words(int k) { return (u64)SKM_THREADS * skm_twords(k); }
+
+// bin digits of a minimizer hash: the minimum of WIN hashes is far from uniform, its finalised image is
+__host__ __device__ __forceinline__ u32 skm_digits(u32 h) {
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    return h;
+}
+
+struct SkmGeom {
+    int k, canonical, b0, b1;
+};
+
+// multi-GPU: rank q owns the level-0 bins [first[q], first[q + 1]); base0 / cap0 then describe this source's
+// private region of every bin inside the owner's buffer
+struct SkmPeers {
+    ulonglong2 *ptr[MSD_MAX_PEERS];
+    u32 first[MSD_MAX_PEERS + 1];
+    int n;
+};
+__device__ __forceinline__ int skm_owner(const SkmPeers &pt, u32 b) {
+    int o = 0;
+#pragma unroll
+    for (int q = 1; q < MSD_MAX_PEERS; ++q) o += (q < pt.n && b >= pt.first[q]) ? 1 : 0;
+    return o;
+}
+
+// One record: `len` consecutive windows starting at base `start` (len + k - 1 <= 48 bases, left-aligned in 128
+// bits: .x = bases 0..31, top half of .y = bases 32..47); low 32 bits of .y = meta: len - 1 (5 bits) |
+// level-1 digit << 5 | further digit bits << 17.
+__device__ __forceinline__ ulonglong2 skm_make_record(const u64 *__restrict__ packed, u64 start, u32 len, int k, u32 meta) {
+    const u32 nb = len + (u32)k - 1u;  // 17 .. 48
+    const u64 j = start >> 5;
+    const int r2 = 2 * (int)(start & 31);
+    const u64 w0 = packed[j], w1 = packed[j + 1], w2 = packed[j + 2];
+    u64 hi = r2 ? ((w0 << r2) | (w1 >> (64 - r2))) : w0;
+    u64 lo = r2 ? ((w1 << r2) | (w2 >> (64 - r2))) : w1;
+    if (nb <= 32) { hi &= ~0ULL << (64 - 2 * nb); lo = 0; }
+    else lo &= ~0ULL << (64 - 2 * (nb - 32));
+    return make_ulonglong2(hi, lo | (u64)meta);
+}
+
+struct SkmScanSmem {
+    ulonglong2 srec[SKM_STAGE_CAP];     // staged records of the tile
+    u32 sq[32 * SKM_THREADS];           // per-thread queue: minimizer hash of every run that starts in the current word
+    u32 hist[1 << SKM_MAX_B0];          // records per level-0 bin, then the running cursor inside the reserved run
+    u32 gbase[1 << SKM_MAX_B0];         // first record slot of this tile's run in every bin (absolute index into the buffer)
+    u32 glim[1 << SKM_MAX_B0];          // end of the bin's region
+    u16 sbin[SKM_STAGE_CAP];
+    u32 s_n;
+};
+// MODE 0: count records per level-0 bin at SKM_MAX_B0 bits (hist0); MODE 1: scatter the records.
+// The launch covers the packed words [w0, w1); CTA c handles tile number c * stride of 256 * TWORDS words
+// (stride > 1: sampling for the capacity estimate).  Records are staged in shared memory, space is reserved once
+// per (tile, bin) -- one global atomic per ~6 records on cursors that sit in different L2 slices -- and the tile's
+// records of a bin land next to each other.
+template <int LOGW, int MODE, bool PEER>
+__global__ void __launch_bounds__(SKM_THREADS, 2) skm_scan_kernel(const u64 *__restrict__ packed, const u32 *__restrict__ valid, u64 w0, u64 w1,
+                                                                  u32 stride, SkmGeom g, u32 *__restrict__ hist0, u32 *__restrict__ cur0,
+                                                                  const u32 *__restrict__ base0, const u32 *__restrict__ cap0,
+                                                                  ulonglong2 *__restrict__ out, u32 *__restrict__ hist1,
+                                                                  unsigned long long *__restrict__ totals /* [0] instances, [1] records */,
+                                                                  u32 *__restrict__ ovf, SkmPeers pt) {
+    constexpr int WIN = (1 << LOGW) + 1;
+    constexpr int NH = 32 + WIN - 1;      // m-mer positions the 32 windows of a word look at
+    constexpr int TWORDS = LOGW == 4 ? 4 : 2;
+    extern __shared__ __align__(16) u8 smem_raw[];
+    SkmScanSmem &S = *reinterpret_cast<SkmScanSmem *>(smem_raw);
+    const int k = g.k, m = k - WIN + 1;   // 9 <= m <= 16
+    const int b0 = MODE == 0 ? SKM_MAX_B0 : g.b0;
+    const u32 nb0 = 1u << b0;
+    const u32 mmask = m == 16 ? 0xFFFFFFFFu : ((1u << (2 * m)) - 1u);
+    const u32 rmul = 1u << (2 * m - 2);
+    const u64 tbase = w0 + ((u64)blockIdx.x * stride) * (SKM_THREADS * TWORDS) + (u64)threadIdx.x * TWORDS;
+    u32 o_len = 0, o_h = 0;   // run open at the end of the previous word of this thread
+    u64 o_start = 0;
+    u32 n_inst = 0, n_rec = 0;
+    for (u32 i = threadIdx.x; i < nb0; i += SKM_THREADS) S.hist[i] = 0;
+    if (threadIdx.x == 0) S.s_n = 0;
+    __syncthreads();
+
+    auto emit = [&](u64 start, u32 len, u32 h) {
+        n_inst += len; n_rec += 1;
+        const u32 d = skm_digits(h);
+        const u32 bin0 = b0 ? (d >> (32 - b0)) : 0u;
+        if (MODE == 0) { atomicAdd(&S.hist[bin0], 1u); return; }
+        const u32 rest = b0 ? (d << b0) : d;  // digit bits below bin0, left-aligned
+        const u32 bin1 = g.b1 ? (rest >> (32 - g.b1)) : 0u;
+        const u32 meta = (len - 1u) | (bin1 << 5) | ((((g.b1 ? (rest << g.b1) : rest)) >> 17) << 17);
+        const ulonglong2 rec = skm_make_record(packed, start, len, k, meta);
+        atomicAdd(&hist1[((u64)bin0 << g.b1) | bin1], 1u);
+        const u32 slot = atomicAdd(&S.s_n, 1u);
+        if (slot < SKM_STAGE_CAP) {
+            S.srec[slot] = rec;
+            S.sbin[slot] = (u16)bin0;
+            atomicAdd(&S.hist[bin0], 1u);
+        } else {  // staging area full (far more runs than random minimizers give): reserve record by record
+            const u32 pos = atomicAdd(&cur0[(u64)bin0 * SKM_CUR_STRIDE], 1u);
+            if (pos < cap0[bin0]) {
+                if (PEER) pt.ptr[skm_owner(pt, bin0)][(u64)base0[bin0] + pos] = rec;
+                else out[(u64)base0[bin0] + pos] = rec;
+            } else *ovf = 1u;
+        }
+    };
+
+#pragma unroll 1
+    for (int it = 0; it < TWORDS; ++it) {
+        const u64 t = tbase + it;
+        if (t >= w1) break;
+        const u32 vm = valid[t];
+        if (vm == 0) {  // no k-mer starts in this word: the open run ends here
+            if (o_len) { emit(o_start, o_len, o_h); o_len = 0; }
+            continue;
+        }
+        const u64 a0 = packed[t], a1 = packed[t + 1];
+        // ---- hash of the canonical m-mer at every position 0 .. NH-1 (forward and reverse complement rolled) ----
+        u32 h[NH];
+        {
+            u32 f = (u32)(a0 >> (64 - 2 * m));
+            u32 r = (u32)rev2_u64(~a0) & mmask;
+            const u64 xh = (a0 << (2 * m)) | (a1 >> (64 - 2 * m)), xl = a1 << (2 * m);  // bases m, m+1, ... left-aligned
+#pragma unroll
+            for (int q = 0; q < NH; ++q) {
+                h[q] = min(f, r) * 0x9E3779B1u;
+                if (q + 1 < NH) {
+                    const u32 nbq = q < 32 ? ((u32)(xh >> (62 - 2 * q)) & 3u) : ((u32)(xl >> (62 - 2 * (q - 32))) & 3u);
+                    f = ((f << 2) | nbq) & mmask;
+                    r = (r >> 2) + (3u - nbq) * rmul;
+                }
+            }
+        }
+        // ---- sliding minimum over WIN positions: doubling to 2^LOGW, then one more ----
+#pragma unroll
+        for (int s = 0; s < LOGW; ++s) {
+            const int d = 1 << s;
+#pragma unroll
+            for (int q = 0; q < NH; ++q)
+                if (q + 2 * d - 1 < NH) h[q] = min(h[q], h[q + d]);
+        }
+#pragma unroll
+        for (int q = 0; q < 32; ++q) h[q] = min(h[q], h[q + 1]);
+        // ---- runs: consecutive valid windows with one minimizer hash, at most WIN long ----
+        u32 nm = 0, nq = 0;  // nm: bit j set <=> window j starts a run
+        {
+            u32 rl = o_len, rh = o_h;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const bool v = (vm >> (31 - j)) & 1u;
+                const bool cont = v && rl != 0 && h[j] == rh && rl < (u32)WIN;
+                if (v && !cont) {
+                    S.sq[nq * SKM_THREADS + threadIdx.x] = h[j];
+                    ++nq;
+                    nm |= 1u << j;
+                    rh = h[j];
+                    rl = 0;
+                }
+                rl = v ? rl + 1 : 0;
+            }
+        }
+        const u32 V = __brev(vm);   // bit j <=> window j valid
+        const u32 cm = V & ~nm;     // window j continues the run of window j - 1
+        if (o_len) {                // the carried run takes the leading continuation windows and ends in this word (WIN < 32)
+            o_len += (u32)__ffs((int)~cm) - 1u;
+            emit(o_start, o_len, o_h);
+            o_len = 0;
+        }
+        u32 mask = nm, qi = 0;
+        while (mask) {
+            const int j = __ffs((int)mask) - 1;
+            mask &= mask - 1;
+            const u32 hq = S.sq[qi * SKM_THREADS + threadIdx.x];
+            ++qi;
+            const u32 rest = j == 31 ? 0u : (cm >> (j + 1));
+            const u32 len = 1u + (u32)__ffs((int)~rest) - 1u;  // rest has zeros shifted in at the top: never all ones
+            const u64 start = (t << 5) + (u64)j;
+            if ((u32)j + len == 32u) { o_start = start; o_len = len; o_h = hq; }  // still open at the end of the word
+            else emit(start, len, hq);
+        }
+    }
+    if (o_len) emit(o_start, o_len, o_h);
+    // totals: one atomic per warp
+    for (int d = 16; d > 0; d >>= 1) { n_inst += __shfl_xor_sync(FULL_MASK, n_inst, d); n_rec += __shfl_xor_sync(FULL_MASK, n_rec, d); }
+    if (lane_id() == 0 && n_rec) { atomicAdd(&totals[0], (unsigned long long)n_inst); atomicAdd(&totals[1], (unsigned long long)n_rec); }
+    __syncthreads();
+    if (MODE == 0) {
+        for (u32 b = threadIdx.x; b < nb0; b += SKM_THREADS)
+            if (S.hist[b]) atomicAdd(&hist0[b], S.hist[b]);
+        return;
+    }
+    // ---- one reservation per (tile, bin), then the staged records go out grouped by bin ----
+    const u32 n = min(S.s_n, (u32)SKM_STAGE_CAP);
+    for (u32 b = threadIdx.x; b < nb0; b += SKM_THREADS) {
+        const u32 c = S.hist[b];
+        const u32 base = base0[b], lim = base + cap0[b];
+        const u32 gpos = c ? atomicAdd(&cur0[(u64)b * SKM_CUR_STRIDE], c) : 0u;
+        if (c && (u64)gpos + c > (u64)cap0[b]) *ovf = 1u;
+        S.gbase[b] = base + min(gpos, cap0[b]);
+        S.glim[b] = lim;
+        S.hist[b] = 0;
+    }
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < n; i += SKM_THREADS) {
+        const u32 b = S.sbin[i];
+        const u32 p = S.gbase[b] + atomicAdd(&S.hist[b], 1u);
+        if (p < S.glim[b]) {
+            if (PEER) pt.ptr[skm_owner(pt, b)][p] = S.srec[i];
+            else out[p] = S.srec[i];
+        }
+    }
+}
+
+// Capacities of the level-0 regions from a (sampled) histogram taken at hb bits and collapsed to b0 <= hb bits: region r
+// gets round_up(scale * c * 1.25 + 4 * scale * sqrt(c + 1) + 1024, SKM_ALIGN) records (exact counts: round_up(c, SKM_ALIGN)).
+// One CTA.  base has nreg + 1 entries; *total_cap gets the sum.
+__global__ void __launch_bounds__(1024) skm_caps_kernel(const u32 *__restrict__ hist, int hb, int b0, float scale, int exact, u32 *__restrict__ base,
+                                                        u32 *__restrict__ cap, u64 *__restrict__ total_cap, u32 force_cap) {
+    __shared__ u32 ws[33];
+    __shared__ u64 s_run;
+    const u32 nreg = 1u << b0, grp = 1u << (hb - b0);
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    for (u32 r0 = 0; r0 < nreg; r0 += 1024) {
+        const u32 r = r0 + threadIdx.x;
+        u32 c = 0;
+        if (r < nreg) {
+            u64 cnt = 0;
+            for (u32 i = 0; i < grp; ++i) cnt += hist[r * grp + i];
+            const float hv = (float)cnt;
+            double want = exact ? (double)cnt : (double)(scale * hv * 1.25f + 4.0f * scale * sqrtf(hv + 1.0f) + 1024.0f);
+            if (force_cap) want = force_cap;  // tests: provoke the overflow path
+            u64 w = (u64)want;
+            w = ((w + SKM_ALIGN - 1) / SKM_ALIGN) * SKM_ALIGN;
+            if (w == 0) w = SKM_ALIGN;
+            c = (u32)(w / SKM_ALIGN);  // in units of SKM_ALIGN: the block scan stays within 32 bits
+        }
+        u32 tot;
+        const u32 ex = block_excl_scan(c, ws, &tot);
+        if (r < nreg) {
+            const u64 bb = (s_run + ex) * SKM_ALIGN;
+            base[r] = bb > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)bb;
+            cap[r] = c * SKM_ALIGN;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_run += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const u64 bb = s_run * SKM_ALIGN;
+        base[nreg] = bb > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)bb;
+        *total_cap = bb;
+    }
+}
+
+// ---- pass 1: level-0 regions -> leaf bins ---------------------------------------------------------
+// Region r (a level-0 bin, or a (bin, source) pair on the multi-GPU path) holds cnt[r * cnt_stride] records at
+// base[r]; its records belong to the local level-0 bin r / nsrc.
+__global__ void __launch_bounds__(256) skm_l1_kernel(const ulonglong2 *__restrict__ in, const u32 *__restrict__ base, const u32 *__restrict__ cnt,
+                                                     u32 cnt_stride, u32 nreg, u32 nsrc, int b1, const u32 *__restrict__ lbeg,
+                                                     u32 *__restrict__ cur1, ulonglong2 *__restrict__ out) {
+    const u64 tile0 = (u64)blockIdx.x * SKM_ALIGN;
+    if (tile0 >= base[nreg]) return;
+    u32 lo = 0, hi = nreg;  // largest r with base[r] <= tile0
+    while (hi - lo > 1) {
+        const u32 mid = (lo + hi) >> 1;
+        if ((u64)base[mid] <= tile0) lo = mid; else hi = mid;
+    }
+    const u32 r = lo, n = cnt[(u64)r * cnt_stride];
+    const u32 rel0 = (u32)(tile0 - base[r]);
+    const u64 leaf0 = (u64)(r / nsrc) << b1;
+    const u32 m1 = (1u << b1) - 1u;
+#pragma unroll
+    for (int u = 0; u < SKM_ALIGN / 256; ++u) {
+        const u32 rel = rel0 + u * 256 + threadIdx.x;
+        if (rel < n) {
+            const ulonglong2 rec = in[tile0 - rel0 + rel];
+            const u64 leaf = leaf0 | (((u32)rec.y >> 5) & m1);
+            const u32 pos = atomicAdd(&cur1[leaf], 1u);
+            out[(u64)lbeg[leaf] + pos] = rec;
+        }
+    }
+}
+__global__ void skm_gather_strided_kernel(const u32 *__restrict__ in, u32 stride, u32 n, u32 *__restrict__ out) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[(u64)i * stride];
+}
+
+// ---- pass E: one CTA per leaf bin -------------------------------------------------------------------
+template <int THREADS, int LOG_HT>
+struct SkmLeafSmem {
+    static constexpr int HT = 1 << LOG_HT;
+    u64 tab[HT];
+    u32 tcnt[HT];  // occurrences beyond the first one
+    u32 ws[33];
+    u32 s_ovf;
+    unsigned long long s_gbase;
+};
+__device__ __forceinline__ u32 skm_slot(u64 key, int lh) { return (((u32)key ^ (u32)(key >> 32)) * 0x9E3779B1u) >> (32 - lh); }
+
+// Leaf bin l = records recs[lbeg[l] .. + lcnt[l]); CTA c takes the bins c, c + grid, ... (the bins are near-uniform).
+// Kept keys (count >= min_freq) are appended to okeys / ocnts at *kept_cursor.  A bin whose table fills up is put on
+// the overflow list instead (finished by the host path).
+template <int THREADS, int LOG_HT, int LOGW>
+__global__ void __launch_bounds__(THREADS) skm_leaf_kernel(const ulonglong2 *__restrict__ recs, const u32 *__restrict__ lbeg,
+                                                           const u32 *__restrict__ lcnt, u32 nleaf, int k, int canonical, u32 min_freq,
+                                                           u64 *__restrict__ okeys, u32 *__restrict__ ocnts, unsigned long long *kept_cursor,
+                                                           u32 *__restrict__ ovf_list, u32 *ovf_n, u32 test_ovf_mod) {
+    constexpr int WIN = (1 << LOGW) + 1;
+    extern __shared__ __align__(16) u8 smem_raw[];
+    SkmLeafSmem<THREADS, LOG_HT> &S = *reinterpret_cast<SkmLeafSmem<THREADS, LOG_HT> *>(smem_raw);
+    const int s = 64 - 2 * k;
+    const u64 topmask = ~0ULL << s;
+    for (u32 leaf = blockIdx.x; leaf < nleaf; leaf += gridDim.x) {
+        const u32 n = lcnt[leaf];
+        if (n == 0) continue;
+        const ulonglong2 *rp = recs + lbeg[leaf];
+        // table size from the record count (instances <= n * WIN; a table of >= 2 x instances cannot fill up)
+        int lh = LOG_HT;
+        while (lh > 9 && (1u << (lh - 1)) >= 2u * n * (u32)WIN) --lh;
+        const u32 HT = 1u << lh, HM = HT - 1u;
+        __syncthreads();  // the previous bin's sweep is over
+        {
+            ulonglong2 *t2 = reinterpret_cast<ulonglong2 *>(S.tab);
+            for (u32 i = threadIdx.x; i < HT / 2; i += THREADS) t2[i] = make_ulonglong2(MSD_EMPTY, MSD_EMPTY);
+            uint4 *c4 = reinterpret_cast<uint4 *>(S.tcnt);
+            for (u32 i = threadIdx.x; i < HT / 4; i += THREADS) c4[i] = make_uint4(0, 0, 0, 0);
+            if (threadIdx.x == 0) S.s_ovf = (test_ovf_mod && leaf % test_ovf_mod == 0) ? 1u : 0u;
+        }
+        __syncthreads();
+        volatile u32 *ovf = &S.s_ovf;
+        if (!*ovf) {
+            for (u32 i = threadIdx.x; i < n; i += THREADS) {
+                const ulonglong2 rec = rp[i];
+                const u32 len = ((u32)rec.y & 31u) + 1u;
+                const u64 a0 = rec.x, a1 = rec.y & 0xFFFFFFFF00000000ULL;
+                const u64 nbc = ~(k == 32 ? a1 : ((a0 << (2 * k)) | (a1 >> s)));  // complemented bases k, k+1, ... of the record
+                u64 rl = rev2_u64(~a0) << s;                                       // reverse complement of window 0, left-aligned
+#pragma unroll
+                for (int j = 0; j < WIN; ++j) {
+                    if ((u32)j < len) {
+                        const u64 fl = (j == 0 ? a0 : ((a0 << (2 * j)) | (a1 >> (64 - 2 * j)))) & topmask;
+                        const u64 key = ((canonical && rl < fl) ? rl : fl) >> s;
+                        u32 slot = skm_slot(key, lh);
+                        int probes = 0;
+                        for (;;) {
+                            u64 c = S.tab[slot];
+                            if (c == MSD_EMPTY) {
+                                c = atomicCAS((unsigned long long *)&S.tab[slot], (unsigned long long)MSD_EMPTY, (unsigned long long)key);
+                                if (c == MSD_EMPTY) break;  // claimed: first occurrence
+                            }
+                            if (c == key) { atomicAdd(&S.tcnt[slot], 1u); break; }
+                            slot = (slot + 1) & HM;
+                            if (++probes > SKM_MAXPROBE) { *ovf = 1; break; }
+                        }
+                    }
+                    if (j + 1 < WIN) rl = ((rl >> 2) & topmask) | ((nbc << (2 * j)) & 0xC000000000000000ULL);
+                }
+                if (*ovf) break;
+            }
+        }
+        __syncthreads();
+        if (S.s_ovf) {
+            if (threadIdx.x == 0) ovf_list[atomicAdd(ovf_n, 1u)] = leaf;
+            continue;
+        }
+        // ---- kept keys -> global list (two sweeps over the table: count, then write) ----
+        u32 c = 0;
+        for (u32 slot = threadIdx.x; slot < HT; slot += THREADS)
+            c += (S.tab[slot] != MSD_EMPTY && S.tcnt[slot] + 1u >= min_freq) ? 1u : 0u;
+        u32 total;
+        const u32 ex = block_excl_scan(c, S.ws, &total);
+        if (total) {
+            if (threadIdx.x == 0) S.s_gbase = atomicAdd(kept_cursor, (unsigned long long)total);
+            __syncthreads();
+            u64 o = S.s_gbase + ex;
+            for (u32 slot = threadIdx.x; slot < HT; slot += THREADS) {
+                const u64 key = S.tab[slot];
+                const u32 cnt = S.tcnt[slot] + 1u;
+                if (key != MSD_EMPTY && cnt >= min_freq) { okeys[o] = key; ocnts[o] = cnt; ++o; }
+            }
+        }
+    }
+}
+
+// ---- overflowed leaf bins: all their k-mers as plain keys (finished with the generic sort + run-length path) ----
+__global__ void skm_ovf_size_kernel(const ulonglong2 *__restrict__ recs, const u32 *__restrict__ lbeg, const u32 *__restrict__ lcnt,
+                                    const u32 *__restrict__ ovf_list, u32 n_ovf, unsigned long long *__restrict__ total) {
+    for (u32 q = blockIdx.x; q < n_ovf; q += gridDim.x) {
+        const u32 leaf = ovf_list[q];
+        const ulonglong2 *rp = recs + lbeg[leaf];
+        u32 mine = 0;
+        for (u32 i = threadIdx.x; i < lcnt[leaf]; i += blockDim.x) mine += ((u32)rp[i].y & 31u) + 1u;
+        mine = warp_sum(mine);
+        if (lane_id() == 0 && mine) atomicAdd(total, (unsigned long long)mine);
+    }
+}
+__global__ void skm_ovf_expand_kernel(const ulonglong2 *__restrict__ recs, const u32 *__restrict__ lbeg, const u32 *__restrict__ lcnt,
+                                      const u32 *__restrict__ ovf_list, u32 n_ovf, int k, int canonical, u64 *__restrict__ out,
+                                      unsigned long long *__restrict__ cursor) {
+    const int s = 64 - 2 * k;
+    const u64 topmask = ~0ULL << s;
+    for (u32 q = blockIdx.x; q < n_ovf; q += gridDim.x) {
+        const u32 leaf = ovf_list[q];
+        const ulonglong2 *rp = recs + lbeg[leaf];
+        for (u32 i = threadIdx.x; i < lcnt[leaf]; i += blockDim.x) {
+            const ulonglong2 rec = rp[i];
+            const u32 len = ((u32)rec.y & 31u) + 1u;
+            const u64 a0 = rec.x, a1 = rec.y & 0xFFFFFFFF00000000ULL;
+            u64 o = atomicAdd(cursor, (unsigned long long)len);
+            for (u32 j = 0; j < len; ++j) {
+                const u64 fl = (j == 0 ? a0 : ((a0 << (2 * j)) | (a1 >> (64 - 2 * j)))) & topmask;
+                const u64 fw = fl >> s;
+                Kmer<1> x; x.w[0] = fw;
+                const u64 rc = km_rc<1>(x, k).w[0];
+                out[o + j] = (canonical && rc < fw) ? rc : fw;
+            }
+        }
+    }
+}
+
+// ---- pass F: kept pairs -> ascending key order ------------------------------------------------------
+#define SKM_SORT_CAP 8192   // pairs one CTA orders in shared memory
+__global__ void skm_sort_hist_kernel(const u64 *__restrict__ keys, u64 n, int sh, u32 *__restrict__ hist) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) atomicAdd(&hist[(u32)(keys[i] >> sh)], 1u);
+}
+__global__ void skm_sort_scatter_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ cnts, u64 n, int sh, const u32 *__restrict__ bstart,
+                                        u32 *__restrict__ cursor, u64 *__restrict__ okeys, u32 *__restrict__ ocnts) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        const u64 key = keys[i];
+        const u32 b = (u32)(key >> sh);
+        const u32 pos = bstart[b] + atomicAdd(&cursor[b], 1u);
+        okeys[pos] = key;
+        ocnts[pos] = cnts[i];
+    }
+}
+// max bucket size -> *mx; buckets larger than SKM_SORT_CAP -> big list (first 1024 of them)
+__global__ void skm_sort_big_kernel(const u32 *__restrict__ hist, u32 nb, u32 *__restrict__ big, u32 *__restrict__ nbig) {
+    const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nb && hist[b] > SKM_SORT_CAP) {
+        const u32 p = atomicAdd(nbig, 1u);
+        if (p < 1024) big[p] = b;
+    }
+}
+// One CTA per bucket (grid-stride): pairs IN[bstart[b] ..) of one top-bits bucket are ordered by key into OUT.
+// Keys are distinct.  Order-preserving bins on the bits below the bucket digit + rank-by-counting inside a bin.
+__global__ void __launch_bounds__(256) skm_sort_bucket_kernel(const u64 *__restrict__ ik, const u32 *__restrict__ ic, const u32 *__restrict__ bstart,
+                                                              u32 nb, int sh, u64 *__restrict__ ok, u32 *__restrict__ oc) {
+    extern __shared__ __align__(16) u8 smem_raw[];
+    u64 *sk = reinterpret_cast<u64 *>(smem_raw);              // SKM_SORT_CAP
+    u32 *sc = reinterpret_cast<u32 *>(sk + SKM_SORT_CAP);     // SKM_SORT_CAP
+    __shared__ u32 bins[1025], bincur[1024], ws[33];
+    const int bb = sh < 10 ? sh : 10, bsh = sh - bb;
+    const u32 bm = (1u << bb) - 1u;
+    const int nbins = 1 << bb;
+    for (u32 b = blockIdx.x; b < nb; b += gridDim.x) {
+        const u32 s0 = bstart[b], n = bstart[b + 1] - s0;
+        if (n == 0) continue;
+        if (n > SKM_SORT_CAP) continue;  // handled by the host (generic radix sort of that range)
+        if (n == 1) { if (threadIdx.x == 0) { ok[s0] = ik[s0]; oc[s0] = ic[s0]; } continue; }
+        __syncthreads();
+        for (int i = threadIdx.x; i <= nbins; i += 256) bins[i] = 0;
+        __syncthreads();
+        for (u32 i = threadIdx.x; i < n; i += 256) atomicAdd(&bins[(u32)(ik[s0 + i] >> bsh) & bm], 1u);
+        __syncthreads();
+        {   // exclusive scan of bins[0 .. nbins) in place
+            const int bpt = (nbins + 255) / 256;
+            const int lo = min(nbins, (int)threadIdx.x * bpt), hi = min(nbins, lo + bpt);
+            u32 s = 0;
+            for (int i = lo; i < hi; ++i) s += bins[i];
+            u32 tot;
+            u32 run = block_excl_scan(s, ws, &tot);
+            for (int i = lo; i < hi; ++i) { const u32 c = bins[i]; bins[i] = run; bincur[i] = run; run += c; }
+            if (threadIdx.x == 0) bins[nbins] = n;
+        }
+        __syncthreads();
+        for (u32 i = threadIdx.x; i < n; i += 256) {
+            const u64 key = ik[s0 + i];
+            const u32 p = atomicAdd(&bincur[(u32)(key >> bsh) & bm], 1u);
+            sk[p] = key;
+            sc[p] = ic[s0 + i];
+        }
+        __syncthreads();
+        for (u32 i = threadIdx.x; i < n; i += 256) {
+            const u64 key = sk[i];
+            const u32 bi = (u32)(key >> bsh) & bm;
+            const u32 lo = bins[bi], hi = bins[bi + 1];
+            u32 rank = 0;
+            for (u32 q = lo; q < hi; ++q) rank += sk[q] < key;
+            ok[s0 + lo + rank] = key;
+            oc[s0 + lo + rank] = sc[i];
+        }
+    }
+}
+__global__ void skm_widen_kernel(const u32 *__restrict__ in, u64 n, u64 *__restrict__ out) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+}
+__global__ void skm_narrow_kernel(const u64 *__restrict__ in, u64 n, u32 *__restrict__ out) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (u32)in[i];
+}
+
+// ------------------------------------- host side -------------------------------------------------
+struct SkmTune {
+    u32 bin_inst = 2048;   // target k-mer instances per leaf bin (distinct <= instances <= half the leaf table for most bins)
+    int variant = 0;       // leaf geometry
+    u32 sample = 16;       // capacity estimate from every `sample`-th tile
+    u32 test_ovf_mod = 0;  // tests (GG_SKM_TEST_OVERFLOW=m): every leaf bin with index % m == 0 takes the overflow path
+    u32 force_cap = 0;     // tests (GG_SKM_TEST_CAP=c): level-0 capacities of c records -> provokes the exact repeat
+};
+static SkmTune skm_tune() {
+    SkmTune t;
+    if (const char *e = getenv("GG_SKM_VARIANT")) t.variant = atoi(e);
+    if (t.variant == 2) t.bin_inst = 4096;
+    if (const char *e = getenv("GG_SKM_BIN")) t.bin_inst = (u32)atoi(e);
+    if (const char *e = getenv("GG_SKM_SAMPLE")) t.sample = (u32)atoi(e);
+    if (const char *e = getenv("GG_SKM_TEST_OVERFLOW")) t.test_ovf_mod = (u32)atoi(e);
+    if (const char *e = getenv("GG_SKM_TEST_CAP")) t.force_cap = (u32)atoi(e);
+    if (t.bin_inst < 64) t.bin_inst = 64;
+    if (t.sample < 1) t.sample = 1;
+    return t;
+}
+// digit widths from the (estimated) number of instances
+static SkmGeom skm_geom(u64 n_inst_est, int k, int canonical, const SkmTune &t) {
+    SkmGeom g;
+    g.k = k; g.canonical = canonical;
+    int bits = 0;
+    while (bits < SKM_MAX_B0 + SKM_MAX_B1 && (n_inst_est >> bits) > t.bin_inst) ++bits;
+    g.b0 = bits < SKM_MAX_B0 ? bits : SKM_MAX_B0;
+    g.b1 = bits - g.b0;
+    return g;
+}
+
+template <int MODE, bool PEER>
+static void skm_scan_launch(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, u64 w0, u64 w1, u32 stride, const SkmGeom &g, u32 *hist0, u32 *cur0,
+                            const u32 *base0, const u32 *cap0, ulonglong2 *out, u32 *hist1, u64 *totals, u32 *ovf, const SkmPeers *pt) {
+    if (w1 <= w0) return;
+    const u64 ntiles = ceil_div(w1 - w0, skm_tile_words(g.k));
+    const u64 grid = ceil_div(ntiles, stride);
+    SkmPeers none;
+    memset(&none, 0, sizeof(none));
+    const size_t smem = sizeof(SkmScanSmem);
+    if (skm_logw(g.k) == 4) {
+        set_max_smem(ctx, skm_scan_kernel<4, MODE, PEER>, smem);
+        LAUNCH(ctx, (skm_scan_kernel<4, MODE, PEER>), (unsigned)grid, SKM_THREADS, smem, pr.packed.p, valid, w0, w1, stride, g, hist0, cur0, base0, cap0, out,
+               hist1, (unsigned long long *)totals, ovf, pt ? *pt : none);
+    } else {
+        set_max_smem(ctx, skm_scan_kernel<3, MODE, PEER>, smem);
+        LAUNCH(ctx, (skm_scan_kernel<3, MODE, PEER>), (unsigned)grid, SKM_THREADS, smem, pr.packed.p, valid, w0, w1, stride, g, hist0, cur0, base0, cap0, out,
+               hist1, (unsigned long long *)totals, ovf, pt ? *pt : none);
+    }
+}
+
+template <int THREADS, int LOG_HT>
+static void skm_launch_leaf(gg_ctx *ctx, int ctas_per_sm, const ulonglong2 *recs, const u32 *lbeg, const u32 *lcnt, u32 nleaf, const SkmGeom &g,
+                            u32 min_freq, u64 *okeys, u32 *ocnts, u64 *kept_cursor, u32 *ovf_list, u32 *ovf_n, u32 test_ovf_mod) {
+    const size_t smem = sizeof(SkmLeafSmem<THREADS, LOG_HT>);
+    u32 grid = (u32)ctx->num_sms * ctas_per_sm;
+    if (grid > nleaf) grid = nleaf;
+    if (skm_logw(g.k) == 4) {
+        set_max_smem(ctx, skm_leaf_kernel<THREADS, LOG_HT, 4>, smem);
+        LAUNCH(ctx, (skm_leaf_kernel<THREADS, LOG_HT, 4>), grid, THREADS, smem, recs, lbeg, lcnt, nleaf, g.k, g.canonical, min_freq, okeys, ocnts,
+               (unsigned long long *)kept_cursor, ovf_list, ovf_n, test_ovf_mod);
+    } else {
+        set_max_smem(ctx, skm_leaf_kernel<THREADS, LOG_HT, 3>, smem);
+        LAUNCH(ctx, (skm_leaf_kernel<THREADS, LOG_HT, 3>), grid, THREADS, smem, recs, lbeg, lcnt, nleaf, g.k, g.canonical, min_freq, okeys, ocnts,
+               (unsigned long long *)kept_cursor, ovf_list, ovf_n, test_ovf_mod);
+    }
+}
+
+// kept pairs (unordered, n of them in kk / kc) -> sorted ukeys / ucounts (new buffers)
+static void skm_sort_pairs(gg_ctx *ctx, u64 *kk, u32 *kc, u64 n, int k, DBuf<u64> &ukeys, DBuf<u32> &ucounts) {
+    ukeys.alloc(ctx, n ? n : 1);
+    ucounts.alloc(ctx, n ? n : 1);
+    if (n == 0) return;
+    if (n >= 0xFFFFFFFFull) GG_THROW(GG_ERR_LIMIT, "%llu distinct k-mers exceed the 2^32-1 per-GPU limit", (unsigned long long)n);
+    auto generic = [&](u64 *keys_io, u32 *cnts_io, u64 cnt, u64 *ok, u32 *oc) {  // LSD radix sort with the count as payload
+        DBuf<u64> alt(ctx, cnt), pay(ctx, cnt), pay_alt(ctx, cnt);
+        LAUNCH(ctx, skm_widen_kernel, (unsigned)ceil_div(cnt, 256), 256, 0, cnts_io, cnt, pay.p);
+        u64 *a = keys_io, *b = alt.p, *p = pay.p, *q = pay_alt.p;
+        std::vector<BitRange> ranges = {{0, 2 * k}};
+        radix_sort<1>(ctx, &a, &b, &p, &q, cnt, ranges);
+        CK(cudaMemcpyAsync(ok, a, cnt * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream));
+        LAUNCH(ctx, skm_narrow_kernel, (unsigned)ceil_div(cnt, 256), 256, 0, p, cnt, oc);
+    };
+    if (n <= 4096) { generic(kk, kc, n, ukeys.p, ucounts.p); return; }
+    int tb = 0;
+    while (tb < 22 && tb < 2 * k && (n >> tb) > 1024) ++tb;
+    const int sh = 2 * k - tb;
+    const u32 nb = 1u << tb;
+    DBuf<u32> hist(ctx, nb + 1), bstart(ctx, nb + 1), cursor(ctx, nb), big(ctx, 1024), nbig(ctx, 1);
+    DBuf<u64> tk(ctx, n);
+    DBuf<u32> tc(ctx, n);
+    dfill(ctx, hist.p, (u64)(nb + 1) * sizeof(u32), 0u);
+    dfill(ctx, cursor.p, (u64)nb * sizeof(u32), 0u);
+    dfill(ctx, nbig.p, sizeof(u32), 0u);
+    const unsigned sgrid = (unsigned)std::min<u64>(ceil_div(n, 256), (u64)ctx->num_sms * 32);
+    prof_bytes(ctx, 8.0 * (double)n);
+    LAUNCH(ctx, skm_sort_hist_kernel, sgrid, 256, 0, kk, n, sh, hist.p);
+    exclusive_scan_u32(ctx, hist.p, bstart.p, nb + 1, nullptr);
+    LAUNCH(ctx, skm_sort_big_kernel, (unsigned)ceil_div(nb, 256), 256, 0, hist.p, nb, big.p, nbig.p);
+    prof_bytes(ctx, 24.0 * (double)n);
+    LAUNCH(ctx, skm_sort_scatter_kernel, sgrid, 256, 0, kk, kc, n, sh, bstart.p, cursor.p, tk.p, tc.p);
+    const size_t smem = (size_t)SKM_SORT_CAP * 12;
+    set_max_smem(ctx, skm_sort_bucket_kernel, smem);
+    prof_bytes(ctx, 24.0 * (double)n);
+    LAUNCH(ctx, skm_sort_bucket_kernel, (unsigned)std::min<u64>(nb, (u64)ctx->num_sms * 8), 256, smem, tk.p, tc.p, bstart.p, nb, sh, ukeys.p, ucounts.p);
+    const u32 h_nbig = read_scalar<u32>(ctx, nbig.p);
+    if (h_nbig > 1024) { generic(kk, kc, n, ukeys.p, ucounts.p); return; }  // hopeless skew: sort everything the slow way
+    if (h_nbig) {
+        std::vector<u32> hb(h_nbig), hs(2);
+        CK(cudaMemcpyAsync(hb.data(), big.p, h_nbig * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (u32 b : hb) {
+            CK(cudaMemcpyAsync(hs.data(), bstart.p + b, 2 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            generic(tk.p + hs[0], tc.p + hs[0], (u64)hs[1] - hs[0], ukeys.p + hs[0], ucounts.p + hs[0]);
+        }
+    }
+}
+
+// Level-0 state of a scatter (also filled chunk by chunk by the pipelined host path).
+struct SkmL0 {
+    SkmGeom g;
+    DBuf<u32> hist0, cur0, base0, cap0, hist1, ovf;   // hist0: SKM_MAX_B0 bits; cur0: strided (SKM_CUR_STRIDE)
+    DBuf<u64> totals, total_cap;   // totals: [0] instances, [1] records
+    DBuf<ulonglong2> rec0;
+    u64 cap_total = 0;
+    bool exact = false;
+    void alloc_sample(gg_ctx *ctx) {
+        hist0.alloc(ctx, (1u << SKM_MAX_B0) + 1);
+        totals.alloc(ctx, 2);
+        dfill(ctx, hist0.p, (u64)((1u << SKM_MAX_B0) + 1) * sizeof(u32), 0u);
+        dfill(ctx, totals.p, 2 * sizeof(u64), 0u);
+    }
+};
+// after the sample pass (hist0 / totals filled by skm_scan_kernel<.., 0, ..> over 1 / scale of the input): geometry from the
+// instance estimate, capacities, record buffer, zeroed scatter state.  One stream synchronisation.
+static void skm_l0_prepare(gg_ctx *ctx, SkmL0 &L, int k, int canonical, double scale, bool exact, const SkmTune &tune) {
+    L.total_cap.alloc(ctx, 1);
+    const u64 n_inst_sample = read_scalar<u64>(ctx, L.totals.p);
+    L.g = skm_geom((u64)((double)n_inst_sample * scale), k, canonical, tune);
+    const u32 nb0 = 1u << L.g.b0;
+    const u64 nleaf = 1ULL << (L.g.b0 + L.g.b1);
+    L.base0.alloc(ctx, nb0 + 1); L.cap0.alloc(ctx, nb0); L.cur0.alloc(ctx, (u64)nb0 * SKM_CUR_STRIDE); L.hist1.alloc(ctx, nleaf + 1);
+    L.ovf.alloc(ctx, 1);
+    LAUNCH(ctx, skm_caps_kernel, 1, 1024, 0, L.hist0.p, SKM_MAX_B0, L.g.b0, (float)scale, exact ? 1 : 0, L.base0.p, L.cap0.p, L.total_cap.p,
+           exact ? 0u : tune.force_cap);
+    L.cap_total = read_scalar<u64>(ctx, L.total_cap.p);
+    if (L.cap_total >= 0xFFFFFFFFull) GG_THROW(GG_ERR_LIMIT, "%llu super-k-mer records exceed the 2^32-1 per-GPU limit", (unsigned long long)L.cap_total);
+    L.rec0.alloc(ctx, L.cap_total ? L.cap_total : 1);
+    dfill(ctx, L.cur0.p, (u64)nb0 * SKM_CUR_STRIDE * sizeof(u32), 0u);
+    dfill(ctx, L.hist1.p, (nleaf + 1) * sizeof(u32), 0u);
+    dfill(ctx, L.ovf.p, sizeof(u32), 0u);
+    dfill(ctx, L.totals.p, 2 * sizeof(u64), 0u);
+    L.exact = exact;
+}
+
+// Everything after a successful level-0 scatter: regions (base / cnt, nreg = nb_local * nsrc regions of `in`) ->
+// sorted unique keys + counts.  hist1: records per leaf bin of the local bins (nleaf + 1 entries, last 0).
+static u64 skm_finish(gg_ctx *ctx, const ulonglong2 *in, const u32 *base, const u32 *cnt, u32 cnt_stride, u32 nb_local, u32 nsrc, u64 in_cap,
+                      const SkmGeom &g, const u32 *hist1, u64 n_inst, u64 n_rec, u32 min_freq, const SkmTune &tune, DBuf<u64> &ukeys,
+                      DBuf<u32> &ucounts) {
+    if (n_rec == 0 || nb_local == 0) { ukeys.alloc(ctx, 1); ucounts.alloc(ctx, 1); return 0; }
+    const u64 nleaf = (u64)nb_local << g.b1;
+    stage_begin(ctx, ST_SORT);
+    DBuf<u32> lbeg(ctx, nleaf + 1), cur1, dense;
+    DBuf<ulonglong2> rec1;
+    const ulonglong2 *leaf_recs = in;
+    const u32 *leaf_beg = base, *leaf_cnt = cnt;
+    if (g.b1 > 0 || nsrc > 1) {
+        exclusive_scan_u32(ctx, hist1, lbeg.p, nleaf + 1, nullptr);
+        cur1.alloc(ctx, nleaf);
+        dfill(ctx, cur1.p, nleaf * sizeof(u32), 0u);
+        rec1.alloc(ctx, n_rec);
+        prof_bytes(ctx, 32.0 * (double)n_rec);
+        LAUNCH(ctx, skm_l1_kernel, (unsigned)ceil_div(in_cap, SKM_ALIGN), 256, 0, in, base, cnt, cnt_stride, nb_local * nsrc, nsrc, g.b1, lbeg.p, cur1.p,
+               rec1.p);
+        leaf_recs = rec1.p; leaf_beg = lbeg.p; leaf_cnt = hist1;
+    } else if (cnt_stride != 1) {
+        dense.alloc(ctx, nleaf);
+        LAUNCH(ctx, skm_gather_strided_kernel, (unsigned)ceil_div(nleaf, 256), 256, 0, cnt, cnt_stride, (u32)nleaf, dense.p);
+        leaf_cnt = dense.p;
+    }
+    // ---- E: leaves ----
+    const u64 kept_cap = n_inst / (min_freq ? min_freq : 1) + 1;  // every kept key has >= min_freq instances
+    DBuf<u64> kk(ctx, kept_cap), cursor(ctx, 2);
+    DBuf<u32> kc(ctx, kept_cap), ovf_n(ctx, 2), ovf_list(ctx, nleaf);
+    dfill(ctx, cursor.p, 2 * sizeof(u64), 0u);
+    dfill(ctx, ovf_n.p, 2 * sizeof(u32), 0u);
+    prof_bytes(ctx, 16.0 * (double)n_rec);
+    if (tune.variant == 1)
+        skm_launch_leaf<256, 13>(ctx, 2, leaf_recs, leaf_beg, leaf_cnt, (u32)nleaf, g, min_freq, kk.p, kc.p, cursor.p, ovf_list.p, ovf_n.p, tune.test_ovf_mod);
+    else if (tune.variant == 2)
+        skm_launch_leaf<512, 13>(ctx, 2, leaf_recs, leaf_beg, leaf_cnt, (u32)nleaf, g, min_freq, kk.p, kc.p, cursor.p, ovf_list.p, ovf_n.p, tune.test_ovf_mod);
+    else
+        skm_launch_leaf<256, 12>(ctx, 4, leaf_recs, leaf_beg, leaf_cnt, (u32)nleaf, g, min_freq, kk.p, kc.p, cursor.p, ovf_list.p, ovf_n.p, tune.test_ovf_mod);
+    CK(cudaMemcpyAsync(ctx->h_scalar, cursor.p, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_scalar + 1, ovf_n.p, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    u64 U = ctx->h_scalar[0];
+    const u32 n_ovf = (u32)ctx->h_scalar[1];
+    prof_add_bytes(ctx, "skm_leaf_kernel", 12.0 * (double)U);
+    if (n_ovf) {  // bins whose table filled up: their k-mers as plain keys -> radix sort + run-length count + filter
+        DBuf<u64> tot(ctx, 2);
+        dfill(ctx, tot.p, 2 * sizeof(u64), 0u);
+        LAUNCH(ctx, skm_ovf_size_kernel, (unsigned)std::min<u32>(n_ovf, (u32)ctx->num_sms * 8), 256, 0, leaf_recs, leaf_beg, leaf_cnt, ovf_list.p, n_ovf,
+               (unsigned long long *)tot.p);
+        const u64 n_keys = read_scalar<u64>(ctx, tot.p);
+        DBuf<u64> keys(ctx, n_keys + 1), alt(ctx, n_keys + 1);
+        LAUNCH(ctx, skm_ovf_expand_kernel, (unsigned)std::min<u32>(n_ovf, (u32)ctx->num_sms * 8), 256, 0, leaf_recs, leaf_beg, leaf_cnt, ovf_list.p, n_ovf, g.k,
+               g.canonical, keys.p, (unsigned long long *)(tot.p + 1));
+        u64 *a = keys.p, *b = alt.p;
+        std::vector<BitRange> ranges = {{0, 2 * g.k}};
+        radix_sort<1>(ctx, &a, &b, nullptr, nullptr, n_keys, ranges);
+        DBuf<u64> uk;
+        DBuf<u32> uc;
+        const u64 nu = run_length_count<1>(ctx, a, n_keys, uk, uc);
+        FilterF<1> f{uk.p, uc.p, kk.p + U, kc.p + U, (u64)min_freq, 0};
+        Compactor<FilterF<1>> cp(ctx, nu, "filter");
+        const u64 nk = cp.count(f);
+        cp.emit(f);
+        U += nk;
+    }
+    stage_end(ctx, ST_SORT);
+    // ---- F: order the kept pairs ----
+    stage_begin(ctx, ST_COUNT);
+    skm_sort_pairs(ctx, kk.p, kc.p, U, g.k, ukeys, ucounts);
+    stage_end(ctx, ST_COUNT);
+    return U;
+}
+
+// packed reads -> sorted unique k-mers + counts (count >= min_freq only).  skm_supported(k, canonical).
+static u64 skm_count(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int k, int canonical, u32 min_freq, DBuf<u64> &ukeys, DBuf<u32> &ucounts,
+                     u64 *n_instances) {
+    *n_instances = 0;
+    if (pr.nwords == 0) { ukeys.alloc(ctx, 1); ucounts.alloc(ctx, 1); return 0; }
+    const SkmTune tune = skm_tune();
+    stage_begin(ctx, ST_EXTRACT);
+    const u64 ntiles = ceil_div(pr.nwords, skm_tile_words(k));
+    u32 stride = ntiles >= 256 ? tune.sample : 1;
+    SkmL0 L;
+    SkmGeom g0;  // the sample pass only needs k
+    g0.k = k; g0.canonical = canonical; g0.b0 = SKM_MAX_B0; g0.b1 = 0;
+    for (int attempt = 0;; ++attempt) {
+        L.alloc_sample(ctx);
+        prof_bytes(ctx, 12.0 * (double)pr.nwords / stride);
+        skm_scan_launch<0, false>(ctx, pr, valid, 0, pr.nwords, stride, g0, L.hist0.p, nullptr, nullptr, nullptr, nullptr, nullptr, L.totals.p, nullptr, nullptr);
+        skm_l0_prepare(ctx, L, k, canonical, (double)stride, stride == 1 && !(attempt == 0 && tune.force_cap), tune);
+        prof_bytes(ctx, 12.0 * (double)pr.nwords);  // + 16 B per record, added once the count is known
+        skm_scan_launch<1, false>(ctx, pr, valid, 0, pr.nwords, 1, L.g, nullptr, L.cur0.p, L.base0.p, L.cap0.p, L.rec0.p, L.hist1.p, L.totals.p, L.ovf.p,
+                                  nullptr);
+        CK(cudaMemcpyAsync(ctx->h_scalar, L.totals.p, 2 * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_scalar + 2, L.ovf.p, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if ((u32)ctx->h_scalar[2] == 0) break;
+        if (L.exact || attempt > 0) GG_THROW(GG_ERR_CUDA, "super-k-mer scatter overflowed exact capacities");
+        stride = 1;  // a bin outgrew its sampled share: repeat with exact counts
+        L.rec0.release();
+    }
+    const u64 n_inst = ctx->h_scalar[0], n_rec = ctx->h_scalar[1];
+    prof_add_bytes(ctx, "skm_scan_kernel", 16.0 * (double)n_rec);
+    *n_instances = n_inst;
+    stage_end(ctx, ST_EXTRACT);
+    return skm_finish(ctx, L.rec0.p, L.base0.p, L.cur0.p, SKM_CUR_STRIDE, 1u << L.g.b0, 1, L.cap_total, L.g, L.hist1.p, n_inst, n_rec, min_freq, tune, ukeys,
+                      ucounts);
+}

@@ -342,7 +342,7 @@ def dbg_arrays(kmers_or_counts, k=None, min_freq=None, ctx=None):
     if isinstance(kmers_or_counts, MerCounts):
         counts, own = kmers_or_counts, False
         if min_freq is not None:
-            counts.filter_(min_freq)
+            counts.filter_(min_freq, u8_saturated=True)   # freq(x) is the UInt8-saturated count (src/dbg.jl:275)
     else:
         if k is None:
             raise ValueError("Didn't provide a collection of kmers for the `kmers` parameter did ya?")  # src/dbg.jl:263

@@ -72,7 +72,8 @@ int gg_ctx_event_elapsed_ms(gg_ctx *ctx, int slot_a, int slot_b, float *ms);
 int gg_ctx_sync(gg_ctx *ctx);
 /* per-kernel profile of the next pipeline calls (events around every launch; slows the call
  * down, never enabled inside a timed region).  gg_ctx_kernel_profile returns
- * "kernel\tlaunches\ttotal_ms\n" lines for the last pipeline call. */
+ * "kernel\tlaunches\ttotal_ms\talgorithmic_bytes\n" lines for the last pipeline call (bytes = sum over the
+ * launches of the compulsory traffic of each launch's own element counts; 0 where no streaming model applies). */
 int gg_ctx_set_profile(gg_ctx *ctx, int enabled);
 const char *gg_ctx_kernel_profile(gg_ctx *ctx);
 

@@ -247,3 +247,50 @@ EXPORT int ggo_max_threads(void) {
     return 1;
 #endif
 }
+
+/* ---- deterministic synthetic reads ---------------------------------
+ * C restatement of the counter-based generator in genomegraphs.jl_b200/csrc/synth.cuh, so that
+ * the CPU legs of bench.py (cpu_baseline, --impl reference) build their input without loading
+ * the product library.  Same bytes as gg_synth_reads_range_host / _dev (tests/test_oracle.py). */
+static inline uint64_t osy_mix(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+static inline uint64_t osy_key(uint64_t seed, uint64_t stream) { return osy_mix(seed + stream * 0x9E3779B97F4A7C15ULL); }
+static inline uint64_t osy_rnd(uint64_t key, uint64_t i) { return osy_mix(key + i * 0xD6E8FEB86659FD93ULL); }
+
+EXPORT int ggo_synth_reads_range(uint64_t seed, uint64_t genome_len, uint64_t first_read, uint64_t nreads, uint32_t read_len,
+                                 int paired, uint32_t frag_len, uint32_t err_ppm, uint32_t n_ppm, uint8_t *out, int threads) {
+    const uint64_t F = paired ? frag_len : read_len;
+    if (!out || read_len == 0 || F < read_len || genome_len < F || (paired && (first_read & 1))) return -1;
+    const uint64_t gkey = osy_key(seed, 1), skey = osy_key(seed, 2), dkey = osy_key(seed, 3), ekey = osy_key(seed, 4), nkey = osy_key(seed, 5);
+    if (threads < 1) threads = 1;
+#pragma omp parallel for schedule(static) num_threads(threads)
+    for (long long rr = 0; rr < (long long)nreads; ++rr) {
+        const uint64_t r = first_read + (uint64_t)rr;
+        const uint64_t j = paired ? (r >> 1) : r;
+        const uint32_t mate = paired ? (uint32_t)(r & 1) : 0u;
+        const uint64_t start = (uint64_t)(((unsigned __int128)osy_rnd(skey, j) * (genome_len - F + 1)) >> 64);
+        const uint32_t strand = (uint32_t)(osy_rnd(dkey, j) & 1u);
+        for (uint32_t p = 0; p < read_len; ++p) {
+            const uint64_t t = mate ? (F - 1 - p) : p;
+            const uint64_t g = strand ? (start + F - 1 - t) : (start + t);
+            uint32_t b = (uint32_t)(osy_rnd(gkey, g >> 5) >> (2 * (g & 31))) & 3u;
+            if (mate ^ strand) b = 3u - b;
+            const uint64_t idx = r * (uint64_t)read_len + p;
+            if (err_ppm) {
+                const uint64_t e = osy_rnd(ekey, idx);
+                if ((uint32_t)(((uint64_t)(uint32_t)e * 1000000ULL) >> 32) < err_ppm) b = (b + 1u + (uint32_t)((e >> 32) % 3u)) & 3u;
+            }
+            uint8_t c = (uint8_t)(0x54474341u >> (8 * b));
+            if (n_ppm) {
+                const uint64_t e = osy_rnd(nkey, idx);
+                if ((uint32_t)(((uint64_t)(uint32_t)e * 1000000ULL) >> 32) < n_ppm) c = (uint8_t)'N';
+            }
+            out[(uint64_t)rr * read_len + p] = c;
+        }
+    }
+    return 0;
+}

@@ -46,6 +46,9 @@ def lib():
         L.ggo_unique_mer_index.restype = C.c_uint64
         L.ggo_unique_mer_index.argtypes = [u8p, u64p, C.c_uint64, C.c_int, u64p, i64p, u32p, u64p, u64p]
         L.ggo_max_threads.restype = C.c_int
+        L.ggo_synth_reads_range.restype = C.c_int
+        L.ggo_synth_reads_range.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32,
+                                            C.c_uint32, u8p, C.c_int]
         _LIB = L
     return _LIB
 
@@ -160,6 +163,17 @@ def unique_mer_index(node_seqs, k):
     u = lib().ggo_unique_mer_index(_p(seq, C.c_uint8), _p(offs, C.c_uint64), nn, k, _p(keys, C.c_uint64),
                                    _p(node, C.c_int64), _p(pos, C.c_uint32), _p(upn, C.c_uint64), _p(tpn, C.c_uint64))
     return keys[:u], node[:u], pos[:u], upn[:nn], tpn[:nn]
+
+
+def synth_reads(seed, genome_len, nreads, read_len, paired=False, frag_len=0, err_ppm=0, n_ppm=0, first_read=0, threads=1):
+    """Deterministic synthetic reads -> (seq_bytes, offsets); the same bytes as the product's gg_synth_reads_range_host / _dev
+    (C restatement of csrc/synth.cuh inside the oracle library, so the CPU legs of bench.py need not load the product)."""
+    out = np.zeros(int(nreads) * int(read_len), dtype=np.uint8)
+    rc = lib().ggo_synth_reads_range(int(seed), int(genome_len), int(first_read), int(nreads), int(read_len), int(bool(paired)), int(frag_len),
+                                     int(err_ppm), int(n_ppm), _p(out, C.c_uint8), int(threads))
+    if rc != 0:
+        raise ValueError("bad synthetic read parameters")
+    return out, np.arange(int(nreads) + 1, dtype=np.uint64) * np.uint64(read_len)
 
 
 # ---- helpers shared by tests (string <-> word conversion) -------------------------------

@@ -109,15 +109,32 @@ def test_gfa_writer(pkg, tmp_path):
 
 
 def test_bench_reference_arm_contract():
-    """`bench.py --impl reference` (CPU port of the reference algorithm) prints one JSON line with the contract keys."""
+    """`bench.py --impl reference` (CPU port of the reference algorithm) prints one JSON line with the contract keys, with the
+    arm's own thread count stated, the same `config` as the GPU arm would print, and WITHOUT mapping the product library."""
     import json
     import subprocess
     import sys
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                        "--cpu-sample-frac", "0.004"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300, cwd=ROOT)
+    code = ("import sys; sys.path.insert(0, %r); sys.argv = ['bench.py', '--impl', 'reference', '--workload', 'tiny', '--steps', '1', '--warmup', '0']; "
+            "import bench; bench.main(); print('MAPS_HAS_PRODUCT', 'libggb200' in open('/proc/self/maps').read())" % ROOT)
+    env = dict(os.environ, OMP_NUM_THREADS="1")   # what torch.distributed.run exports: the arm must not inherit it
+    r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300, cwd=ROOT, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
-    d = json.loads(r.stdout.strip().splitlines()[-1])
+    lines = r.stdout.strip().splitlines()
+    assert lines[-1] == "MAPS_HAS_PRODUCT False"
+    d = json.loads(lines[-2])
     assert d["impl"] == "reference" and d["unit"] == "k-mers/s" and d["higher_is_better"] is True and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
+    assert d["cpu_baseline"]["kind"] == "port" and "sample" in d["cpu_baseline"]
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
-    assert d["config"]["workload"] == "c2_ecoli50x_k31"
+    assert d["config"]["workload"] == "tiny" and "sample" not in d["config"]
+    import bench
+    args = type("A", (), {"workload": "tiny", "scaling": "strong", "gpus": 1})()
+    assert d["config"] == bench.base_config(args, dict(bench.WORKLOADS["tiny"]), 1)
+    assert bench.DEFAULT_WORKLOAD == "c3_100mbp30x_k31"
+
+
+def test_bench_shard_range_matches_package(pkg):
+    import bench
+    for n, world in [(101, 3), (20000000, 8), (6, 4), (0, 2)]:
+        for r in range(world):
+            assert bench.shard_range(n, r, world, 2) == pkg.dist.shard_range(n, r, world, 2)

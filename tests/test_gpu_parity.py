@@ -232,6 +232,7 @@ def test_count_overflow_paths(pkg, ctx, k, mod, monkeypatch):
     re-partition; k > 32: host-driven radix sort + run-length count of the child's segment)."""
     monkeypatch.setenv("GG_MSD_TEST_OVERFLOW", str(mod))
     monkeypatch.setenv("GG_MSD_DT", "64")   # many small children even on a small input
+    monkeypatch.setenv("GG_FORCE_MSD", "1")  # 17 <= k <= 32 would take the super-k-mer route otherwise
     seq, offs = pkg.synth_reads(seed=300 + k, genome_len=6000, nreads=1600, read_len=150, paired=True, frag_len=400, err_ppm=5000)
     for min_freq in (1, 2):
         okeys, ocnt = O.count_kmers(seq, offs, k)
@@ -244,6 +245,74 @@ def test_count_overflow_paths(pkg, ctx, k, mod, monkeypatch):
         counts.free()
 
 
+# ------------------------------ super-k-mer route (17 <= k <= 32) -----------------------------
+@pytest.mark.parametrize("k", [17, 18, 20, 24, 25, 27, 31, 32])
+def test_skm_count_and_graph(pkg, ctx, k):
+    """minimizer-partitioned counting: every k of both window geometries (WIN = 9 for k <= 24, 17 above), reads with N,
+    lower case, reads shorter than k, heavy duplication; counts, saturated view, fused min-count filter, graph."""
+    rnd = random.Random(4000 + k)
+    base = _random_reads(rnd, 80, 10, 4 * k + 70, "ACGT" * 40 + "Nacgt")
+    reads = [rnd.choice(base)[rnd.randint(0, 7):] for _ in range(4000)] + ["A" * 200, "ACGT" * 60, "", "AC"]
+    seq, offs = pkg.pack_reads(reads)
+    okeys, ocnt = O.count_kmers(seq, offs, k)
+    for mode in (pkg.CANONICAL, pkg.NONCANONICAL):
+        if mode == pkg.NONCANONICAL and k == 32:
+            continue
+        counts = pkg.serial_mem(k, mode, ctx=ctx)((seq, offs))
+        keys, c32, c8 = counts.export()
+        wk, wc = (okeys, ocnt) if mode == pkg.CANONICAL else O.count_kmers(seq, offs, k, canonical=False)
+        assert counts.n_instances == len(O.extract(seq, offs, k))
+        assert np.array_equal(keys, wk) and np.array_equal(c32, wc), (k, mode)
+        assert np.array_equal(c8, np.minimum(wc, 255).astype(np.uint8))
+        counts.free()
+    for mf in (1, 2, 5, 256):
+        ga = pkg.dbg_from_reads((seq, offs), k, mf, ctx=ctx)
+        og = O.dbg(O.filter_counts(okeys, ocnt, k, mf, u8=True), k)   # freq(x) is UInt8-saturated: nothing passes 256
+        _graph_equal(ga, og, (k, mf))
+
+
+@pytest.mark.parametrize("k", [21, 31, 32])
+@pytest.mark.parametrize("variant", ["leaf_overflow_all", "leaf_overflow_some", "tiny_bins", "huge_bins_cap_overflow", "leaf_variants"])
+def test_skm_stress_paths(pkg, ctx, k, variant, monkeypatch):
+    """GG_SKM_TEST_OVERFLOW=m: every m-th leaf bin goes to the overflow list (generic sort + run-length + filter);
+    GG_SKM_BIN: target instances per leaf bin (64: thousands of near-empty bins; 200000: few bins whose tables really
+    overflow); GG_SKM_TEST_CAP: level-0 capacities too small -> exact repeat of the scatter."""
+    env = {"leaf_overflow_all": {"GG_SKM_TEST_OVERFLOW": "1"}, "leaf_overflow_some": {"GG_SKM_TEST_OVERFLOW": "3", "GG_SKM_BIN": "512"},
+           "tiny_bins": {"GG_SKM_BIN": "64"}, "huge_bins_cap_overflow": {"GG_SKM_BIN": "200000", "GG_SKM_TEST_CAP": "1"},
+           "leaf_variants": {"GG_SKM_VARIANT": "1"}}[variant]
+    for a, b in env.items():
+        monkeypatch.setenv(a, b)
+    seq, offs = pkg.synth_reads(seed=600 + k, genome_len=40000, nreads=8000, read_len=150, paired=True, frag_len=400, err_ppm=5000, n_ppm=200)
+    okeys, ocnt = O.count_kmers(seq, offs, k, threads=4)
+    counts = pkg.serial_mem(k, pkg.CANONICAL, ctx=ctx)((seq, offs))
+    keys, c32, _ = counts.export()
+    assert np.array_equal(keys, okeys) and np.array_equal(c32, ocnt), (k, variant)
+    counts.free()
+    for mf in (2, 3):
+        ga = pkg.dbg_from_reads((seq, offs), k, mf, ctx=ctx)
+        og = O.dbg(O.filter_counts(okeys, ocnt, k, mf), k)
+        _graph_equal(ga, og, (k, variant, mf))
+    if variant == "leaf_variants":
+        monkeypatch.setenv("GG_SKM_VARIANT", "2")
+        c2 = pkg.serial_mem(k, pkg.CANONICAL, ctx=ctx)((seq, offs))
+        assert np.array_equal(c2.export()[0], okeys)
+        c2.free()
+
+
+def test_skm_larger_input_sampled_capacities(pkg, ctx):
+    """>= 256 tiles (8.4 M windows): capacities come from a 1/16 sample of the tiles; kept-pair sort takes the bucket route."""
+    k = 31
+    seq, offs = pkg.synth_reads(seed=91, genome_len=1500000, nreads=80000, read_len=150, paired=True, frag_len=500, err_ppm=10000)
+    okeys, ocnt = O.count_kmers(seq, offs, k, threads=8)
+    counts = pkg.serial_mem(k, pkg.CANONICAL, ctx=ctx)((seq, offs))
+    keys, c32, _ = counts.export()
+    assert np.array_equal(keys, okeys) and np.array_equal(c32, ocnt)
+    counts.free()
+    ga = pkg.dbg_from_reads((seq, offs), k, 1, ctx=ctx)
+    og = O.dbg(okeys, k)
+    assert np.array_equal(ga.bases, og.bases) and np.array_equal(ga.link_triples, og.link_tri)
+
+
 # ------------------------------ error behaviour at the boundary -------------------------------
 def test_error_behaviour(pkg, ctx):
     """Bad arguments come back as status codes (ValueError = the reference's ArgumentError), never as crashes,
@@ -254,6 +323,17 @@ def test_error_behaviour(pkg, ctx):
     bad_offs = np.array([0, 8, 4, 12], dtype=np.uint64)  # decreasing
     assert L.gg_count_kmers(ctx.h, seq.ctypes.data_as(C.c_void_p), bad_offs.ctypes.data_as(C.c_void_p), 3, 4, 1, C.byref(h)) == N.GG_ERR_ARG
     assert b"non-decreasing" in L.gg_last_error(ctx.h)
+    off0 = np.array([4, 8, 12], dtype=np.uint64)        # bytes before the first read: rejected (the reference has no such thing)
+    assert L.gg_count_kmers(ctx.h, seq.ctypes.data_as(C.c_void_p), off0.ctypes.data_as(C.c_void_p), 2, 4, 1, C.byref(h)) == N.GG_ERR_ARG
+    d_seq, d_off = C.c_void_p(), C.c_void_p()
+    N.check(ctx.h, L.gg_dev_alloc(ctx.h, 64, C.byref(d_seq)))
+    N.check(ctx.h, L.gg_dev_alloc(ctx.h, 64, C.byref(d_off)))
+    N.check(ctx.h, L.gg_memcpy_h2d(ctx.h, d_seq, seq.ctypes.data_as(C.c_void_p), 12))
+    for bad in (bad_offs, off0, np.array([0, 4, 8, 11], dtype=np.uint64)):   # decreasing / gap at the start / not ending at nbytes
+        N.check(ctx.h, L.gg_memcpy_h2d(ctx.h, d_off, bad.ctypes.data_as(C.c_void_p), bad.nbytes))
+        assert L.gg_count_kmers_dev(ctx.h, d_seq, d_off, len(bad) - 1, 12, 4, 1, C.byref(h)) == N.GG_ERR_ARG
+        assert L.gg_dbg_from_reads_dev(ctx.h, d_seq, d_off, len(bad) - 1, 12, 4, 1, C.byref(h)) == N.GG_ERR_ARG
+    L.gg_dev_free(ctx.h, d_seq); L.gg_dev_free(ctx.h, d_off)
     offs = np.array([0, 12], dtype=np.uint64)
     for k in (0, -3, 129):
         assert L.gg_count_kmers(ctx.h, seq.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(C.c_void_p), 1, k, 1, C.byref(h)) == N.GG_ERR_ARG

@@ -147,3 +147,18 @@ def test_unique_mer_index_vs_pyref(k):
     assert node.tolist() == [u[1] for u in uniq]
     assert pos.tolist() == [u[2] for u in uniq]
     assert upn.tolist() == upn_r and tpn.tolist() == tot_r
+
+
+def test_oracle_synth_matches_product_generator():
+    """The oracle's C restatement of the synthetic read generator gives the product generator's bytes
+    (the CPU legs of bench.py use the oracle's, so that they never load libggb200.so)."""
+    import __graft_entry__ as G
+    pkg = G.build()
+    for args in [(7, 5000, 400, 60, True, 200, 0, 0, 0), (3, 20000, 501, 150, False, 0, 20000, 500, 0),
+                 (1, 4641652, 2000, 150, True, 700, 1000, 0, 1000), (2, 100000, 64, 150, True, 700, 10000, 100, 4000)]:
+        seed, glen, n, rl, paired, fl, err, nppm, first = args
+        a, ao = pkg.synth_reads(seed, glen, n, rl, paired, fl, err, nppm, first_read=first)
+        b, bo = O.synth_reads(seed, glen, n, rl, paired, fl, err, nppm, first_read=first, threads=3)
+        assert np.array_equal(a, b) and np.array_equal(ao, bo)
+    with pytest.raises(ValueError):
+        O.synth_reads(7, 10, 4, 60)
