@@ -99,6 +99,15 @@ static inline void prof_add_bytes(gg_ctx *ctx, const char *name, double bytes) {
 }
 
 static inline u64 ceil_div(u64 a, u64 b) { return (a + b - 1) / b; }
+// GG_TRACE=1: synchronise and print a marker (debugging aid for hangs on the GPU box; never set while timing)
+static inline void gg_trace(gg_ctx *ctx, const char *what) {
+    static int on = -1;
+    if (on < 0) on = getenv("GG_TRACE") ? 1 : 0;
+    if (!on) return;
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    fprintf(stderr, "[gg_trace] %s: %s\n", what, cudaGetErrorString(e));
+    fflush(stderr);
+}
 
 // Raise a kernel's dynamic shared-memory limit once per context: the attribute belongs to the device, so a process
 // that drives several GPUs must set it on each of them.

@@ -28,7 +28,7 @@
 #include "msdcount.cuh"
 
 #define SKM_THREADS 256
-#define SKM_STAGE_CAP 4096    // records a CTA stages in shared memory before it reserves space in the bins
+#define SKM_STAGE_CAP 8704    // runs a CTA stages in shared memory before it reserves space in the bins (>= 8192 + 256: one word per thread always fits)
 #define SKM_CUR_STRIDE 64     // the level-0 cursors sit 256 bytes apart: neighbours would serialise in one L2 slice
 #define SKM_MAX_B0 9
 #define SKM_MAX_B1 12
@@ -81,19 +81,22 @@ __device__ __forceinline__ ulonglong2 skm_make_record(const u64 *__restrict__ pa
 }
 
 struct SkmScanSmem {
-    ulonglong2 srec[SKM_STAGE_CAP];     // staged records of the tile
+    u32 dh[SKM_STAGE_CAP];              // staged run: minimizer hash
+    u32 ds[SKM_STAGE_CAP];              // staged run: (first base - first base of the tile) << 5 | (windows - 1)
     u32 sq[32 * SKM_THREADS];           // per-thread queue: minimizer hash of every run that starts in the current word
-    u32 hist[1 << SKM_MAX_B0];          // records per level-0 bin, then the running cursor inside the reserved run
-    u32 gbase[1 << SKM_MAX_B0];         // first record slot of this tile's run in every bin (absolute index into the buffer)
+    u32 hist[1 << SKM_MAX_B0];          // runs per level-0 bin, then the running cursor inside the reserved space
+    u32 gbase[1 << SKM_MAX_B0];         // first record slot of this tile's runs in every bin (absolute index into the buffer)
     u32 glim[1 << SKM_MAX_B0];          // end of the bin's region
-    u16 sbin[SKM_STAGE_CAP];
     u32 s_n;
 };
 // MODE 0: count records per level-0 bin at SKM_MAX_B0 bits (hist0); MODE 1: scatter the records.
 // The launch covers the packed words [w0, w1); CTA c handles tile number c * stride of 256 * TWORDS words
-// (stride > 1: sampling for the capacity estimate).  Records are staged in shared memory, space is reserved once
-// per (tile, bin) -- one global atomic per ~6 records on cursors that sit in different L2 slices -- and the tile's
-// records of a bin land next to each other.
+// (stride > 1: sampling for the capacity estimate).
+// Phase 1 (every lane busy, no calls, no divergent loops): roll the m-mer hashes of a word, sliding minimum, and note
+// every run (start, length, minimizer hash) in the CTA's staging list.  Phases B-D run over the staged runs with all
+// lanes: bin digits + per-bin count, ONE global reservation per (tile, bin) -- cursors 256 bytes apart, so that they
+// sit in different L2 slices -- then the records are built from the packed words and stored next to each other.
+// A tile with more runs than the list holds (only adversarial input: > 0.26 runs per window) is redone word by word.
 template <int LOGW, int MODE, bool PEER>
 __global__ void __launch_bounds__(SKM_THREADS, 2) skm_scan_kernel(const u64 *__restrict__ packed, const u32 *__restrict__ valid, u64 w0, u64 w1,
                                                                   u32 stride, SkmGeom g, u32 *__restrict__ hist0, u32 *__restrict__ cur0,
@@ -104,6 +107,7 @@ __global__ void __launch_bounds__(SKM_THREADS, 2) skm_scan_kernel(const u64 *__r
     constexpr int WIN = (1 << LOGW) + 1;
     constexpr int NH = 32 + WIN - 1;      // m-mer positions the 32 windows of a word look at
     constexpr int TWORDS = LOGW == 4 ? 4 : 2;
+    constexpr u32 NOSLOT = 0xFFFFFFFFu;
     extern __shared__ __align__(16) u8 smem_raw[];
     SkmScanSmem &S = *reinterpret_cast<SkmScanSmem *>(smem_raw);
     const int k = g.k, m = k - WIN + 1;   // 9 <= m <= 16
@@ -111,142 +115,164 @@ __global__ void __launch_bounds__(SKM_THREADS, 2) skm_scan_kernel(const u64 *__r
     const u32 nb0 = 1u << b0;
     const u32 mmask = m == 16 ? 0xFFFFFFFFu : ((1u << (2 * m)) - 1u);
     const u32 rmul = 1u << (2 * m - 2);
-    const u64 tbase = w0 + ((u64)blockIdx.x * stride) * (SKM_THREADS * TWORDS) + (u64)threadIdx.x * TWORDS;
-    u32 o_len = 0, o_h = 0;   // run open at the end of the previous word of this thread
-    u64 o_start = 0;
-    u32 n_inst = 0, n_rec = 0;
-    for (u32 i = threadIdx.x; i < nb0; i += SKM_THREADS) S.hist[i] = 0;
-    if (threadIdx.x == 0) S.s_n = 0;
-    __syncthreads();
-
-    auto emit = [&](u64 start, u32 len, u32 h) {
-        n_inst += len; n_rec += 1;
-        const u32 d = skm_digits(h);
-        const u32 bin0 = b0 ? (d >> (32 - b0)) : 0u;
-        if (MODE == 0) { atomicAdd(&S.hist[bin0], 1u); return; }
-        const u32 rest = b0 ? (d << b0) : d;  // digit bits below bin0, left-aligned
-        const u32 bin1 = g.b1 ? (rest >> (32 - g.b1)) : 0u;
-        const u32 meta = (len - 1u) | (bin1 << 5) | ((((g.b1 ? (rest << g.b1) : rest)) >> 17) << 17);
-        const ulonglong2 rec = skm_make_record(packed, start, len, k, meta);
-        atomicAdd(&hist1[((u64)bin0 << g.b1) | bin1], 1u);
-        const u32 slot = atomicAdd(&S.s_n, 1u);
-        if (slot < SKM_STAGE_CAP) {
-            S.srec[slot] = rec;
-            S.sbin[slot] = (u16)bin0;
-            atomicAdd(&S.hist[bin0], 1u);
-        } else {  // staging area full (far more runs than random minimizers give): reserve record by record
-            const u32 pos = atomicAdd(&cur0[(u64)bin0 * SKM_CUR_STRIDE], 1u);
-            if (pos < cap0[bin0]) {
-                if (PEER) pt.ptr[skm_owner(pt, bin0)][(u64)base0[bin0] + pos] = rec;
-                else out[(u64)base0[bin0] + pos] = rec;
-            } else *ovf = 1u;
-        }
-    };
-
+    const u64 tile_w0 = w0 + ((u64)blockIdx.x * stride) * (SKM_THREADS * TWORDS);
+    const u64 tbase = tile_w0 + (u64)threadIdx.x * TWORDS;
+    u32 tot_inst = 0, tot_rec = 0;
+    int it0 = 0, it1 = TWORDS;
+    bool fallback = false;
+    for (;;) {
+        for (u32 i = threadIdx.x; i < nb0; i += SKM_THREADS) S.hist[i] = 0;
+        if (threadIdx.x == 0) S.s_n = 0;
+        __syncthreads();
+        // ---------------- phase 1 ----------------
+        u32 rl = 0, rh = 0, rslot = NOSLOT;   // open run: windows so far, minimizer hash, staging slot
+        u32 n_inst = 0, n_rec = 0;
 #pragma unroll 1
-    for (int it = 0; it < TWORDS; ++it) {
-        const u64 t = tbase + it;
-        if (t >= w1) break;
-        const u32 vm = valid[t];
-        if (vm == 0) {  // no k-mer starts in this word: the open run ends here
-            if (o_len) { emit(o_start, o_len, o_h); o_len = 0; }
-            continue;
-        }
-        const u64 a0 = packed[t], a1 = packed[t + 1];
-        // ---- hash of the canonical m-mer at every position 0 .. NH-1 (forward and reverse complement rolled) ----
-        u32 h[NH];
-        {
-            u32 f = (u32)(a0 >> (64 - 2 * m));
-            u32 r = (u32)rev2_u64(~a0) & mmask;
-            const u64 xh = (a0 << (2 * m)) | (a1 >> (64 - 2 * m)), xl = a1 << (2 * m);  // bases m, m+1, ... left-aligned
+        for (int it = it0; it < it1; ++it) {
+            const u64 t = tbase + it;
+            const u32 vm = t < w1 ? valid[t] : 0u;
+            __syncwarp();
+            if (vm != 0) {
+                const u64 a0 = packed[t], a1 = packed[t + 1];
+                // hash of the canonical m-mer at every position 0 .. NH-1 (forward and reverse complement rolled)
+                u32 h[NH];
+                {
+                    u32 f = (u32)(a0 >> (64 - 2 * m));
+                    u32 r = (u32)rev2_u64(~a0) & mmask;
+                    const u64 xh = (a0 << (2 * m)) | (a1 >> (64 - 2 * m)), xl = a1 << (2 * m);  // bases m, m+1, ... left-aligned
 #pragma unroll
-            for (int q = 0; q < NH; ++q) {
-                h[q] = min(f, r) * 0x9E3779B1u;
-                if (q + 1 < NH) {
-                    const u32 nbq = q < 32 ? ((u32)(xh >> (62 - 2 * q)) & 3u) : ((u32)(xl >> (62 - 2 * (q - 32))) & 3u);
-                    f = ((f << 2) | nbq) & mmask;
-                    r = (r >> 2) + (3u - nbq) * rmul;
+                    for (int q = 0; q < NH; ++q) {
+                        h[q] = min(f, r) * 0x9E3779B1u;
+                        if (q + 1 < NH) {
+                            const u32 nbq = q < 32 ? ((u32)(xh >> (62 - 2 * q)) & 3u) : ((u32)(xl >> (62 - 2 * (q - 32))) & 3u);
+                            f = ((f << 2) | nbq) & mmask;
+                            r = (r >> 2) + (3u - nbq) * rmul;
+                        }
+                    }
                 }
-            }
-        }
-        // ---- sliding minimum over WIN positions: doubling to 2^LOGW, then one more ----
+                // sliding minimum over WIN positions: doubling to 2^LOGW, then one more
 #pragma unroll
-        for (int s = 0; s < LOGW; ++s) {
-            const int d = 1 << s;
+                for (int s = 0; s < LOGW; ++s) {
+                    const int d = 1 << s;
 #pragma unroll
-            for (int q = 0; q < NH; ++q)
-                if (q + 2 * d - 1 < NH) h[q] = min(h[q], h[q + d]);
-        }
+                    for (int q = 0; q < NH; ++q)
+                        if (q + 2 * d - 1 < NH) h[q] = min(h[q], h[q + d]);
+                }
 #pragma unroll
-        for (int q = 0; q < 32; ++q) h[q] = min(h[q], h[q + 1]);
-        // ---- runs: consecutive valid windows with one minimizer hash, at most WIN long ----
-        u32 nm = 0, nq = 0;  // nm: bit j set <=> window j starts a run
-        {
-            u32 rl = o_len, rh = o_h;
+                for (int q = 0; q < 32; ++q) h[q] = min(h[q], h[q + 1]);
+                // runs: consecutive valid windows with one minimizer hash, at most WIN long.  Sweep over the windows
+                // (straight-line code): mask of the run starts, their hashes queued in order.
+                u32 nm = 0, nq = 0;
+                {
+                    u32 l = rl, hh = rh;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const bool v = (vm >> (31 - j)) & 1u;
-                const bool cont = v && rl != 0 && h[j] == rh && rl < (u32)WIN;
-                if (v && !cont) {
-                    S.sq[nq * SKM_THREADS + threadIdx.x] = h[j];
-                    ++nq;
-                    nm |= 1u << j;
-                    rh = h[j];
+                    for (int j = 0; j < 32; ++j) {
+                        const bool v = (vm >> (31 - j)) & 1u;
+                        const bool cont = v && l != 0 && h[j] == hh && l < (u32)WIN;
+                        if (v && !cont) {
+                            S.sq[nq * SKM_THREADS + threadIdx.x] = h[j];
+                            ++nq;
+                            nm |= 1u << j;
+                            hh = h[j];
+                            l = 0;
+                        }
+                        l = v ? l + 1 : 0;
+                    }
+                }
+                const u32 cm = __brev(vm) & ~nm;   // bit j <=> window j continues the run of window j - 1
+                if (rl != 0) {                     // the carried run takes the leading continuation windows and ends in this word (WIN < 32)
+                    rl += (u32)__ffs((int)~cm) - 1u;
+                    if (rslot < SKM_STAGE_CAP) S.ds[rslot] += rl - 1u;
+                    n_inst += rl;
                     rl = 0;
                 }
-                rl = v ? rl + 1 : 0;
+                n_rec += nq;
+                const u32 sbase = nq ? atomicAdd(&S.s_n, nq) : 0u;   // one reservation per thread and word
+                const u32 rel = (u32)(t - tile_w0) << 5;
+                u32 mask = nm, qi = 0;
+                while (mask) {
+                    const int j = __ffs((int)mask) - 1;
+                    mask &= mask - 1;
+                    const u32 rest = j == 31 ? 0u : (cm >> (j + 1));
+                    const u32 len = (u32)__ffs((int)~rest);  // 1 + continuation windows (zeros are shifted in at the top of rest)
+                    const u32 slot = sbase + qi;
+                    const u32 hq = S.sq[qi * SKM_THREADS + threadIdx.x];
+                    ++qi;
+                    if ((u32)j + len == 32u) {  // still open at the end of the word: the length is added when it ends
+                        if (slot < SKM_STAGE_CAP) { S.dh[slot] = hq; S.ds[slot] = (rel + (u32)j) << 5; }
+                        rl = len; rh = hq; rslot = slot;
+                    } else {
+                        if (slot < SKM_STAGE_CAP) { S.dh[slot] = hq; S.ds[slot] = ((rel + (u32)j) << 5) | (len - 1u); }
+                        n_inst += len;
+                    }
+                }
+            } else if (rl != 0) {  // no k-mer starts in this word: the open run ends here
+                if (rslot < SKM_STAGE_CAP) S.ds[rslot] += rl - 1u;
+                n_inst += rl;
+                rl = 0;
             }
         }
-        const u32 V = __brev(vm);   // bit j <=> window j valid
-        const u32 cm = V & ~nm;     // window j continues the run of window j - 1
-        if (o_len) {                // the carried run takes the leading continuation windows and ends in this word (WIN < 32)
-            o_len += (u32)__ffs((int)~cm) - 1u;
-            emit(o_start, o_len, o_h);
-            o_len = 0;
+        __syncwarp();
+        if (rl != 0) {
+            if (rslot < SKM_STAGE_CAP) S.ds[rslot] += rl - 1u;
+            n_inst += rl;
         }
-        u32 mask = nm, qi = 0;
-        while (mask) {
-            const int j = __ffs((int)mask) - 1;
-            mask &= mask - 1;
-            const u32 hq = S.sq[qi * SKM_THREADS + threadIdx.x];
-            ++qi;
-            const u32 rest = j == 31 ? 0u : (cm >> (j + 1));
-            const u32 len = 1u + (u32)__ffs((int)~rest) - 1u;  // rest has zeros shifted in at the top: never all ones
-            const u64 start = (t << 5) + (u64)j;
-            if ((u32)j + len == 32u) { o_start = start; o_len = len; o_h = hq; }  // still open at the end of the word
-            else emit(start, len, hq);
+        __syncthreads();
+        const u32 ntot = S.s_n;
+        if (ntot > SKM_STAGE_CAP) {  // cannot happen with one word per thread (<= 8192 + 256 runs)
+            __syncthreads();
+            fallback = true;
+            it0 = 0; it1 = 1;
+            continue;
         }
+        tot_inst += n_inst; tot_rec += n_rec;
+        // ---------------- phase B: bin of every staged run ----------------
+        for (u32 i = threadIdx.x; i < ntot; i += SKM_THREADS) {
+            const u32 d = skm_digits(S.dh[i]);
+            atomicAdd(&S.hist[b0 ? (d >> (32 - b0)) : 0u], 1u);
+        }
+        __syncthreads();
+        if (MODE == 0) {
+            for (u32 b = threadIdx.x; b < nb0; b += SKM_THREADS)
+                if (S.hist[b]) atomicAdd(&hist0[b], S.hist[b]);
+        } else {
+            // ---------------- phase C: one reservation per (tile, bin) ----------------
+            for (u32 b = threadIdx.x; b < nb0; b += SKM_THREADS) {
+                const u32 c = S.hist[b];
+                const u32 cap = cap0[b], base = base0[b];
+                const u32 gpos = c ? atomicAdd(&cur0[(u64)b * SKM_CUR_STRIDE], c) : 0u;
+                if (c && (u64)gpos + c > (u64)cap) *ovf = 1u;
+                S.gbase[b] = base + min(gpos, cap);
+                S.glim[b] = base + cap;
+                S.hist[b] = 0;
+            }
+            __syncthreads();
+            // ---------------- phase D: records built and stored, grouped by bin ----------------
+            const u64 tile_b0 = tile_w0 << 5;
+            for (u32 i = threadIdx.x; i < ntot; i += SKM_THREADS) {
+                const u32 d = skm_digits(S.dh[i]);
+                const u32 b = b0 ? (d >> (32 - b0)) : 0u;
+                const u32 p = S.gbase[b] + atomicAdd(&S.hist[b], 1u);
+                const u32 rest = b0 ? (d << b0) : d;  // digit bits below bin0, left-aligned
+                const u32 bin1 = g.b1 ? (rest >> (32 - g.b1)) : 0u;
+                const u32 dsv = S.ds[i];
+                const u32 len = (dsv & 31u) + 1u;
+                const u32 meta = (len - 1u) | (bin1 << 5) | ((((g.b1 ? (rest << g.b1) : rest)) >> 17) << 17);
+                atomicAdd(&hist1[((u64)b << g.b1) | bin1], 1u);
+                if (p < S.glim[b]) {
+                    const ulonglong2 rec = skm_make_record(packed, tile_b0 + (dsv >> 5), len, k, meta);
+                    if (PEER) pt.ptr[skm_owner(pt, b)][p] = rec;
+                    else out[p] = rec;
+                }
+            }
+        }
+        if (!fallback || it1 == TWORDS) break;
+        __syncthreads();
+        it0 = it1; it1 = it0 + 1;
     }
-    if (o_len) emit(o_start, o_len, o_h);
     // totals: one atomic per warp
-    for (int d = 16; d > 0; d >>= 1) { n_inst += __shfl_xor_sync(FULL_MASK, n_inst, d); n_rec += __shfl_xor_sync(FULL_MASK, n_rec, d); }
-    if (lane_id() == 0 && n_rec) { atomicAdd(&totals[0], (unsigned long long)n_inst); atomicAdd(&totals[1], (unsigned long long)n_rec); }
-    __syncthreads();
-    if (MODE == 0) {
-        for (u32 b = threadIdx.x; b < nb0; b += SKM_THREADS)
-            if (S.hist[b]) atomicAdd(&hist0[b], S.hist[b]);
-        return;
-    }
-    // ---- one reservation per (tile, bin), then the staged records go out grouped by bin ----
-    const u32 n = min(S.s_n, (u32)SKM_STAGE_CAP);
-    for (u32 b = threadIdx.x; b < nb0; b += SKM_THREADS) {
-        const u32 c = S.hist[b];
-        const u32 base = base0[b], lim = base + cap0[b];
-        const u32 gpos = c ? atomicAdd(&cur0[(u64)b * SKM_CUR_STRIDE], c) : 0u;
-        if (c && (u64)gpos + c > (u64)cap0[b]) *ovf = 1u;
-        S.gbase[b] = base + min(gpos, cap0[b]);
-        S.glim[b] = lim;
-        S.hist[b] = 0;
-    }
-    __syncthreads();
-    for (u32 i = threadIdx.x; i < n; i += SKM_THREADS) {
-        const u32 b = S.sbin[i];
-        const u32 p = S.gbase[b] + atomicAdd(&S.hist[b], 1u);
-        if (p < S.glim[b]) {
-            if (PEER) pt.ptr[skm_owner(pt, b)][p] = S.srec[i];
-            else out[p] = S.srec[i];
-        }
-    }
+    for (int d = 16; d > 0; d >>= 1) { tot_inst += __shfl_xor_sync(FULL_MASK, tot_inst, d); tot_rec += __shfl_xor_sync(FULL_MASK, tot_rec, d); }
+    if (lane_id() == 0 && tot_rec) { atomicAdd(&totals[0], (unsigned long long)tot_inst); atomicAdd(&totals[1], (unsigned long long)tot_rec); }
 }
 
 // Capacities of the level-0 regions from a (sampled) histogram taken at hb bits and collapsed to b0 <= hb bits: region r
@@ -293,31 +319,39 @@ __global__ void __launch_bounds__(1024) skm_caps_kernel(const u32 *__restrict__ 
 
 // ---- pass 1: level-0 regions -> leaf bins ---------------------------------------------------------
 // Region r (a level-0 bin, or a (bin, source) pair on the multi-GPU path) holds cnt[r * cnt_stride] records at
-// base[r]; its records belong to the local level-0 bin r / nsrc.
+// base[r]; its records belong to the local level-0 bin r / nsrc.  tile_reg[t] = region of the t-th tile of SKM_ALIGN slots.
+__global__ void skm_tilemap_kernel(const u32 *__restrict__ base, u32 nreg, u32 *__restrict__ tile_reg) {
+    const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nreg) return;
+    for (u32 t = base[r] / SKM_ALIGN; t < base[r + 1] / SKM_ALIGN; ++t) tile_reg[t] = r;
+}
 __global__ void __launch_bounds__(256) skm_l1_kernel(const ulonglong2 *__restrict__ in, const u32 *__restrict__ base, const u32 *__restrict__ cnt,
-                                                     u32 cnt_stride, u32 nreg, u32 nsrc, int b1, const u32 *__restrict__ lbeg,
-                                                     u32 *__restrict__ cur1, ulonglong2 *__restrict__ out) {
+                                                     u32 cnt_stride, const u32 *__restrict__ tile_reg, u32 nsrc, int b1,
+                                                     const u32 *__restrict__ lbeg, u32 *__restrict__ cur1, ulonglong2 *__restrict__ out) {
     const u64 tile0 = (u64)blockIdx.x * SKM_ALIGN;
-    if (tile0 >= base[nreg]) return;
-    u32 lo = 0, hi = nreg;  // largest r with base[r] <= tile0
-    while (hi - lo > 1) {
-        const u32 mid = (lo + hi) >> 1;
-        if ((u64)base[mid] <= tile0) lo = mid; else hi = mid;
-    }
-    const u32 r = lo, n = cnt[(u64)r * cnt_stride];
+    const u32 r = tile_reg[blockIdx.x];
+    const u32 n = cnt[(u64)r * cnt_stride];
     const u32 rel0 = (u32)(tile0 - base[r]);
+    if (rel0 >= n) return;
     const u64 leaf0 = (u64)(r / nsrc) << b1;
     const u32 m1 = (1u << b1) - 1u;
+    constexpr int U = SKM_ALIGN / 256;
+    ulonglong2 rec[U];
+    u32 pos[U];
+    u64 leaf[U];
 #pragma unroll
-    for (int u = 0; u < SKM_ALIGN / 256; ++u) {
+    for (int u = 0; u < U; ++u) {
         const u32 rel = rel0 + u * 256 + threadIdx.x;
-        if (rel < n) {
-            const ulonglong2 rec = in[tile0 - rel0 + rel];
-            const u64 leaf = leaf0 | (((u32)rec.y >> 5) & m1);
-            const u32 pos = atomicAdd(&cur1[leaf], 1u);
-            out[(u64)lbeg[leaf] + pos] = rec;
-        }
+        rec[u] = rel < n ? in[tile0 + u * 256 + threadIdx.x] : make_ulonglong2(0, 0);
     }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        leaf[u] = leaf0 | (((u32)rec[u].y >> 5) & m1);
+        pos[u] = (rel0 + u * 256 + threadIdx.x < n) ? atomicAdd(&cur1[leaf[u]], 1u) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        if (rel0 + u * 256 + threadIdx.x < n) out[(u64)lbeg[leaf[u]] + pos[u]] = rec[u];
 }
 __global__ void skm_gather_strided_kernel(const u32 *__restrict__ in, u32 stride, u32 n, u32 *__restrict__ out) {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -328,96 +362,127 @@ __global__ void skm_gather_strided_kernel(const u32 *__restrict__ in, u32 stride
 template <int THREADS, int LOG_HT>
 struct SkmLeafSmem {
     static constexpr int HT = 1 << LOG_HT;
+    static constexpr int LIST = HT / 4 * 3;
     u64 tab[HT];
-    u32 tcnt[HT];  // occurrences beyond the first one
+    u32 tcnt[HT];      // occurrences beyond the first one
+    u16 list[LIST];    // claimed slots of the current bin: the sweeps and the clean-up touch only these
     u32 ws[33];
-    u32 s_ovf;
+    u32 s_ovf, s_nd;
     unsigned long long s_gbase;
 };
 __device__ __forceinline__ u32 skm_slot(u64 key, int lh) { return (((u32)key ^ (u32)(key >> 32)) * 0x9E3779B1u) >> (32 - lh); }
 
 // Leaf bin l = records recs[lbeg[l] .. + lcnt[l]); CTA c takes the bins c, c + grid, ... (the bins are near-uniform).
-// Kept keys (count >= min_freq) are appended to okeys / ocnts at *kept_cursor.  A bin whose table fills up is put on
-// the overflow list instead (finished by the host path).
+// The table is cleared once per CTA; every bin leaves it clean again by resetting the slots it claimed, so the cost of
+// a bin is proportional to its instances + distinct keys, not to the table size.  Kept keys (count >= min_freq) are
+// appended to okeys / ocnts at *kept_cursor.  A bin whose table fills up is put on the overflow list instead.
 template <int THREADS, int LOG_HT, int LOGW>
 __global__ void __launch_bounds__(THREADS) skm_leaf_kernel(const ulonglong2 *__restrict__ recs, const u32 *__restrict__ lbeg,
                                                            const u32 *__restrict__ lcnt, u32 nleaf, int k, int canonical, u32 min_freq,
                                                            u64 *__restrict__ okeys, u32 *__restrict__ ocnts, unsigned long long *kept_cursor,
                                                            u32 *__restrict__ ovf_list, u32 *ovf_n, u32 test_ovf_mod) {
     constexpr int WIN = (1 << LOGW) + 1;
+    constexpr u32 HT = 1u << LOG_HT, HM = HT - 1u, LIST = SkmLeafSmem<THREADS, LOG_HT>::LIST;
     extern __shared__ __align__(16) u8 smem_raw[];
     SkmLeafSmem<THREADS, LOG_HT> &S = *reinterpret_cast<SkmLeafSmem<THREADS, LOG_HT> *>(smem_raw);
     const int s = 64 - 2 * k;
-    const u64 topmask = ~0ULL << s;
+    const u64 topmask = ~0ULL << s, kmask = ~0ULL >> s;
+    {
+        ulonglong2 *t2 = reinterpret_cast<ulonglong2 *>(S.tab);
+        for (u32 i = threadIdx.x; i < HT / 2; i += THREADS) t2[i] = make_ulonglong2(MSD_EMPTY, MSD_EMPTY);
+        uint4 *c4 = reinterpret_cast<uint4 *>(S.tcnt);
+        for (u32 i = threadIdx.x; i < HT / 4; i += THREADS) c4[i] = make_uint4(0, 0, 0, 0);
+        if (threadIdx.x == 0) S.s_nd = 0;
+    }
     for (u32 leaf = blockIdx.x; leaf < nleaf; leaf += gridDim.x) {
         const u32 n = lcnt[leaf];
         if (n == 0) continue;
         const ulonglong2 *rp = recs + lbeg[leaf];
-        // table size from the record count (instances <= n * WIN; a table of >= 2 x instances cannot fill up)
-        int lh = LOG_HT;
-        while (lh > 9 && (1u << (lh - 1)) >= 2u * n * (u32)WIN) --lh;
-        const u32 HT = 1u << lh, HM = HT - 1u;
-        __syncthreads();  // the previous bin's sweep is over
-        {
-            ulonglong2 *t2 = reinterpret_cast<ulonglong2 *>(S.tab);
-            for (u32 i = threadIdx.x; i < HT / 2; i += THREADS) t2[i] = make_ulonglong2(MSD_EMPTY, MSD_EMPTY);
-            uint4 *c4 = reinterpret_cast<uint4 *>(S.tcnt);
-            for (u32 i = threadIdx.x; i < HT / 4; i += THREADS) c4[i] = make_uint4(0, 0, 0, 0);
-            if (threadIdx.x == 0) S.s_ovf = (test_ovf_mod && leaf % test_ovf_mod == 0) ? 1u : 0u;
-        }
-        __syncthreads();
+        if (threadIdx.x == 0) S.s_ovf = (test_ovf_mod && leaf % test_ovf_mod == 0) ? 1u : 0u;
+        __syncthreads();  // table clean, flags set
         volatile u32 *ovf = &S.s_ovf;
-        if (!*ovf) {
-            for (u32 i = threadIdx.x; i < n; i += THREADS) {
-                const ulonglong2 rec = rp[i];
-                const u32 len = ((u32)rec.y & 31u) + 1u;
+        // (the flag is polled with warp votes: lanes of one warp must agree on leaving, they meet again in the shuffles)
+        if (!__any_sync(FULL_MASK, *ovf != 0)) {
+            // A warp takes 32 records at a time and spreads their windows over its lanes: lane i handles instance p + i of
+            // the chunk (record and window found with one OR-reduction + ballot; the record travels by shuffle), so every
+            // lane inserts, whatever the record lengths are.
+            for (u32 c0 = (threadIdx.x >> 5) * 32u; c0 < n; c0 += (THREADS / 32) * 32u) {
+                const u32 ri = c0 + lane_id();
+                ulonglong2 rec = make_ulonglong2(0, 0);
+                if (ri < n) rec = rp[ri];
+                const u32 len = ri < n ? ((u32)rec.y & 31u) + 1u : 0u;
+                const u32 incl = warp_incl_scan(len), start = incl - len;
+                const u32 T = __shfl_sync(FULL_MASK, incl, 31);
                 const u64 a0 = rec.x, a1 = rec.y & 0xFFFFFFFF00000000ULL;
-                const u64 nbc = ~(k == 32 ? a1 : ((a0 << (2 * k)) | (a1 >> s)));  // complemented bases k, k+1, ... of the record
-                u64 rl = rev2_u64(~a0) << s;                                       // reverse complement of window 0, left-aligned
-#pragma unroll
-                for (int j = 0; j < WIN; ++j) {
-                    if ((u32)j < len) {
-                        const u64 fl = (j == 0 ? a0 : ((a0 << (2 * j)) | (a1 >> (64 - 2 * j)))) & topmask;
-                        const u64 key = ((canonical && rl < fl) ? rl : fl) >> s;
-                        u32 slot = skm_slot(key, lh);
+                for (u32 p = 0; p < T; p += 32) {
+                    const u32 rel = start - p;  // wraps to a huge value for records that start before p
+                    const u32 smask = __reduce_or_sync(FULL_MASK, (len != 0 && rel < 32u) ? (1u << rel) : 0u);
+                    const u32 nbefore = __popc(__ballot_sync(FULL_MASK, len != 0 && start <= p));
+                    const u32 le = lane_id() == 31 ? 0xFFFFFFFFu : ((2u << lane_id()) - 1u);
+                    const u32 r = nbefore - 1u + __popc(smask & 0xFFFFFFFEu & le);
+                    const u64 A0 = __shfl_sync(FULL_MASK, a0, r & 31u), A1 = __shfl_sync(FULL_MASK, a1, r & 31u);
+                    const u32 st = __shfl_sync(FULL_MASK, start, r & 31u);
+                    const u32 q = p + lane_id();
+                    if (q < T) {
+                        const int j2 = 2 * (int)(q - st);  // window q - st of record r
+                        const u64 fl = ((A0 << j2) | ((A1 >> 1) >> (63 - j2))) & topmask;
+                        const u64 fw = fl >> s;
+                        const u64 rc = rev2_u64(~fl) & kmask;
+                        const u64 key = (canonical && rc < fw) ? rc : fw;
+                        u32 slot = skm_slot(key, LOG_HT);
                         int probes = 0;
                         for (;;) {
                             u64 c = S.tab[slot];
                             if (c == MSD_EMPTY) {
                                 c = atomicCAS((unsigned long long *)&S.tab[slot], (unsigned long long)MSD_EMPTY, (unsigned long long)key);
-                                if (c == MSD_EMPTY) break;  // claimed: first occurrence
+                                if (c == MSD_EMPTY) {  // claimed: first occurrence
+                                    const u32 li = atomicAdd(&S.s_nd, 1u);
+                                    if (li < LIST) S.list[li] = (u16)slot; else *ovf = 1;
+                                    break;
+                                }
                             }
                             if (c == key) { atomicAdd(&S.tcnt[slot], 1u); break; }
                             slot = (slot + 1) & HM;
                             if (++probes > SKM_MAXPROBE) { *ovf = 1; break; }
                         }
                     }
-                    if (j + 1 < WIN) rl = ((rl >> 2) & topmask) | ((nbc << (2 * j)) & 0xC000000000000000ULL);
                 }
-                if (*ovf) break;
+                if (__any_sync(FULL_MASK, *ovf != 0)) break;
             }
         }
         __syncthreads();
-        if (S.s_ovf) {
+        const u32 nd_all = S.s_nd, nd = min(nd_all, LIST);
+        const bool over = S.s_ovf != 0;
+        if (over) {
             if (threadIdx.x == 0) ovf_list[atomicAdd(ovf_n, 1u)] = leaf;
-            continue;
-        }
-        // ---- kept keys -> global list (two sweeps over the table: count, then write) ----
-        u32 c = 0;
-        for (u32 slot = threadIdx.x; slot < HT; slot += THREADS)
-            c += (S.tab[slot] != MSD_EMPTY && S.tcnt[slot] + 1u >= min_freq) ? 1u : 0u;
-        u32 total;
-        const u32 ex = block_excl_scan(c, S.ws, &total);
-        if (total) {
-            if (threadIdx.x == 0) S.s_gbase = atomicAdd(kept_cursor, (unsigned long long)total);
-            __syncthreads();
-            u64 o = S.s_gbase + ex;
-            for (u32 slot = threadIdx.x; slot < HT; slot += THREADS) {
-                const u64 key = S.tab[slot];
-                const u32 cnt = S.tcnt[slot] + 1u;
-                if (key != MSD_EMPTY && cnt >= min_freq) { okeys[o] = key; ocnts[o] = cnt; ++o; }
+        } else {
+            // ---- kept keys -> global list ----
+            u32 c = 0;
+            for (u32 i = threadIdx.x; i < nd; i += THREADS) c += (S.tcnt[S.list[i]] + 1u >= min_freq) ? 1u : 0u;
+            u32 total;
+            const u32 ex = block_excl_scan(c, S.ws, &total);
+            if (total) {
+                if (threadIdx.x == 0) S.s_gbase = atomicAdd(kept_cursor, (unsigned long long)total);
+                __syncthreads();
+                u64 o = S.s_gbase + ex;
+                for (u32 i = threadIdx.x; i < nd; i += THREADS) {
+                    const u32 slot = S.list[i];
+                    const u32 cnt = S.tcnt[slot] + 1u;
+                    if (cnt >= min_freq) { okeys[o] = S.tab[slot]; ocnts[o] = cnt; ++o; }
+                }
             }
         }
+        __syncthreads();
+        // ---- leave the table clean ----
+        if (nd_all > LIST) {  // slots were claimed that the list does not hold
+            ulonglong2 *t2 = reinterpret_cast<ulonglong2 *>(S.tab);
+            for (u32 i = threadIdx.x; i < HT / 2; i += THREADS) t2[i] = make_ulonglong2(MSD_EMPTY, MSD_EMPTY);
+            uint4 *c4 = reinterpret_cast<uint4 *>(S.tcnt);
+            for (u32 i = threadIdx.x; i < HT / 4; i += THREADS) c4[i] = make_uint4(0, 0, 0, 0);
+        } else {
+            for (u32 i = threadIdx.x; i < nd; i += THREADS) { const u32 slot = S.list[i]; S.tab[slot] = MSD_EMPTY; S.tcnt[slot] = 0; }
+        }
+        if (threadIdx.x == 0) S.s_nd = 0;
     }
 }
 
@@ -541,7 +606,7 @@ __global__ void skm_narrow_kernel(const u64 *__restrict__ in, u64 n, u32 *__rest
 
 // ------------------------------------- host side -------------------------------------------------
 struct SkmTune {
-    u32 bin_inst = 2048;   // target k-mer instances per leaf bin (distinct <= instances <= half the leaf table for most bins)
+    u32 bin_inst = 4096;   // target k-mer instances per leaf bin (distinct <= instances <= half the leaf table for most bins)
     int variant = 0;       // leaf geometry
     u32 sample = 16;       // capacity estimate from every `sample`-th tile
     u32 test_ovf_mod = 0;  // tests (GG_SKM_TEST_OVERFLOW=m): every leaf bin with index % m == 0 takes the overflow path
@@ -550,7 +615,7 @@ struct SkmTune {
 static SkmTune skm_tune() {
     SkmTune t;
     if (const char *e = getenv("GG_SKM_VARIANT")) t.variant = atoi(e);
-    if (t.variant == 2) t.bin_inst = 4096;
+    if (t.variant == 1) t.bin_inst = 2048;
     if (const char *e = getenv("GG_SKM_BIN")) t.bin_inst = (u32)atoi(e);
     if (const char *e = getenv("GG_SKM_SAMPLE")) t.sample = (u32)atoi(e);
     if (const char *e = getenv("GG_SKM_TEST_OVERFLOW")) t.test_ovf_mod = (u32)atoi(e);
@@ -712,15 +777,18 @@ static u64 skm_finish(gg_ctx *ctx, const ulonglong2 *in, const u32 *base, const 
         cur1.alloc(ctx, nleaf);
         dfill(ctx, cur1.p, nleaf * sizeof(u32), 0u);
         rec1.alloc(ctx, n_rec);
+        const u32 ntile = (u32)ceil_div(in_cap, SKM_ALIGN);
+        DBuf<u32> tile_reg(ctx, ntile + 1);
+        LAUNCH(ctx, skm_tilemap_kernel, (unsigned)ceil_div((u64)nb_local * nsrc, 128), 128, 0, base, nb_local * nsrc, tile_reg.p);
         prof_bytes(ctx, 32.0 * (double)n_rec);
-        LAUNCH(ctx, skm_l1_kernel, (unsigned)ceil_div(in_cap, SKM_ALIGN), 256, 0, in, base, cnt, cnt_stride, nb_local * nsrc, nsrc, g.b1, lbeg.p, cur1.p,
-               rec1.p);
+        LAUNCH(ctx, skm_l1_kernel, ntile, 256, 0, in, base, cnt, cnt_stride, tile_reg.p, nsrc, g.b1, lbeg.p, cur1.p, rec1.p);
         leaf_recs = rec1.p; leaf_beg = lbeg.p; leaf_cnt = hist1;
     } else if (cnt_stride != 1) {
         dense.alloc(ctx, nleaf);
         LAUNCH(ctx, skm_gather_strided_kernel, (unsigned)ceil_div(nleaf, 256), 256, 0, cnt, cnt_stride, (u32)nleaf, dense.p);
         leaf_cnt = dense.p;
     }
+    gg_trace(ctx, "skm level 1");
     // ---- E: leaves ----
     const u64 kept_cap = n_inst / (min_freq ? min_freq : 1) + 1;  // every kept key has >= min_freq instances
     DBuf<u64> kk(ctx, kept_cap), cursor(ctx, 2);
@@ -728,17 +796,18 @@ static u64 skm_finish(gg_ctx *ctx, const ulonglong2 *in, const u32 *base, const 
     dfill(ctx, cursor.p, 2 * sizeof(u64), 0u);
     dfill(ctx, ovf_n.p, 2 * sizeof(u32), 0u);
     prof_bytes(ctx, 16.0 * (double)n_rec);
-    if (tune.variant == 1)
-        skm_launch_leaf<256, 13>(ctx, 2, leaf_recs, leaf_beg, leaf_cnt, (u32)nleaf, g, min_freq, kk.p, kc.p, cursor.p, ovf_list.p, ovf_n.p, tune.test_ovf_mod);
-    else if (tune.variant == 2)
-        skm_launch_leaf<512, 13>(ctx, 2, leaf_recs, leaf_beg, leaf_cnt, (u32)nleaf, g, min_freq, kk.p, kc.p, cursor.p, ovf_list.p, ovf_n.p, tune.test_ovf_mod);
-    else
+    if (tune.variant == 1)   // 4 CTAs / SM, 4096-slot tables, bins of <= 2048 instances
         skm_launch_leaf<256, 12>(ctx, 4, leaf_recs, leaf_beg, leaf_cnt, (u32)nleaf, g, min_freq, kk.p, kc.p, cursor.p, ovf_list.p, ovf_n.p, tune.test_ovf_mod);
+    else if (tune.variant == 2)
+        skm_launch_leaf<256, 13>(ctx, 2, leaf_recs, leaf_beg, leaf_cnt, (u32)nleaf, g, min_freq, kk.p, kc.p, cursor.p, ovf_list.p, ovf_n.p, tune.test_ovf_mod);
+    else                     // 2 CTAs / SM, 8192-slot tables, bins of <= 4096 instances
+        skm_launch_leaf<512, 13>(ctx, 2, leaf_recs, leaf_beg, leaf_cnt, (u32)nleaf, g, min_freq, kk.p, kc.p, cursor.p, ovf_list.p, ovf_n.p, tune.test_ovf_mod);
     CK(cudaMemcpyAsync(ctx->h_scalar, cursor.p, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_scalar + 1, ovf_n.p, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     u64 U = ctx->h_scalar[0];
     const u32 n_ovf = (u32)ctx->h_scalar[1];
+    gg_trace(ctx, "skm leaves");
     prof_add_bytes(ctx, "skm_leaf_kernel", 12.0 * (double)U);
     if (n_ovf) {  // bins whose table filled up: their k-mers as plain keys -> radix sort + run-length count + filter
         DBuf<u64> tot(ctx, 2);
@@ -761,10 +830,12 @@ static u64 skm_finish(gg_ctx *ctx, const ulonglong2 *in, const u32 *base, const 
         cp.emit(f);
         U += nk;
     }
+    gg_trace(ctx, "skm overflow bins");
     stage_end(ctx, ST_SORT);
     // ---- F: order the kept pairs ----
     stage_begin(ctx, ST_COUNT);
     skm_sort_pairs(ctx, kk.p, kc.p, U, g.k, ukeys, ucounts);
+    gg_trace(ctx, "skm sort");
     stage_end(ctx, ST_COUNT);
     return U;
 }
@@ -785,6 +856,7 @@ static u64 skm_count(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int k
         L.alloc_sample(ctx);
         prof_bytes(ctx, 12.0 * (double)pr.nwords / stride);
         skm_scan_launch<0, false>(ctx, pr, valid, 0, pr.nwords, stride, g0, L.hist0.p, nullptr, nullptr, nullptr, nullptr, nullptr, L.totals.p, nullptr, nullptr);
+        gg_trace(ctx, "skm sample");
         skm_l0_prepare(ctx, L, k, canonical, (double)stride, stride == 1 && !(attempt == 0 && tune.force_cap), tune);
         prof_bytes(ctx, 12.0 * (double)pr.nwords);  // + 16 B per record, added once the count is known
         skm_scan_launch<1, false>(ctx, pr, valid, 0, pr.nwords, 1, L.g, nullptr, L.cur0.p, L.base0.p, L.cap0.p, L.rec0.p, L.hist1.p, L.totals.p, L.ovf.p,
@@ -792,6 +864,7 @@ static u64 skm_count(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int k
         CK(cudaMemcpyAsync(ctx->h_scalar, L.totals.p, 2 * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(ctx->h_scalar + 2, L.ovf.p, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
+        gg_trace(ctx, "skm scatter");
         if ((u32)ctx->h_scalar[2] == 0) break;
         if (L.exact || attempt > 0) GG_THROW(GG_ERR_CUDA, "super-k-mer scatter overflowed exact capacities");
         stride = 1;  // a bin outgrew its sampled share: repeat with exact counts

@@ -3,9 +3,9 @@
 tag=${1:-x}; kexpr=${2:-}
 mkdir -p gpurun_out
 if [ -n "$kexpr" ]; then
-  timeout 900 python -m pytest tests -m gpu -x -q -k "$kexpr" > gpurun_out/tests_$tag.log 2>&1; echo "tests rc=$?"
+  timeout 900 python -m pytest tests -m gpu -x -q --timeout=150 -k "$kexpr" > gpurun_out/tests_$tag.log 2>&1; echo "tests rc=$?"
 else
-  timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/tests_$tag.log 2>&1; echo "tests rc=$?"
+  timeout 1200 python -m pytest tests -m gpu -x -q --timeout=150 > gpurun_out/tests_$tag.log 2>&1; echo "tests rc=$?"
 fi
 tail -30 gpurun_out/tests_$tag.log
 for wl in c2_ecoli50x_k31 c3_100mbp30x_k31; do
