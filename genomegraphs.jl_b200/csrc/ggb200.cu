@@ -471,17 +471,17 @@ static gg_counts *count_kmers_host_pipelined(gg_ctx *ctx, const u8 *seq, const u
         if (skm_supported(k, canonical) && !getenv("GG_FORCE_MSD")) {
             const SkmTune tune = skm_tune();
             SkmL0 L;
-            SkmGeom g0;
-            g0.k = k; g0.canonical = canonical; g0.b0 = SKM_MAX_B0; g0.b1 = 0;
             const bool speculate = nch >= 3 && !getenv("GG_NO_SPEC");
             bool scattered = false;
             host_pipeline_front(ctx, seq, offs, nreads, nbytes, k, dseq, doffs, pr, valid, GG_H2D_CHUNK, [&](u64 ci, u64 w0, u64 w1) {
                 if (!speculate) return;
-                if (ci == 0) {  // geometry and capacities from the first chunk's records, scaled to the whole input
+                if (ci == 0) {  // geometry and capacities from the first chunk's windows and records, scaled to the whole input
+                    const double scale = (double)pr.nwords / (double)(w1 - w0);
+                    L.g = skm_geom((u64)((double)skm_count_windows(ctx, valid.p, w0, w1) * scale), k, canonical, tune);
                     L.alloc_sample(ctx);
-                    skm_scan_launch<0, false>(ctx, pr, valid.p, w0, w1, 1, g0, L.hist0.p, nullptr, nullptr, nullptr, nullptr, nullptr, L.totals.p, nullptr,
+                    skm_scan_launch<0, false>(ctx, pr, valid.p, w0, w1, 1, L.g, L.hist0.p, nullptr, nullptr, nullptr, nullptr, nullptr, L.totals.p, nullptr,
                                               nullptr);
-                    skm_l0_prepare(ctx, L, k, canonical, (double)pr.nwords / (double)(w1 - w0), false, tune);
+                    skm_l0_prepare(ctx, L, scale, false, tune);
                     scattered = true;
                 }
                 skm_scan_launch<1, false>(ctx, pr, valid.p, w0, w1, 1, L.g, nullptr, L.cur0.p, L.base0.p, L.cap0.p, L.rec0.p, L.hist1.p, L.totals.p,
@@ -497,7 +497,7 @@ static gg_counts *count_kmers_host_pipelined(gg_ctx *ctx, const u8 *seq, const u
                     const u64 n_inst = ctx->h_scalar[0], n_rec = ctx->h_scalar[1];
                     c->n_instances = n_inst;
                     stage_end(ctx, ST_EXTRACT);
-                    c->n_unique = skm_finish(ctx, L.rec0.p, L.base0.p, L.cur0.p, SKM_CUR_STRIDE, 1u << L.g.b0, 1, L.cap_total, L.g, L.hist1.p, n_inst, n_rec,
+                    c->n_unique = skm_finish(ctx, L.rec0.p, L.base0.p, L.cur0.p, SKM_CUR_STRIDE, L.g.nb0, 1, L.cap_total, L.g, L.hist1.p, n_inst, n_rec,
                                              mf, tune, ukeys, counts);
                     done = true;
                 } else L.rec0.release();  // a bin outgrew the share the first chunk predicted (reads sorted by content, say): exact repeat

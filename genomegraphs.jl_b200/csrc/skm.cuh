@@ -15,7 +15,7 @@
 //                               instances of a canonical k-mer meet in one bin.  Multi-GPU: the bins
 //                               are owned by ranks and the records are stored straight into the
 //                               owner's buffer over NVLink (dist.cuh).
-//   1  skm_l1_kernel            records -> 2^(b0+b1) leaf bins (exact sizes from pass 0's histogram)
+//   1  skm_l1_kernel            records -> nb0 x nb1 leaf bins (exact sizes from pass 0's histogram)
 //   E  skm_leaf_kernel          one CTA per leaf bin: records expanded to canonical k-mers in
 //                               registers, counted in a shared-memory hash table; keys with
 //                               count >= min_freq appended (unordered) to the kept list
@@ -30,9 +30,9 @@
 #define SKM_THREADS 256
 #define SKM_STAGE_CAP 8704    // runs a CTA stages in shared memory before it reserves space in the bins (>= 8192 + 256: one word per thread always fits)
 #define SKM_CUR_STRIDE 64     // the level-0 cursors sit 256 bytes apart: neighbours would serialise in one L2 slice
-#define SKM_MAX_B0 9
-#define SKM_MAX_B1 12
-#define SKM_ALIGN 1024        // level-0 regions are multiples of this many records (tiles of pass 1 never straddle a region)
+#define SKM_MAX_NB0 512       // level-0 bins
+#define SKM_MAX_NB1 8192      // leaf bins per level-0 bin (13 bits of the record's meta word)
+#define SKM_ALIGN 8192        // level-0 regions are multiples of this many records (tiles of pass 1 never straddle a region)
 #define SKM_MAXPROBE 64
 
 static inline bool skm_supported(int k, int canonical) { return k >= 17 && k <= 32 && (canonical || k < 32); }
@@ -48,8 +48,18 @@ __host__ __device__ __forceinline__ u32 skm_digits(u32 h) {
 }
 
 struct SkmGeom {
-    int k, canonical, b0, b1;
+    int k, canonical;
+    u32 nb0, nb1;   // level-0 bins x leaf bins per level-0 bin (any counts: the digits are range-reduced by multiply-high)
 };
+// bins of a minimizer: d uniform in [0, 2^32) -> bin0 = floor(d * nb0 / 2^32); the low word of that product is uniform
+// again -> bin1 likewise; `rest` = what is left for further splits
+__device__ __forceinline__ void skm_bins(u32 d, u32 nb0, u32 nb1, u32 &bin0, u32 &bin1, u32 &rest) {
+    const u64 p0 = (u64)d * nb0;
+    bin0 = (u32)(p0 >> 32);
+    const u64 p1 = (u64)(u32)p0 * nb1;
+    bin1 = (u32)(p1 >> 32);
+    rest = (u32)p1;
+}
 
 // multi-GPU: rank q owns the level-0 bins [first[q], first[q + 1]); base0 / cap0 then describe this source's
 // private region of every bin inside the owner's buffer
@@ -67,7 +77,7 @@ __device__ __forceinline__ int skm_owner(const SkmPeers &pt, u32 b) {
 
 // One record: `len` consecutive windows starting at base `start` (len + k - 1 <= 48 bases, left-aligned in 128
 // bits: .x = bases 0..31, top half of .y = bases 32..47); low 32 bits of .y = meta: len - 1 (5 bits) |
-// level-1 digit << 5 | further digit bits << 17.
+// leaf bin inside the level-0 bin << 5 (13 bits) | further digit bits << 18.
 __device__ __forceinline__ ulonglong2 skm_make_record(const u64 *__restrict__ packed, u64 start, u32 len, int k, u32 meta) {
     const u32 nb = len + (u32)k - 1u;  // 17 .. 48
     const u64 j = start >> 5;
@@ -84,12 +94,12 @@ struct SkmScanSmem {
     u32 dh[SKM_STAGE_CAP];              // staged run: minimizer hash
     u32 ds[SKM_STAGE_CAP];              // staged run: (first base - first base of the tile) << 5 | (windows - 1)
     u32 sq[32 * SKM_THREADS];           // per-thread queue: minimizer hash of every run that starts in the current word
-    u32 hist[1 << SKM_MAX_B0];          // runs per level-0 bin, then the running cursor inside the reserved space
-    u32 gbase[1 << SKM_MAX_B0];         // first record slot of this tile's runs in every bin (absolute index into the buffer)
-    u32 glim[1 << SKM_MAX_B0];          // end of the bin's region
+    u32 hist[SKM_MAX_NB0];              // runs per level-0 bin, then the running cursor inside the reserved space
+    u32 gbase[SKM_MAX_NB0];             // first record slot of this tile's runs in every bin (absolute index into the buffer)
+    u32 glim[SKM_MAX_NB0];              // end of the bin's region
     u32 s_n;
 };
-// MODE 0: count records per level-0 bin at SKM_MAX_B0 bits (hist0); MODE 1: scatter the records.
+// MODE 0: count records per level-0 bin (hist0); MODE 1: scatter the records.
 // The launch covers the packed words [w0, w1); CTA c handles tile number c * stride of 256 * TWORDS words
 // (stride > 1: sampling for the capacity estimate).
 // Phase 1 (every lane busy, no calls, no divergent loops): roll the m-mer hashes of a word, sliding minimum, and note
@@ -111,8 +121,7 @@ __global__ void __launch_bounds__(SKM_THREADS, 2) skm_scan_kernel(const u64 *__r
     extern __shared__ __align__(16) u8 smem_raw[];
     SkmScanSmem &S = *reinterpret_cast<SkmScanSmem *>(smem_raw);
     const int k = g.k, m = k - WIN + 1;   // 9 <= m <= 16
-    const int b0 = MODE == 0 ? SKM_MAX_B0 : g.b0;
-    const u32 nb0 = 1u << b0;
+    const u32 nb0 = g.nb0;
     const u32 mmask = m == 16 ? 0xFFFFFFFFu : ((1u << (2 * m)) - 1u);
     const u32 rmul = 1u << (2 * m - 2);
     const u64 tile_w0 = w0 + ((u64)blockIdx.x * stride) * (SKM_THREADS * TWORDS);
@@ -228,8 +237,7 @@ __global__ void __launch_bounds__(SKM_THREADS, 2) skm_scan_kernel(const u64 *__r
         tot_inst += n_inst; tot_rec += n_rec;
         // ---------------- phase B: bin of every staged run ----------------
         for (u32 i = threadIdx.x; i < ntot; i += SKM_THREADS) {
-            const u32 d = skm_digits(S.dh[i]);
-            atomicAdd(&S.hist[b0 ? (d >> (32 - b0)) : 0u], 1u);
+            atomicAdd(&S.hist[__umulhi(skm_digits(S.dh[i]), nb0)], 1u);
         }
         __syncthreads();
         if (MODE == 0) {
@@ -250,15 +258,13 @@ __global__ void __launch_bounds__(SKM_THREADS, 2) skm_scan_kernel(const u64 *__r
             // ---------------- phase D: records built and stored, grouped by bin ----------------
             const u64 tile_b0 = tile_w0 << 5;
             for (u32 i = threadIdx.x; i < ntot; i += SKM_THREADS) {
-                const u32 d = skm_digits(S.dh[i]);
-                const u32 b = b0 ? (d >> (32 - b0)) : 0u;
+                u32 b, bin1, rest;
+                skm_bins(skm_digits(S.dh[i]), nb0, g.nb1, b, bin1, rest);
                 const u32 p = S.gbase[b] + atomicAdd(&S.hist[b], 1u);
-                const u32 rest = b0 ? (d << b0) : d;  // digit bits below bin0, left-aligned
-                const u32 bin1 = g.b1 ? (rest >> (32 - g.b1)) : 0u;
                 const u32 dsv = S.ds[i];
                 const u32 len = (dsv & 31u) + 1u;
-                const u32 meta = (len - 1u) | (bin1 << 5) | ((((g.b1 ? (rest << g.b1) : rest)) >> 17) << 17);
-                atomicAdd(&hist1[((u64)b << g.b1) | bin1], 1u);
+                const u32 meta = (len - 1u) | (bin1 << 5) | ((rest >> 18) << 18);
+                atomicAdd(&hist1[(u64)b * g.nb1 + bin1], 1u);
                 if (p < S.glim[b]) {
                     const ulonglong2 rec = skm_make_record(packed, tile_b0 + (dsv >> 5), len, k, meta);
                     if (PEER) pt.ptr[skm_owner(pt, b)][p] = rec;
@@ -275,22 +281,20 @@ __global__ void __launch_bounds__(SKM_THREADS, 2) skm_scan_kernel(const u64 *__r
     if (lane_id() == 0 && tot_rec) { atomicAdd(&totals[0], (unsigned long long)tot_inst); atomicAdd(&totals[1], (unsigned long long)tot_rec); }
 }
 
-// Capacities of the level-0 regions from a (sampled) histogram taken at hb bits and collapsed to b0 <= hb bits: region r
-// gets round_up(scale * c * 1.25 + 4 * scale * sqrt(c + 1) + 1024, SKM_ALIGN) records (exact counts: round_up(c, SKM_ALIGN)).
+// Capacities of the level-0 regions from a (sampled) histogram: region r gets
+// round_up(scale * c * 1.25 + 4 * scale * sqrt(c + 1) + 1024, SKM_ALIGN) records (exact counts: round_up(c, SKM_ALIGN)).
 // One CTA.  base has nreg + 1 entries; *total_cap gets the sum.
-__global__ void __launch_bounds__(1024) skm_caps_kernel(const u32 *__restrict__ hist, int hb, int b0, float scale, int exact, u32 *__restrict__ base,
+__global__ void __launch_bounds__(1024) skm_caps_kernel(const u32 *__restrict__ hist, u32 nreg, float scale, int exact, u32 *__restrict__ base,
                                                         u32 *__restrict__ cap, u64 *__restrict__ total_cap, u32 force_cap) {
     __shared__ u32 ws[33];
     __shared__ u64 s_run;
-    const u32 nreg = 1u << b0, grp = 1u << (hb - b0);
     if (threadIdx.x == 0) s_run = 0;
     __syncthreads();
     for (u32 r0 = 0; r0 < nreg; r0 += 1024) {
         const u32 r = r0 + threadIdx.x;
         u32 c = 0;
         if (r < nreg) {
-            u64 cnt = 0;
-            for (u32 i = 0; i < grp; ++i) cnt += hist[r * grp + i];
+            const u64 cnt = hist[r];
             const float hv = (float)cnt;
             double want = exact ? (double)cnt : (double)(scale * hv * 1.25f + 4.0f * scale * sqrtf(hv + 1.0f) + 1024.0f);
             if (force_cap) want = force_cap;  // tests: provoke the overflow path
@@ -325,33 +329,40 @@ __global__ void skm_tilemap_kernel(const u32 *__restrict__ base, u32 nreg, u32 *
     if (r >= nreg) return;
     for (u32 t = base[r] / SKM_ALIGN; t < base[r + 1] / SKM_ALIGN; ++t) tile_reg[t] = r;
 }
-__global__ void __launch_bounds__(256) skm_l1_kernel(const ulonglong2 *__restrict__ in, const u32 *__restrict__ base, const u32 *__restrict__ cnt,
-                                                     u32 cnt_stride, const u32 *__restrict__ tile_reg, u32 nsrc, int b1,
-                                                     const u32 *__restrict__ lbeg, u32 *__restrict__ cur1, ulonglong2 *__restrict__ out) {
+// One CTA per tile of SKM_ALIGN record slots.  Two sweeps over the tile's records (the second one hits L2): count per
+// leaf bin in shared memory, ONE global reservation per (tile, leaf bin), then the records are stored, those of one bin next
+// to each other.  (Per-record global atomics serialise on the few cursors one level-0 bin's tiles share.)
+#define SKM_L1_THREADS 512
+__global__ void __launch_bounds__(SKM_L1_THREADS) skm_l1_kernel(const ulonglong2 *__restrict__ in, const u32 *__restrict__ base,
+                                                                const u32 *__restrict__ cnt, u32 cnt_stride, const u32 *__restrict__ tile_reg,
+                                                                u32 nsrc, u32 nb1, const u32 *__restrict__ lbeg, u32 *__restrict__ cur1,
+                                                                ulonglong2 *__restrict__ out) {
+    extern __shared__ __align__(16) u8 smem_raw[];
+    u32 *hist = reinterpret_cast<u32 *>(smem_raw);   // nb1
+    u32 *gpos = hist + nb1;                          // nb1
     const u64 tile0 = (u64)blockIdx.x * SKM_ALIGN;
     const u32 r = tile_reg[blockIdx.x];
     const u32 n = cnt[(u64)r * cnt_stride];
     const u32 rel0 = (u32)(tile0 - base[r]);
     if (rel0 >= n) return;
-    const u64 leaf0 = (u64)(r / nsrc) << b1;
-    const u32 m1 = (1u << b1) - 1u;
-    constexpr int U = SKM_ALIGN / 256;
-    ulonglong2 rec[U];
-    u32 pos[U];
-    u64 leaf[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const u32 rel = rel0 + u * 256 + threadIdx.x;
-        rec[u] = rel < n ? in[tile0 + u * 256 + threadIdx.x] : make_ulonglong2(0, 0);
+    const u32 m = min(n - rel0, (u32)SKM_ALIGN);     // records of this tile
+    const u64 leaf0 = (u64)(r / nsrc) * nb1;
+    const ulonglong2 *tp = in + tile0;
+    for (u32 i = threadIdx.x; i < nb1; i += SKM_L1_THREADS) hist[i] = 0;
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < m; i += SKM_L1_THREADS) atomicAdd(&hist[((u32)tp[i].y >> 5) & (SKM_MAX_NB1 - 1u)], 1u);
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < nb1; i += SKM_L1_THREADS) {
+        const u32 c = hist[i];
+        gpos[i] = c ? lbeg[leaf0 + i] + atomicAdd(&cur1[leaf0 + i], c) : 0u;
+        hist[i] = 0;
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        leaf[u] = leaf0 | (((u32)rec[u].y >> 5) & m1);
-        pos[u] = (rel0 + u * 256 + threadIdx.x < n) ? atomicAdd(&cur1[leaf[u]], 1u) : 0u;
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < m; i += SKM_L1_THREADS) {
+        const ulonglong2 rec = tp[i];
+        const u32 b = ((u32)rec.y >> 5) & (SKM_MAX_NB1 - 1u);
+        out[(u64)gpos[b] + atomicAdd(&hist[b], 1u)] = rec;
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-        if (rel0 + u * 256 + threadIdx.x < n) out[(u64)lbeg[leaf[u]] + pos[u]] = rec[u];
 }
 __global__ void skm_gather_strided_kernel(const u32 *__restrict__ in, u32 stride, u32 n, u32 *__restrict__ out) {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -604,6 +615,14 @@ __global__ void skm_narrow_kernel(const u64 *__restrict__ in, u64 n, u32 *__rest
     if (i < n) out[i] = (u32)in[i];
 }
 
+// number of k-mer windows of the packed words [w0, w1): popcount of the window masks
+__global__ void __launch_bounds__(256) skm_popc_kernel(const u32 *__restrict__ valid, u64 w0, u64 w1, unsigned long long *__restrict__ total) {
+    u64 c = 0;
+    for (u64 t = w0 + (u64)blockIdx.x * blockDim.x + threadIdx.x; t < w1; t += (u64)gridDim.x * blockDim.x) c += __popc(valid[t]);
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(FULL_MASK, c, d);
+    if (lane_id() == 0 && c) atomicAdd(total, (unsigned long long)c);
+}
+
 // ------------------------------------- host side -------------------------------------------------
 struct SkmTune {
     u32 bin_inst = 4096;   // target k-mer instances per leaf bin (distinct <= instances <= half the leaf table for most bins)
@@ -624,15 +643,25 @@ static SkmTune skm_tune() {
     if (t.sample < 1) t.sample = 1;
     return t;
 }
-// digit widths from the (estimated) number of instances
-static SkmGeom skm_geom(u64 n_inst_est, int k, int canonical, const SkmTune &t) {
+// bin counts from the number of instances: leaf bins of ~bin_inst instances
+static SkmGeom skm_geom(u64 n_inst, int k, int canonical, const SkmTune &t) {
     SkmGeom g;
     g.k = k; g.canonical = canonical;
-    int bits = 0;
-    while (bits < SKM_MAX_B0 + SKM_MAX_B1 && (n_inst_est >> bits) > t.bin_inst) ++bits;
-    g.b0 = bits < SKM_MAX_B0 ? bits : SKM_MAX_B0;
-    g.b1 = bits - g.b0;
+    u64 nleaf = ceil_div(n_inst ? n_inst : 1, t.bin_inst);
+    g.nb0 = (u32)(nleaf < SKM_MAX_NB0 ? nleaf : SKM_MAX_NB0);
+    const u64 nb1 = ceil_div(nleaf, g.nb0);
+    g.nb1 = (u32)(nb1 < SKM_MAX_NB1 ? nb1 : SKM_MAX_NB1);
     return g;
+}
+// exact number of k-mer windows of the packed words [w0, w1) (one pass over the 4-byte window masks, one synchronisation)
+static u64 skm_count_windows(gg_ctx *ctx, const u32 *valid, u64 w0, u64 w1) {
+    if (w1 <= w0) return 0;
+    DBuf<u64> tot(ctx, 1);
+    dfill(ctx, tot.p, sizeof(u64), 0u);
+    const u64 grid = std::min<u64>(ceil_div(w1 - w0, 256 * 8), (u64)ctx->num_sms * 16);
+    prof_bytes(ctx, 4.0 * (double)(w1 - w0));
+    LAUNCH(ctx, skm_popc_kernel, (unsigned)grid, 256, 0, valid, w0, w1, (unsigned long long *)tot.p);
+    return read_scalar<u64>(ctx, tot.p);
 }
 
 template <int MODE, bool PEER>
@@ -726,29 +755,27 @@ static void skm_sort_pairs(gg_ctx *ctx, u64 *kk, u32 *kc, u64 n, int k, DBuf<u64
 // Level-0 state of a scatter (also filled chunk by chunk by the pipelined host path).
 struct SkmL0 {
     SkmGeom g;
-    DBuf<u32> hist0, cur0, base0, cap0, hist1, ovf;   // hist0: SKM_MAX_B0 bits; cur0: strided (SKM_CUR_STRIDE)
+    DBuf<u32> hist0, cur0, base0, cap0, hist1, ovf;   // cur0: strided (SKM_CUR_STRIDE)
     DBuf<u64> totals, total_cap;   // totals: [0] instances, [1] records
     DBuf<ulonglong2> rec0;
     u64 cap_total = 0;
     bool exact = false;
-    void alloc_sample(gg_ctx *ctx) {
-        hist0.alloc(ctx, (1u << SKM_MAX_B0) + 1);
+    void alloc_sample(gg_ctx *ctx) {   // g is set
+        hist0.alloc(ctx, g.nb0 + 1);
         totals.alloc(ctx, 2);
-        dfill(ctx, hist0.p, (u64)((1u << SKM_MAX_B0) + 1) * sizeof(u32), 0u);
+        dfill(ctx, hist0.p, (u64)(g.nb0 + 1) * sizeof(u32), 0u);
         dfill(ctx, totals.p, 2 * sizeof(u64), 0u);
     }
 };
-// after the sample pass (hist0 / totals filled by skm_scan_kernel<.., 0, ..> over 1 / scale of the input): geometry from the
-// instance estimate, capacities, record buffer, zeroed scatter state.  One stream synchronisation.
-static void skm_l0_prepare(gg_ctx *ctx, SkmL0 &L, int k, int canonical, double scale, bool exact, const SkmTune &tune) {
+// after the sample pass (hist0 filled by skm_scan_kernel<.., 0, ..> over 1 / scale of the input): capacities, record
+// buffer, zeroed scatter state.  One stream synchronisation.
+static void skm_l0_prepare(gg_ctx *ctx, SkmL0 &L, double scale, bool exact, const SkmTune &tune) {
     L.total_cap.alloc(ctx, 1);
-    const u64 n_inst_sample = read_scalar<u64>(ctx, L.totals.p);
-    L.g = skm_geom((u64)((double)n_inst_sample * scale), k, canonical, tune);
-    const u32 nb0 = 1u << L.g.b0;
-    const u64 nleaf = 1ULL << (L.g.b0 + L.g.b1);
+    const u32 nb0 = L.g.nb0;
+    const u64 nleaf = (u64)L.g.nb0 * L.g.nb1;
     L.base0.alloc(ctx, nb0 + 1); L.cap0.alloc(ctx, nb0); L.cur0.alloc(ctx, (u64)nb0 * SKM_CUR_STRIDE); L.hist1.alloc(ctx, nleaf + 1);
     L.ovf.alloc(ctx, 1);
-    LAUNCH(ctx, skm_caps_kernel, 1, 1024, 0, L.hist0.p, SKM_MAX_B0, L.g.b0, (float)scale, exact ? 1 : 0, L.base0.p, L.cap0.p, L.total_cap.p,
+    LAUNCH(ctx, skm_caps_kernel, 1, 1024, 0, L.hist0.p, nb0, (float)scale, exact ? 1 : 0, L.base0.p, L.cap0.p, L.total_cap.p,
            exact ? 0u : tune.force_cap);
     L.cap_total = read_scalar<u64>(ctx, L.total_cap.p);
     if (L.cap_total >= 0xFFFFFFFFull) GG_THROW(GG_ERR_LIMIT, "%llu super-k-mer records exceed the 2^32-1 per-GPU limit", (unsigned long long)L.cap_total);
@@ -766,13 +793,13 @@ static u64 skm_finish(gg_ctx *ctx, const ulonglong2 *in, const u32 *base, const 
                       const SkmGeom &g, const u32 *hist1, u64 n_inst, u64 n_rec, u32 min_freq, const SkmTune &tune, DBuf<u64> &ukeys,
                       DBuf<u32> &ucounts) {
     if (n_rec == 0 || nb_local == 0) { ukeys.alloc(ctx, 1); ucounts.alloc(ctx, 1); return 0; }
-    const u64 nleaf = (u64)nb_local << g.b1;
+    const u64 nleaf = (u64)nb_local * g.nb1;
     stage_begin(ctx, ST_SORT);
     DBuf<u32> lbeg(ctx, nleaf + 1), cur1, dense;
     DBuf<ulonglong2> rec1;
     const ulonglong2 *leaf_recs = in;
     const u32 *leaf_beg = base, *leaf_cnt = cnt;
-    if (g.b1 > 0 || nsrc > 1) {
+    if (g.nb1 > 1 || nsrc > 1) {
         exclusive_scan_u32(ctx, hist1, lbeg.p, nleaf + 1, nullptr);
         cur1.alloc(ctx, nleaf);
         dfill(ctx, cur1.p, nleaf * sizeof(u32), 0u);
@@ -781,7 +808,9 @@ static u64 skm_finish(gg_ctx *ctx, const ulonglong2 *in, const u32 *base, const 
         DBuf<u32> tile_reg(ctx, ntile + 1);
         LAUNCH(ctx, skm_tilemap_kernel, (unsigned)ceil_div((u64)nb_local * nsrc, 128), 128, 0, base, nb_local * nsrc, tile_reg.p);
         prof_bytes(ctx, 32.0 * (double)n_rec);
-        LAUNCH(ctx, skm_l1_kernel, ntile, 256, 0, in, base, cnt, cnt_stride, tile_reg.p, nsrc, g.b1, lbeg.p, cur1.p, rec1.p);
+        const size_t smem1 = (size_t)g.nb1 * 8;
+        set_max_smem(ctx, skm_l1_kernel, (size_t)SKM_MAX_NB1 * 8);
+        LAUNCH(ctx, skm_l1_kernel, ntile, SKM_L1_THREADS, smem1, in, base, cnt, cnt_stride, tile_reg.p, nsrc, g.nb1, lbeg.p, cur1.p, rec1.p);
         leaf_recs = rec1.p; leaf_beg = lbeg.p; leaf_cnt = hist1;
     } else if (cnt_stride != 1) {
         dense.alloc(ctx, nleaf);
@@ -850,14 +879,13 @@ static u64 skm_count(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int k
     const u64 ntiles = ceil_div(pr.nwords, skm_tile_words(k));
     u32 stride = ntiles >= 256 ? tune.sample : 1;
     SkmL0 L;
-    SkmGeom g0;  // the sample pass only needs k
-    g0.k = k; g0.canonical = canonical; g0.b0 = SKM_MAX_B0; g0.b1 = 0;
+    L.g = skm_geom(skm_count_windows(ctx, valid, 0, pr.nwords), k, canonical, tune);
     for (int attempt = 0;; ++attempt) {
         L.alloc_sample(ctx);
         prof_bytes(ctx, 12.0 * (double)pr.nwords / stride);
-        skm_scan_launch<0, false>(ctx, pr, valid, 0, pr.nwords, stride, g0, L.hist0.p, nullptr, nullptr, nullptr, nullptr, nullptr, L.totals.p, nullptr, nullptr);
+        skm_scan_launch<0, false>(ctx, pr, valid, 0, pr.nwords, stride, L.g, L.hist0.p, nullptr, nullptr, nullptr, nullptr, nullptr, L.totals.p, nullptr, nullptr);
         gg_trace(ctx, "skm sample");
-        skm_l0_prepare(ctx, L, k, canonical, (double)stride, stride == 1 && !(attempt == 0 && tune.force_cap), tune);
+        skm_l0_prepare(ctx, L, (double)stride, stride == 1 && !(attempt == 0 && tune.force_cap), tune);
         prof_bytes(ctx, 12.0 * (double)pr.nwords);  // + 16 B per record, added once the count is known
         skm_scan_launch<1, false>(ctx, pr, valid, 0, pr.nwords, 1, L.g, nullptr, L.cur0.p, L.base0.p, L.cap0.p, L.rec0.p, L.hist1.p, L.totals.p, L.ovf.p,
                                   nullptr);
@@ -874,6 +902,6 @@ static u64 skm_count(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int k
     prof_add_bytes(ctx, "skm_scan_kernel", 16.0 * (double)n_rec);
     *n_instances = n_inst;
     stage_end(ctx, ST_EXTRACT);
-    return skm_finish(ctx, L.rec0.p, L.base0.p, L.cur0.p, SKM_CUR_STRIDE, 1u << L.g.b0, 1, L.cap_total, L.g, L.hist1.p, n_inst, n_rec, min_freq, tune, ukeys,
+    return skm_finish(ctx, L.rec0.p, L.base0.p, L.cur0.p, SKM_CUR_STRIDE, L.g.nb0, 1, L.cap_total, L.g, L.hist1.p, n_inst, n_rec, min_freq, tune, ukeys,
                       ucounts);
 }
