@@ -376,11 +376,11 @@ struct SkmLeafSmem {
     static constexpr int LIST = HT / 4 * 3;
     u64 tab[HT];
     u32 tcnt[HT];      // occurrences beyond the first one
-    u16 list[LIST];    // claimed slots of the current bin: the sweeps and the clean-up touch only these
-    u32 ws[33];
-    u32 s_ovf, s_nd;
-    unsigned long long s_gbase;
+    u16 list[LIST];    // claimed slots of the current bin: the sweep and the clean-up touch only these
+    u32 s_ovf, s_nd[2], s_kpos, s_newblk;   // s_nd alternates between consecutive bins (reset without an extra barrier)
+    unsigned long long s_kbase;       // the CTA's current block of the kept list
 };
+#define SKM_KBLOCK 65536   // kept-list slots a CTA reserves at a time (unused slots are marked empty and skipped by the sort)
 __device__ __forceinline__ u32 skm_slot(u64 key, int lh) { return (((u32)key ^ (u32)(key >> 32)) * 0x9E3779B1u) >> (32 - lh); }
 
 // Leaf bin l = records recs[lbeg[l] .. + lcnt[l]); CTA c takes the bins c, c + grid, ... (the bins are near-uniform).
@@ -403,15 +403,18 @@ __global__ void __launch_bounds__(THREADS) skm_leaf_kernel(const ulonglong2 *__r
         for (u32 i = threadIdx.x; i < HT / 2; i += THREADS) t2[i] = make_ulonglong2(MSD_EMPTY, MSD_EMPTY);
         uint4 *c4 = reinterpret_cast<uint4 *>(S.tcnt);
         for (u32 i = threadIdx.x; i < HT / 4; i += THREADS) c4[i] = make_uint4(0, 0, 0, 0);
-        if (threadIdx.x == 0) S.s_nd = 0;
+        if (threadIdx.x == 0) { S.s_nd[0] = 0; S.s_nd[1] = 0; S.s_kpos = SKM_KBLOCK; S.s_kbase = 0; }  // no block yet
     }
+    u32 par = 0;
     for (u32 leaf = blockIdx.x; leaf < nleaf; leaf += gridDim.x) {
         const u32 n = lcnt[leaf];
         if (n == 0) continue;
         const ulonglong2 *rp = recs + lbeg[leaf];
         if (threadIdx.x == 0) S.s_ovf = (test_ovf_mod && leaf % test_ovf_mod == 0) ? 1u : 0u;
-        __syncthreads();  // table clean, flags set
+        __syncthreads();  // table clean, flags set, the previous bin's sweep is over
+        if (threadIdx.x == 0) S.s_newblk = (S.s_kpos + LIST > SKM_KBLOCK) ? 1u : 0u;  // this bin may keep up to LIST keys (read after the next barrier)
         volatile u32 *ovf = &S.s_ovf;
+        u32 *ndp = &S.s_nd[par];
         // (the flag is polled with warp votes: lanes of one warp must agree on leaving, they meet again in the shuffles)
         if (!__any_sync(FULL_MASK, *ovf != 0)) {
             // A warp takes 32 records at a time and spreads their windows over its lanes: lane i handles instance p + i of
@@ -424,15 +427,17 @@ __global__ void __launch_bounds__(THREADS) skm_leaf_kernel(const ulonglong2 *__r
                 const u32 len = ri < n ? ((u32)rec.y & 31u) + 1u : 0u;
                 const u32 incl = warp_incl_scan(len), start = incl - len;
                 const u32 T = __shfl_sync(FULL_MASK, incl, 31);
-                const u64 a0 = rec.x, a1 = rec.y & 0xFFFFFFFF00000000ULL;
+                const u64 a0 = rec.x;
+                const u32 a1h = (u32)(rec.y >> 32);
                 for (u32 p = 0; p < T; p += 32) {
                     const u32 rel = start - p;  // wraps to a huge value for records that start before p
                     const u32 smask = __reduce_or_sync(FULL_MASK, (len != 0 && rel < 32u) ? (1u << rel) : 0u);
                     const u32 nbefore = __popc(__ballot_sync(FULL_MASK, len != 0 && start <= p));
                     const u32 le = lane_id() == 31 ? 0xFFFFFFFFu : ((2u << lane_id()) - 1u);
-                    const u32 r = nbefore - 1u + __popc(smask & 0xFFFFFFFEu & le);
-                    const u64 A0 = __shfl_sync(FULL_MASK, a0, r & 31u), A1 = __shfl_sync(FULL_MASK, a1, r & 31u);
-                    const u32 st = __shfl_sync(FULL_MASK, start, r & 31u);
+                    const u32 r = (nbefore - 1u + __popc(smask & 0xFFFFFFFEu & le)) & 31u;
+                    const u64 A0 = __shfl_sync(FULL_MASK, a0, r);
+                    const u64 A1 = (u64)__shfl_sync(FULL_MASK, a1h, r) << 32;
+                    const u32 st = __shfl_sync(FULL_MASK, start, r);
                     const u32 q = p + lane_id();
                     if (q < T) {
                         const int j2 = 2 * (int)(q - st);  // window q - st of record r
@@ -447,7 +452,7 @@ __global__ void __launch_bounds__(THREADS) skm_leaf_kernel(const ulonglong2 *__r
                             if (c == MSD_EMPTY) {
                                 c = atomicCAS((unsigned long long *)&S.tab[slot], (unsigned long long)MSD_EMPTY, (unsigned long long)key);
                                 if (c == MSD_EMPTY) {  // claimed: first occurrence
-                                    const u32 li = atomicAdd(&S.s_nd, 1u);
+                                    const u32 li = atomicAdd(ndp, 1u);
                                     if (li < LIST) S.list[li] = (u16)slot; else *ovf = 1;
                                     break;
                                 }
@@ -462,38 +467,47 @@ __global__ void __launch_bounds__(THREADS) skm_leaf_kernel(const ulonglong2 *__r
             }
         }
         __syncthreads();
-        const u32 nd_all = S.s_nd, nd = min(nd_all, LIST);
+        const u32 nd_all = *ndp, nd = min(nd_all, LIST);
         const bool over = S.s_ovf != 0;
-        if (over) {
-            if (threadIdx.x == 0) ovf_list[atomicAdd(ovf_n, 1u)] = leaf;
-        } else {
-            // ---- kept keys -> global list ----
-            u32 c = 0;
-            for (u32 i = threadIdx.x; i < nd; i += THREADS) c += (S.tcnt[S.list[i]] + 1u >= min_freq) ? 1u : 0u;
-            u32 total;
-            const u32 ex = block_excl_scan(c, S.ws, &total);
-            if (total) {
-                if (threadIdx.x == 0) S.s_gbase = atomicAdd(kept_cursor, (unsigned long long)total);
-                __syncthreads();
-                u64 o = S.s_gbase + ex;
-                for (u32 i = threadIdx.x; i < nd; i += THREADS) {
-                    const u32 slot = S.list[i];
-                    const u32 cnt = S.tcnt[slot] + 1u;
-                    if (cnt >= min_freq) { okeys[o] = S.tab[slot]; ocnts[o] = cnt; ++o; }
-                }
-            }
+        if (S.s_newblk) {  // (uniform) the bin's keys may not fit the rest of the CTA's block: next block
+            const u32 kp = S.s_kpos;
+            const unsigned long long kb = S.s_kbase;
+            __syncthreads();
+            for (u32 i = kp + threadIdx.x; i < SKM_KBLOCK; i += THREADS) okeys[kb + i] = MSD_EMPTY;   // unused tail: skipped later
+            if (threadIdx.x == 0) { S.s_kbase = atomicAdd(kept_cursor, (unsigned long long)SKM_KBLOCK); S.s_kpos = 0; }
+            __syncthreads();
         }
-        __syncthreads();
-        // ---- leave the table clean ----
-        if (nd_all > LIST) {  // slots were claimed that the list does not hold
+        if (threadIdx.x == 0) {
+            S.s_nd[par ^ 1u] = 0;
+            if (over) ovf_list[atomicAdd(ovf_n, 1u)] = leaf;
+        }
+        // ---- one sweep over the claimed slots: kept keys -> the CTA's block of the kept list; the table is left clean ----
+        if (nd_all > LIST) {  // slots were claimed that the list does not hold (the bin is on the overflow list)
             ulonglong2 *t2 = reinterpret_cast<ulonglong2 *>(S.tab);
             for (u32 i = threadIdx.x; i < HT / 2; i += THREADS) t2[i] = make_ulonglong2(MSD_EMPTY, MSD_EMPTY);
             uint4 *c4 = reinterpret_cast<uint4 *>(S.tcnt);
             for (u32 i = threadIdx.x; i < HT / 4; i += THREADS) c4[i] = make_uint4(0, 0, 0, 0);
         } else {
-            for (u32 i = threadIdx.x; i < nd; i += THREADS) { const u32 slot = S.list[i]; S.tab[slot] = MSD_EMPTY; S.tcnt[slot] = 0; }
+            const unsigned long long kb = S.s_kbase;
+            for (u32 i = threadIdx.x; i < nd; i += THREADS) {
+                const u32 slot = S.list[i];
+                const u32 cnt = S.tcnt[slot] + 1u;
+                if (!over && cnt >= min_freq) {
+                    const u32 o = atomicAdd(&S.s_kpos, 1u);
+                    okeys[kb + o] = S.tab[slot];
+                    ocnts[kb + o] = cnt;
+                }
+                S.tab[slot] = MSD_EMPTY;
+                S.tcnt[slot] = 0;
+            }
         }
-        if (threadIdx.x == 0) S.s_nd = 0;
+        par ^= 1u;
+    }
+    // the rest of the CTA's last block
+    __syncthreads();
+    if (S.s_kpos < SKM_KBLOCK) {
+        const unsigned long long kb = S.s_kbase;
+        for (u32 i = S.s_kpos + threadIdx.x; i < SKM_KBLOCK; i += THREADS) okeys[kb + i] = MSD_EMPTY;
     }
 }
 
@@ -536,12 +550,16 @@ __global__ void skm_ovf_expand_kernel(const ulonglong2 *__restrict__ recs, const
 // ---- pass F: kept pairs -> ascending key order ------------------------------------------------------
 #define SKM_SORT_CAP 8192   // pairs one CTA orders in shared memory
 __global__ void skm_sort_hist_kernel(const u64 *__restrict__ keys, u64 n, int sh, u32 *__restrict__ hist) {
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) atomicAdd(&hist[(u32)(keys[i] >> sh)], 1u);
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        const u64 key = keys[i];
+        if (key != MSD_EMPTY) atomicAdd(&hist[(u32)(key >> sh)], 1u);  // empty: unused slot of a leaf CTA's block
+    }
 }
 __global__ void skm_sort_scatter_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ cnts, u64 n, int sh, const u32 *__restrict__ bstart,
                                         u32 *__restrict__ cursor, u64 *__restrict__ okeys, u32 *__restrict__ ocnts) {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
         const u64 key = keys[i];
+        if (key == MSD_EMPTY) continue;
         const u32 b = (u32)(key >> sh);
         const u32 pos = bstart[b] + atomicAdd(&cursor[b], 1u);
         okeys[pos] = key;
@@ -701,13 +719,21 @@ static void skm_launch_leaf(gg_ctx *ctx, int ctas_per_sm, const ulonglong2 *recs
     }
 }
 
-// kept pairs (unordered, n of them in kk / kc) -> sorted ukeys / ucounts (new buffers)
-static void skm_sort_pairs(gg_ctx *ctx, u64 *kk, u32 *kc, u64 n, int k, DBuf<u64> &ukeys, DBuf<u32> &ucounts) {
-    ukeys.alloc(ctx, n ? n : 1);
-    ucounts.alloc(ctx, n ? n : 1);
-    if (n == 0) return;
-    if (n >= 0xFFFFFFFFull) GG_THROW(GG_ERR_LIMIT, "%llu distinct k-mers exceed the 2^32-1 per-GPU limit", (unsigned long long)n);
+struct SkmLiveF {   // compaction of the kept list: drop the unused slots
+    const u64 *k;
+    const u32 *c;
+    u64 *ok;
+    u32 *oc;
+    __device__ bool pred(u64 i) const { return k[i] != MSD_EMPTY; }
+    __device__ void emit(u64 i, u64 dst) const { ok[dst] = k[i]; oc[dst] = c[i]; }
+};
+// kept list (unordered; nslots slots in kk / kc, unused ones hold MSD_EMPTY) -> sorted ukeys / ucounts (new buffers);
+// returns the number of pairs
+static u64 skm_sort_pairs(gg_ctx *ctx, u64 *kk, u32 *kc, u64 nslots, int k, DBuf<u64> &ukeys, DBuf<u32> &ucounts) {
+    if (nslots == 0) { ukeys.alloc(ctx, 1); ucounts.alloc(ctx, 1); return 0; }
+    if (nslots >= 0xFFFFFFFFull) GG_THROW(GG_ERR_LIMIT, "%llu kept-list slots exceed the 2^32-1 per-GPU limit", (unsigned long long)nslots);
     auto generic = [&](u64 *keys_io, u32 *cnts_io, u64 cnt, u64 *ok, u32 *oc) {  // LSD radix sort with the count as payload
+        if (cnt == 0) return;
         DBuf<u64> alt(ctx, cnt), pay(ctx, cnt), pay_alt(ctx, cnt);
         LAUNCH(ctx, skm_widen_kernel, (unsigned)ceil_div(cnt, 256), 256, 0, cnts_io, cnt, pay.p);
         u64 *a = keys_io, *b = alt.p, *p = pay.p, *q = pay_alt.p;
@@ -716,30 +742,51 @@ static void skm_sort_pairs(gg_ctx *ctx, u64 *kk, u32 *kc, u64 n, int k, DBuf<u64
         CK(cudaMemcpyAsync(ok, a, cnt * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream));
         LAUNCH(ctx, skm_narrow_kernel, (unsigned)ceil_div(cnt, 256), 256, 0, p, cnt, oc);
     };
-    if (n <= 4096) { generic(kk, kc, n, ukeys.p, ucounts.p); return; }
+    auto compact_generic = [&]() -> u64 {  // drop the unused slots, then the generic sort
+        SkmLiveF f{kk, kc, nullptr, nullptr};
+        Compactor<SkmLiveF> cp(ctx, nslots, "live");
+        const u64 n = cp.count(f);
+        DBuf<u64> ck(ctx, n ? n : 1);
+        DBuf<u32> cc(ctx, n ? n : 1);
+        f.ok = ck.p; f.oc = cc.p;
+        cp.emit(f);
+        ukeys.alloc(ctx, n ? n : 1);
+        ucounts.alloc(ctx, n ? n : 1);
+        generic(ck.p, cc.p, n, ukeys.p, ucounts.p);
+        CK(cudaStreamSynchronize(ctx->stream));  // ck / cc go back to the allocator
+        return n;
+    };
     int tb = 0;
-    while (tb < 22 && tb < 2 * k && (n >> tb) > 1024) ++tb;
+    while (tb < 22 && tb < 2 * k && (nslots >> tb) > 1024) ++tb;   // sized on the slots: the pairs are fewer
+    if (tb < 4) return compact_generic();
     const int sh = 2 * k - tb;
     const u32 nb = 1u << tb;
     DBuf<u32> hist(ctx, nb + 1), bstart(ctx, nb + 1), cursor(ctx, nb), big(ctx, 1024), nbig(ctx, 1);
-    DBuf<u64> tk(ctx, n);
-    DBuf<u32> tc(ctx, n);
     dfill(ctx, hist.p, (u64)(nb + 1) * sizeof(u32), 0u);
     dfill(ctx, cursor.p, (u64)nb * sizeof(u32), 0u);
     dfill(ctx, nbig.p, sizeof(u32), 0u);
-    const unsigned sgrid = (unsigned)std::min<u64>(ceil_div(n, 256), (u64)ctx->num_sms * 32);
-    prof_bytes(ctx, 8.0 * (double)n);
-    LAUNCH(ctx, skm_sort_hist_kernel, sgrid, 256, 0, kk, n, sh, hist.p);
+    const unsigned sgrid = (unsigned)std::min<u64>(ceil_div(nslots, 256), (u64)ctx->num_sms * 32);
+    prof_bytes(ctx, 8.0 * (double)nslots);
+    LAUNCH(ctx, skm_sort_hist_kernel, sgrid, 256, 0, kk, nslots, sh, hist.p);
     exclusive_scan_u32(ctx, hist.p, bstart.p, nb + 1, nullptr);
     LAUNCH(ctx, skm_sort_big_kernel, (unsigned)ceil_div(nb, 256), 256, 0, hist.p, nb, big.p, nbig.p);
-    prof_bytes(ctx, 24.0 * (double)n);
-    LAUNCH(ctx, skm_sort_scatter_kernel, sgrid, 256, 0, kk, kc, n, sh, bstart.p, cursor.p, tk.p, tc.p);
+    CK(cudaMemcpyAsync(ctx->h_scalar, bstart.p + nb, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_scalar + 1, nbig.p, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const u64 n = (u32)ctx->h_scalar[0];
+    const u32 h_nbig = (u32)ctx->h_scalar[1];
+    if (h_nbig > 1024) return compact_generic();  // hopeless skew: sort everything the slow way
+    ukeys.alloc(ctx, n ? n : 1);
+    ucounts.alloc(ctx, n ? n : 1);
+    if (n == 0) return 0;
+    DBuf<u64> tk(ctx, n);
+    DBuf<u32> tc(ctx, n);
+    prof_bytes(ctx, 8.0 * (double)nslots + 16.0 * (double)n);
+    LAUNCH(ctx, skm_sort_scatter_kernel, sgrid, 256, 0, kk, kc, nslots, sh, bstart.p, cursor.p, tk.p, tc.p);
     const size_t smem = (size_t)SKM_SORT_CAP * 12;
     set_max_smem(ctx, skm_sort_bucket_kernel, smem);
     prof_bytes(ctx, 24.0 * (double)n);
     LAUNCH(ctx, skm_sort_bucket_kernel, (unsigned)std::min<u64>(nb, (u64)ctx->num_sms * 8), 256, smem, tk.p, tc.p, bstart.p, nb, sh, ukeys.p, ucounts.p);
-    const u32 h_nbig = read_scalar<u32>(ctx, nbig.p);
-    if (h_nbig > 1024) { generic(kk, kc, n, ukeys.p, ucounts.p); return; }  // hopeless skew: sort everything the slow way
     if (h_nbig) {
         std::vector<u32> hb(h_nbig), hs(2);
         CK(cudaMemcpyAsync(hb.data(), big.p, h_nbig * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
@@ -750,6 +797,8 @@ static void skm_sort_pairs(gg_ctx *ctx, u64 *kk, u32 *kc, u64 n, int k, DBuf<u64
             generic(tk.p + hs[0], tc.p + hs[0], (u64)hs[1] - hs[0], ukeys.p + hs[0], ucounts.p + hs[0]);
         }
     }
+    CK(cudaStreamSynchronize(ctx->stream));  // tk / tc go back to the allocator
+    return n;
 }
 
 // Level-0 state of a scatter (also filled chunk by chunk by the pipelined host path).
@@ -819,7 +868,10 @@ static u64 skm_finish(gg_ctx *ctx, const ulonglong2 *in, const u32 *base, const 
     }
     gg_trace(ctx, "skm level 1");
     // ---- E: leaves ----
-    const u64 kept_cap = n_inst / (min_freq ? min_freq : 1) + 1;  // every kept key has >= min_freq instances
+    // every kept key has >= min_freq instances; the CTAs of the leaf kernel take the kept list in blocks of SKM_KBLOCK slots and
+    // leave up to 3/4 of a leaf table unused at the end of each
+    const u64 kept_bound = n_inst / (min_freq ? min_freq : 1) + 1;
+    const u64 kept_cap = kept_bound + kept_bound / 8 + (u64)(ctx->num_sms * 4 + 2) * SKM_KBLOCK;
     DBuf<u64> kk(ctx, kept_cap), cursor(ctx, 2);
     DBuf<u32> kc(ctx, kept_cap), ovf_n(ctx, 2), ovf_list(ctx, nleaf);
     dfill(ctx, cursor.p, 2 * sizeof(u64), 0u);
@@ -834,10 +886,9 @@ static u64 skm_finish(gg_ctx *ctx, const ulonglong2 *in, const u32 *base, const 
     CK(cudaMemcpyAsync(ctx->h_scalar, cursor.p, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_scalar + 1, ovf_n.p, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    u64 U = ctx->h_scalar[0];
+    u64 U = ctx->h_scalar[0];   // slots of the kept list handed out so far (unused ones are marked empty)
     const u32 n_ovf = (u32)ctx->h_scalar[1];
     gg_trace(ctx, "skm leaves");
-    prof_add_bytes(ctx, "skm_leaf_kernel", 12.0 * (double)U);
     if (n_ovf) {  // bins whose table filled up: their k-mers as plain keys -> radix sort + run-length count + filter
         DBuf<u64> tot(ctx, 2);
         dfill(ctx, tot.p, 2 * sizeof(u64), 0u);
@@ -863,7 +914,8 @@ static u64 skm_finish(gg_ctx *ctx, const ulonglong2 *in, const u32 *base, const 
     stage_end(ctx, ST_SORT);
     // ---- F: order the kept pairs ----
     stage_begin(ctx, ST_COUNT);
-    skm_sort_pairs(ctx, kk.p, kc.p, U, g.k, ukeys, ucounts);
+    U = skm_sort_pairs(ctx, kk.p, kc.p, U, g.k, ukeys, ucounts);
+    prof_add_bytes(ctx, "skm_leaf_kernel", 12.0 * (double)U);
     gg_trace(ctx, "skm sort");
     stage_end(ctx, ST_COUNT);
     return U;
