@@ -377,7 +377,8 @@ struct SkmLeafSmem {
     u64 tab[HT];
     u32 tcnt[HT];      // occurrences beyond the first one
     u16 list[LIST];    // claimed slots of the current bin: the sweep and the clean-up touch only these
-    u32 s_ovf, s_nd[2], s_kpos, s_newblk;   // s_nd alternates between consecutive bins (reset without an extra barrier)
+    u32 s_ovf[2], s_nd[2], s_kpos, s_newblk;   // s_ovf / s_nd alternate between consecutive bins (set / reset without an extra barrier:
+                                               // a slow warp may still read bin i's values when thread 0 prepares bin i + 1)
     unsigned long long s_kbase;       // the CTA's current block of the kept list
 };
 #define SKM_KBLOCK 65536   // kept-list slots a CTA reserves at a time (unused slots are marked empty and skipped by the sort)
@@ -406,14 +407,15 @@ __global__ void __launch_bounds__(THREADS) skm_leaf_kernel(const ulonglong2 *__r
         if (threadIdx.x == 0) { S.s_nd[0] = 0; S.s_nd[1] = 0; S.s_kpos = SKM_KBLOCK; S.s_kbase = 0; }  // no block yet
     }
     u32 par = 0;
+    unsigned long long ctot = 0;   // (thread 0) kept pairs of this CTA's finished blocks
     for (u32 leaf = blockIdx.x; leaf < nleaf; leaf += gridDim.x) {
         const u32 n = lcnt[leaf];
         if (n == 0) continue;
         const ulonglong2 *rp = recs + lbeg[leaf];
-        if (threadIdx.x == 0) S.s_ovf = (test_ovf_mod && leaf % test_ovf_mod == 0) ? 1u : 0u;
+        if (threadIdx.x == 0) S.s_ovf[par] = (test_ovf_mod && leaf % test_ovf_mod == 0) ? 1u : 0u;
         __syncthreads();  // table clean, flags set, the previous bin's sweep is over
         if (threadIdx.x == 0) S.s_newblk = (S.s_kpos + LIST > SKM_KBLOCK) ? 1u : 0u;  // this bin may keep up to LIST keys (read after the next barrier)
-        volatile u32 *ovf = &S.s_ovf;
+        volatile u32 *ovf = &S.s_ovf[par];
         u32 *ndp = &S.s_nd[par];
         // (the flag is polled with warp votes: lanes of one warp must agree on leaving, they meet again in the shuffles)
         if (!__any_sync(FULL_MASK, *ovf != 0)) {
@@ -468,13 +470,17 @@ __global__ void __launch_bounds__(THREADS) skm_leaf_kernel(const ulonglong2 *__r
         }
         __syncthreads();
         const u32 nd_all = *ndp, nd = min(nd_all, LIST);
-        const bool over = S.s_ovf != 0;
+        const bool over = *ovf != 0;
         if (S.s_newblk) {  // (uniform) the bin's keys may not fit the rest of the CTA's block: next block
             const u32 kp = S.s_kpos;
             const unsigned long long kb = S.s_kbase;
             __syncthreads();
             for (u32 i = kp + threadIdx.x; i < SKM_KBLOCK; i += THREADS) okeys[kb + i] = MSD_EMPTY;   // unused tail: skipped later
-            if (threadIdx.x == 0) { S.s_kbase = atomicAdd(kept_cursor, (unsigned long long)SKM_KBLOCK); S.s_kpos = 0; }
+            if (threadIdx.x == 0) {
+                if (kp < SKM_KBLOCK) ctot += kp;
+                S.s_kbase = atomicAdd(kept_cursor, (unsigned long long)SKM_KBLOCK);
+                S.s_kpos = 0;
+            }
             __syncthreads();
         }
         if (threadIdx.x == 0) {
@@ -508,7 +514,9 @@ __global__ void __launch_bounds__(THREADS) skm_leaf_kernel(const ulonglong2 *__r
     if (S.s_kpos < SKM_KBLOCK) {
         const unsigned long long kb = S.s_kbase;
         for (u32 i = S.s_kpos + threadIdx.x; i < SKM_KBLOCK; i += THREADS) okeys[kb + i] = MSD_EMPTY;
+        if (threadIdx.x == 0) ctot += S.s_kpos;
     }
+    if (threadIdx.x == 0 && ctot) atomicAdd(kept_cursor + 1, ctot);   // [1]: kept pairs, [0]: slots handed out
 }
 
 // ---- overflowed leaf bins: all their k-mers as plain keys (finished with the generic sort + run-length path) ----
@@ -643,7 +651,7 @@ __global__ void __launch_bounds__(256) skm_popc_kernel(const u32 *__restrict__ v
 
 // ------------------------------------- host side -------------------------------------------------
 struct SkmTune {
-    u32 bin_inst = 4096;   // target k-mer instances per leaf bin (distinct <= instances <= half the leaf table for most bins)
+    u32 bin_inst = 2048;   // target k-mer instances per leaf bin (distinct <= instances <= half the leaf table for most bins)
     int variant = 0;       // leaf geometry
     u32 sample = 16;       // capacity estimate from every `sample`-th tile
     u32 test_ovf_mod = 0;  // tests (GG_SKM_TEST_OVERFLOW=m): every leaf bin with index % m == 0 takes the overflow path
@@ -652,7 +660,8 @@ struct SkmTune {
 static SkmTune skm_tune() {
     SkmTune t;
     if (const char *e = getenv("GG_SKM_VARIANT")) t.variant = atoi(e);
-    if (t.variant == 1) t.bin_inst = 2048;
+    if (t.variant == 2 || t.variant == 5) t.bin_inst = 4096;
+    if (t.variant == 3) t.bin_inst = 1024;
     if (const char *e = getenv("GG_SKM_BIN")) t.bin_inst = (u32)atoi(e);
     if (const char *e = getenv("GG_SKM_SAMPLE")) t.sample = (u32)atoi(e);
     if (const char *e = getenv("GG_SKM_TEST_OVERFLOW")) t.test_ovf_mod = (u32)atoi(e);
@@ -729,7 +738,7 @@ struct SkmLiveF {   // compaction of the kept list: drop the unused slots
 };
 // kept list (unordered; nslots slots in kk / kc, unused ones hold MSD_EMPTY) -> sorted ukeys / ucounts (new buffers);
 // returns the number of pairs
-static u64 skm_sort_pairs(gg_ctx *ctx, u64 *kk, u32 *kc, u64 nslots, int k, DBuf<u64> &ukeys, DBuf<u32> &ucounts) {
+static u64 skm_sort_pairs(gg_ctx *ctx, u64 *kk, u32 *kc, u64 nslots, u64 n_pairs, int k, DBuf<u64> &ukeys, DBuf<u32> &ucounts) {
     if (nslots == 0) { ukeys.alloc(ctx, 1); ucounts.alloc(ctx, 1); return 0; }
     if (nslots >= 0xFFFFFFFFull) GG_THROW(GG_ERR_LIMIT, "%llu kept-list slots exceed the 2^32-1 per-GPU limit", (unsigned long long)nslots);
     auto generic = [&](u64 *keys_io, u32 *cnts_io, u64 cnt, u64 *ok, u32 *oc) {  // LSD radix sort with the count as payload
@@ -757,7 +766,7 @@ static u64 skm_sort_pairs(gg_ctx *ctx, u64 *kk, u32 *kc, u64 nslots, int k, DBuf
         return n;
     };
     int tb = 0;
-    while (tb < 22 && tb < 2 * k && (nslots >> tb) > 1024) ++tb;   // sized on the slots: the pairs are fewer
+    while (tb < 22 && tb < 2 * k && (n_pairs >> tb) > 1024) ++tb;
     if (tb < 4) return compact_generic();
     const int sh = 2 * k - tb;
     const u32 nb = 1u << tb;
@@ -871,7 +880,7 @@ static u64 skm_finish(gg_ctx *ctx, const ulonglong2 *in, const u32 *base, const 
     // every kept key has >= min_freq instances; the CTAs of the leaf kernel take the kept list in blocks of SKM_KBLOCK slots and
     // leave up to 3/4 of a leaf table unused at the end of each
     const u64 kept_bound = n_inst / (min_freq ? min_freq : 1) + 1;
-    const u64 kept_cap = kept_bound + kept_bound / 8 + (u64)(ctx->num_sms * 4 + 2) * SKM_KBLOCK;
+    const u64 kept_cap = kept_bound + kept_bound / 8 + (u64)(ctx->num_sms * 8 + 2) * SKM_KBLOCK;
     DBuf<u64> kk(ctx, kept_cap), cursor(ctx, 2);
     DBuf<u32> kc(ctx, kept_cap), ovf_n(ctx, 2), ovf_list(ctx, nleaf);
     dfill(ctx, cursor.p, 2 * sizeof(u64), 0u);
@@ -879,15 +888,22 @@ static u64 skm_finish(gg_ctx *ctx, const ulonglong2 *in, const u32 *base, const 
     prof_bytes(ctx, 16.0 * (double)n_rec);
     if (tune.variant == 1)   // 4 CTAs / SM, 4096-slot tables, bins of <= 2048 instances
         skm_launch_leaf<256, 12>(ctx, 4, leaf_recs, leaf_beg, leaf_cnt, (u32)nleaf, g, min_freq, kk.p, kc.p, cursor.p, ovf_list.p, ovf_n.p, tune.test_ovf_mod);
+    else if (tune.variant == 3)   // 8 CTAs / SM, 2048-slot tables, bins of <= 1024 instances
+        skm_launch_leaf<256, 11>(ctx, 8, leaf_recs, leaf_beg, leaf_cnt, (u32)nleaf, g, min_freq, kk.p, kc.p, cursor.p, ovf_list.p, ovf_n.p, tune.test_ovf_mod);
+    else if (tune.variant == 4)   // 4 CTAs / SM of 512 threads, 4096-slot tables
+        skm_launch_leaf<512, 12>(ctx, 4, leaf_recs, leaf_beg, leaf_cnt, (u32)nleaf, g, min_freq, kk.p, kc.p, cursor.p, ovf_list.p, ovf_n.p, tune.test_ovf_mod);
     else if (tune.variant == 2)
         skm_launch_leaf<256, 13>(ctx, 2, leaf_recs, leaf_beg, leaf_cnt, (u32)nleaf, g, min_freq, kk.p, kc.p, cursor.p, ovf_list.p, ovf_n.p, tune.test_ovf_mod);
-    else                     // 2 CTAs / SM, 8192-slot tables, bins of <= 4096 instances
+    else if (tune.variant == 5)   // 2 CTAs / SM, 8192-slot tables, bins of <= 4096 instances
         skm_launch_leaf<512, 13>(ctx, 2, leaf_recs, leaf_beg, leaf_cnt, (u32)nleaf, g, min_freq, kk.p, kc.p, cursor.p, ovf_list.p, ovf_n.p, tune.test_ovf_mod);
-    CK(cudaMemcpyAsync(ctx->h_scalar, cursor.p, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->h_scalar + 1, ovf_n.p, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    else                     // 4 CTAs / SM of 512 threads (64 warps per SM), 4096-slot tables, bins of <= 2048 instances
+        skm_launch_leaf<512, 12>(ctx, 4, leaf_recs, leaf_beg, leaf_cnt, (u32)nleaf, g, min_freq, kk.p, kc.p, cursor.p, ovf_list.p, ovf_n.p, tune.test_ovf_mod);
+    CK(cudaMemcpyAsync(ctx->h_scalar, cursor.p, 2 * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_scalar + 2, ovf_n.p, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     u64 U = ctx->h_scalar[0];   // slots of the kept list handed out so far (unused ones are marked empty)
-    const u32 n_ovf = (u32)ctx->h_scalar[1];
+    u64 n_pairs = ctx->h_scalar[1];
+    const u32 n_ovf = (u32)ctx->h_scalar[2];
     gg_trace(ctx, "skm leaves");
     if (n_ovf) {  // bins whose table filled up: their k-mers as plain keys -> radix sort + run-length count + filter
         DBuf<u64> tot(ctx, 2);
@@ -909,12 +925,13 @@ static u64 skm_finish(gg_ctx *ctx, const ulonglong2 *in, const u32 *base, const 
         const u64 nk = cp.count(f);
         cp.emit(f);
         U += nk;
+        n_pairs += nk;
     }
     gg_trace(ctx, "skm overflow bins");
     stage_end(ctx, ST_SORT);
     // ---- F: order the kept pairs ----
     stage_begin(ctx, ST_COUNT);
-    U = skm_sort_pairs(ctx, kk.p, kc.p, U, g.k, ukeys, ucounts);
+    U = skm_sort_pairs(ctx, kk.p, kc.p, U, n_pairs, g.k, ukeys, ucounts);
     prof_add_bytes(ctx, "skm_leaf_kernel", 12.0 * (double)U);
     gg_trace(ctx, "skm sort");
     stage_end(ctx, ST_COUNT);
