@@ -16,7 +16,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
 import pyref  # noqa: E402
+from hand_traced import HAND_TRACED  # noqa: E402
 
 
 def graph_case(name, kmers):
@@ -42,6 +44,9 @@ def mutate(rnd, s, rate):
 def main():
     rnd = random.Random(20261019)
     graphs = [graph_case("G1 (docs/src/DeBruijnGraph.md:57-76, canonicalised)", ["AATC", "AATG", "ACGA", "ATTC", "CGAA", "CGTA", "CGTC"])]
+    for h in HAND_TRACED[1:]:   # G2..G4: expected values from the hand traces (tests/golden/hand_traced.py), not from pyref
+        graphs.append({"name": h["name"] + " (hand-traced through src/dbg.jl)", "k": h["k"], "kmers": h["kmers"], "nodes": h["nodes"],
+                       "links": [[list(t) for t in ls] for ls in h["links"]]})
     graphs.append(graph_case("single k-mer self loop", ["AAA"]))
     graphs.append(graph_case("palindromes k=4", ["ACGT", "AATT", "CGCG", "AACG", "ACGA"]))
     graphs.append(graph_case("hairpin k=3", ["AAC", "ACG", "CGT"[::-1].translate(str.maketrans("ACGT", "TGCA")), "ACC"]))

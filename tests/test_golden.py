@@ -2,6 +2,7 @@
 the independent Python transliteration) against the C oracle (CPU) and the CUDA path (gpu)."""
 import json
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -11,6 +12,8 @@ from oracle import oracle as O
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "dbg_golden.json")))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+from hand_traced import HAND_TRACED  # noqa: E402  (G1..G4: src/dbg.jl traced by hand, independent of pyref and of the oracle)
 
 
 def _links(ls):
@@ -22,6 +25,13 @@ def test_oracle_graph_golden(case):
     g = O.dbg(O.kmers_from_strings(case["kmers"]), case["k"])
     assert g.nodes() == case["nodes"]
     assert g.links() == _links(case["links"])
+
+
+@pytest.mark.parametrize("case", HAND_TRACED, ids=lambda c: c["name"])
+def test_oracle_hand_traced(case):
+    g = O.dbg(O.kmers_from_strings(case["kmers"]), case["k"])
+    assert g.nodes() == case["nodes"]
+    assert g.links() == case["links"]
 
 
 @pytest.mark.parametrize("case", GOLD["reads"], ids=lambda c: c["name"])
@@ -51,6 +61,15 @@ def test_gpu_graph_golden(gpu, case):
     ga = pkg.dbg_arrays(O.kmers_from_strings(case["kmers"]), k=case["k"], ctx=ctx)
     assert ga.node_strings() == case["nodes"]
     assert ga.link_lists() == _links(case["links"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", HAND_TRACED, ids=lambda c: c["name"])
+def test_gpu_hand_traced(gpu, case):
+    pkg, ctx = gpu
+    ga = pkg.dbg_arrays(O.kmers_from_strings(case["kmers"]), k=case["k"], ctx=ctx)
+    assert ga.node_strings() == case["nodes"]
+    assert ga.link_lists() == case["links"]
 
 
 @pytest.mark.gpu
