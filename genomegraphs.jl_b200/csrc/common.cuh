@@ -46,6 +46,7 @@ struct gg_ctx {
     // user events (gg_ctx_event_record / gg_ctx_event_elapsed_ms)
     cudaEvent_t user_ev[8];
     struct GgArena *arena = nullptr;  // caching device allocator (below)
+    int coop_blocks = -1;             // co-resident CTAs per SM of the cooperative list-ranking kernel on this device (-1: not asked yet)
     std::set<const void *> smem_attr_done;  // kernels whose dynamic shared-memory limit was raised on THIS device
 };
 

@@ -18,6 +18,7 @@
 #include <chrono>
 #include "msdcount.cuh"
 #include "msdcountw.cuh"
+#include "skm.cuh"
 
 struct NcclApi {
     void *h = nullptr;
@@ -77,6 +78,7 @@ struct gg_comm {
     u64 cap = 0;                       // keys
     u64 *peerR[MSD_MAX_PEERS] = {};    // peerR[rank] == R
     int ipc_state = 0;                 // 0 untried, 1 usable, -1 unavailable (NCCL send/recv is used instead)
+    u64 *agree = nullptr;              // status word of dist_guard (plain cudaMalloc)
 };
 
 static void dist_close_peers(gg_comm *cm) {
@@ -335,5 +337,291 @@ static u64 dist_msd_count(gg_comm *cm, const PackedReads &pr, const u32 *valid, 
         fprintf(stderr, "[dist rank %d] t0=%.3f size-allreduce %.2f | passA+allgather %.2f | passB %.2f | exchange %.2f (send %.1f MB, recv %.1f MB) | finish %.2f ms\n",
                 me, tmark[0], tmark[1] - tmark[0], tmark[2] - tmark[1], tmark[3] - tmark[2], tmark[4] - tmark[3],
                 (double)(N_loc - scnt[me]) * 8e-6 * W, (double)(N_recv - rcnt[me]) * 8e-6 * W, tmark[5] - tmark[4]);
+    return U;
+}
+
+// ---- error agreement -------------------------------------------------------------------------------
+// A failure that only one rank sees (out of memory, a CUDA error) must not leave the peers waiting in the next
+// collective: local phases run under dist_guard, which catches the failure, lets every rank learn the worst status
+// with ONE ncclAllReduce(min) and then throws on all ranks together.  `f` must not contain collectives.
+template <class F>
+static void dist_guard(gg_comm *cm, const char *what, F f) {
+    NcclApi *nc = nccl_api();
+    gg_ctx *ctx = cm->ctx;
+    GgError mine{GG_OK, ""};
+    try { f(); } catch (const GgError &e) { mine = e; cudaGetLastError(); } catch (const std::bad_alloc &) { mine = GgError{GG_ERR_OOM, "host allocation failed"}; }
+    if (!cm->agree) {   // one word of plain device memory outside the arena (the arena itself may be what failed)
+        if (cudaMalloc((void **)&cm->agree, sizeof(u64)) != cudaSuccess) GG_THROW(GG_ERR_OOM, "no memory for the status word");
+    }
+    const u64 ok = mine.code == GG_OK ? 1 : 0;
+    CK(cudaMemcpyAsync(cm->agree, &ok, sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    NCK(nc->AllReduce(cm->agree, cm->agree, 1, ncclUint64, ncclMin, cm->comm, ctx->stream));
+    u64 all = 0;
+    CK(cudaMemcpyAsync(&all, cm->agree, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (mine.code != GG_OK) throw mine;
+    if (!all) GG_THROW(GG_ERR_CUDA, "a peer rank failed in: %s", what);
+}
+
+// ---- super-k-mer route over several GPUs (skm.cuh) -------------------------------------------------
+// The level-0 bins of the minimizer hash are owned by ranks (rank q: bins [first[q], first[q + 1]), equal shares: the
+// bin digit is a hash).  Every source gets a PRIVATE region per bin inside the owner's receive buffer -- regions are
+// source-major, r = p * nbl + bl, so a source's regions are one contiguous segment -- sized from that source's own
+// sampled record histogram; the capacities are all-gathered, after which every rank computes the same layout.
+// skm_scan_kernel<.., PEER> then stores its records straight into the owners' buffers over NVLink (CUDA IPC mappings);
+// without peer mapping the same segments move with one grouped ncclSend / ncclRecv.  The all-gather of the per-region
+// record counts that follows doubles as the barrier after which the buffer is consumed (level 1 + leaves).
+struct SkmFirst { u32 first[MSD_MAX_PEERS + 1]; };
+// one CTA per owner q: bases of its regions; this rank keeps base0_src[b] (where ITS records of bin b start inside the
+// owner's buffer) and, for q == me, mybase[r] (+ the end sentinel); rtotal[q] = slots of q's buffer
+__global__ void __launch_bounds__(1024) skm_dist_layout_kernel(const u32 *__restrict__ capall, u32 nb0, int P, int me, SkmFirst fs,
+                                                               u32 *__restrict__ base0_src, u32 *__restrict__ mybase, u64 *__restrict__ rtotal) {
+    __shared__ u32 ws[33];
+    __shared__ u64 s_run;
+    const int q = blockIdx.x;
+    const u32 f0 = fs.first[q], nbl = fs.first[q + 1] - f0, nreg = nbl * (u32)P;
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    for (u32 r0 = 0; r0 < nreg; r0 += 1024) {
+        const u32 r = r0 + threadIdx.x;
+        u32 c = 0, p = 0, bl = 0;
+        if (r < nreg) { p = r / nbl; bl = r % nbl; c = capall[(u64)p * nb0 + f0 + bl] / SKM_ALIGN; }
+        u32 tot;
+        const u32 ex = block_excl_scan(c, ws, &tot);
+        if (r < nreg) {
+            const u64 bb = (s_run + ex) * SKM_ALIGN;
+            const u32 b32 = bb > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)bb;
+            if ((int)p == me) base0_src[f0 + bl] = b32;
+            if (q == me) mybase[r] = b32;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_run += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const u64 bb = s_run * SKM_ALIGN;
+        rtotal[q] = bb;
+        if (q == me) mybase[nreg] = bb > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)bb;
+    }
+}
+// what a source tells the owners after its scatter: records per bin (dense), overflow flag, instance / record totals
+#define SKM_DIST_TAIL 8
+__global__ void skm_dist_pack_kernel(const u32 *__restrict__ cur0, const u32 *__restrict__ cap0, u32 nb0, const u32 *__restrict__ ovf,
+                                     const u64 *__restrict__ totals, u32 *__restrict__ out) {
+    const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nb0) out[b] = min(cur0[(u64)b * SKM_CUR_STRIDE], cap0[b]);
+    if (b == 0) {
+        out[nb0] = *ovf;
+        out[nb0 + 1] = (u32)totals[0]; out[nb0 + 2] = (u32)(totals[0] >> 32);
+        out[nb0 + 3] = (u32)totals[1]; out[nb0 + 4] = (u32)(totals[1] >> 32);
+        out[nb0 + 5] = out[nb0 + 6] = out[nb0 + 7] = 0;
+    }
+}
+__global__ void skm_dist_mycnt_kernel(const u32 *__restrict__ allc, u32 row, u32 f0, u32 nbl, u32 nreg, u32 *__restrict__ mycnt) {
+    const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < nreg) mycnt[r] = allc[(u64)(r / nbl) * row + f0 + r % nbl];
+}
+
+// lb[b] = first index whose key's top digit is >= b (b = 0 .. nbh): the digit histogram of a SORTED key list
+__global__ void range_lb_kernel(const u64 *__restrict__ keys, u64 n, int sh, u32 nbh, u32 *__restrict__ lb) {
+    const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > nbh) return;
+    u64 lo = 0, hi = n;
+    while (lo < hi) {
+        const u64 mid = lo + ((hi - lo) >> 1);
+        if ((keys[mid] >> sh) < (u64)b) lo = mid + 1; else hi = mid;
+    }
+    lb[b] = (u32)lo;
+}
+// Second exchange: every rank holds the sorted kept (k-mer, count) pairs of ITS minimizer bins; afterwards rank r
+// holds the r-th contiguous KEY RANGE of the global sorted table (ranges balanced on the all-gathered digit
+// histogram), which is the reference's output order (Vector{MerCount} sorted by k-mer) cut into P pieces.
+static u64 dist_range_repartition(gg_comm *cm, DBuf<u64> &uk, DBuf<u32> &uc, u64 U, int k, DBuf<u64> &ukeys, DBuf<u32> &ucounts) {
+    NcclApi *nc = nccl_api();
+    gg_ctx *ctx = cm->ctx;
+    const int P = cm->world, me = cm->rank;
+    if (P == 1) { ukeys = std::move(uk); ucounts = std::move(uc); return U; }
+    const int tb = 2 * k < 14 ? 2 * k : 14, sh = 2 * k - tb;
+    const u32 nbh = 1u << tb, row = nbh + 1;
+    DBuf<u32> lb, all_lb;
+    dist_guard(cm, "range histogram", [&] {
+        lb.alloc(ctx, row); all_lb.alloc(ctx, (u64)P * row);
+        LAUNCH(ctx, range_lb_kernel, (unsigned)ceil_div(row, 256), 256, 0, uk.p, U, sh, nbh, lb.p);
+    });
+    NCK(nc->AllGather(lb.p, all_lb.p, row, ncclUint32, cm->comm, ctx->stream));
+    std::vector<u32> h((size_t)P * row);
+    CK(cudaMemcpyAsync(h.data(), all_lb.p, h.size() * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<u64> gh(nbh, 0);
+    for (int p = 0; p < P; ++p)
+        for (u32 b = 0; b < nbh; ++b) gh[b] += h[(size_t)p * row + b + 1] - h[(size_t)p * row + b];
+    std::vector<u32> first(P + 1);
+    dist_splitters(gh.data(), nbh, P, first.data());
+    std::vector<u64> soff(P), scnt(P), roff(P), rcnt(P);
+    u64 n_recv = 0;
+    for (int p = 0; p < P; ++p) {
+        soff[p] = h[(size_t)me * row + first[p]];
+        scnt[p] = h[(size_t)me * row + first[p + 1]] - soff[p];
+        roff[p] = n_recv;
+        rcnt[p] = h[(size_t)p * row + first[me + 1]] - h[(size_t)p * row + first[me]];
+        n_recv += rcnt[p];
+    }
+    DBuf<u64> rk;
+    DBuf<u32> rc;
+    dist_guard(cm, "range exchange buffers", [&] {
+        if (n_recv >= 0xFFFFFFFFull) GG_THROW(GG_ERR_LIMIT, "%llu kept k-mers exceed the 2^32-1 per-GPU limit", (unsigned long long)n_recv);
+        rk.alloc(ctx, n_recv + 1); rc.alloc(ctx, n_recv + 1);
+    });
+    dist_alltoallv(cm, uk.p, soff.data(), scnt.data(), rk.p, roff.data(), rcnt.data(), sizeof(u64));
+    dist_alltoallv(cm, uc.p, soff.data(), scnt.data(), rc.p, roff.data(), rcnt.data(), sizeof(u32));
+    u64 Uout = 0;
+    dist_guard(cm, "merge of the received runs", [&] {
+        CK(cudaStreamSynchronize(ctx->stream));
+        uk.release(); uc.release();
+        Uout = skm_sort_pairs(ctx, rk.p, rc.p, n_recv, n_recv, k, ukeys, ucounts);   // P sorted runs -> one (partition by top bits + bucket ordering)
+    });
+    return Uout;
+}
+
+// reads of this rank -> this rank's key-range slice of the global sorted (k-mer, count) table; skm_supported(k, canonical)
+static u64 dist_skm_count(gg_comm *cm, const PackedReads &pr, const u32 *valid, int k, int canonical, u32 min_freq, DBuf<u64> &ukeys,
+                          DBuf<u32> &ucounts, u64 *n_instances_local, u64 *n_instances_global) {
+    NcclApi *nc = nccl_api();
+    gg_ctx *ctx = cm->ctx;
+    const int P = cm->world, me = cm->rank;
+    if (P > MSD_MAX_PEERS) GG_THROW(GG_ERR_LIMIT, "at most %d ranks", MSD_MAX_PEERS);
+    const SkmTune tune = skm_tune();
+    stage_begin(ctx, ST_EXTRACT);
+    // ---- global number of windows -> one geometry on every rank ----
+    DBuf<u64> sz;
+    u64 win_local = 0;
+    dist_guard(cm, "window count", [&] {
+        sz.alloc(ctx, 2);
+        win_local = skm_count_windows(ctx, valid, 0, pr.nwords);
+        CK(cudaMemcpyAsync(sz.p, &win_local, sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    });
+    NCK(nc->AllReduce(sz.p, sz.p, 1, ncclUint64, ncclSum, cm->comm, ctx->stream));
+    const u64 win_glob = read_scalar<u64>(ctx, sz.p);
+    *n_instances_local = win_local;
+    *n_instances_global = win_glob;
+    const SkmGeom g = skm_geom(win_glob, k, canonical, tune);
+    const u32 nb0 = g.nb0, row = nb0 + SKM_DIST_TAIL;
+    const u64 nleaf = (u64)nb0 * g.nb1;
+    SkmFirst fs;
+    for (int q = 0; q <= P; ++q) fs.first[q] = (u32)(((u64)q * nb0) / (u64)P);
+    for (int q = P + 1; q <= MSD_MAX_PEERS; ++q) fs.first[q] = nb0;
+    const u32 f0 = fs.first[me], nbl = fs.first[me + 1] - f0, nreg = nbl * (u32)P;
+    const u64 ntiles = ceil_div(pr.nwords, skm_tile_words(k));
+    SkmL0 L;
+    L.g = g;
+    DBuf<u32> capall, base_src, mybase, mine, allc;
+    DBuf<u64> rtotal;
+    DBuf<ulonglong2> sbuf, rtmp;
+    std::vector<u64> h_rtotal(P);
+    std::vector<u32> h_allc;
+    const ulonglong2 *R = nullptr;
+    for (int attempt = 0;; ++attempt) {
+        const u32 stride = (ntiles >= 256 && attempt == 0) ? tune.sample : 1;
+        const bool exact = stride == 1 && !(attempt == 0 && tune.force_cap);
+        // ---- sample: my records per bin -> capacities of my regions; all-gathered -> the layout of every owner's buffer ----
+        dist_guard(cm, "super-k-mer sample", [&] {
+            L.alloc_sample(ctx);
+            prof_bytes(ctx, 12.0 * (double)pr.nwords / stride);
+            skm_scan_launch<0, false>(ctx, pr, valid, 0, pr.nwords, stride, g, L.hist0.p, nullptr, nullptr, nullptr, nullptr, nullptr, L.totals.p, nullptr, nullptr);
+            L.base0.alloc(ctx, nb0 + 1); L.cap0.alloc(ctx, nb0); L.total_cap.alloc(ctx, 1);
+            LAUNCH(ctx, skm_caps_kernel, 1, 1024, 0, L.hist0.p, nb0, (float)stride, exact ? 1 : 0, L.base0.p, L.cap0.p, L.total_cap.p, exact ? 0u : tune.force_cap);
+            capall.alloc(ctx, (u64)P * nb0); base_src.alloc(ctx, nb0); mybase.alloc(ctx, (u64)nreg + 1); rtotal.alloc(ctx, P);
+            mine.alloc(ctx, row); allc.alloc(ctx, (u64)P * row);
+        });
+        NCK(nc->AllGather(L.cap0.p, capall.p, nb0, ncclUint32, cm->comm, ctx->stream));
+        LAUNCH(ctx, skm_dist_layout_kernel, (unsigned)P, 1024, 0, capall.p, nb0, P, me, fs, base_src.p, mybase.p, rtotal.p);
+        CK(cudaMemcpyAsync(h_rtotal.data(), rtotal.p, P * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        u64 need = 1;
+        for (int q = 0; q < P; ++q) need = h_rtotal[q] > need ? h_rtotal[q] : need;
+        if (need >= 0xFFFFFFFFull) GG_THROW(GG_ERR_LIMIT, "%llu super-k-mer records exceed the 2^32-1 per-GPU limit", (unsigned long long)need);  // same on all ranks
+        const bool ipc = dist_ensure_recv(cm, 2 * need);   // collective; the buffer holds u64 words, a record is two
+        // ---- scatter: records go to the owner of their minimizer's bin ----
+        u64 local_cap = 0;
+        dist_guard(cm, "super-k-mer scatter", [&] {
+            L.cur0.alloc(ctx, (u64)nb0 * SKM_CUR_STRIDE); L.hist1.alloc(ctx, nleaf + 1); L.ovf.alloc(ctx, 1);
+            dfill(ctx, L.cur0.p, (u64)nb0 * SKM_CUR_STRIDE * sizeof(u32), 0u);
+            dfill(ctx, L.hist1.p, (nleaf + 1) * sizeof(u32), 0u);
+            dfill(ctx, L.ovf.p, sizeof(u32), 0u);
+            dfill(ctx, L.totals.p, 2 * sizeof(u64), 0u);
+            prof_bytes(ctx, 12.0 * (double)pr.nwords);
+            if (ipc) {
+                SkmPeers pt;
+                memset(&pt, 0, sizeof(pt));
+                pt.n = P;
+                for (int q = 0; q < P; ++q) pt.ptr[q] = reinterpret_cast<ulonglong2 *>(cm->peerR[q]);
+                for (int q = 0; q <= MSD_MAX_PEERS; ++q) pt.first[q] = fs.first[q];
+                skm_scan_launch<1, true>(ctx, pr, valid, 0, pr.nwords, 1, g, nullptr, L.cur0.p, base_src.p, L.cap0.p, nullptr, L.hist1.p, L.totals.p, L.ovf.p, &pt);
+            } else {   // my segments next to each other in a send buffer (the local layout of skm_caps_kernel: bins in order = owners in order)
+                local_cap = read_scalar<u64>(ctx, L.total_cap.p);
+                if (local_cap >= 0xFFFFFFFFull) GG_THROW(GG_ERR_LIMIT, "%llu super-k-mer records exceed the 2^32-1 per-GPU limit", (unsigned long long)local_cap);
+                sbuf.alloc(ctx, local_cap ? local_cap : 1);
+                skm_scan_launch<1, false>(ctx, pr, valid, 0, pr.nwords, 1, g, nullptr, L.cur0.p, L.base0.p, L.cap0.p, sbuf.p, L.hist1.p, L.totals.p, L.ovf.p, nullptr);
+            }
+            LAUNCH(ctx, skm_dist_pack_kernel, (unsigned)ceil_div(nb0, 256), 256, 0, L.cur0.p, L.cap0.p, nb0, L.ovf.p, L.totals.p, mine.p);
+        });
+        // ---- what every source stored where (IPC route: also the barrier after which all stores have landed) ----
+        NCK(nc->AllGather(mine.p, allc.p, row, ncclUint32, cm->comm, ctx->stream));
+        h_allc.resize((size_t)P * row);
+        CK(cudaMemcpyAsync(h_allc.data(), allc.p, h_allc.size() * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        bool any_ovf = false;
+        for (int p = 0; p < P; ++p) any_ovf = any_ovf || h_allc[(size_t)p * row + nb0] != 0;
+        if (any_ovf) {   // a region outgrew its sampled share somewhere: everybody repeats with exact counts
+            if (exact || attempt > 0) GG_THROW(GG_ERR_CUDA, "super-k-mer scatter overflowed exact capacities");
+            sbuf.release();
+            continue;
+        }
+        if (ipc) R = reinterpret_cast<const ulonglong2 *>(cm->R);
+        else {
+            std::vector<u32> h_lbase(nb0 + 1), h_my((size_t)nreg + 1);
+            dist_guard(cm, "receive buffer", [&] {
+                CK(cudaMemcpyAsync(h_lbase.data(), L.base0.p, (nb0 + 1) * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaMemcpyAsync(h_my.data(), mybase.p, ((size_t)nreg + 1) * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+                rtmp.alloc(ctx, h_rtotal[me] ? h_rtotal[me] : 1);
+            });
+            std::vector<u64> soff(P), scnt(P), roff(P), rcnt(P);
+            for (int q = 0; q < P; ++q) {
+                soff[q] = h_lbase[fs.first[q]];
+                scnt[q] = (u64)h_lbase[fs.first[q + 1]] - soff[q];
+                roff[q] = h_my[(size_t)q * nbl];
+                rcnt[q] = (u64)h_my[(size_t)(q + 1) * nbl] - roff[q];
+            }
+            dist_alltoallv(cm, sbuf.p, soff.data(), scnt.data(), rtmp.p, roff.data(), rcnt.data(), sizeof(ulonglong2));
+            CK(cudaStreamSynchronize(ctx->stream));
+            sbuf.release();
+            R = rtmp.p;
+        }
+        break;
+    }
+    stage_end(ctx, ST_EXTRACT);
+    gg_trace(ctx, "dist skm scatter + exchange");
+    // ---- leaf-bin sizes: the sources' histograms summed ----
+    NCK(nc->AllReduce(L.hist1.p, L.hist1.p, nleaf, ncclUint32, ncclSum, cm->comm, ctx->stream));
+    u64 n_rec_recv = 0;
+    for (int p = 0; p < P; ++p)
+        for (u32 bl = 0; bl < nbl; ++bl) n_rec_recv += h_allc[(size_t)p * row + f0 + bl];
+    DBuf<u64> uk;
+    DBuf<u32> uc;
+    u64 U = 0;
+    dist_guard(cm, "super-k-mer counting", [&] {
+        DBuf<u32> mycnt(ctx, (u64)nreg + 1);
+        if (nreg) LAUNCH(ctx, skm_dist_mycnt_kernel, (unsigned)ceil_div(nreg, 256), 256, 0, allc.p, row, f0, nbl, nreg, mycnt.p);
+        // instances behind the received records: counted by level 1 (a single rank knows its own total, and may skip level 1)
+        const u64 inst_me = (u64)h_allc[(size_t)me * row + nb0 + 1] | ((u64)h_allc[(size_t)me * row + nb0 + 2] << 32);
+        U = skm_finish(ctx, R, mybase.p, mycnt.p, 1, nbl, (u32)P, h_rtotal[me], g, L.hist1.p + (u64)f0 * g.nb1, P == 1 ? inst_me : ~0ULL, n_rec_recv, min_freq,
+                       tune, uk, uc);
+        CK(cudaStreamSynchronize(ctx->stream));
+    });
+    rtmp.release();
+    stage_begin(ctx, ST_FILTER);   // the second exchange is booked under "filter" (with the all-gather of the graph stage)
+    U = dist_range_repartition(cm, uk, uc, U, k, ukeys, ucounts);
+    stage_end(ctx, ST_FILTER);
     return U;
 }

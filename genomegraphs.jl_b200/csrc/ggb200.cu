@@ -9,6 +9,7 @@
 #include "skm.cuh"
 #include "dist.cuh"
 #include "graph.cuh"
+#include "graphdist.cuh"
 #include "umi.cuh"
 #include "synth.cuh"
 
@@ -722,6 +723,18 @@ int gg_extract_kmers(gg_ctx *ctx, const uint8_t *seq, const uint64_t *offs, uint
 }
 
 // ------------------------------------- graph ----------------------------------------------
+}  // extern "C"
+// sorted unique canonical k-mers (the whole table, on every rank of cm) -> graph.  The sharded formulation
+// (graphdist.cuh) is the default, on one GPU too; inputs with perfect circles take graph.cuh's.
+template <int W>
+static gg_graph *build_graph_auto(gg_ctx *ctx, const u64 *keys, u64 U, int k, gg_comm *cm = nullptr) {
+    if (!getenv("GG_GRAPH_REPLICATED")) {
+        gg_graph *g = build_graph_sharded<W>(ctx, keys, U, k, cm);
+        if (g) return g;
+    }
+    return build_graph<W>(ctx, keys, U, k, cm);
+}
+extern "C" {
 int gg_dbg_build(gg_ctx *ctx, gg_counts *counts, gg_graph **out) {
     API_BEGIN(ctx)
     if (!out || !counts) GG_THROW(GG_ERR_ARG, "null argument");
@@ -729,7 +742,7 @@ int gg_dbg_build(gg_ctx *ctx, gg_counts *counts, gg_graph **out) {
     CK(cudaSetDevice(_c->device));
     timing_reset(_c);
     stage_begin(_c, ST_TOTAL);
-    DISPATCH_W(counts->W, *out = build_graph<W>(_c, counts->d_keys, counts->n_unique, counts->k));
+    DISPATCH_W(counts->W, *out = build_graph_auto<W>(_c, counts->d_keys, counts->n_unique, counts->k));
     stage_end(_c, ST_TOTAL);
     timing_collect(_c);
     API_END
@@ -742,7 +755,7 @@ static void dbg_from_reads_dev(gg_ctx *ctx, const u8 *d_seq, const u64 *d_offs, 
     DISPATCH_W(kmer_words(k), c = count_kmers_dev_impl<W>(ctx, d_seq, d_offs, nreads, nbytes, k, 1, min_freq, &filtered));
     try {
         if (!filtered) { DISPATCH_W(c->W, filter_impl<W>(c, min_freq, 1)); }
-        DISPATCH_W(c->W, *out = build_graph<W>(ctx, c->d_keys, c->n_unique, c->k));
+        DISPATCH_W(c->W, *out = build_graph_auto<W>(ctx, c->d_keys, c->n_unique, c->k));
     } catch (...) {
         gg_counts_free(c);
         throw;
@@ -774,7 +787,7 @@ int gg_dbg_from_reads(gg_ctx *ctx, const uint8_t *seq, const uint64_t *offs, uin
         stage_begin(_c, ST_TOTAL);
         gg_counts *c = count_kmers_host_pipelined(_c, seq, offs, nreads, k, 1, dbg_min_freq(min_freq), nullptr);
         try {
-            DISPATCH_W(c->W, *out = build_graph<W>(_c, c->d_keys, c->n_unique, c->k));
+            DISPATCH_W(c->W, *out = build_graph_auto<W>(_c, c->d_keys, c->n_unique, c->k));
         } catch (...) {
             gg_counts_free(c);
             throw;
@@ -915,6 +928,7 @@ void gg_comm_destroy(gg_comm *cm) {
     cudaStreamSynchronize(cm->ctx->stream);
     dist_close_peers(cm);
     if (cm->R) cudaFree(cm->R);
+    if (cm->agree) cudaFree(cm->agree);
     if (cm->comm) nccl_api()->CommDestroy(cm->comm);
     delete cm;
 }
@@ -943,7 +957,10 @@ static gg_counts *dist_count_impl(gg_comm *cm, const u8 *d_seq, const u64 *d_off
         DBuf<u32> counts;
         u32 mf = min_freq > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)min_freq;
         u64 ng = 0;
-        c->n_unique = dist_msd_count<W>(cm, pr, valid.p, k, canonical, mf < 1 ? 1 : mf, ukeys, counts, &c->n_instances, &ng);
+        if (W == 1 && skm_supported(k, canonical) && !getenv("GG_FORCE_MSD"))
+            c->n_unique = dist_skm_count(cm, pr, valid.p, k, canonical, mf < 1 ? 1 : mf, ukeys, counts, &c->n_instances, &ng);
+        else
+            c->n_unique = dist_msd_count<W>(cm, pr, valid.p, k, canonical, mf < 1 ? 1 : mf, ukeys, counts, &c->n_instances, &ng);
         if (n_glob) *n_glob = ng;
         c->d_keys = ukeys.take();
         c->d_counts = counts.take();
@@ -1038,20 +1055,20 @@ int gg_dist_dbg_from_reads_dev(gg_comm *cm, const uint8_t *d_seq, const uint64_t
     CK(cudaSetDevice(_c->device));
     timing_reset(_c);
     stage_begin(_c, ST_TOTAL);
-    gg_counts *c = nullptr, *f = nullptr;
+    gg_counts *c = nullptr;
     DISPATCH_W(kmer_words(k), c = dist_count_impl<W>(cm, d_seq, d_offs, nreads, nbytes, k, 1, dbg_min_freq(min_freq), n_instances_global));
     try {
         stage_begin(_c, ST_FILTER);  // the all-gather of the kept k-mers is booked under "filter"
-        f = counts_allgather_impl(cm, c);
+        DBuf<u64> all;
+        u64 U = 0;
+        DISPATCH_W(c->W, U = keys_allgatherv<W>(cm, c->d_keys, c->n_unique, all));
         stage_end(_c, ST_FILTER);
-        DISPATCH_W(f->W, *out = build_graph<W>(_c, f->d_keys, f->n_unique, f->k, cm));
+        DISPATCH_W(c->W, *out = build_graph_auto<W>(_c, all.p, U, c->k, cm));
     } catch (...) {
         gg_counts_free(c);
-        gg_counts_free(f);
         throw;
     }
     gg_counts_free(c);
-    gg_counts_free(f);
     stage_end(_c, ST_TOTAL);
     timing_collect(_c);
     API_END

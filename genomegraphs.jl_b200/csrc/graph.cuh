@@ -493,6 +493,38 @@ struct gg_graph {
 
 static inline int ilog2_ceil(u64 x) { int b = 0; while ((1ULL << b) < x) ++b; return b; }
 
+
+// pointer jumping over the reduced (splitter) list: a[i] = dist << 32 | next (V_TERM: list end).  Returns the buffer
+// that holds the ranked records.  One cooperative launch when the device supports it.
+static u64 *rank_reduced_list(gg_ctx *ctx, u64 *ra, u64 *rb, u64 ns) {
+    if (ns == 0) return ra;
+    int rounds = ilog2_ceil(ns) + 2;  // fixed count: no host round trips
+    if (ctx->coop_blocks < 0) {       // co-resident CTAs per SM of the fused kernel on THIS device (0: not supported)
+        int supported = 0, nb = 0;
+        cudaDeviceGetAttribute(&supported, cudaDevAttrCooperativeLaunch, ctx->device);
+        if (supported) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wyllie_fused_kernel, 256, 0);
+        ctx->coop_blocks = supported ? nb : 0;
+    }
+    if (ctx->coop_blocks > 0 && !getenv("GG_NO_COOP")) {
+        u64 grid = ceil_div(ns, 256);
+        if (grid > (u64)ctx->coop_blocks * ctx->num_sms) grid = (u64)ctx->coop_blocks * ctx->num_sms;
+        u64 nsv = ns;
+        void *args[] = {&ra, &rb, &nsv, &rounds};
+        cudaEvent_t pa = nullptr, pb = nullptr;
+        if (ctx->profile) { pa = prof_event(ctx); pb = prof_event(ctx); cudaEventRecord(pa, ctx->stream); }
+        CK(cudaLaunchCooperativeKernel((void *)wyllie_fused_kernel, dim3((unsigned)grid), dim3(256), args, 0, ctx->stream));
+        ctx->launches++;
+        if (ctx->profile) { cudaEventRecord(pb, ctx->stream); ctx->prof.push_back({std::string("wyllie_fused_kernel"), pa, pb}); }
+        return (rounds & 1) ? rb : ra;
+    }
+    DBuf<u32> flag(ctx, 1);
+    for (int r = 0; r < rounds; ++r) {
+        LAUNCH(ctx, wyllie_kernel, (unsigned)ceil_div(ns, 256), 256, 0, ra, rb, ns, flag.p);
+        std::swap(ra, rb);
+    }
+    return ra;
+}
+
 template <int W>
 static void build_links(gg_ctx *ctx, gg_graph *g, const u64 *keys, const u32 *node_first, const u32 *node_last) {
     const int k = g->k;
@@ -625,34 +657,7 @@ static gg_graph *build_graph(gg_ctx *ctx, const u64 *keys, u64 U, int k, gg_comm
             DBuf<u32> red_tail(ctx, ns + 1), red_vertex(ctx, ns + 1);
             LAUNCH(ctx, split_list_kernel, (unsigned)ceil_div(nv, 256), 256, 0, sflag.p, sidx.p, nv, red_vertex.p);
             if (ns) LAUNCH(ctx, split_walk_kernel, (unsigned)ceil_div(ns, 128), 128, 0, succ.p, red_vertex.p, sidx.p, ns, sl, ownloc.p, redA.p, red_tail.p);
-            u64 *ra = redA.p, *rb = redB.p;
-            if (ns) {
-                int rounds = ilog2_ceil(ns) + 2;  // fixed count: no host round trips
-                static int coop_blocks = -1;      // co-resident CTAs per SM of the fused kernel (0: not supported)
-                if (coop_blocks < 0) {
-                    int supported = 0, nb = 0;
-                    cudaDeviceGetAttribute(&supported, cudaDevAttrCooperativeLaunch, ctx->device);
-                    if (supported) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wyllie_fused_kernel, 256, 0);
-                    coop_blocks = supported ? nb : 0;
-                }
-                if (coop_blocks > 0 && !getenv("GG_NO_COOP")) {
-                    u64 grid = ceil_div(ns, 256);
-                    if (grid > (u64)coop_blocks * ctx->num_sms) grid = (u64)coop_blocks * ctx->num_sms;
-                    u64 nsv = ns;
-                    void *args[] = {&ra, &rb, &nsv, &rounds};
-                    cudaEvent_t pa = nullptr, pb = nullptr;
-                    if (ctx->profile) { pa = prof_event(ctx); pb = prof_event(ctx); cudaEventRecord(pa, ctx->stream); }
-                    CK(cudaLaunchCooperativeKernel((void *)wyllie_fused_kernel, dim3((unsigned)grid), dim3(256), args, 0, ctx->stream));
-                    ctx->launches++;
-                    if (ctx->profile) { cudaEventRecord(pb, ctx->stream); ctx->prof.push_back({std::string("wyllie_fused_kernel"), pa, pb}); }
-                    if (rounds & 1) std::swap(ra, rb);
-                } else {
-                    for (int r = 0; r < rounds; ++r) {
-                        LAUNCH(ctx, wyllie_kernel, (unsigned)ceil_div(ns, 256), 256, 0, ra, rb, ns, d_flag.p);
-                        std::swap(ra, rb);
-                    }
-                }
-            }
+            u64 *ra = rank_reduced_list(ctx, redA.p, redB.p, ns);
             LAUNCH(ctx, split_expand_kernel, (unsigned)ceil_div(nv, 256), 256, 0, ra, red_tail.p, sflag.p, sidx.p, ownloc.p, nv, rin);
         }
         CK(cudaMemsetAsync(d_flag.p, 0, sizeof(u32), ctx->stream));

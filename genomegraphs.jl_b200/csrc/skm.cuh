@@ -322,8 +322,9 @@ __global__ void __launch_bounds__(1024) skm_caps_kernel(const u32 *__restrict__ 
 }
 
 // ---- pass 1: level-0 regions -> leaf bins ---------------------------------------------------------
-// Region r (a level-0 bin, or a (bin, source) pair on the multi-GPU path) holds cnt[r * cnt_stride] records at
-// base[r]; its records belong to the local level-0 bin r / nsrc.  tile_reg[t] = region of the t-th tile of SKM_ALIGN slots.
+// Region r (a level-0 bin, or a (source, bin) pair on the multi-GPU path: source-major, so that one source's regions are
+// one contiguous segment) holds cnt[r * cnt_stride] records at base[r]; its records belong to the local level-0 bin
+// r % nb_local.  tile_reg[t] = region of the t-th tile of SKM_ALIGN slots.
 __global__ void skm_tilemap_kernel(const u32 *__restrict__ base, u32 nreg, u32 *__restrict__ tile_reg) {
     const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nreg) return;
@@ -335,8 +336,8 @@ __global__ void skm_tilemap_kernel(const u32 *__restrict__ base, u32 nreg, u32 *
 #define SKM_L1_THREADS 512
 __global__ void __launch_bounds__(SKM_L1_THREADS) skm_l1_kernel(const ulonglong2 *__restrict__ in, const u32 *__restrict__ base,
                                                                 const u32 *__restrict__ cnt, u32 cnt_stride, const u32 *__restrict__ tile_reg,
-                                                                u32 nsrc, u32 nb1, const u32 *__restrict__ lbeg, u32 *__restrict__ cur1,
-                                                                ulonglong2 *__restrict__ out) {
+                                                                u32 nb_local, u32 nb1, const u32 *__restrict__ lbeg, u32 *__restrict__ cur1,
+                                                                ulonglong2 *__restrict__ out, unsigned long long *__restrict__ inst_total) {
     extern __shared__ __align__(16) u8 smem_raw[];
     u32 *hist = reinterpret_cast<u32 *>(smem_raw);   // nb1
     u32 *gpos = hist + nb1;                          // nb1
@@ -346,11 +347,20 @@ __global__ void __launch_bounds__(SKM_L1_THREADS) skm_l1_kernel(const ulonglong2
     const u32 rel0 = (u32)(tile0 - base[r]);
     if (rel0 >= n) return;
     const u32 m = min(n - rel0, (u32)SKM_ALIGN);     // records of this tile
-    const u64 leaf0 = (u64)(r / nsrc) * nb1;
+    const u64 leaf0 = (u64)(r % nb_local) * nb1;
     const ulonglong2 *tp = in + tile0;
     for (u32 i = threadIdx.x; i < nb1; i += SKM_L1_THREADS) hist[i] = 0;
     __syncthreads();
-    for (u32 i = threadIdx.x; i < m; i += SKM_L1_THREADS) atomicAdd(&hist[((u32)tp[i].y >> 5) & (SKM_MAX_NB1 - 1u)], 1u);
+    u32 inst = 0;
+    for (u32 i = threadIdx.x; i < m; i += SKM_L1_THREADS) {
+        const u32 meta = (u32)tp[i].y;
+        atomicAdd(&hist[(meta >> 5) & (SKM_MAX_NB1 - 1u)], 1u);
+        inst += (meta & 31u) + 1u;
+    }
+    if (inst_total) {   // multi-GPU: the owner learns how many k-mer instances it received
+        inst = warp_sum(inst);
+        if (lane_id() == 0 && inst) atomicAdd(inst_total, (unsigned long long)inst);
+    }
     __syncthreads();
     for (u32 i = threadIdx.x; i < nb1; i += SKM_L1_THREADS) {
         const u32 c = hist[i];
@@ -845,12 +855,13 @@ static void skm_l0_prepare(gg_ctx *ctx, SkmL0 &L, double scale, bool exact, cons
     L.exact = exact;
 }
 
-// Everything after a successful level-0 scatter: regions (base / cnt, nreg = nb_local * nsrc regions of `in`) ->
-// sorted unique keys + counts.  hist1: records per leaf bin of the local bins (nleaf + 1 entries, last 0).
+// Everything after a successful level-0 scatter: regions (base / cnt, nreg = nsrc * nb_local regions of `in`, source-major) ->
+// sorted unique keys + counts.  hist1: records per leaf bin of the local bins (nleaf entries).  n_inst: k-mer instances in
+// the regions, or ~0 when unknown (multi-GPU owner: counted by level 1).
 static u64 skm_finish(gg_ctx *ctx, const ulonglong2 *in, const u32 *base, const u32 *cnt, u32 cnt_stride, u32 nb_local, u32 nsrc, u64 in_cap,
                       const SkmGeom &g, const u32 *hist1, u64 n_inst, u64 n_rec, u32 min_freq, const SkmTune &tune, DBuf<u64> &ukeys,
-                      DBuf<u32> &ucounts) {
-    if (n_rec == 0 || nb_local == 0) { ukeys.alloc(ctx, 1); ucounts.alloc(ctx, 1); return 0; }
+                      DBuf<u32> &ucounts, u64 *n_inst_out = nullptr) {
+    if (n_rec == 0 || nb_local == 0) { ukeys.alloc(ctx, 1); ucounts.alloc(ctx, 1); if (n_inst_out) *n_inst_out = 0; return 0; }
     const u64 nleaf = (u64)nb_local * g.nb1;
     stage_begin(ctx, ST_SORT);
     DBuf<u32> lbeg(ctx, nleaf + 1), cur1, dense;
@@ -868,13 +879,19 @@ static u64 skm_finish(gg_ctx *ctx, const ulonglong2 *in, const u32 *base, const 
         prof_bytes(ctx, 32.0 * (double)n_rec);
         const size_t smem1 = (size_t)g.nb1 * 8;
         set_max_smem(ctx, skm_l1_kernel, (size_t)SKM_MAX_NB1 * 8);
-        LAUNCH(ctx, skm_l1_kernel, ntile, SKM_L1_THREADS, smem1, in, base, cnt, cnt_stride, tile_reg.p, nsrc, g.nb1, lbeg.p, cur1.p, rec1.p);
+        DBuf<u64> itot;
+        if (n_inst == ~0ULL) { itot.alloc(ctx, 1); dfill(ctx, itot.p, sizeof(u64), 0u); }
+        LAUNCH(ctx, skm_l1_kernel, ntile, SKM_L1_THREADS, smem1, in, base, cnt, cnt_stride, tile_reg.p, nb_local, g.nb1, lbeg.p, cur1.p, rec1.p,
+               (unsigned long long *)itot.p);
+        if (n_inst == ~0ULL) n_inst = read_scalar<u64>(ctx, itot.p);
         leaf_recs = rec1.p; leaf_beg = lbeg.p; leaf_cnt = hist1;
     } else if (cnt_stride != 1) {
         dense.alloc(ctx, nleaf);
         LAUNCH(ctx, skm_gather_strided_kernel, (unsigned)ceil_div(nleaf, 256), 256, 0, cnt, cnt_stride, (u32)nleaf, dense.p);
         leaf_cnt = dense.p;
     }
+    if (n_inst == ~0ULL) GG_THROW(GG_ERR_ARG, "skm_finish: instance count needed when level 1 is skipped");
+    if (n_inst_out) *n_inst_out = n_inst;
     gg_trace(ctx, "skm level 1");
     // ---- E: leaves ----
     // every kept key has >= min_freq instances; the CTAs of the leaf kernel take the kept list in blocks of SKM_KBLOCK slots and
