@@ -95,6 +95,9 @@ __global__ void gs_list_kernel(const u64 *__restrict__ sel, u32 v0, u32 nvl, u32
     const u32 v = v0 + t;
     if (sel_bit(sel, v)) red_vertex[sel_rank(sel, v) - soff] = v;
 }
+// (Measured on one GPU: keeping succ[v] and the label of v in ONE 16-byte entry, so that a step would touch a single
+// sector, made this kernel 5-6x SLOWER, 14 -> 75-93 ms on C3, whichever of the load / store came first: stores into
+// sectors whose fill is still in flight do not pipeline.  Successors and labels therefore stay in separate arrays.)
 // one thread per own splitter: walk to the next splitter (only a hash-sampled one can be met: heads have no
 // predecessor) or to the tail; every passed vertex learns (splitter, distance) in its owner's shard
 __global__ void gs_walk_kernel(const u32 *__restrict__ succ, const u32 *__restrict__ red_vertex, const u64 *__restrict__ sel, u32 ns_own, u32 soff,
@@ -265,7 +268,11 @@ static gg_graph *build_graph_sharded(gg_ctx *ctx, const u64 *keys, u64 U, int k,
         const u64 i0 = chunk * me < U ? chunk * me : U, i1 = i0 + chunk < U ? i0 + chunk : U;
         const u32 nvl = (u32)(2 * chunk), v0 = (u32)(2 * chunk * me);
         const u64 nvp = 2 * chunk * P;   // padded vertex count
-        const int sl = getenv("GG_SPLIT_LOG") ? atoi(getenv("GG_SPLIT_LOG")) : (P > 1 ? 6 : 4);
+        // splitters: heads + a 2^-sl hash sample.  Fewer splitters shrink the reduced list (ranked on every rank) and make its
+        // records cache-resident for the expansion, as long as every rank keeps >= ~2^18 walks in flight (measured on C2 / C3)
+        int sl = 4;
+        while (sl < 7 && (nvp / (u64)P) >> (sl + 1) >= (1ULL << 18)) ++sl;
+        if (getenv("GG_SPLIT_LOG")) sl = atoi(getenv("GG_SPLIT_LOG"));
         // ---- K5: neighbour lookup of the own k-mers ----
         stage_begin(ctx, ST_LOOKUP);
         int pbits = ilog2_ceil(U) - 1;

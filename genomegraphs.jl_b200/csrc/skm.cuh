@@ -395,6 +395,10 @@ struct SkmLeafSmem {
 __device__ __forceinline__ u32 skm_slot(u64 key, int lh) { return (((u32)key ^ (u32)(key >> 32)) * 0x9E3779B1u) >> (32 - lh); }
 
 // Leaf bin l = records recs[lbeg[l] .. + lcnt[l]); CTA c takes the bins c, c + grid, ... (the bins are near-uniform).
+// (Measured alternatives on C3, 19.0 ms as is: no list and a 128-bit sweep of the whole table after every bin 21.8 ms --
+// the sweep sits on the critical path between two barriers, the list upkeep overlaps with the insertions; geometries
+// 256 x 4096 slots x 4 CTAs 21.4, 256 x 2048 x 8 19.3, 512 x 8192 x 2 22.8, 256 x 8192 x 2 31.5 ms: what counts is the number
+// of resident warps, the kernel is bound by instruction issue, ~180 warp instructions per 32 insertions.)
 // The table is cleared once per CTA; every bin leaves it clean again by resetting the slots it claimed, so the cost of
 // a bin is proportional to its instances + distinct keys, not to the table size.  Kept keys (count >= min_freq) are
 // appended to okeys / ocnts at *kept_cursor.  A bin whose table fills up is put on the overflow list instead.
@@ -432,11 +436,15 @@ __global__ void __launch_bounds__(THREADS) skm_leaf_kernel(const ulonglong2 *__r
             // A warp takes 32 records at a time and spreads their windows over its lanes: lane i handles instance p + i of
             // the chunk (record and window found with one OR-reduction + ballot; the record travels by shuffle), so every
             // lane inserts, whatever the record lengths are.
-            for (u32 c0 = (threadIdx.x >> 5) * 32u; c0 < n; c0 += (THREADS / 32) * 32u) {
+            // (a bin holds a few hundred records: the warps share them evenly, `per` <= 32 records each at a time, so that
+            // none of them sits out the bin)
+            const u32 per = min(32u, (n + (THREADS / 32) - 1u) / (THREADS / 32));
+            for (u32 c0 = (threadIdx.x >> 5) * per; c0 < n; c0 += (THREADS / 32) * per) {
                 const u32 ri = c0 + lane_id();
+                const bool mine = lane_id() < per && ri < n;
                 ulonglong2 rec = make_ulonglong2(0, 0);
-                if (ri < n) rec = rp[ri];
-                const u32 len = ri < n ? ((u32)rec.y & 31u) + 1u : 0u;
+                if (mine) rec = rp[ri];
+                const u32 len = mine ? ((u32)rec.y & 31u) + 1u : 0u;
                 const u32 incl = warp_incl_scan(len), start = incl - len;
                 const u32 T = __shfl_sync(FULL_MASK, incl, 31);
                 const u64 a0 = rec.x;
