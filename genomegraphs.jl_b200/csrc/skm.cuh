@@ -391,7 +391,7 @@ struct SkmLeafSmem {
                                                // a slow warp may still read bin i's values when thread 0 prepares bin i + 1)
     unsigned long long s_kbase;       // the CTA's current block of the kept list
 };
-#define SKM_KBLOCK 65536   // kept-list slots a CTA reserves at a time (unused slots are marked empty and skipped by the sort)
+#define SKM_KBLOCK 32768   // kept-list slots a CTA reserves at a time (unused slots are marked empty and skipped by the sort)
 __device__ __forceinline__ u32 skm_slot(u64 key, int lh) { return (((u32)key ^ (u32)(key >> 32)) * 0x9E3779B1u) >> (32 - lh); }
 
 // Leaf bin l = records recs[lbeg[l] .. + lcnt[l]); CTA c takes the bins c, c + grid, ... (the bins are near-uniform).
@@ -575,22 +575,111 @@ __global__ void skm_ovf_expand_kernel(const ulonglong2 *__restrict__ recs, const
 
 // ---- pass F: kept pairs -> ascending key order ------------------------------------------------------
 #define SKM_SORT_CAP 8192   // pairs one CTA orders in shared memory
-__global__ void skm_sort_hist_kernel(const u64 *__restrict__ keys, u64 n, int sh, u32 *__restrict__ hist) {
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
-        const u64 key = keys[i];
-        if (key != MSD_EMPTY) atomicAdd(&hist[(u32)(key >> sh)], 1u);  // empty: unused slot of a leaf CTA's block
+// ---- staged partition of (key, count) pairs by a key digit -------------------------------------------------------
+// The slots are cut into tiles of PS_TILE; tile t belongs to region tile_reg[t] (a bucket of the previous pass; null: one
+// region) that holds rcnt[r] pairs from rbase[r] on (a multiple of PS_TILE).  MODE 0 adds the tile's digit histogram to
+// hist[r * nb + digit].  MODE 1 stages the tile's pairs in shared memory grouped by digit (rank inside the group from the
+// shared-memory histogram atomics), reserves ONE range per (tile, digit) in the output bucket and writes the groups as
+// runs -- instead of one global atomic and one 12-byte scattered store per pair.  Empty slots (MSD_EMPTY) are skipped.
+#define PS_TILE 8192
+#define PS_THREADS 512
+#define PS_MAX_NB 512
+template <int MODE>
+__global__ void __launch_bounds__(PS_THREADS) pair_part_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ cnts, const u32 *__restrict__ tile_reg,
+                                                               const u32 *__restrict__ rbase, const u32 *__restrict__ rcnt, u64 n_all, int sh, u32 nb,
+                                                               u32 *__restrict__ hist, const u32 *__restrict__ ostart, u64 *__restrict__ okeys,
+                                                               u32 *__restrict__ ocnts) {
+    constexpr int PER = PS_TILE / PS_THREADS;
+    extern __shared__ __align__(16) u8 smem_raw[];
+    u32 *h = reinterpret_cast<u32 *>(smem_raw);           // PS_MAX_NB: pairs per digit, then the running start
+    u32 *gp = h + PS_MAX_NB;                              // PS_MAX_NB: output position of the group minus its start in the tile
+    u64 *sk = reinterpret_cast<u64 *>(gp + PS_MAX_NB);    // PS_TILE
+    u32 *sc = reinterpret_cast<u32 *>(sk + PS_TILE);      // PS_TILE
+    __shared__ u32 ws[33];
+    const u64 tile0 = (u64)blockIdx.x * PS_TILE;
+    u32 r = 0;
+    u64 m = n_all - tile0 < PS_TILE ? n_all - tile0 : PS_TILE;
+    if (tile_reg) {
+        r = tile_reg[blockIdx.x];
+        const u64 rel0 = tile0 - rbase[r];
+        if (rel0 >= rcnt[r]) return;
+        m = rcnt[r] - rel0 < PS_TILE ? rcnt[r] - rel0 : PS_TILE;
+    }
+    const u32 dm = nb - 1u;
+    for (u32 i = threadIdx.x; i < nb; i += PS_THREADS) h[i] = 0;
+    __syncthreads();
+    u64 kr[PER];
+    u32 pos[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const u32 j = threadIdx.x + (u32)i * PS_THREADS;
+        kr[i] = j < m ? keys[tile0 + j] : MSD_EMPTY;
+        pos[i] = kr[i] != MSD_EMPTY ? atomicAdd(&h[(u32)(kr[i] >> sh) & dm], 1u) : 0u;
+    }
+    __syncthreads();
+    if (MODE == 0) {
+        for (u32 b = threadIdx.x; b < nb; b += PS_THREADS)
+            if (h[b]) atomicAdd(&hist[(u64)r * nb + b], h[b]);
+        return;
+    }
+    {   // starts of the groups inside the tile; one reservation per (tile, digit)
+        const u32 c = threadIdx.x < nb ? h[threadIdx.x] : 0u;
+        u32 tot;
+        const u32 ex = block_excl_scan(c, ws, &tot);
+        if (threadIdx.x < nb) {
+            h[threadIdx.x] = ex;
+            const u64 ob = (u64)r * nb + threadIdx.x;
+            gp[threadIdx.x] = c ? ostart[ob] + atomicAdd(&hist[ob], c) - ex : 0u;   // hist doubles as the cursor array (zeroed)
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const u32 j = threadIdx.x + (u32)i * PS_THREADS;
+            if (kr[i] != MSD_EMPTY) {
+                const u32 q = h[(u32)(kr[i] >> sh) & dm] + pos[i];
+                sk[q] = kr[i];
+                sc[q] = cnts[tile0 + j];
+            }
+        }
+        __syncthreads();
+        for (u32 q = threadIdx.x; q < tot; q += PS_THREADS) {
+            const u64 key = sk[q];
+            const u32 o = gp[(u32)(key >> sh) & dm] + q;
+            okeys[o] = key;
+            ocnts[o] = sc[q];
+        }
     }
 }
-__global__ void skm_sort_scatter_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ cnts, u64 n, int sh, const u32 *__restrict__ bstart,
-                                        u32 *__restrict__ cursor, u64 *__restrict__ okeys, u32 *__restrict__ ocnts) {
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
-        const u64 key = keys[i];
-        if (key == MSD_EMPTY) continue;
-        const u32 b = (u32)(key >> sh);
-        const u32 pos = bstart[b] + atomicAdd(&cursor[b], 1u);
-        okeys[pos] = key;
-        ocnts[pos] = cnts[i];
+// bucket starts of a pass: exact (compact) or every bucket rounded up to whole tiles (its tiles then belong to it alone)
+__global__ void __launch_bounds__(1024) pair_starts_kernel(const u32 *__restrict__ hist, u32 n, int padded, u32 *__restrict__ start, u64 *__restrict__ total) {
+    __shared__ u32 ws[33];
+    __shared__ u64 s_run;
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    for (u32 b0 = 0; b0 < n; b0 += 1024) {
+        const u32 b = b0 + threadIdx.x;
+        u32 c = b < n ? hist[b] : 0u;
+        if (padded) c = (c + PS_TILE - 1) / PS_TILE;   // in tiles: stays within 32 bits
+        u32 tot;
+        const u32 ex = block_excl_scan(c, ws, &tot);
+        if (b < n) {
+            const u64 v = (s_run + ex) * (padded ? (u64)PS_TILE : 1ULL);
+            start[b] = v > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)v;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_run += tot;
+        __syncthreads();
     }
+    if (threadIdx.x == 0) {
+        const u64 v = s_run * (padded ? (u64)PS_TILE : 1ULL);
+        start[n] = v > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)v;
+        *total = v;
+    }
+}
+__global__ void pair_tilemap_kernel(const u32 *__restrict__ start, u32 nreg, u32 *__restrict__ tile_reg) {
+    const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nreg) return;
+    for (u32 t = start[r] / PS_TILE; t < start[r + 1] / PS_TILE; ++t) tile_reg[t] = r;
 }
 // max bucket size -> *mx; buckets larger than SKM_SORT_CAP -> big list (first 1024 of them)
 __global__ void skm_sort_big_kernel(const u32 *__restrict__ hist, u32 nb, u32 *__restrict__ big, u32 *__restrict__ nbig) {
@@ -784,32 +873,68 @@ static u64 skm_sort_pairs(gg_ctx *ctx, u64 *kk, u32 *kc, u64 nslots, u64 n_pairs
         return n;
     };
     int tb = 0;
-    while (tb < 22 && tb < 2 * k && (n_pairs >> tb) > 1024) ++tb;
+    while (tb < 24 && tb < 2 * k && (n_pairs >> tb) > 1024) ++tb;
     if (tb < 4) return compact_generic();
+    // ---- MSD partition on the top tb key bits in passes of <= 9 bits (staged tiles), then one ordering pass per bucket ----
+    const int npass = tb <= 9 ? 1 : tb <= 18 ? 2 : 3;
     const int sh = 2 * k - tb;
     const u32 nb = 1u << tb;
-    DBuf<u32> hist(ctx, nb + 1), bstart(ctx, nb + 1), cursor(ctx, nb), big(ctx, 1024), nbig(ctx, 1);
-    dfill(ctx, hist.p, (u64)(nb + 1) * sizeof(u32), 0u);
-    dfill(ctx, cursor.p, (u64)nb * sizeof(u32), 0u);
+    DBuf<u32> hist, bstart, big(ctx, 1024), nbig(ctx, 1);
+    DBuf<u64> tk, tot(ctx, 1);
+    DBuf<u32> tc;
     dfill(ctx, nbig.p, sizeof(u32), 0u);
-    const unsigned sgrid = (unsigned)std::min<u64>(ceil_div(nslots, 256), (u64)ctx->num_sms * 32);
-    prof_bytes(ctx, 8.0 * (double)nslots);
-    LAUNCH(ctx, skm_sort_hist_kernel, sgrid, 256, 0, kk, nslots, sh, hist.p);
-    exclusive_scan_u32(ctx, hist.p, bstart.p, nb + 1, nullptr);
-    LAUNCH(ctx, skm_sort_big_kernel, (unsigned)ceil_div(nb, 256), 256, 0, hist.p, nb, big.p, nbig.p);
-    CK(cudaMemcpyAsync(ctx->h_scalar, bstart.p + nb, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->h_scalar + 1, nbig.p, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    const u64 n = (u32)ctx->h_scalar[0];
-    const u32 h_nbig = (u32)ctx->h_scalar[1];
+    const size_t ps_smem = (size_t)PS_MAX_NB * 8 + (size_t)PS_TILE * 12;
+    set_max_smem(ctx, pair_part_kernel<0>, ps_smem);
+    set_max_smem(ctx, pair_part_kernel<1>, ps_smem);
+    u64 n = 0;
+    {
+        const u64 *ik = kk;
+        const u32 *ic = kc;
+        u64 in_slots = nslots;
+        DBuf<u32> rbase, rcnt, tile_reg;   // regions of the current input (none for the first pass)
+        u32 nreg = 1;
+        int bits_done = 0;
+        for (int pass = 0; pass < npass; ++pass) {
+            const int bits = (tb - bits_done + (npass - pass) - 1) / (npass - pass);
+            const int psh = 2 * k - bits_done - bits;
+            const u32 pnb = 1u << bits;
+            const bool last = pass == npass - 1;
+            const u64 nbuck = (u64)nreg * pnb;
+            DBuf<u32> h(ctx, nbuck + 1), st(ctx, nbuck + 1);
+            dfill(ctx, h.p, (nbuck + 1) * sizeof(u32), 0u);
+            const unsigned ntile = (unsigned)ceil_div(in_slots, PS_TILE);
+            prof_bytes(ctx, 8.0 * (double)in_slots);
+            LAUNCH(ctx, pair_part_kernel<0>, ntile, PS_THREADS, ps_smem, ik, ic, tile_reg.p, rbase.p, rcnt.p, in_slots, psh, pnb, h.p, nullptr, nullptr, nullptr);
+            LAUNCH(ctx, pair_starts_kernel, 1, 1024, 0, h.p, (u32)nbuck, last ? 0 : 1, st.p, tot.p);
+            if (last) LAUNCH(ctx, skm_sort_big_kernel, (unsigned)ceil_div(nbuck, 256), 256, 0, h.p, (u32)nbuck, big.p, nbig.p);
+            const u64 out_slots = read_scalar<u64>(ctx, tot.p);
+            if (out_slots >= 0xFFFFFFFFull) GG_THROW(GG_ERR_LIMIT, "%llu padded pair slots exceed the 2^32-1 per-GPU limit", (unsigned long long)out_slots);
+            DBuf<u64> ok(ctx, out_slots + 1);
+            DBuf<u32> oc(ctx, out_slots + 1), cnt_keep(ctx, nbuck + 1);
+            CK(cudaMemcpyAsync(cnt_keep.p, h.p, (nbuck + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
+            dfill(ctx, h.p, (nbuck + 1) * sizeof(u32), 0u);   // now the cursors
+            prof_bytes(ctx, 12.0 * (double)in_slots + 12.0 * (double)n_pairs);
+            LAUNCH(ctx, pair_part_kernel<1>, ntile, PS_THREADS, ps_smem, ik, ic, tile_reg.p, rbase.p, rcnt.p, in_slots, psh, pnb, h.p, st.p, ok.p, oc.p);
+            if (last) { n = out_slots; bstart = std::move(st); }
+            else {   // the buckets become the regions of the next pass
+                tile_reg.alloc(ctx, out_slots / PS_TILE + 1);
+                LAUNCH(ctx, pair_tilemap_kernel, (unsigned)ceil_div(nbuck, 128), 128, 0, st.p, (u32)nbuck, tile_reg.p);
+                rbase = std::move(st);
+                rcnt = std::move(cnt_keep);
+                nreg = (u32)nbuck;
+            }
+            CK(cudaStreamSynchronize(ctx->stream));   // the previous pass's buffers go back to the allocator
+            tk = std::move(ok); tc = std::move(oc);
+            ik = tk.p; ic = tc.p;
+            in_slots = out_slots;
+            bits_done += bits;
+        }
+    }
+    const u32 h_nbig = read_scalar<u32>(ctx, nbig.p);
     if (h_nbig > 1024) return compact_generic();  // hopeless skew: sort everything the slow way
     ukeys.alloc(ctx, n ? n : 1);
     ucounts.alloc(ctx, n ? n : 1);
     if (n == 0) return 0;
-    DBuf<u64> tk(ctx, n);
-    DBuf<u32> tc(ctx, n);
-    prof_bytes(ctx, 8.0 * (double)nslots + 16.0 * (double)n);
-    LAUNCH(ctx, skm_sort_scatter_kernel, sgrid, 256, 0, kk, kc, nslots, sh, bstart.p, cursor.p, tk.p, tc.p);
     const size_t smem = (size_t)SKM_SORT_CAP * 12;
     set_max_smem(ctx, skm_sort_bucket_kernel, smem);
     prof_bytes(ctx, 24.0 * (double)n);
@@ -905,7 +1030,8 @@ static u64 skm_finish(gg_ctx *ctx, const ulonglong2 *in, const u32 *base, const 
     // every kept key has >= min_freq instances; the CTAs of the leaf kernel take the kept list in blocks of SKM_KBLOCK slots and
     // leave up to 3/4 of a leaf table unused at the end of each
     const u64 kept_bound = n_inst / (min_freq ? min_freq : 1) + 1;
-    const u64 kept_cap = kept_bound + kept_bound / 8 + (u64)(ctx->num_sms * 8 + 2) * SKM_KBLOCK;
+    // (a block is given up with < LIST <= 6144 free slots: at most 6144 / (32768 - 6144) = 23 % of the slots stay unused)
+    const u64 kept_cap = kept_bound + kept_bound / 4 + (u64)(ctx->num_sms * 8 + 2) * SKM_KBLOCK;
     DBuf<u64> kk(ctx, kept_cap), cursor(ctx, 2);
     DBuf<u32> kc(ctx, kept_cap), ovf_n(ctx, 2), ovf_list(ctx, nleaf);
     dfill(ctx, cursor.p, 2 * sizeof(u64), 0u);
