@@ -33,9 +33,12 @@ __device__ __forceinline__ u32 sel_rank(const u64 *__restrict__ sel, u32 x) {
     return (u32)(e >> 32) + __popc((u32)e & ((1u << (x & 31u)) - 1u));
 }
 __device__ __forceinline__ bool sel_bit(const u64 *__restrict__ sel, u32 x) { return ((u32)sel[x >> 5] >> (x & 31u)) & 1u; }
-__device__ __forceinline__ bool gs_dead(const u8 *__restrict__ flags, u32 v, u64 U) {
-    return (u64)(v >> 1) >= U || ((v & 1u) && ((flags[v >> 1] >> 6) & 1u));
+// pf: the flags when k is even, null when k is odd -- no k-mer of odd length equals its own reverse complement, so the
+// palindrome bit needs no (random) look-up and the mirror vertex is v ^ 1
+__device__ __forceinline__ bool gs_dead(const u8 *__restrict__ pf, u32 v, u64 U) {
+    return (u64)(v >> 1) >= U || (pf && (v & 1u) && ((pf[v >> 1] >> 6) & 1u));
 }
+__device__ __forceinline__ u32 gs_mirror(const u8 *__restrict__ pf, u32 v) { return (pf && ((pf[v >> 1] >> 6) & 1u)) ? v : (v ^ 1u); }
 
 // is_end_fw / is_end_bw (src/dbg.jl:44-68) of the own k-mers -> successor pointers of their two vertices
 __global__ void gs_succ_kernel(const u8 *__restrict__ flags, const u32 *__restrict__ nbF, const u32 *__restrict__ nbB, u64 i0, u64 chunk, u64 U,
@@ -71,7 +74,7 @@ __global__ void gs_flag_kernel(const u32 *__restrict__ succ, const u8 *__restric
     if (t < nvl) {
         const u32 v = v0 + t;
         if (!gs_dead(flags, v, U)) {
-            const u32 mv = mirror_of(flags, v);
+            const u32 mv = gs_mirror(flags, v);
             f = succ[mv] == V_NONE || hash_splitter(v, sl);  // no predecessor  <=>  the mirror vertex has no successor
         }
     }
@@ -153,20 +156,20 @@ __global__ void __launch_bounds__(256) gs_resolve_kernel(const u64 *__restrict__
     const u32 ptr = (u32)r;
     if (ptr == V_NONE) { vhead[t] = V_NONE; vrank[t] = 0; return; }
     const u32 tail = ptr & ~V_TERM, dist = (u32)(r >> 32);
-    const bool pal = (flags[v >> 1] >> 6) & 1u;
+    const bool pal = flags && ((flags[v >> 1] >> 6) & 1u);
     const u64 rm = rec[pal ? t : (t ^ 1u)];
-    const u32 head = mirror_of(flags, ((u32)rm) & ~V_TERM);
+    const u32 head = gs_mirror(flags, ((u32)rm) & ~V_TERM);
     const u32 rank = (u32)(rm >> 32);
     const u32 n = rank + dist + 1;
     vhead[t] = head;
     vrank[t] = rank;
-    const bool sm = mirror_of(flags, tail) == head;  // the path is its own mirror image
+    const bool sm = gs_mirror(flags, tail) == head;  // the path is its own mirror image
     uint4 out;
     bool emit = false;
     if (!sm) {
         if (rank == 0) {
             // canonical!(s): keep the orientation whose first k-mer is smaller (src/dbg.jl:156)
-            const Kmer<W> a = vertex_kmer<W>(keys, v, k), b = vertex_kmer<W>(keys, mirror_of(flags, tail), k);
+            const Kmer<W> a = vertex_kmer<W>(keys, v, k), b = vertex_kmer<W>(keys, gs_mirror(flags, tail), k);
             if (km_lt<W>(a, b)) { out = make_uint4(min(v >> 1, tail >> 1), v, 0u, n); emit = true; }
         }
     } else {
@@ -198,7 +201,7 @@ __global__ void gs_nodelen_kernel(const uint4 *__restrict__ ntab, u64 nn, u32 *_
 template <int W>
 __global__ void __launch_bounds__(256) gs_emit_kernel(const u64 *__restrict__ keys, const u64 *__restrict__ rec, const u32 *__restrict__ vhead,
                                                       const u32 *__restrict__ vrank, u32 v0, u32 nvl, int k, const u64 *__restrict__ nsel,
-                                                      const uint4 *__restrict__ ntab, const u32 *__restrict__ node_off, u8 *__restrict__ bases,
+                                                      const uint4 *__restrict__ ntab, const u32 *__restrict__ node_off, u32 *__restrict__ packed,
                                                       u32 *__restrict__ node_first, u32 *__restrict__ node_last) {
     const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nvl) return;
@@ -214,13 +217,36 @@ __global__ void __launch_bounds__(256) gs_emit_kernel(const u64 *__restrict__ ke
     const u32 j = rank - re;
     const u64 off = node_off[id];
     const Kmer<W> x = vertex_kmer<W>(keys, v, k);
+    // 2-bit codes OR-ed into a zeroed packed array (16 bases per word): the vertices of a node sit at random table
+    // positions, and the packed array of all nodes is small enough to stay in L2, where the atomics are served
     if (j == 0) {
-        for (int q = 0; q < k; ++q) bases[off + q] = code_to_ascii(km_base<W>(x, q, k));
+        for (int q = 0; q < k; ++q) {
+            const u32 c = km_base<W>(x, q, k);
+            if (c) atomicOr(&packed[(off + q) >> 4], c << (2 * ((off + q) & 15)));
+        }
         node_first[id] = v;
     } else {
-        bases[off + k - 1 + j] = code_to_ascii((u32)(x.w[W - 1] & 3ULL));
+        const u32 c = (u32)(x.w[W - 1] & 3ULL);
+        const u64 p = off + k - 1 + j;
+        if (c) atomicOr(&packed[p >> 4], c << (2 * (p & 15)));
     }
     if (j == cnt - 1) node_last[id] = v;
+}
+// packed 2-bit codes -> ASCII, 16 bases per thread
+__global__ void gs_unpack_kernel(const u32 *__restrict__ packed, u64 nbases, u8 *__restrict__ bases) {
+    const u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w * 16 >= nbases) return;
+    const u32 x = packed[w];
+    u32 o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        u32 v = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v |= (u32)code_to_ascii((x >> (2 * (4 * q + e))) & 3u) << (8 * e);
+        o[q] = v;
+    }
+    if (w * 16 + 16 <= nbases) reinterpret_cast<uint4 *>(bases)[w] = make_uint4(o[0], o[1], o[2], o[3]);
+    else for (u64 e = 0; w * 16 + e < nbases; ++e) bases[w * 16 + e] = (u8)(o[e >> 2] >> (8 * (e & 3)));
 }
 
 // rank p's piece buf[off[p] .. + cnt[p]) (elements of esz bytes) -> every rank, in place
@@ -280,6 +306,7 @@ static gg_graph *build_graph_sharded(gg_ctx *ctx, const u64 *keys, u64 U, int k,
         if (pbits > 2 * k) pbits = 2 * k;
         if (pbits < 0) pbits = 0;
         DBuf<u8> flags;
+        const bool even_k = (k & 1) == 0;
         DBuf<u32> nbF, nbB, succ;
         auto local1 = [&] {
             DBuf<u32> start(ctx, (1ULL << pbits) + 1);
@@ -320,7 +347,7 @@ static gg_graph *build_graph_sharded(gg_ctx *ctx, const u64 *keys, u64 U, int k,
         if (nc) dist_guard(cm, "successor pointers", local2); else local2();
         if (nc) NCK(nc->AllGather(succ.p + (u64)nvl * me, succ.p, nvl, ncclUint32, cm->comm, ctx->stream));
         // ---- K7: splitters, walks, reduced list ----
-        LAUNCH(ctx, gs_flag_kernel, (unsigned)ceil_div(nvl, 256), 256, 0, succ.p, flags.p, U, v0, nvl, sl, bits.p);
+        LAUNCH(ctx, gs_flag_kernel, (unsigned)ceil_div(nvl, 256), 256, 0, succ.p, even_k ? flags.p : (const u8 *)nullptr, U, v0, nvl, sl, bits.p);
         if (nc) NCK(nc->AllGather(bits.p + (u64)(nvl / 32) * me, bits.p, nvl / 32, ncclUint32, cm->comm, ctx->stream));
         DBuf<u64> sel, redA, redB;
         DBuf<u32> red_tail, red_vertex;
@@ -353,7 +380,7 @@ static gg_graph *build_graph_sharded(gg_ctx *ctx, const u64 *keys, u64 U, int k,
         if (!nc) ownloc = own_full.p;
         cyc = cycb.p;
         const u64 *ra = rank_reduced_list(ctx, redA.p, redB.p, ns);
-        LAUNCH(ctx, gs_expand_kernel, (unsigned)ceil_div(nvl, 256), 256, 0, ra, red_tail.p, sel.p, ownloc, flags.p, U, v0, nvl, rec.p, cyc);
+        LAUNCH(ctx, gs_expand_kernel, (unsigned)ceil_div(nvl, 256), 256, 0, ra, red_tail.p, sel.p, ownloc, even_k ? flags.p : (const u8 *)nullptr, U, v0, nvl, rec.p, cyc);
         if (nc) NCK(nc->AllReduce(cyc, cyc, 1, ncclUint32, ncclMax, cm->comm, ctx->stream));
         if (read_scalar<u32>(ctx, cyc) != 0) {   // perfect circles somewhere: the replicated formulation handles them
             delete g;
@@ -368,7 +395,7 @@ static gg_graph *build_graph_sharded(gg_ctx *ctx, const u64 *keys, u64 U, int k,
             vhead.alloc(ctx, nvl); vrank.alloc(ctx, nvl); nodemap.alloc(ctx, nmw + 1); list_n.alloc(ctx, 4); list.alloc(ctx, chunk + 1);
             dfill(ctx, nodemap.p, (nmw + 1) * sizeof(u32), 0u);
             dfill(ctx, list_n.p, 16, 0u);
-            LAUNCH(ctx, gs_resolve_kernel<W>, (unsigned)ceil_div(nvl, 256), 256, 0, keys, flags.p, rec.p, v0, nvl, k, vhead.p, vrank.p, list.p, list_n.p, nodemap.p);
+            LAUNCH(ctx, gs_resolve_kernel<W>, (unsigned)ceil_div(nvl, 256), 256, 0, keys, even_k ? flags.p : (const u8 *)nullptr, rec.p, v0, nvl, k, vhead.p, vrank.p, list.p, list_n.p, nodemap.p);
         };
         if (nc) dist_guard(cm, "node discovery", local4); else local4();
         if (nc) NCK(nc->AllReduce(nodemap.p, nodemap.p, nmw, ncclUint32, ncclSum, cm->comm, ctx->stream));   // disjoint bits: sum = or
@@ -385,7 +412,7 @@ static gg_graph *build_graph_sharded(gg_ctx *ctx, const u64 *keys, u64 U, int k,
         if (nc) dist_guard(cm, "node table", local5); else local5();
         if (nc && nn) NCK(nc->AllReduce(ntab.p, ntab.p, 4 * nn, ncclUint32, ncclSum, cm->comm, ctx->stream));
         g->n_nodes = nn;
-        DBuf<u32> node_off32, node_first, node_last;
+        DBuf<u32> node_off32, node_first, node_last, packed;
         u64 total_bases = 0;
         auto local6 = [&] {
             DBuf<u32> node_len(ctx, nn + 1);
@@ -399,22 +426,24 @@ static gg_graph *build_graph_sharded(gg_ctx *ctx, const u64 *keys, u64 U, int k,
             g->d_bases = dalloc<u8>(ctx, total_bases + 16);
             g->d_node_off = dalloc<u64>(ctx, nn + 1);
             LAUNCH(ctx, widen_offsets_kernel, (unsigned)ceil_div(nn + 1, 256), 256, 0, node_off32.p, nn, total_bases, g->d_node_off);
-            if (nc) {   // every rank contributes the bases / end vertices of its own vertices: zero elsewhere, summed below
-                dfill(ctx, g->d_bases, total_bases, 0u);
+            packed.alloc(ctx, total_bases / 16 + 4);
+            dfill(ctx, packed.p, (total_bases / 16 + 1) * sizeof(u32), 0u);
+            if (nc) {   // every rank contributes the codes / end vertices of its own vertices: zero elsewhere, summed below
                 dfill(ctx, node_first.p, (nn + 1) * sizeof(u32), 0u);
                 dfill(ctx, node_last.p, (nn + 1) * sizeof(u32), 0u);
             }
             LAUNCH(ctx, gs_emit_kernel<W>, (unsigned)ceil_div(nvl, 256), 256, 0, keys, rec.p, vhead.p, vrank.p, v0, nvl, k, nsel.p, ntab.p, node_off32.p,
-                   g->d_bases, node_first.p, node_last.p);
+                   packed.p, node_first.p, node_last.p);
         };
         if (nc) dist_guard(cm, "node emission", local6); else local6();
         if (nc) {
-            if (total_bases) NCK(nc->AllReduce(g->d_bases, g->d_bases, total_bases, ncclUint8, ncclSum, cm->comm, ctx->stream));
+            if (total_bases) NCK(nc->AllReduce(packed.p, packed.p, total_bases / 16 + 1, ncclUint32, ncclSum, cm->comm, ctx->stream));   // disjoint bits
             if (nn) {
                 NCK(nc->AllReduce(node_first.p, node_first.p, nn, ncclUint32, ncclSum, cm->comm, ctx->stream));
                 NCK(nc->AllReduce(node_last.p, node_last.p, nn, ncclUint32, ncclSum, cm->comm, ctx->stream));
             }
         }
+        if (total_bases) LAUNCH(ctx, gs_unpack_kernel, (unsigned)ceil_div(ceil_div(total_bases, 16), 256), 256, 0, packed.p, total_bases, g->d_bases);
         stage_end(ctx, ST_UNITIG);
         // ---- K8: links (on every rank: two records per node) ----
         stage_begin(ctx, ST_LINKS);
