@@ -46,8 +46,30 @@ struct gg_ctx {
     // user events (gg_ctx_event_record / gg_ctx_event_elapsed_ms)
     cudaEvent_t user_ev[8];
     struct GgArena *arena = nullptr;  // caching device allocator (below)
+    int live_handles = 0;             // gg_counts / gg_graph / gg_umi / gg_comm objects that still own memory of this context
+    bool dying = false;               // gg_ctx_destroy was called while handles were alive: the last handle tears the context down
     int coop_blocks = -1;             // co-resident CTAs per SM of the cooperative list-ranking kernel on this device (-1: not asked yet)
     std::set<const void *> smem_attr_done;  // kernels whose dynamic shared-memory limit was raised on THIS device
+};
+
+// Handles keep their context alive: host languages with garbage collection (the Julia layer's finalizers) free
+// objects in no particular order, so gg_ctx_destroy only marks a context that still has live handles and the last
+// handle's release performs the teardown.
+static void gg_ctx_destroy_now(gg_ctx *ctx);
+struct CtxRef {
+    gg_ctx *p = nullptr;
+    CtxRef() {}
+    CtxRef(const CtxRef &) = delete;
+    CtxRef &operator=(const CtxRef &) = delete;
+    CtxRef &operator=(gg_ctx *c) { release(); p = c; if (p) ++p->live_handles; return *this; }
+    operator gg_ctx *() const { return p; }
+    gg_ctx *operator->() const { return p; }
+    void release() {
+        gg_ctx *c = p;
+        p = nullptr;
+        if (c && --c->live_handles == 0 && c->dying) gg_ctx_destroy_now(c);
+    }
+    ~CtxRef() { release(); }
 };
 
 struct GgError {

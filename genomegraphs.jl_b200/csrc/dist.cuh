@@ -70,7 +70,7 @@ static NcclApi *nccl_api() {
     } while (0)
 
 struct gg_comm {
-    gg_ctx *ctx = nullptr;
+    CtxRef ctx;
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
     // receive buffer of the fused scatter + exchange, mapped into every peer with CUDA IPC

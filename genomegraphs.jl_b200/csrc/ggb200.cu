@@ -14,7 +14,7 @@
 #include "synth.cuh"
 
 struct gg_counts {
-    gg_ctx *ctx = nullptr;
+    CtxRef ctx;
     int k = 0, W = 0;
     u64 n_unique = 0, n_instances = 0;
     u64 *d_keys = nullptr;   // n_unique * W, sorted ascending
@@ -115,6 +115,11 @@ int gg_ctx_create(int device, gg_ctx **out) {
 }
 void gg_ctx_destroy(gg_ctx *ctx) {
     if (!ctx) return;
+    if (ctx->live_handles > 0) { ctx->dying = true; return; }   // the last handle to go finishes the job (CtxRef::release)
+    gg_ctx_destroy_now(ctx);
+}
+}  // extern "C"
+static void gg_ctx_destroy_now(gg_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 2 * GG_NSTAGE; ++i) cudaEventDestroy(ctx->ev[i]);
@@ -132,6 +137,7 @@ void gg_ctx_destroy(gg_ctx *ctx) {
     for (auto e : ctx->chunk_ev) cudaEventDestroy(e);
     delete ctx;
 }
+extern "C" {
 const char *gg_last_error(gg_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 int gg_host_alloc(gg_ctx *ctx, uint64_t bytes, void **out) {

@@ -482,7 +482,7 @@ __global__ void fill_u64_kernel(u64 *p, u64 n, u64 v) {
 }
 
 struct gg_graph {
-    gg_ctx *ctx = nullptr;
+    CtxRef ctx;
     int k = 0;
     u64 n_nodes = 0, total_bases = 0, n_link_entries = 0;
     u64 *d_node_off = nullptr;  // n_nodes + 1

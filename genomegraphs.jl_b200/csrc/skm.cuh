@@ -455,13 +455,15 @@ __global__ void __launch_bounds__(THREADS) skm_leaf_kernel(const ulonglong2 *__r
                     const u32 nbefore = __popc(__ballot_sync(FULL_MASK, len != 0 && start <= p));
                     const u32 le = lane_id() == 31 ? 0xFFFFFFFFu : ((2u << lane_id()) - 1u);
                     const u32 r = (nbefore - 1u + __popc(smask & 0xFFFFFFFEu & le)) & 31u;
-                    const u64 A0 = __shfl_sync(FULL_MASK, a0, r);
-                    const u64 A1 = (u64)__shfl_sync(FULL_MASK, a1h, r) << 32;
+                    const u32 W0 = __shfl_sync(FULL_MASK, (u32)(a0 >> 32), r);   // bases 0..15 of the record
+                    const u32 W1 = __shfl_sync(FULL_MASK, (u32)a0, r);           // 16..31
+                    const u32 W2 = __shfl_sync(FULL_MASK, a1h, r);               // 32..47
                     const u32 st = __shfl_sync(FULL_MASK, start, r);
                     const u32 q = p + lane_id();
+                    u32 claimed = 0xFFFFFFFFu;   // slot this lane claimed (first occurrence of its key in the bin)
                     if (q < T) {
-                        const int j2 = 2 * (int)(q - st);  // window q - st of record r
-                        const u64 fl = ((A0 << j2) | ((A1 >> 1) >> (63 - j2))) & topmask;
+                        const u32 j2 = 2u * (q - st);  // window q - st of record r: 64 bits from bit offset j2 <= 32 (two funnel shifts)
+                        const u64 fl = (((u64)__funnelshift_lc(W1, W0, j2) << 32) | __funnelshift_lc(W2, W1, j2)) & topmask;
                         const u64 fw = fl >> s;
                         const u64 rc = rev2_u64(~fl) & kmask;
                         const u64 key = (canonical && rc < fw) ? rc : fw;
@@ -471,16 +473,20 @@ __global__ void __launch_bounds__(THREADS) skm_leaf_kernel(const ulonglong2 *__r
                             u64 c = S.tab[slot];
                             if (c == MSD_EMPTY) {
                                 c = atomicCAS((unsigned long long *)&S.tab[slot], (unsigned long long)MSD_EMPTY, (unsigned long long)key);
-                                if (c == MSD_EMPTY) {  // claimed: first occurrence
-                                    const u32 li = atomicAdd(ndp, 1u);
-                                    if (li < LIST) S.list[li] = (u16)slot; else *ovf = 1;
-                                    break;
-                                }
+                                if (c == MSD_EMPTY) { claimed = slot; break; }
                             }
                             if (c == key) { atomicAdd(&S.tcnt[slot], 1u); break; }
                             slot = (slot + 1) & HM;
                             if (++probes > SKM_MAXPROBE) { *ovf = 1; break; }
                         }
+                    }
+                    // the claimed slots go on the bin's list: one reservation per warp and round
+                    const u32 cm = __ballot_sync(FULL_MASK, claimed != 0xFFFFFFFFu);
+                    if (cm) {
+                        u32 lb = 0;
+                        if (lane_id() == 0) lb = atomicAdd(ndp, (u32)__popc(cm));
+                        lb = __shfl_sync(FULL_MASK, lb, 0) + __popc(cm & lanemask_lt());
+                        if (claimed != 0xFFFFFFFFu) { if (lb < LIST) S.list[lb] = (u16)claimed; else *ovf = 1; }
                     }
                 }
                 if (__any_sync(FULL_MASK, *ovf != 0)) break;

@@ -8,7 +8,7 @@
 #include "sort.cuh"
 
 struct gg_umi {
-    gg_ctx *ctx = nullptr;
+    CtxRef ctx;
     int k = 0, W = 0;
     u64 n_unique = 0, n_nodes = 0;
     u64 *d_keys = nullptr;   // n_unique * W

@@ -28,8 +28,11 @@ function find_unique_mer(idx::UniqueMerIndex{M}, mer::M) where {M<:AbstractMer}
     return pos != GraphStrandPosition(0, 0), pos
 end
 
-mer_from_words(::Type{M}, w, i) where {M<:Mer} = M(w[i])
-mer_from_words(::Type{M}, w, i) where {M<:BigMer} = M((UInt128(w[2i - 1]) << 64) | UInt128(w[2i]))
+# (the library picks the word count from k, not from the Julia type: BigMer{A,K} with K <= 32 is one word)
+function mer_from_words(::Type{M}, words, i, w) where {M<:AbstractMer}
+    x = w == 1 ? UInt128(words[i]) : ((UInt128(words[2i - 1]) << 64) | UInt128(words[2i]))
+    return M <: BigMer ? M(x) : M(UInt64(x))
+end
 
 function UniqueMerIndex{M}(sg::Graphs.SequenceDistanceGraph; ctx::LibGG.Context = LibGG.default_context()) where {M<:AbstractMer}
     buf = IOBuffer()
@@ -38,11 +41,11 @@ function UniqueMerIndex{M}(sg::Graphs.SequenceDistanceGraph; ctx::LibGG.Context 
         print(buf, n.seq)
         push!(offs, UInt64(position(buf)))
     end
-    words, node, pos, upn, tpn, _ = LibGG.unique_mer_index(ctx, take!(buf), offs, BioSequences.ksize(M))
+    words, node, pos, upn, tpn, w = LibGG.unique_mer_index(ctx, take!(buf), offs, BioSequences.ksize(M))
     d = Dict{M,GraphStrandPosition}()
     sizehint!(d, length(node))
     for i in eachindex(node)
-        d[mer_from_words(M, words, i)] = GraphStrandPosition(node[i], pos[i])
+        d[mer_from_words(M, words, i, w)] = GraphStrandPosition(node[i], pos[i])
     end
     return UniqueMerIndex{M}(d, upn, tpn)
 end

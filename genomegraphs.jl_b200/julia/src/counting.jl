@@ -39,11 +39,7 @@ function (gc::GPUCounter{M,C})(reads) where {M,C}
 end
 
 "Device table -> `Vector{MerCount{M}}` (sorted by k-mer, UInt8-saturated counts)."
-function Base.collect(c::DeviceMerCounts{M}) where {M<:Mer}
-    words, c8, _ = LibGG.counts_export(c.ctx, c.h)
-    return [MerCount{M}(M(words[i]), c8[i]) for i in eachindex(c8)]
-end
-function Base.collect(c::DeviceMerCounts{M}) where {M<:BigMer}
-    words, c8, _ = LibGG.counts_export(c.ctx, c.h)
-    return [MerCount{M}(M((UInt128(words[2i - 1]) << 64) | UInt128(words[2i])), c8[i]) for i in eachindex(c8)]
+function Base.collect(c::DeviceMerCounts{M}) where {M<:AbstractMer}
+    words, c8, w = LibGG.counts_export(c.ctx, c.h)
+    return [MerCount{M}(mer_from_words(M, words, i, w), c8[i]) for i in eachindex(c8)]
 end

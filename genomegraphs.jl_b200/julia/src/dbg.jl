@@ -6,45 +6,58 @@
 
 const GRAPH_TYPE = Graphs.SequenceDistanceGraph{LongSequence{DNAAlphabet{4}}}
 
-# k-mer value -> W little-endian UInt64 words, most significant word first (include/ggb200.h)
-@inline kmer_words!(dst::Vector{UInt64}, i::Int, m::Mer{A,K}) where {A,K} =
-    (@inbounds dst[i] = UInt64(BioSequences.encoded_data(m)); nothing)
-@inline function kmer_words!(dst::Vector{UInt64}, i::Int, m::BigMer{A,K}) where {A,K}
-    x = UInt128(BioSequences.encoded_data(m))
-    @inbounds dst[2i - 1] = UInt64(x >> 64)
-    @inbounds dst[2i] = UInt64(x & typemax(UInt64))
-    nothing
-end
-words_per_mer(::Type{<:Mer}) = 1
-words_per_mer(::Type{<:BigMer}) = 2
+# k-mer value -> W UInt64 words, most significant word first (include/ggb200.h).  W comes from the LIBRARY
+# (gg_kmer_words(k): 1 word for k <= 32, 2 for k <= 64), not from the Julia type: BigMer{A,K} with K <= 32 is legal
+# in the reference and still travels as one word.
+@inline kmer_value(m::AbstractMer) = UInt128(BioSequences.encoded_data(m))
+words_per_mer(::Type{M}) where {M<:AbstractMer} = LibGG.kmer_words(BioSequences.ksize(M))
 
 function pack_kmers(kmers::AbstractVector{M}) where {M<:AbstractMer}
     w = words_per_mer(M)
+    w in (1, 2) || throw(ArgumentError("k-mers of this length are not representable as Mer / BigMer"))
     words = Vector{UInt64}(undef, w * length(kmers))
     for (i, m) in enumerate(kmers)
-        kmer_words!(words, i, m)
+        x = kmer_value(m)
+        if w == 1
+            @inbounds words[i] = UInt64(x & typemax(UInt64))
+        else
+            @inbounds words[2i - 1] = UInt64(x >> 64)
+            @inbounds words[2i] = UInt64(x & typemax(UInt64))
+        end
     end
     return words
+end
+
+"word `i` (1-based k-mer index) of an exported table of `w`-word k-mers -> `M`"
+@inline function mer_from_words(::Type{M}, words::Vector{UInt64}, i::Int, w::Int) where {M<:AbstractMer}
+    x = w == 1 ? UInt128(words[i]) : ((UInt128(words[2i - 1]) << 64) | UInt128(words[2i]))
+    return M <: BigMer ? M(x) : M(UInt64(x))
 end
 
 @inline function dbg_message(x::AbstractVector{M}) where {M<:AbstractMer}
     return string("Constructing a compressed de-bruijn graph from ", length(x), ' ', BioSequences.ksize(M), "-mers")
 end
 
-# fill the (empty) graph from the exported arrays
+# Append the exported nodes and links to the graph.  Like build_unitigs! (src/dbg.jl:156, :179) the nodes are pushed
+# behind whatever the graph already holds, so on a non-empty graph the new ids (and the ids inside the new links) are
+# shifted by the number of nodes that were there.  One deviation, stated: the reference's link pass
+# (src/dbg.jl:224-240) runs over ALL nodes of the graph and would also link old nodes with new ones (and re-add the old
+# links a second time); here only the links among the new nodes are made -- dbg! is meant for an empty graph
+# (`empty_graph`, docs/src/man/assembly.md:165-190), which is the case in which both agree exactly.
 function fill_graph!(sdg::GRAPH_TYPE, node_off, bases, link_row, tri)
     nn = length(node_off) - 1
     base_id = Graphs.n_nodes(sdg)
-    base_id == 0 || throw(ArgumentError("dbg! expects an empty graph (link ids are absolute)"))
-    sizehint!(Graphs.nodes(sdg), nn)
+    base_id == 0 || @warn "dbg! on a non-empty graph: links between the existing nodes and the new unitigs are not created"
+    sizehint!(Graphs.nodes(sdg), base_id + nn)
     for i in 1:nn
         lo, hi = Int(node_off[i]) + 1, Int(node_off[i + 1])
         Graphs.add_node!(sdg, LongSequence{DNAAlphabet{4}}(String(bases[lo:hi])))
     end
+    shift(id) = id > 0 ? id + base_id : id - base_id
     for i in 1:nn
-        lv = Graphs.links(sdg)[i]
+        lv = Graphs.links(sdg)[base_id + i]
         for j in (Int(link_row[i]) + 1):Int(link_row[i + 1])
-            push!(lv, Graphs.SDGLink(tri[3j - 2], tri[3j - 1], tri[3j]))
+            push!(lv, Graphs.SDGLink(shift(tri[3j - 2]), shift(tri[3j - 1]), tri[3j]))
         end
     end
     return sdg
@@ -67,6 +80,11 @@ function dbg!(sdg::GRAPH_TYPE, kmers; ctx::LibGG.Context = LibGG.default_context
     end
     @info dbg_message(kmers)
     M = eltype(kmers)
+    # build_unitigs! sorts the CALLER's vector when it is not sorted (src/dbg.jl:98-100): same visible side effect
+    # (the device would sort its own copy otherwise, leaving the caller's order unchanged)
+    if kmers isa AbstractVector && !issorted(kmers)
+        sort!(kmers)
+    end
     c = LibGG.counts_from_kmers(ctx, pack_kmers(kmers), length(kmers), BioSequences.ksize(M))
     try
         dbg_from_handle!(sdg, ctx, c)

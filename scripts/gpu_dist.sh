@@ -6,8 +6,9 @@ nvidia-smi -L > gpurun_out/dist_${tag}_gpus.txt
 timeout 900 python -m pytest tests/test_dist.py -m gpu -x -q --timeout=600 > gpurun_out/dist_${tag}_tests.log 2>&1; echo "dist tests rc=$?"; tail -25 gpurun_out/dist_${tag}_tests.log
 GG_DIST_NO_IPC=1 timeout 900 python -m pytest tests/test_dist.py -m gpu -x -q --timeout=600 > gpurun_out/dist_${tag}_tests_noipc.log 2>&1; echo "dist tests (no IPC) rc=$?"; tail -5 gpurun_out/dist_${tag}_tests_noipc.log
 if [ "$N" -gt 1 ]; then
+  nvidia-smi nvlink -gt d -i 0 > gpurun_out/dist_${tag}_nvlink_before.txt 2>&1
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29600+N)) bench.py --gpus $N --steps 5 --warmup 3 --workload $wl > gpurun_out/scale_${tag}_n$N.json 2> gpurun_out/scale_${tag}_n$N.err
-  echo "bench N=$N rc=$?"; grep -v OMP_NUM gpurun_out/scale_${tag}_n$N.err | tail -8
+  echo "bench N=$N rc=$?"; nvidia-smi nvlink -gt d -i 0 > gpurun_out/dist_${tag}_nvlink_after.txt 2>&1; grep -v OMP_NUM gpurun_out/scale_${tag}_n$N.err | tail -8
   python - gpurun_out/scale_${tag}_n$N.json <<'PY'
 import json,sys
 try:

@@ -71,3 +71,12 @@ def test_gpu_dist_world2(pkg):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     _launch("gpu", 2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [4, 8])
+def test_gpu_dist_world_n(pkg, world):
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    _launch("gpu", world)
