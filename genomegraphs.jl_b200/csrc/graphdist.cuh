@@ -22,6 +22,7 @@
 //
 // Perfect circles (src/dbg.jl:160-181) are rare; when any rank sees one, all ranks fall back to graph.cuh.
 #pragma once
+#include <memory>
 #include "graph.cuh"
 
 struct GsPeers {
@@ -249,6 +250,18 @@ __global__ void gs_unpack_kernel(const u32 *__restrict__ packed, u64 nbases, u8 
     else for (u64 e = 0; w * 16 + e < nbases; ++e) bases[w * 16 + e] = (u8)(o[e >> 2] >> (8 * (e & 3)));
 }
 
+// walk labels a rank wrote for vertices of ANOTHER rank's range: compacted to (vertex index inside the range, label)
+struct LabelF {
+    const u64 *lab;   // the range of the full-size label array
+    u32 *oidx;
+    u64 *olab;
+    __device__ bool pred(u64 i) const { return lab[i] != ~0ULL; }
+    __device__ void emit(u64 i, u64 dst) const { oidx[dst] = (u32)i; olab[dst] = lab[i]; }
+};
+__global__ void gs_apply_labels_kernel(const u32 *__restrict__ idx, const u64 *__restrict__ lab, u64 n, u64 *__restrict__ shard) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) shard[idx[i]] = lab[i];
+}
 // rank p's piece buf[off[p] .. + cnt[p]) (elements of esz bytes) -> every rank, in place
 static void dist_allgatherv_inplace(gg_comm *cm, void *buf, const u64 *off, const u64 *cnt, size_t esz) {
     NcclApi *nc = nccl_api();
@@ -324,12 +337,17 @@ static gg_graph *build_graph_sharded(gg_ctx *ctx, const u64 *keys, u64 U, int k,
         // ---- K6: successor pointers ----
         stage_begin(ctx, ST_UNITIG);
         DBuf<u32> bits;
+        // walk labels: 0 = every rank labels into a full-size local array and the labels that belong to other ranks are
+        // compacted and exchanged in bulk (default); 1 = peer stores into the owners' shards (CUDA IPC); 2 = full-size
+        // arrays merged with ncclAllReduce(min).  Measured on 4 x B200 (C3): the 8-byte peer stores, random over the
+        // owner's shard, reach 0.4 G stores/s per GPU -- 110 ms for the walks against 4 ms here.
+        const int label_route = getenv("GG_GRAPH_LABELS") ? atoi(getenv("GG_GRAPH_LABELS")) : 0;
         bool ipc = false;
         DBuf<u64> own_full;
         GsPeers pt;
         memset(&pt, 0, sizeof(pt));
         pt.vchunk = nvl;
-        if (nc) ipc = dist_ensure_recv(cm, nvl);   // collective: the exchange buffer doubles as the ownloc shard
+        if (nc && label_route == 1) ipc = dist_ensure_recv(cm, nvl);   // collective: the exchange buffer doubles as the label shard
         auto local2 = [&] {
             succ.alloc(ctx, nvp);
             LAUNCH(ctx, gs_succ_kernel, (unsigned)ceil_div(chunk, 256), 256, 0, flags.p, nbF.p, nbB.p, chunk * me, chunk, U, succ.p);
@@ -374,7 +392,40 @@ static gg_graph *build_graph_sharded(gg_ctx *ctx, const u64 *keys, u64 U, int k,
             for (int q = 0; q < P; ++q) { off[q] = soffs[q]; cnt[q] = soffs[q + 1] - soffs[q]; }
             dist_allgatherv_inplace(cm, redA.p, off, cnt, sizeof(u64));      // (also: every rank's peer stores have landed)
             dist_allgatherv_inplace(cm, red_tail.p, off, cnt, sizeof(u32));
-            if (!ipc) NCK(nc->AllReduce(own_full.p, own_full.p, nvp, ncclUint64, ncclMin, cm->comm, ctx->stream));
+            if (!ipc && label_route == 2) NCK(nc->AllReduce(own_full.p, own_full.p, nvp, ncclUint64, ncclMin, cm->comm, ctx->stream));
+            if (!ipc && label_route != 2) {
+                // ---- labels of foreign vertices: compacted per owner, counts all-gathered, one exchange, applied by the owner ----
+                DBuf<u32> sidx_, ridx_;
+                DBuf<u64> slab_, rlab_, cntd;
+                std::vector<u64> scnt(P, 0), soff(P, 0), rcnt(P, 0), roff(P, 0), allc((size_t)P * P, 0);
+                dist_guard(cm, "label compaction", [&] {
+                    cntd.alloc(ctx, (u64)P * P + P);
+                    std::vector<std::unique_ptr<Compactor<LabelF>>> cps(P);
+                    u64 run = 0;
+                    for (int q = 0; q < P; ++q) {
+                        soff[q] = run;
+                        if (q == me) continue;
+                        cps[q].reset(new Compactor<LabelF>(ctx, nvl, "label"));
+                        scnt[q] = cps[q]->count(LabelF{own_full.p + (u64)q * nvl, nullptr, nullptr});
+                        run += scnt[q];
+                    }
+                    sidx_.alloc(ctx, run + 1); slab_.alloc(ctx, run + 1);
+                    for (int q = 0; q < P; ++q)
+                        if (q != me) cps[q]->emit(LabelF{own_full.p + (u64)q * nvl, sidx_.p + soff[q], slab_.p + soff[q]});
+                    CK(cudaStreamSynchronize(ctx->stream));   // the compactors' tile counts go back to the allocator
+                    CK(cudaMemcpyAsync(cntd.p + (u64)P * P, scnt.data(), P * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+                });
+                NCK(nc->AllGather(cntd.p + (u64)P * P, cntd.p, P, ncclUint64, cm->comm, ctx->stream));
+                CK(cudaMemcpyAsync(allc.data(), cntd.p, (size_t)P * P * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+                u64 nrecv = 0;
+                for (int p = 0; p < P; ++p) { roff[p] = nrecv; rcnt[p] = allc[(size_t)p * P + me]; nrecv += rcnt[p]; }
+                dist_guard(cm, "label receive buffers", [&] { ridx_.alloc(ctx, nrecv + 1); rlab_.alloc(ctx, nrecv + 1); });
+                dist_alltoallv(cm, sidx_.p, soff.data(), scnt.data(), ridx_.p, roff.data(), rcnt.data(), sizeof(u32));
+                dist_alltoallv(cm, slab_.p, soff.data(), scnt.data(), rlab_.p, roff.data(), rcnt.data(), sizeof(u64));
+                if (nrecv) LAUNCH(ctx, gs_apply_labels_kernel, (unsigned)ceil_div(nrecv, 256), 256, 0, ridx_.p, rlab_.p, nrecv, own_full.p + (u64)nvl * me);
+                CK(cudaStreamSynchronize(ctx->stream));   // the exchange buffers go back to the allocator
+            }
         }
         const u64 *ownloc = ipc ? cm->R : (own_full.p + (u64)nvl * me);
         if (!nc) ownloc = own_full.p;
@@ -458,7 +509,15 @@ static gg_graph *build_graph_sharded(gg_ctx *ctx, const u64 *keys, u64 U, int k,
     }
 }
 
-// every rank's sorted slice (slices in key order by rank) -> the whole table on every rank, pieces received in place
+// every rank's sorted slice (slices in key order by rank) -> the whole table on every rank.  The slices are balanced, so
+// they are padded to the largest one and moved with ONE ncclAllGather (ring / NVLS inside NCCL: a mesh of sends costs
+// several times more at 8 ranks), then compacted.
+__global__ void keys_compact_kernel(const u64 *__restrict__ pk, u64 maxw, int P, const u64 *__restrict__ nw, const u64 *__restrict__ offw, u64 *__restrict__ keys) {
+    for (int p = 0; p < P; ++p) {
+        const u64 np = nw[p], o = offw[p];
+        for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < np; i += (u64)gridDim.x * blockDim.x) keys[o + i] = pk[(u64)p * maxw + i];
+    }
+}
 template <int W>
 static u64 keys_allgatherv(gg_comm *cm, const u64 *slice, u64 n_local, DBuf<u64> &keys) {
     NcclApi *nc = nccl_api();
@@ -466,18 +525,23 @@ static u64 keys_allgatherv(gg_comm *cm, const u64 *slice, u64 n_local, DBuf<u64>
     const int P = cm->world;
     DBuf<u64> sz;
     dist_guard(cm, "table sizes", [&] {
-        sz.alloc(ctx, P + 1);
-        CK(cudaMemcpyAsync(sz.p + P, &n_local, sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+        sz.alloc(ctx, 3 * (u64)P + 1);
+        CK(cudaMemcpyAsync(sz.p + 3 * P, &n_local, sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
     });
-    NCK(nc->AllGather(sz.p + P, sz.p, 1, ncclUint64, cm->comm, ctx->stream));
-    u64 n[MSD_MAX_PEERS], off[MSD_MAX_PEERS], total = 0;
+    NCK(nc->AllGather(sz.p + 3 * P, sz.p, 1, ncclUint64, cm->comm, ctx->stream));
+    u64 n[MSD_MAX_PEERS], nwo[2 * MSD_MAX_PEERS], total = 0, maxn = 1;
     CK(cudaMemcpyAsync(n, sz.p, P * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    for (int p = 0; p < P; ++p) { off[p] = total; total += n[p]; }
+    for (int p = 0; p < P; ++p) { nwo[p] = n[p] * W; nwo[P + p] = total * W; total += n[p]; maxn = n[p] > maxn ? n[p] : maxn; }
+    DBuf<u64> mk, pk;
     dist_guard(cm, "gathered table", [&] {
         keys.alloc(ctx, (total ? total : 1) * W);
-        if (n_local) CK(cudaMemcpyAsync(keys.p + off[cm->rank] * W, slice, n_local * W * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream));
+        mk.alloc(ctx, maxn * W); pk.alloc(ctx, (u64)P * maxn * W);
+        CK(cudaMemcpyAsync(sz.p + P, nwo, 2 * P * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+        if (n_local) CK(cudaMemcpyAsync(mk.p, slice, n_local * W * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream));
     });
-    dist_allgatherv_inplace(cm, keys.p, off, n, sizeof(u64) * W);
+    NCK(nc->AllGather(mk.p, pk.p, maxn * W, ncclUint64, cm->comm, ctx->stream));
+    LAUNCH(ctx, keys_compact_kernel, (unsigned)(ctx->num_sms * 8), 256, 0, pk.p, maxn * W, P, sz.p + P, sz.p + 2 * P, keys.p);
+    CK(cudaStreamSynchronize(ctx->stream));   // nwo / the padded buffers
     return total;
 }
