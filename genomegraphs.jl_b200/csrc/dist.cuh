@@ -478,7 +478,12 @@ static u64 dist_range_repartition(gg_comm *cm, DBuf<u64> &uk, DBuf<u32> &uc, u64
     dist_guard(cm, "merge of the received runs", [&] {
         CK(cudaStreamSynchronize(ctx->stream));
         uk.release(); uc.release();
-        Uout = skm_sort_pairs(ctx, rk.p, rc.p, n_recv, n_recv, k, ukeys, ucounts);   // P sorted runs -> one (partition by top bits + bucket ordering)
+        // P sorted runs -> one (partition + bucket ordering on the bits below this rank's range prefix)
+        const u64 kbase = (u64)first[me] << sh;
+        const u64 span = (u64)(first[me + 1] - first[me]) << sh;
+        int kbits = 0;
+        while (kbits < 2 * k && (1ULL << kbits) < span) ++kbits;
+        Uout = skm_sort_pairs(ctx, rk.p, rc.p, n_recv, n_recv, k, ukeys, ucounts, kbase, kbits);
     });
     return Uout;
 }

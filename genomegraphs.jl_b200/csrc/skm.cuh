@@ -592,7 +592,7 @@ __global__ void skm_ovf_expand_kernel(const ulonglong2 *__restrict__ recs, const
 #define PS_MAX_NB 512
 template <int MODE>
 __global__ void __launch_bounds__(PS_THREADS) pair_part_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ cnts, const u32 *__restrict__ tile_reg,
-                                                               const u32 *__restrict__ rbase, const u32 *__restrict__ rcnt, u64 n_all, int sh, u32 nb,
+                                                               const u32 *__restrict__ rbase, const u32 *__restrict__ rcnt, u64 n_all, u64 kbase, int sh, u32 nb,
                                                                u32 *__restrict__ hist, const u32 *__restrict__ ostart, u64 *__restrict__ okeys,
                                                                u32 *__restrict__ ocnts) {
     constexpr int PER = PS_TILE / PS_THREADS;
@@ -620,7 +620,7 @@ __global__ void __launch_bounds__(PS_THREADS) pair_part_kernel(const u64 *__rest
     for (int i = 0; i < PER; ++i) {
         const u32 j = threadIdx.x + (u32)i * PS_THREADS;
         kr[i] = j < m ? keys[tile0 + j] : MSD_EMPTY;
-        pos[i] = kr[i] != MSD_EMPTY ? atomicAdd(&h[(u32)(kr[i] >> sh) & dm], 1u) : 0u;
+        pos[i] = kr[i] != MSD_EMPTY ? atomicAdd(&h[(u32)((kr[i] - kbase) >> sh) & dm], 1u) : 0u;
     }
     __syncthreads();
     if (MODE == 0) {
@@ -642,7 +642,7 @@ __global__ void __launch_bounds__(PS_THREADS) pair_part_kernel(const u64 *__rest
         for (int i = 0; i < PER; ++i) {
             const u32 j = threadIdx.x + (u32)i * PS_THREADS;
             if (kr[i] != MSD_EMPTY) {
-                const u32 q = h[(u32)(kr[i] >> sh) & dm] + pos[i];
+                const u32 q = h[(u32)((kr[i] - kbase) >> sh) & dm] + pos[i];
                 sk[q] = kr[i];
                 sc[q] = cnts[tile0 + j];
             }
@@ -650,7 +650,7 @@ __global__ void __launch_bounds__(PS_THREADS) pair_part_kernel(const u64 *__rest
         __syncthreads();
         for (u32 q = threadIdx.x; q < tot; q += PS_THREADS) {
             const u64 key = sk[q];
-            const u32 o = gp[(u32)(key >> sh) & dm] + q;
+            const u32 o = gp[(u32)((key - kbase) >> sh) & dm] + q;
             okeys[o] = key;
             ocnts[o] = sc[q];
         }
@@ -698,7 +698,7 @@ __global__ void skm_sort_big_kernel(const u32 *__restrict__ hist, u32 nb, u32 *_
 // One CTA per bucket (grid-stride): pairs IN[bstart[b] ..) of one top-bits bucket are ordered by key into OUT.
 // Keys are distinct.  Order-preserving bins on the bits below the bucket digit + rank-by-counting inside a bin.
 __global__ void __launch_bounds__(256) skm_sort_bucket_kernel(const u64 *__restrict__ ik, const u32 *__restrict__ ic, const u32 *__restrict__ bstart,
-                                                              u32 nb, int sh, u64 *__restrict__ ok, u32 *__restrict__ oc) {
+                                                              u32 nb, u64 kbase, int sh, u64 *__restrict__ ok, u32 *__restrict__ oc) {
     extern __shared__ __align__(16) u8 smem_raw[];
     u64 *sk = reinterpret_cast<u64 *>(smem_raw);              // SKM_SORT_CAP
     u32 *sc = reinterpret_cast<u32 *>(sk + SKM_SORT_CAP);     // SKM_SORT_CAP
@@ -714,7 +714,7 @@ __global__ void __launch_bounds__(256) skm_sort_bucket_kernel(const u64 *__restr
         __syncthreads();
         for (int i = threadIdx.x; i <= nbins; i += 256) bins[i] = 0;
         __syncthreads();
-        for (u32 i = threadIdx.x; i < n; i += 256) atomicAdd(&bins[(u32)(ik[s0 + i] >> bsh) & bm], 1u);
+        for (u32 i = threadIdx.x; i < n; i += 256) atomicAdd(&bins[(u32)((ik[s0 + i] - kbase) >> bsh) & bm], 1u);
         __syncthreads();
         {   // exclusive scan of bins[0 .. nbins) in place
             const int bpt = (nbins + 255) / 256;
@@ -729,14 +729,14 @@ __global__ void __launch_bounds__(256) skm_sort_bucket_kernel(const u64 *__restr
         __syncthreads();
         for (u32 i = threadIdx.x; i < n; i += 256) {
             const u64 key = ik[s0 + i];
-            const u32 p = atomicAdd(&bincur[(u32)(key >> bsh) & bm], 1u);
+            const u32 p = atomicAdd(&bincur[(u32)((key - kbase) >> bsh) & bm], 1u);
             sk[p] = key;
             sc[p] = ic[s0 + i];
         }
         __syncthreads();
         for (u32 i = threadIdx.x; i < n; i += 256) {
             const u64 key = sk[i];
-            const u32 bi = (u32)(key >> bsh) & bm;
+            const u32 bi = (u32)((key - kbase) >> bsh) & bm;
             const u32 lo = bins[bi], hi = bins[bi + 1];
             u32 rank = 0;
             for (u32 q = lo; q < hi; ++q) rank += sk[q] < key;
@@ -851,7 +851,11 @@ struct SkmLiveF {   // compaction of the kept list: drop the unused slots
 };
 // kept list (unordered; nslots slots in kk / kc, unused ones hold MSD_EMPTY) -> sorted ukeys / ucounts (new buffers);
 // returns the number of pairs
-static u64 skm_sort_pairs(gg_ctx *ctx, u64 *kk, u32 *kc, u64 nslots, u64 n_pairs, int k, DBuf<u64> &ukeys, DBuf<u32> &ucounts) {
+// (kbase, kbits): every key lies in [kbase, kbase + 2^kbits) -- the whole key space by default; a rank of the multi-GPU
+// path hands over its key range, so that the partition digits are taken below the range's common prefix
+static u64 skm_sort_pairs(gg_ctx *ctx, u64 *kk, u32 *kc, u64 nslots, u64 n_pairs, int k, DBuf<u64> &ukeys, DBuf<u32> &ucounts, u64 kbase = 0,
+                          int kbits = -1) {
+    if (kbits < 0 || kbits > 2 * k) { kbits = 2 * k; kbase = 0; }
     if (nslots == 0) { ukeys.alloc(ctx, 1); ucounts.alloc(ctx, 1); return 0; }
     if (nslots >= 0xFFFFFFFFull) GG_THROW(GG_ERR_LIMIT, "%llu kept-list slots exceed the 2^32-1 per-GPU limit", (unsigned long long)nslots);
     auto generic = [&](u64 *keys_io, u32 *cnts_io, u64 cnt, u64 *ok, u32 *oc) {  // LSD radix sort with the count as payload
@@ -879,11 +883,11 @@ static u64 skm_sort_pairs(gg_ctx *ctx, u64 *kk, u32 *kc, u64 nslots, u64 n_pairs
         return n;
     };
     int tb = 0;
-    while (tb < 24 && tb < 2 * k && (n_pairs >> tb) > 1024) ++tb;
+    while (tb < 24 && tb < kbits && (n_pairs >> tb) > 1024) ++tb;
     if (tb < 4) return compact_generic();
     // ---- MSD partition on the top tb key bits in passes of <= 9 bits (staged tiles), then one ordering pass per bucket ----
     const int npass = tb <= 9 ? 1 : tb <= 18 ? 2 : 3;
-    const int sh = 2 * k - tb;
+    const int sh = kbits - tb;
     const u32 nb = 1u << tb;
     DBuf<u32> hist, bstart, big(ctx, 1024), nbig(ctx, 1);
     DBuf<u64> tk, tot(ctx, 1);
@@ -902,7 +906,7 @@ static u64 skm_sort_pairs(gg_ctx *ctx, u64 *kk, u32 *kc, u64 nslots, u64 n_pairs
         int bits_done = 0;
         for (int pass = 0; pass < npass; ++pass) {
             const int bits = (tb - bits_done + (npass - pass) - 1) / (npass - pass);
-            const int psh = 2 * k - bits_done - bits;
+            const int psh = kbits - bits_done - bits;
             const u32 pnb = 1u << bits;
             const bool last = pass == npass - 1;
             const u64 nbuck = (u64)nreg * pnb;
@@ -910,7 +914,7 @@ static u64 skm_sort_pairs(gg_ctx *ctx, u64 *kk, u32 *kc, u64 nslots, u64 n_pairs
             dfill(ctx, h.p, (nbuck + 1) * sizeof(u32), 0u);
             const unsigned ntile = (unsigned)ceil_div(in_slots, PS_TILE);
             prof_bytes(ctx, 8.0 * (double)in_slots);
-            LAUNCH(ctx, pair_part_kernel<0>, ntile, PS_THREADS, ps_smem, ik, ic, tile_reg.p, rbase.p, rcnt.p, in_slots, psh, pnb, h.p, nullptr, nullptr, nullptr);
+            LAUNCH(ctx, pair_part_kernel<0>, ntile, PS_THREADS, ps_smem, ik, ic, tile_reg.p, rbase.p, rcnt.p, in_slots, kbase, psh, pnb, h.p, nullptr, nullptr, nullptr);
             LAUNCH(ctx, pair_starts_kernel, 1, 1024, 0, h.p, (u32)nbuck, last ? 0 : 1, st.p, tot.p);
             if (last) LAUNCH(ctx, skm_sort_big_kernel, (unsigned)ceil_div(nbuck, 256), 256, 0, h.p, (u32)nbuck, big.p, nbig.p);
             const u64 out_slots = read_scalar<u64>(ctx, tot.p);
@@ -920,7 +924,7 @@ static u64 skm_sort_pairs(gg_ctx *ctx, u64 *kk, u32 *kc, u64 nslots, u64 n_pairs
             CK(cudaMemcpyAsync(cnt_keep.p, h.p, (nbuck + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
             dfill(ctx, h.p, (nbuck + 1) * sizeof(u32), 0u);   // now the cursors
             prof_bytes(ctx, 12.0 * (double)in_slots + 12.0 * (double)n_pairs);
-            LAUNCH(ctx, pair_part_kernel<1>, ntile, PS_THREADS, ps_smem, ik, ic, tile_reg.p, rbase.p, rcnt.p, in_slots, psh, pnb, h.p, st.p, ok.p, oc.p);
+            LAUNCH(ctx, pair_part_kernel<1>, ntile, PS_THREADS, ps_smem, ik, ic, tile_reg.p, rbase.p, rcnt.p, in_slots, kbase, psh, pnb, h.p, st.p, ok.p, oc.p);
             if (last) { n = out_slots; bstart = std::move(st); }
             else {   // the buckets become the regions of the next pass
                 tile_reg.alloc(ctx, out_slots / PS_TILE + 1);
@@ -944,7 +948,7 @@ static u64 skm_sort_pairs(gg_ctx *ctx, u64 *kk, u32 *kc, u64 nslots, u64 n_pairs
     const size_t smem = (size_t)SKM_SORT_CAP * 12;
     set_max_smem(ctx, skm_sort_bucket_kernel, smem);
     prof_bytes(ctx, 24.0 * (double)n);
-    LAUNCH(ctx, skm_sort_bucket_kernel, (unsigned)std::min<u64>(nb, (u64)ctx->num_sms * 8), 256, smem, tk.p, tc.p, bstart.p, nb, sh, ukeys.p, ucounts.p);
+    LAUNCH(ctx, skm_sort_bucket_kernel, (unsigned)std::min<u64>(nb, (u64)ctx->num_sms * 8), 256, smem, tk.p, tc.p, bstart.p, nb, kbase, sh, ukeys.p, ucounts.p);
     if (h_nbig) {
         std::vector<u32> hb(h_nbig), hs(2);
         CK(cudaMemcpyAsync(hb.data(), big.p, h_nbig * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
