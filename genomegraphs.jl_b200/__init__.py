@@ -8,6 +8,7 @@ The directory name carries a dot, so import it through `__graft_entry__.load_pac
 from . import _native  # noqa: F401
 from . import dist  # noqa: F401
 from .host import *  # noqa: F401,F403
-from .host import (CANONICAL, NONCANONICAL, Context, GraphArrays, GraphStrandPosition, MerCounts, SDGLink, SDGNode,  # noqa: F401
+from .host import (CANONICAL, NONCANONICAL, Context, DeviceGraph, GraphArrays, GraphStrandPosition, MerCounts, SDGLink, SDGNode,  # noqa: F401
                    SequenceDistanceGraph, UniqueMerIndex, WorkSpace, dbg_, dbg_arrays, dbg_from_reads, empty_graph, extract_kmers, freq,
-                   mer, pack_reads, read_sequences, serial_mem, spectra, synth_genome, synth_reads)
+                   mer, pack_reads, read_sequences, serial_mem, spectra, synth_genome, synth_reads,
+                   count_kmers_4bit, dbg_from_reads_4bit, pack_4bit, spectra_cn, write_gfa1_arrays)

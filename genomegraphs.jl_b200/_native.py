@@ -48,7 +48,15 @@ SIGNATURES = {
     "gg_counts_filter": (C.c_int, [vp, C.c_uint64, C.c_int]),
     "gg_counts_export": (C.c_int, [vp, vp, vp, vp]),
     "gg_counts_spectrum": (C.c_int, [vp, u64p]),
+    "gg_counts_spectrum_cn": (C.c_int, [vp, vp, u64p]),
     "gg_counts_free": (None, [vp]),
+    "gg_count_kmers_4bit": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_int, C.c_int, vpp]),
+    "gg_dbg_from_reads_4bit": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_int, C.c_uint64, vpp]),
+    "gg_graph_find_tip_nodes": (C.c_int, [vp, C.c_uint64, vp, u64p]),
+    "gg_graph_write_gfa1": (C.c_int, [vp, C.c_char_p]),
+    "gg_gfa1_write": (C.c_int, [C.c_char_p, C.c_uint64, vp, vp, vp, vp]),
+    "gg_graph_load_gfa1": (C.c_int, [vp, C.c_char_p, C.c_char_p, vpp]),
+    "gg_graph_from_arrays": (C.c_int, [vp, C.c_int, C.c_uint64, vp, vp, vp, vp, vpp]),
     "gg_extract_kmers": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_int, C.c_int, vp, u64p]),
     "gg_dbg_build": (C.c_int, [vp, vp, vpp]),
     "gg_dbg_from_reads": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_int, C.c_uint64, vpp]),

@@ -12,6 +12,7 @@
 #include "graphdist.cuh"
 #include "umi.cuh"
 #include "synth.cuh"
+#include "gfa.cuh"
 
 struct gg_counts {
     CtxRef ctx;
@@ -242,7 +243,7 @@ static inline u64 dbg_min_freq(u64 min_freq) { return min_freq > 255 ? 0xFFFFFFF
 // pipeline); *filtered tells the caller whether that happened.
 template <int W>
 static gg_counts *count_kmers_dev_impl(gg_ctx *ctx, const u8 *d_seq, const u64 *d_offs, u64 nreads, u64 nbytes, int k, int canonical,
-                                       u64 min_freq = 1, bool *filtered = nullptr) {
+                                       u64 min_freq = 1, bool *filtered = nullptr, int enc = 0) {
     gg_counts *c = new gg_counts();
     c->ctx = ctx; c->k = k; c->W = W;
     if (filtered) *filtered = false;
@@ -250,7 +251,7 @@ static gg_counts *count_kmers_dev_impl(gg_ctx *ctx, const u8 *d_seq, const u64 *
         if (W == 1 && skm_supported(k, canonical) && !getenv("GG_FORCE_LSD") && !getenv("GG_FORCE_MSD")) {
             stage_begin(ctx, ST_PACK);
             PackedReads pr;
-            pack_reads(ctx, d_seq, d_offs, nreads, nbytes, pr);
+            pack_input(ctx, d_seq, d_offs, nreads, nbytes, enc, pr);
             DBuf<u32> valid;
             window_valid_mask(ctx, pr, k, valid);
             stage_end(ctx, ST_PACK);
@@ -265,7 +266,7 @@ static gg_counts *count_kmers_dev_impl(gg_ctx *ctx, const u8 *d_seq, const u64 *
         if (W == 1 && msd_supported(k, canonical) && !getenv("GG_FORCE_LSD")) {
             stage_begin(ctx, ST_PACK);
             PackedReads pr;
-            pack_reads(ctx, d_seq, d_offs, nreads, nbytes, pr);
+            pack_input(ctx, d_seq, d_offs, nreads, nbytes, enc, pr);
             DBuf<u32> valid;
             window_valid_mask(ctx, pr, k, valid);
             stage_end(ctx, ST_PACK);
@@ -282,7 +283,7 @@ static gg_counts *count_kmers_dev_impl(gg_ctx *ctx, const u8 *d_seq, const u64 *
             if (!getenv("GG_FORCE_LSD")) {
                 stage_begin(ctx, ST_PACK);
                 PackedReads pr;
-                pack_reads(ctx, d_seq, d_offs, nreads, nbytes, pr);
+                pack_input(ctx, d_seq, d_offs, nreads, nbytes, enc, pr);
                 DBuf<u32> valid;
                 window_valid_mask(ctx, pr, k, valid);
                 stage_end(ctx, ST_PACK);
@@ -296,6 +297,7 @@ static gg_counts *count_kmers_dev_impl(gg_ctx *ctx, const u8 *d_seq, const u64 *
                 return c;
             }
         }
+        if (enc != 0) GG_THROW(GG_ERR_ARG, "4-bit input is not available together with GG_FORCE_LSD");
         DBuf<u64> keys;
         u64 n = extract_all<W>(ctx, d_seq, d_offs, nreads, nbytes, k, canonical, keys, 0);
         c->n_instances = n;
@@ -698,6 +700,61 @@ int gg_counts_spectrum(gg_counts *c, uint64_t hist[256]) {
     CK(cudaStreamSynchronize(_c->stream));
     API_END
 }
+}  // extern "C"
+// spectra-cn (docs/src/man/assembly.md:221-228: spectra(reads_kcount, graph_kcount)): joint histogram of the UInt8-saturated
+// counts of every k-mer in two tables; a k-mer missing from one table counts 0 there.  hist[a * 256 + b].
+// A_ROWS: every k-mer of table A, looked up in B.  Otherwise: only the k-mers of A that B lacks (their row is 0).
+template <int W, bool A_ROWS>
+__global__ void __launch_bounds__(256) spectrum_cn_kernel(const u64 *__restrict__ ka, const u32 *__restrict__ ca, u64 na, const u64 *__restrict__ kb,
+                                                          const u32 *__restrict__ cb, const u32 *__restrict__ startb, int k, int pbits,
+                                                          unsigned long long *__restrict__ hist) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 bin = 0xFFFFFFFFu;
+    if (i < na) {
+        const u32 idx = find_key<W>(kb, startb, k, pbits, km_load<W>(ka, i));
+        const u32 mine = ca[i] > 255u ? 255u : ca[i];
+        if (A_ROWS) bin = mine * 256u + (idx == V_NONE ? 0u : (cb[idx] > 255u ? 255u : cb[idx]));
+        else if (idx == V_NONE) bin = mine;
+    }
+    // the mass sits in a few bins: one atomic per warp and bin
+    const u32 peers = __match_any_sync(FULL_MASK, bin);
+    if (bin != 0xFFFFFFFFu && lane_id() == (u32)__ffs((int)peers) - 1u) atomicAdd(&hist[bin], (unsigned long long)__popc(peers));
+}
+template <int W>
+static void spectrum_cn_impl(gg_ctx *ctx, gg_counts *a, gg_counts *b, u64 *d_hist) {
+    auto index = [&](gg_counts *t, DBuf<u32> &start, int &pbits) {
+        pbits = t->n_unique ? ilog2_ceil(t->n_unique) - 1 : 0;
+        if (pbits > 24) pbits = 24;
+        if (pbits > 2 * t->k) pbits = 2 * t->k;
+        if (pbits < 0) pbits = 0;
+        start.alloc(ctx, (1ULL << pbits) + 1);
+        LAUNCH(ctx, prefix_index_kernel<W>, (unsigned)ceil_div(t->n_unique + 1, 256), 256, 0, t->d_keys, t->n_unique, t->k, pbits, start.p);
+    };
+    DBuf<u32> sa, sb;
+    int pa = 0, pb = 0;
+    index(a, sa, pa);
+    index(b, sb, pb);
+    if (a->n_unique)
+        LAUNCH(ctx, (spectrum_cn_kernel<W, true>), (unsigned)ceil_div(a->n_unique, 256), 256, 0, a->d_keys, a->d_counts, a->n_unique, b->d_keys, b->d_counts,
+               sb.p, a->k, pb, (unsigned long long *)d_hist);
+    if (b->n_unique)
+        LAUNCH(ctx, (spectrum_cn_kernel<W, false>), (unsigned)ceil_div(b->n_unique, 256), 256, 0, b->d_keys, b->d_counts, b->n_unique, a->d_keys, a->d_counts,
+               sa.p, a->k, pa, (unsigned long long *)d_hist);
+    CK(cudaStreamSynchronize(ctx->stream));
+}
+extern "C" {
+int gg_counts_spectrum_cn(gg_counts *a, gg_counts *b, uint64_t hist[65536]) {
+    if (!a || !b || !hist) return GG_ERR_ARG;
+    API_BEGIN(a->ctx)
+    if ((gg_ctx *)b->ctx != _c || a->k != b->k) GG_THROW(GG_ERR_ARG, "the two count tables must share the context and k");
+    CK(cudaSetDevice(_c->device));
+    DBuf<u64> h(_c, 65536);
+    CK(cudaMemsetAsync(h.p, 0, 65536 * sizeof(u64), _c->stream));
+    DISPATCH_W(a->W, spectrum_cn_impl<W>(_c, a, b, h.p));
+    CK(cudaMemcpyAsync(hist, h.p, 65536 * sizeof(u64), cudaMemcpyDeviceToHost, _c->stream));
+    CK(cudaStreamSynchronize(_c->stream));
+    API_END
+}
 void gg_counts_free(gg_counts *c) {
     if (!c) return;
     cudaSetDevice(c->ctx->device);
@@ -753,12 +810,12 @@ int gg_dbg_build(gg_ctx *ctx, gg_counts *counts, gg_graph **out) {
     timing_collect(_c);
     API_END
 }
-static void dbg_from_reads_dev(gg_ctx *ctx, const u8 *d_seq, const u64 *d_offs, u64 nreads, u64 nbytes, int k, u64 min_freq, gg_graph **out) {
+static void dbg_from_reads_dev(gg_ctx *ctx, const u8 *d_seq, const u64 *d_offs, u64 nreads, u64 nbytes, int k, u64 min_freq, gg_graph **out, int enc = 0) {
     gg_counts *c = nullptr;
     min_freq = dbg_min_freq(min_freq);
     stage_begin(ctx, ST_TOTAL);
     bool filtered = false;
-    DISPATCH_W(kmer_words(k), c = count_kmers_dev_impl<W>(ctx, d_seq, d_offs, nreads, nbytes, k, 1, min_freq, &filtered));
+    DISPATCH_W(kmer_words(k), c = count_kmers_dev_impl<W>(ctx, d_seq, d_offs, nreads, nbytes, k, 1, min_freq, &filtered, enc));
     try {
         if (!filtered) { DISPATCH_W(c->W, filter_impl<W>(c, min_freq, 1)); }
         DISPATCH_W(c->W, *out = build_graph_auto<W>(ctx, c->d_keys, c->n_unique, c->k));
@@ -808,6 +865,109 @@ int gg_dbg_from_reads(gg_ctx *ctx, const uint8_t *seq, const uint64_t *offs, uin
     dbg_from_reads_dev(_c, s.seq.p, s.offs.p, nreads, s.nbytes, k, min_freq, out);
     API_END
 }
+// 4-bit packed host input: half the bytes of ASCII over PCIe; base offsets instead of byte offsets
+static void stage_reads_4bit(gg_ctx *ctx, const u64 *data4, const u64 *offs, u64 nreads, StagedReads &s) {
+    if (!offs) GG_THROW(GG_ERR_ARG, "read_offsets is null");
+    s.nbytes = offs[nreads];   // bases
+    if (s.nbytes && !data4) GG_THROW(GG_ERR_ARG, "packed sequence data is null");
+    const u64 nw = ceil_div(s.nbytes, 16);
+    s.seq.alloc(ctx, (nw + 2) * sizeof(u64));
+    s.offs.alloc(ctx, nreads + 1);
+    CK(cudaEventRecord(ctx->aux_ev, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->aux, ctx->aux_ev, 0));
+    if (nw) CK(cudaMemcpyAsync(s.seq.p, data4, nw * sizeof(u64), cudaMemcpyHostToDevice, ctx->aux));
+    CK(cudaMemcpyAsync(s.offs.p, offs, (nreads + 1) * sizeof(u64), cudaMemcpyHostToDevice, ctx->aux));
+    CK(cudaEventRecord(ctx->aux_ev, ctx->aux));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->aux_ev, 0));
+    check_offsets_host(ctx, offs, nreads);
+}
+int gg_count_kmers_4bit(gg_ctx *ctx, const uint64_t *data4, const uint64_t *offs, uint64_t nreads, int k, int canonical, gg_counts **out) {
+    API_BEGIN(ctx)
+    if (!out) GG_THROW(GG_ERR_ARG, "null output");
+    *out = nullptr;
+    check_k(k);
+    CK(cudaSetDevice(_c->device));
+    timing_reset(_c);
+    StagedReads s;
+    stage_reads_4bit(_c, data4, offs, nreads, s);
+    stage_begin(_c, ST_TOTAL);
+    DISPATCH_W(kmer_words(k), *out = count_kmers_dev_impl<W>(_c, s.seq.p, s.offs.p, nreads, s.nbytes, k, canonical, 1, nullptr, 1));
+    stage_end(_c, ST_TOTAL);
+    timing_collect(_c);
+    API_END
+}
+int gg_dbg_from_reads_4bit(gg_ctx *ctx, const uint64_t *data4, const uint64_t *offs, uint64_t nreads, int k, uint64_t min_freq, gg_graph **out) {
+    API_BEGIN(ctx)
+    if (!out) GG_THROW(GG_ERR_ARG, "null output");
+    *out = nullptr;
+    check_k(k);
+    CK(cudaSetDevice(_c->device));
+    timing_reset(_c);
+    StagedReads s;
+    stage_reads_4bit(_c, data4, offs, nreads, s);
+    dbg_from_reads_dev(_c, s.seq.p, s.offs.p, nreads, s.nbytes, k, min_freq, out, 1);
+    API_END
+}
+// find_tip_nodes (src/Graphs.jl:778-816): node n (not deleted, length <= min_size) is a tip when it has one forward link
+// and no backward link and the node it leads to has more than one link on that side, the mirror case, or no link at all
+__global__ void tip_kernel(const u64 *__restrict__ node_off, const u64 *__restrict__ row, const i64 *__restrict__ tri, u64 nn, u64 min_size,
+                           u32 *__restrict__ flag) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nn) return;
+    const u64 len = node_off[i + 1] - node_off[i];
+    u32 tip = 0;
+    if (len != 0 && len <= min_size) {
+        const i64 n = (i64)(i + 1);
+        u32 fw = 0, bw = 0;
+        i64 dfw = 0, dbw = 0;
+        for (u64 q = row[i]; q < row[i + 1]; ++q) {
+            const i64 s = tri[3 * q], d = tri[3 * q + 1];
+            if (s == -n) { if (!fw) dfw = d; ++fw; }   // is_forwards_from (src/Graphs.jl:188)
+            if (s == n) { if (!bw) dbw = d; ++bw; }    // is_backwards_from (:191)
+        }
+        auto side = [&](i64 m) {   // links of node |m| whose source is m: backward_links(sg, m) = forward_links(sg, -m)
+            const u64 j = (u64)(m < 0 ? -m : m) - 1;
+            u32 c = 0;
+            for (u64 q = row[j]; q < row[j + 1]; ++q) c += tri[3 * q] == m ? 1u : 0u;
+            return c;
+        };
+        if (fw == 1 && bw == 0 && side(dfw) > 1) tip = 1;
+        if (fw == 0 && bw == 1 && side(dbw) > 1) tip = 1;
+        if (fw == 0 && bw == 0) tip = 1;
+    }
+    flag[i] = tip;
+}
+struct TipF {
+    const u32 *flag;
+    i64 *out;
+    __device__ bool pred(u64 i) const { return flag[i] != 0; }
+    __device__ void emit(u64 i, u64 dst) const { out[dst] = (i64)(i + 1); }
+};
+int gg_graph_find_tip_nodes(gg_graph *g, uint64_t min_size, int64_t *tips, uint64_t *n_tips) {
+    if (!g) return GG_ERR_ARG;
+    API_BEGIN(g->ctx)
+    if (!n_tips) GG_THROW(GG_ERR_ARG, "n_tips is null");
+    CK(cudaSetDevice(_c->device));
+    const u64 nn = g->n_nodes;
+    u64 nt = 0;
+    if (nn) {
+        DBuf<u32> flag(_c, nn);
+        LAUNCH(_c, tip_kernel, (unsigned)ceil_div(nn, 256), 256, 0, g->d_node_off, g->d_link_row, g->d_link_tri, nn, (u64)min_size, flag.p);
+        TipF f{flag.p, nullptr};
+        Compactor<TipF> cp(_c, nn, "tips");
+        nt = cp.count(f);
+        if (tips && nt) {
+            if (*n_tips < nt) GG_THROW(GG_ERR_ARG, "output holds %llu node ids, %llu needed", (unsigned long long)*n_tips, (unsigned long long)nt);
+            DBuf<i64> out(_c, nt);
+            f.out = out.p;
+            cp.emit(f);
+            CK(cudaMemcpyAsync(tips, out.p, nt * sizeof(i64), cudaMemcpyDeviceToHost, _c->stream));
+        }
+        CK(cudaStreamSynchronize(_c->stream));
+    }
+    *n_tips = nt;
+    API_END
+}
 int gg_graph_sizes(gg_graph *g, uint64_t *n_nodes, uint64_t *total_bases, uint64_t *n_link_entries, int *k) {
     if (!g) return GG_ERR_ARG;
     if (n_nodes) *n_nodes = g->n_nodes;
@@ -852,6 +1012,74 @@ void gg_graph_free(gg_graph *g) {
     cudaSetDevice(g->ctx->device);
     dfree(g->ctx, g->d_node_off); dfree(g->ctx, g->d_bases); dfree(g->ctx, g->d_link_row); dfree(g->ctx, g->d_link_tri);
     delete g;
+}
+
+// ------------------------------------- persistence ------------------------------------------
+int gg_gfa1_write(const char *filename, uint64_t n_nodes, const uint64_t *node_offsets, const uint8_t *bases_ascii,
+                  const uint64_t *link_row_offsets, const int64_t *link_triples) {
+    return gfa1_write(filename, n_nodes, node_offsets, bases_ascii, link_row_offsets, link_triples);
+}
+int gg_graph_write_gfa1(gg_graph *g, const char *filename) {
+    if (!g) return GG_ERR_ARG;
+    API_BEGIN(g->ctx)
+    if (!filename) GG_THROW(GG_ERR_ARG, "null file name");
+    std::vector<u64> off(g->n_nodes + 1), row(g->n_nodes + 1);
+    std::vector<u8> bases(g->total_bases ? g->total_bases : 1);
+    std::vector<i64> tri(g->n_link_entries ? 3 * g->n_link_entries : 1);
+    const int rc = gg_graph_export(g, off.data(), bases.data(), row.data(), tri.data());
+    if (rc != GG_OK) return rc;
+    if (gfa1_write(filename, g->n_nodes, off.data(), bases.data(), row.data(), tri.data()) != GG_OK)
+        GG_THROW(GG_ERR_ARG, "cannot write %s.gfa / %s.fasta", filename, filename);
+    API_END
+}
+int gg_graph_from_arrays(gg_ctx *ctx, int k, uint64_t n_nodes, const uint64_t *node_offsets, const uint8_t *bases_ascii,
+                         const uint64_t *link_row_offsets, const int64_t *link_triples, gg_graph **out) {
+    API_BEGIN(ctx)
+    if (!out || !node_offsets || !link_row_offsets) GG_THROW(GG_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (node_offsets[0] != 0 || link_row_offsets[0] != 0) GG_THROW(GG_ERR_ARG, "offset arrays must start at 0");
+    for (u64 i = 0; i < n_nodes; ++i)
+        if (node_offsets[i] > node_offsets[i + 1] || link_row_offsets[i] > link_row_offsets[i + 1]) GG_THROW(GG_ERR_ARG, "offset arrays must be non-decreasing");
+    const u64 nb = node_offsets[n_nodes], nl = link_row_offsets[n_nodes];
+    if ((nb && !bases_ascii) || (nl && !link_triples)) GG_THROW(GG_ERR_ARG, "null argument");
+    for (u64 q = 0; q < nl; ++q) {
+        const i64 s = link_triples[3 * q], d = link_triples[3 * q + 1];
+        if (s == 0 || d == 0 || (u64)(s < 0 ? -s : s) > n_nodes || (u64)(d < 0 ? -d : d) > n_nodes) GG_THROW(GG_ERR_ARG, "link %llu names a node outside 1..n", (unsigned long long)q);
+    }
+    CK(cudaSetDevice(_c->device));
+    gg_graph *g = new gg_graph();
+    g->ctx = _c; g->k = k; g->n_nodes = n_nodes; g->total_bases = nb; g->n_link_entries = nl;
+    try {
+        g->d_node_off = dalloc<u64>(_c, n_nodes + 1);
+        g->d_link_row = dalloc<u64>(_c, n_nodes + 1);
+        g->d_bases = dalloc<u8>(_c, nb + 16);
+        g->d_link_tri = dalloc<i64>(_c, 3 * (nl ? nl : 1));
+        CK(cudaMemcpyAsync(g->d_node_off, node_offsets, (n_nodes + 1) * sizeof(u64), cudaMemcpyHostToDevice, _c->stream));
+        CK(cudaMemcpyAsync(g->d_link_row, link_row_offsets, (n_nodes + 1) * sizeof(u64), cudaMemcpyHostToDevice, _c->stream));
+        if (nb) CK(cudaMemcpyAsync(g->d_bases, bases_ascii, nb, cudaMemcpyHostToDevice, _c->stream));
+        if (nl) CK(cudaMemcpyAsync(g->d_link_tri, link_triples, 3 * nl * sizeof(i64), cudaMemcpyHostToDevice, _c->stream));
+        CK(cudaStreamSynchronize(_c->stream));
+    } catch (...) {
+        dfree(_c, g->d_node_off); dfree(_c, g->d_bases); dfree(_c, g->d_link_row); dfree(_c, g->d_link_tri);
+        delete g;
+        throw;
+    }
+    *out = g;
+    API_END
+}
+int gg_graph_load_gfa1(gg_ctx *ctx, const char *gfa_file, const char *fasta_file, gg_graph **out) {
+    API_BEGIN(ctx)
+    if (!out || !gfa_file || !fasta_file) GG_THROW(GG_ERR_ARG, "null argument");
+    *out = nullptr;
+    GfaGraphHost h;
+    std::string err;
+    if (gfa1_read(gfa_file, fasta_file, h, err) != GG_OK) GG_THROW(GG_ERR_ARG, "%s", err.c_str());
+    i64 ov = 0;   // k - 1 = the overlap of the DBG links (0 when the graph has none)
+    if (!h.tri.empty()) ov = -h.tri[2];
+    const u64 nn = h.node_off.size() - 1;
+    const int rc = gg_graph_from_arrays(ctx, (int)(ov > 0 ? ov + 1 : 0), nn, h.node_off.data(), h.bases.data(), h.link_row.data(), h.tri.data(), out);
+    if (rc != GG_OK) return rc;
+    API_END
 }
 
 // ------------------------------------- UMI -------------------------------------------------

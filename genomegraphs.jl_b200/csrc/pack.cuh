@@ -78,6 +78,29 @@ __global__ void __launch_bounds__(256) pack_kernel(const u8 *__restrict__ seq, u
     u32 other = __shfl_down_sync(FULL_MASK, bd, 1);
     if (g < ngroups + (ngroups & 1) && !(g & 1)) bad[g >> 1] = (bd << 16) | (other & 0xFFFFu);
 }
+// 4-bit input (the reference's read store keeps LongSequence{DNAAlphabet{4}}, src/GenomeGraphs.jl:79-83: BioSequences
+// packs 16 bases per UInt64, base i in bits 4i .. 4i+3, A = 0001, C = 0010, G = 0100, T = 1000, anything else
+// ambiguous): one thread = one input word = 16 bases; same outputs as pack_kernel.
+__global__ void __launch_bounds__(256) pack4bit_kernel(const u64 *__restrict__ data4, u64 nbases, u32 *__restrict__ packed32, u32 *__restrict__ bad,
+                                                       u64 g0, u64 ngroups) {
+    u64 g = g0 + (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 pk = 0, bd = 0xFFFFu;
+    if (g < ngroups) {
+        const u64 w = data4[g];
+        bd = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const u32 x = (u32)(w >> (4 * i)) & 15u;
+            const u32 code = ((x >> 1) - (x >> 3)) & 3u;            // 1 -> 0, 2 -> 1, 4 -> 2, 8 -> 3
+            const u32 isbad = (x == 0u || (x & (x - 1u)) != 0u || g * 16 + i >= nbases) ? 1u : 0u;
+            pk |= (isbad ? 0u : code) << (30 - 2 * i);
+            bd |= isbad << (15 - i);
+        }
+    }
+    if (g < ngroups) packed32[(g & ~1ULL) + (1 - (g & 1))] = pk;
+    u32 other = __shfl_down_sync(FULL_MASK, bd, 1);
+    if (g < ngroups + (ngroups & 1) && !(g & 1)) bad[g >> 1] = (bd << 16) | (other & 0xFFFFu);
+}
 __global__ void brk_kernel(const u64 *__restrict__ offs, u64 nreads, u64 nbytes, u32 *__restrict__ brk) {
     u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nreads) return;
@@ -206,6 +229,14 @@ static void pack_range(gg_ctx *ctx, const u8 *d_seq, u64 nbytes, PackedReads &pr
 static void pack_reads(gg_ctx *ctx, const u8 *d_seq, const u64 *d_offs, u64 nreads, u64 nbytes, PackedReads &pr) {
     pack_prepare(ctx, d_offs, nreads, nbytes, pr);
     pack_range(ctx, d_seq, nbytes, pr, 0, ceil_div(nbytes, 16));
+}
+
+// enc: 0 = ASCII bytes, 1 = 4-bit (d_seq is then an array of u64, 16 bases each; nbytes = number of bases)
+static void pack_input(gg_ctx *ctx, const u8 *d_seq, const u64 *d_offs, u64 nreads, u64 nbytes, int enc, PackedReads &pr) {
+    if (enc == 0) { pack_reads(ctx, d_seq, d_offs, nreads, nbytes, pr); return; }
+    pack_prepare(ctx, d_offs, nreads, nbytes, pr);
+    const u64 ng = ceil_div(nbytes, 16);
+    if (ng) LAUNCH(ctx, pack4bit_kernel, (unsigned)ceil_div(ng + (ng & 1), 256), 256, 0, (const u64 *)d_seq, nbytes, (u32 *)pr.packed.p, pr.bad.p, 0ULL, ng);
 }
 
 // valid-window mask for a given k (nwords u32)

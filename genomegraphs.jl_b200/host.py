@@ -277,7 +277,9 @@ class SequenceDistanceGraph:
                 if n.deleted:
                     continue
                 gfa.write("S\tseq%d\t*\tLN:i:%d\tUR:Z:%s\n" % (nid, len(n.seq), fasta_filename))
-                fa.write(">seq%d\n%s\n" % (nid, n.seq))
+                fa.write(">seq%d\n" % nid)   # FASTX FASTA.Writer: sequence lines of 70 bases
+                for p in range(0, len(n.seq), 70):
+                    fa.write(n.seq[p:p + 70] + "\n")
             for ls in self.links:
                 for l in ls:
                     if l.source <= l.destination:
@@ -312,6 +314,101 @@ class GraphArrays:
         t = self.link_triples.reshape(-1, 3)
         r = self.link_row_offsets
         return [[tuple(int(x) for x in t[j]) for j in range(int(r[i]), int(r[i + 1]))] for i in range(self.n_nodes)]
+
+
+def write_gfa1_arrays(filename, ga):
+    """write_to_gfa1 (src/Graphs.jl:892-926) straight from exported arrays (host code in libggb200, no GPU needed):
+    <filename>.gfa + <filename>.fasta"""
+    nl = len(ga.link_triples) // 3
+    code = N.lib().gg_gfa1_write(str(filename).encode(), ga.n_nodes, _ptr(ga.node_offsets), _ptr(ga.bases) if len(ga.bases) else None,
+                                 _ptr(ga.link_row_offsets), _ptr(ga.link_triples) if nl else None)
+    if code != N.GG_OK:
+        raise OSError("cannot write %s.gfa / %s.fasta" % (filename, filename))
+
+
+class DeviceGraph:
+    """gg_graph handle: the graph stays on the device (find_tip_nodes, GFA1 persistence, export)."""
+
+    def __init__(self, ctx, h):
+        self.ctx, self.h = ctx, h
+
+    @classmethod
+    def from_arrays(cls, ga, ctx=None):
+        c = ctx or Context.default()
+        h = C.c_void_p()
+        nl = len(ga.link_triples) // 3
+        N.check(c.h, N.lib().gg_graph_from_arrays(c.h, int(ga.k), ga.n_nodes, _ptr(np.ascontiguousarray(ga.node_offsets, dtype=np.uint64)),
+                                                  _ptr(ga.bases) if len(ga.bases) else None, _ptr(np.ascontiguousarray(ga.link_row_offsets, dtype=np.uint64)),
+                                                  _ptr(ga.link_triples) if nl else None, C.byref(h)))
+        return cls(c, h)
+
+    @classmethod
+    def load_from_gfa1(cls, gfa_file, fasta_file, ctx=None):
+        """load_from_gfa1!(sg, gfafile, fafile) (unfinished upstream, src/Graphs.jl:943-958)"""
+        c = ctx or Context.default()
+        h = C.c_void_p()
+        N.check(c.h, N.lib().gg_graph_load_gfa1(c.h, str(gfa_file).encode(), str(fasta_file).encode(), C.byref(h)))
+        return cls(c, h)
+
+    def arrays(self):
+        return _export_graph(self.ctx, self.h)
+
+    def write_to_gfa1(self, filename):
+        N.check(self.ctx.h, N.lib().gg_graph_write_gfa1(self.h, str(filename).encode()))
+
+    def find_tip_nodes(self, min_size):
+        """find_tip_nodes(sg, min_size) (src/Graphs.jl:778-816): ascending node ids"""
+        n = C.c_uint64(0)
+        N.check(self.ctx.h, N.lib().gg_graph_find_tip_nodes(self.h, int(min_size), None, C.byref(n)))
+        out = np.zeros(max(n.value, 1), dtype=np.int64)
+        n2 = C.c_uint64(len(out))
+        N.check(self.ctx.h, N.lib().gg_graph_find_tip_nodes(self.h, int(min_size), _ptr(out), C.byref(n2)))
+        return out[:n2.value]
+
+    def free(self):
+        if self.h:
+            N.lib().gg_graph_free(self.h)
+            self.h = None
+
+
+def pack_4bit(reads):
+    """reads -> (uint64 words, base offsets) in the 4-bit encoding of LongSequence{DNAAlphabet{4}} (the reference's read
+    store, src/GenomeGraphs.jl:79-83): 16 bases per word, base i in bits 4i .. 4i+3, A 1, C 2, G 4, T 8, other letters 15"""
+    seq, offs = _as_reads(reads)
+    lut = np.full(256, 15, dtype=np.uint64)
+    for ch, v in (("A", 1), ("C", 2), ("G", 4), ("T", 8)):
+        lut[ord(ch)] = v
+        lut[ord(ch.lower())] = v
+    nib = lut[seq]
+    pad = (-len(nib)) % 16
+    nib = np.concatenate([nib, np.zeros(pad, dtype=np.uint64)]).reshape(-1, 16)
+    words = (nib << (np.arange(16, dtype=np.uint64) * np.uint64(4))).sum(axis=1, dtype=np.uint64) if len(nib) else np.zeros(0, dtype=np.uint64)
+    return np.ascontiguousarray(words, dtype=np.uint64), offs
+
+
+def count_kmers_4bit(data4, offs, k, mode=1, ctx=None):
+    c = ctx or Context.default()
+    h = C.c_void_p()
+    N.check(c.h, N.lib().gg_count_kmers_4bit(c.h, _ptr(data4) if data4.size else None, _ptr(offs), len(offs) - 1, int(k), int(mode), C.byref(h)))
+    return MerCounts(c, h)
+
+
+def dbg_from_reads_4bit(data4, offs, k, min_freq, ctx=None):
+    c = ctx or Context.default()
+    gh = C.c_void_p()
+    N.check(c.h, N.lib().gg_dbg_from_reads_4bit(c.h, _ptr(data4) if data4.size else None, _ptr(offs), len(offs) - 1, int(k), int(min_freq), C.byref(gh)))
+    try:
+        return _export_graph(c, gh)
+    finally:
+        N.lib().gg_graph_free(gh)
+
+
+def spectra_cn(reads_counts, graph_counts):
+    """`spectra(reads_kcount, graph_kcount)` (docs/src/man/assembly.md:221-228): (256, 256) joint histogram of the
+    UInt8-saturated counts, [count in reads, count in graph]"""
+    h = np.zeros(65536, dtype=np.uint64)
+    N.check(reads_counts.ctx.h, N.lib().gg_counts_spectrum_cn(reads_counts.h, graph_counts.h, h.ctypes.data_as(N.u64p)))
+    return h.reshape(256, 256)
 
 
 def _export_graph(ctx, gh):

@@ -104,6 +104,10 @@ int gg_counts_export(gg_counts *c, uint64_t *kmer_words, uint8_t *counts_u8_satu
 /* `spectra(counts)` of KmerAnalysis.jl (docs/src/man/assembly.md:159): 256-bin histogram of
  * min(count, 255) */
 int gg_counts_spectrum(gg_counts *c, uint64_t hist[256]);
+/* spectra-cn, `spectra(reads_kcount, graph_kcount)` (docs/src/man/assembly.md:221-228): joint histogram of the
+ * UInt8-saturated counts of every k-mer of two tables (same context, same k); hist[a_count * 256 + b_count], a
+ * k-mer missing from one table counts 0 there. */
+int gg_counts_spectrum_cn(gg_counts *a, gg_counts *b, uint64_t hist[65536]);
 void gg_counts_free(gg_counts *c);
 
 /* staged entry points (tests / measurement) */
@@ -123,6 +127,14 @@ int gg_dbg_from_reads(gg_ctx *ctx, const uint8_t *seq_bytes, const uint64_t *rea
                       uint64_t nreads, int k, uint64_t min_freq, gg_graph **out);
 int gg_dbg_from_reads_dev(gg_ctx *ctx, const uint8_t *d_seq_bytes, const uint64_t *d_read_offsets,
                           uint64_t nreads, uint64_t nbytes, int k, uint64_t min_freq, gg_graph **out);
+/* 4-bit packed host input -- the encoding of the reference's read store (LongSequence{DNAAlphabet{4}},
+ * src/GenomeGraphs.jl:79-83): 16 bases per uint64, base i of the concatenated reads in bits 4(i%16) .. +3 of word
+ * i/16, A = 1, C = 2, G = 4, T = 8, anything else ambiguous (its windows are skipped).  read_offsets are in BASES.
+ * Half the host-to-device bytes of the ASCII entry points, same results. */
+int gg_count_kmers_4bit(gg_ctx *ctx, const uint64_t *data4, const uint64_t *read_offsets, uint64_t nreads, int k,
+                        int canonical, gg_counts **out);
+int gg_dbg_from_reads_4bit(gg_ctx *ctx, const uint64_t *data4, const uint64_t *read_offsets, uint64_t nreads, int k,
+                           uint64_t min_freq, gg_graph **out);
 int gg_graph_sizes(gg_graph *g, uint64_t *n_nodes, uint64_t *total_bases, uint64_t *n_link_entries, int *k);
 /* node i (id i+1, src/Graphs.jl:418-422) is bases_ascii[node_offsets[i] .. node_offsets[i+1]);
  * links of node i (src/Graphs.jl:198,473-476) are the (source, destination, dist) int64
@@ -131,6 +143,19 @@ int gg_graph_export(gg_graph *g, uint64_t *node_offsets, uint8_t *bases_ascii,
                     uint64_t *link_row_offsets, int64_t *link_triples);
 /* small summary read back without exporting: sum over nodes of an order-independent hash */
 int gg_graph_checksum(gg_graph *g, uint64_t *checksum);
+/* find_tip_nodes(sg, min_size) (src/Graphs.jl:778-816) on the device-resident graph: ids of the tip nodes, ascending
+ * (the reference returns a Set).  Call with tips == NULL to get *n_tips first; *n_tips = capacity on input. */
+int gg_graph_find_tip_nodes(gg_graph *g, uint64_t min_size, int64_t *tips, uint64_t *n_tips);
+/* persistence: write_to_gfa1 (src/Graphs.jl:892-926), <filename>.gfa + <filename>.fasta in the reference's format,
+ * from a graph handle or straight from exported arrays (host only, no context needed); and a loader for that pair of
+ * files (load_from_gfa1! is unfinished upstream, src/Graphs.jl:943-958): nodes by their seq<id> names, one add_link!
+ * (src/Graphs.jl:473-476) per L line. */
+int gg_graph_write_gfa1(gg_graph *g, const char *filename);
+int gg_gfa1_write(const char *filename, uint64_t n_nodes, const uint64_t *node_offsets, const uint8_t *bases_ascii,
+                  const uint64_t *link_row_offsets, const int64_t *link_triples);
+int gg_graph_load_gfa1(gg_ctx *ctx, const char *gfa_file, const char *fasta_file, gg_graph **out);
+int gg_graph_from_arrays(gg_ctx *ctx, int k, uint64_t n_nodes, const uint64_t *node_offsets, const uint8_t *bases_ascii,
+                         const uint64_t *link_row_offsets, const int64_t *link_triples, gg_graph **out);
 void gg_graph_free(gg_graph *g);
 
 /* ---- UniqueMerIndex ---------------------------------------------------------------------
