@@ -559,6 +559,7 @@ static u64 dist_skm_count(gg_comm *cm, const PackedReads &pr, const u32 *valid, 
                 SkmPeers pt;
                 memset(&pt, 0, sizeof(pt));
                 pt.n = P;
+                pt.bulk = getenv("GG_SKM_NO_BULK") ? 0 : 1;
                 for (int q = 0; q < P; ++q) pt.ptr[q] = reinterpret_cast<ulonglong2 *>(cm->peerR[q]);
                 for (int q = 0; q <= MSD_MAX_PEERS; ++q) pt.first[q] = fs.first[q];
                 skm_scan_launch<1, true>(ctx, pr, valid, 0, pr.nwords, 1, g, nullptr, L.cur0.p, base_src.p, L.cap0.p, nullptr, L.hist1.p, L.totals.p, L.ovf.p, &pt);

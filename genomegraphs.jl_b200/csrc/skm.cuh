@@ -67,7 +67,17 @@ struct SkmPeers {
     ulonglong2 *ptr[MSD_MAX_PEERS];
     u32 first[MSD_MAX_PEERS + 1];
     int n;
+    int bulk;   // runs go to the owner with bulk asynchronous copies (TMA) out of a shared-memory staging area
 };
+// shared memory -> global (possibly a peer's memory over NVLink) bulk copy: ONE transaction-sized request per run instead
+// of one 16-byte store per record; bytes and both addresses are multiples of 16
+__device__ __forceinline__ void bulk_store_s2g(void *dst, const void *src_smem, u32 bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"((u32)__cvta_generic_to_shared(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // sources may be reused
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }        // copies complete
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ int skm_owner(const SkmPeers &pt, u32 b) {
     int o = 0;
 #pragma unroll
@@ -97,8 +107,11 @@ struct SkmScanSmem {
     u32 hist[SKM_MAX_NB0];              // runs per level-0 bin, then the running cursor inside the reserved space
     u32 gbase[SKM_MAX_NB0];             // first record slot of this tile's runs in every bin (absolute index into the buffer)
     u32 glim[SKM_MAX_NB0];              // end of the bin's region
+    u32 cnt[SKM_MAX_NB0];               // runs of this tile per bin (bulk route)
+    u32 hstart[256];                    // bulk route: start of the bin's run inside the staging area (bins of the current half)
     u32 s_n;
 };
+#define SKM_BULK_CAP 2048   // records the staging area (the per-thread queues of phase 1, free by then) holds: one half of the bins at a time
 // MODE 0: count records per level-0 bin (hist0); MODE 1: scatter the records.
 // The launch covers the packed words [w0, w1); CTA c handles tile number c * stride of 256 * TWORDS words
 // (stride > 1: sampling for the capacity estimate).
@@ -252,9 +265,52 @@ __global__ void __launch_bounds__(SKM_THREADS, 2) skm_scan_kernel(const u64 *__r
                 if (c && (u64)gpos + c > (u64)cap) *ovf = 1u;
                 S.gbase[b] = base + min(gpos, cap);
                 S.glim[b] = base + cap;
+                S.cnt[b] = (c && (u64)gpos + c <= (u64)cap) ? c : 0u;   // (an overflowing run is dropped: the scatter is repeated anyway)
                 S.hist[b] = 0;
             }
             __syncthreads();
+            if (PEER && pt.bulk) {
+                // ---------------- phase D, bulk route: the records of 256 bins at a time are staged bin by bin, then every bin's
+                // run leaves with one bulk copy into the owner's buffer ----------------
+                __shared__ u32 ws[33];
+                ulonglong2 *srec = reinterpret_cast<ulonglong2 *>(S.sq);
+                static_assert(sizeof(S.sq) >= SKM_BULK_CAP * sizeof(ulonglong2), "staging area");
+                const u64 tile_b0 = tile_w0 << 5;
+                for (u32 h0 = 0; h0 < nb0; h0 += 256) {
+                    const u32 bme = h0 + threadIdx.x;
+                    const u32 c = bme < nb0 ? S.cnt[bme] : 0u;
+                    u32 tot;
+                    const u32 ex = block_excl_scan(c, ws, &tot);
+                    S.hstart[threadIdx.x] = ex;
+                    __syncthreads();
+                    const bool staged = tot <= SKM_BULK_CAP;   // (uniform) otherwise this half goes out record by record
+                    for (u32 i = threadIdx.x; i < ntot; i += SKM_THREADS) {
+                        u32 b, bin1, rest;
+                        skm_bins(skm_digits(S.dh[i]), nb0, g.nb1, b, bin1, rest);
+                        if (b < h0 || b >= h0 + 256) continue;
+                        const u32 r = atomicAdd(&S.hist[b], 1u);
+                        const u32 dsv = S.ds[i];
+                        const u32 len = (dsv & 31u) + 1u;
+                        const u32 meta = (len - 1u) | (bin1 << 5) | ((rest >> 18) << 18);
+                        atomicAdd(&hist1[(u64)b * g.nb1 + bin1], 1u);
+                        const u32 p = S.gbase[b] + r;
+                        if (p < S.glim[b]) {
+                            const ulonglong2 rec = skm_make_record(packed, tile_b0 + (dsv >> 5), len, k, meta);
+                            if (staged && S.cnt[b]) srec[S.hstart[b - h0] + r] = rec;
+                            else pt.ptr[skm_owner(pt, b)][p] = rec;
+                        }
+                    }
+                    fence_async_smem();
+                    __syncthreads();
+                    if (staged && c) {
+                        bulk_store_s2g(pt.ptr[skm_owner(pt, bme)] + S.gbase[bme], srec + ex, c * (u32)sizeof(ulonglong2));
+                        bulk_commit();
+                        bulk_wait_read();
+                    }
+                    __syncthreads();
+                }
+                bulk_wait_all();
+            } else {
             // ---------------- phase D: records built and stored, grouped by bin ----------------
             const u64 tile_b0 = tile_w0 << 5;
             for (u32 i = threadIdx.x; i < ntot; i += SKM_THREADS) {
@@ -270,6 +326,7 @@ __global__ void __launch_bounds__(SKM_THREADS, 2) skm_scan_kernel(const u64 *__r
                     if (PEER) pt.ptr[skm_owner(pt, b)][p] = rec;
                     else out[p] = rec;
                 }
+            }
             }
         }
         if (!fallback || it1 == TWORDS) break;
