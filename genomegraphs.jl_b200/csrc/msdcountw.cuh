@@ -394,6 +394,7 @@ static void msdw_pass_a_launch(gg_ctx *ctx, const PackedReads &pr, const u32 *va
     if (hgrid > (u64)ctx->num_sms * 3) hgrid = (u64)ctx->num_sms * 3;  // 64 KB of histogram per CTA
     const size_t smemA = sizeof(u32) << MSDW_HB;
     set_max_smem(ctx, msdw_hist_kernel<W>, smemA);
+    prof_bytes(ctx, 12.0 * (double)pr.nwords);   // packed words + window masks read once
     LAUNCH(ctx, msdw_hist_kernel<W>, (unsigned)hgrid, 256, smemA, pr.packed.p, valid, pr.nwords, k, canonical, hb, hist.p,
            est_shift ? (0xFFFFFFFFu >> est_shift) : 0xFFFFFFFFu, est.p);
 }
@@ -412,6 +413,7 @@ static void msdw_pass_b(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, in
     if (N == 0) return;
     const size_t smemB = (MsdW<W>::STASH ? 2 : 1) * (size_t)MsdW<W>::TILE_KEYS * W * 8 + 2 * (size_t)(1 << MSDW_B0_MAX) * 4 + (size_t)MsdW<W>::TILE_KEYS * 2;
     set_max_smem(ctx, msdw_scatter_kernel<W>, smemB);
+    prof_bytes(ctx, 12.0 * (double)pr.nwords + 8.0 * W * (double)N);   // masks + packed words in, every key out once
     LAUNCH(ctx, msdw_scatter_kernel<W>, (unsigned)ceil_div(pr.nwords, MsdW<W>::TILE_WORDS), 256, smemB, pr.packed.p, valid, pr.nwords, k,
            canonical, pl.b0, cursor.p, A.p);
 }
@@ -436,11 +438,13 @@ static u64 msdw_finish(gg_ctx *ctx, u64 *IN, u64 n_in, const u32 *vbeg, const u3
         if (!h1) {  // pass C: pass A's histogram is too coarse for b0 + b1 bits
             hist1.alloc(ctx, nchild + 1);
             CK(cudaMemsetAsync(hist1.p, 0, (nchild + 1) * sizeof(u32), ctx->stream));
+            prof_bytes(ctx, 8.0 * W * (double)n_in);
             LAUNCH(ctx, msdw_hist1_kernel<W>, tgrid, 256, 0, IN, tstart.p, vbeg, vcnt, nvb, nsrc, pl.shiftc, pl.b1, hist1.p);
             h1 = hist1.p;
         }
         exclusive_scan_u32(ctx, h1, off.p, nchild + 1, nullptr);
         LAUNCH(ctx, msd_copy_u32_kernel, (unsigned)ceil_div(nchild, 256), 256, 0, off.p, nchild, cursor1.p);
+        prof_bytes(ctx, 16.0 * W * (double)n_in);   // every key in and out once
         LAUNCH(ctx, msdw_scatter1_kernel<W>, tgrid, 256, 0, IN, tstart.p, vbeg, vcnt, nvb, nsrc, pl.shiftc, pl.b1, cursor1.p, B.p);
         X = B.p; SB = IN;
     } else {
@@ -453,6 +457,7 @@ static u64 msdw_finish(gg_ctx *ctx, u64 *IN, u64 n_in, const u32 *vbeg, const u3
         set_max_smem(ctx, msdw_leaf_kernel<W, 512>, smem);
         u32 grid = (u32)ctx->num_sms * 2;
         if (grid > nchild) grid = (u32)nchild;
+        prof_bytes(ctx, 16.0 * W * (double)n_in);   // two sweeps over the child's keys (claim, then count); + (8 W + 4) per kept key, added below
         LAUNCH(ctx, (msdw_leaf_kernel<W, 512>), grid, 512, smem, X, SB, OC.p, off.p, (u32)nchild, pl.shiftc, nu.p, ticket.p, min_freq, tune.test_ovf_mod);
     }
     // children the table could not hold: generic sort + run-length count of that segment
@@ -496,6 +501,7 @@ static u64 msdw_finish(gg_ctx *ctx, u64 *IN, u64 n_in, const u32 *vbeg, const u3
     ucounts.alloc(ctx, U ? U : 1);
     if (U) {
         u32 ggrid = nchild < (u64)ctx->num_sms * 16 ? (u32)nchild : (u32)ctx->num_sms * 16;
+        prof_bytes(ctx, 2.0 * (8.0 * W + 4.0) * (double)U);
         LAUNCH(ctx, msdw_gather_kernel<W>, ggrid, 256, 0, X, OC.p, off.p, nu.p, ustart.p, (u32)nchild, ukeys.p, ucounts.p);
     }
     stage_end(ctx, ST_COUNT);
