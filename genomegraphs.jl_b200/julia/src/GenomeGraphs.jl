@@ -17,7 +17,7 @@ export
     WorkSpace, add_mer_counts!, mer_counts,
     dbg, dbg!,
     # device-side counter (drop-in for serial_mem(M, CANONICAL))
-    gpu_mem, GPUContext
+    gpu_mem, GPUContext, DeviceGraph, load_from_gfa1
 
 using BioSequences
 using KmerAnalysis

@@ -8,7 +8,7 @@ module Graphs
 
 export SequenceDistanceGraph, SDG, SDGNode, SDGLink, SequenceDistanceGraphLink, NodeID,
     nodes, links, node, n_nodes, each_node_id, linksof, sequence, add_node!, add_link!,
-    source, destination, distance, is_forwards_from, is_backwards_from
+    source, destination, distance, is_forwards_from, is_backwards_from, write_to_gfa1, find_tip_nodes
 
 using BioSequences
 
@@ -87,5 +87,9 @@ function add_link!(sg::SDG, src::NodeID, dst::NodeID, dist::Int)
     push!(linksof(sg, src), SDGLink(src, dst, dist))
     push!(linksof(sg, dst), SDGLink(dst, src, dist))
 end
+
+# generic functions the device-graph methods of ../dbg.jl extend (reference src/Graphs.jl:892, :814)
+function write_to_gfa1 end
+function find_tip_nodes end
 
 end # module Graphs

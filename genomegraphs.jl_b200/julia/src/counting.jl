@@ -43,3 +43,7 @@ function Base.collect(c::DeviceMerCounts{M}) where {M<:AbstractMer}
     words, c8, w = LibGG.counts_export(c.ctx, c.h)
     return [MerCount{M}(mer_from_words(M, words, i, w), c8[i]) for i in eachindex(c8)]
 end
+
+"`spectra(counts)` (docs/src/man/assembly.md:159) and spectra-cn `spectra(reads_kcount, graph_kcount)` (:221-228) on the device."
+KmerAnalysis.spectra(c::DeviceMerCounts) = LibGG.counts_spectrum(c.ctx, c.h)
+KmerAnalysis.spectra(a::DeviceMerCounts, b::DeviceMerCounts) = LibGG.counts_spectrum_cn(a.ctx, a.h, b.h)

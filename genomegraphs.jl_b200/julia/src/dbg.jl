@@ -114,3 +114,40 @@ end
 "Non-mutating form (exported but undefined in the reference, src/GenomeGraphs.jl:63)."
 dbg(kmers; kwargs...) = dbg!(empty_graph(LongSequence{DNAAlphabet{4}}), kmers; kwargs...)
 dbg(counted, min_freq::Integer; kwargs...) = dbg!(empty_graph(LongSequence{DNAAlphabet{4}}), counted, min_freq; kwargs...)
+
+
+# ---- the graph kept on the device: persistence and the tip finder ----------------------------------
+"A `gg_graph` handle (device-resident nodes + links)."
+mutable struct DeviceGraph
+    ctx::LibGG.Context
+    h::Ptr{Cvoid}
+    function DeviceGraph(ctx, h)
+        g = new(ctx, h)
+        finalizer(x -> (x.h == C_NULL || LibGG.graph_free(x.h); x.h = C_NULL), g)
+        return g
+    end
+end
+"Upload a host graph (deleted nodes travel as empty sequences)."
+function DeviceGraph(sg::GRAPH_TYPE, k::Integer; ctx::LibGG.Context = LibGG.default_context())
+    buf = IOBuffer(); node_off = UInt64[0]; link_row = UInt64[0]; tri = Int64[]
+    for (i, n) in enumerate(Graphs.nodes(sg))
+        n.deleted || print(buf, n.seq)
+        push!(node_off, UInt64(position(buf)))
+        for l in Graphs.links(sg)[i]
+            push!(tri, l.source, l.destination, l.dist)
+        end
+        push!(link_row, UInt64(length(tri) ÷ 3))
+    end
+    return DeviceGraph(ctx, LibGG.graph_from_arrays(ctx, k, node_off, take!(buf), link_row, tri))
+end
+"`write_to_gfa1(sg, filename)` (src/Graphs.jl:892-926): `filename.gfa` + `filename.fasta`, same bytes."
+Graphs.write_to_gfa1(g::DeviceGraph, filename::String) = LibGG.graph_write_gfa1(g.ctx, g.h, filename)
+"`load_from_gfa1!` is unfinished upstream (src/Graphs.jl:943-958); this loads what `write_to_gfa1` writes."
+load_from_gfa1(gfafile::AbstractString, fafile::AbstractString; ctx::LibGG.Context = LibGG.default_context()) =
+    DeviceGraph(ctx, LibGG.graph_load_gfa1(ctx, gfafile, fafile))
+"`find_tip_nodes(sg, min_size)` (src/Graphs.jl:778-816) on the device graph; ids ascending."
+Graphs.find_tip_nodes(g::DeviceGraph, min_size::Integer) = Set{Graphs.NodeID}(LibGG.graph_find_tip_nodes(g.ctx, g.h, min_size))
+"Device graph -> the reference's graph type."
+function Base.convert(::Type{GRAPH_TYPE}, g::DeviceGraph)
+    return fill_graph!(empty_graph(LongSequence{DNAAlphabet{4}}), LibGG.graph_export(g.ctx, g.h)...)
+end

@@ -131,6 +131,51 @@ end
 
 graph_free(g::Ptr{Cvoid}) = ccall(fptr(:gg_graph_free), Cvoid, (Ptr{Cvoid},), g)
 
+# ---- rows next to the path: spectra-cn, 4-bit input, persistence, tips ------------------------
+function counts_spectrum(ctx::Context, c::Ptr{Cvoid})
+    h = zeros(UInt64, 256)
+    GC.@preserve h check(ctx, ccall(fptr(:gg_counts_spectrum), Cint, (Ptr{Cvoid}, Ptr{UInt64}), c, h))
+    return h
+end
+function counts_spectrum_cn(ctx::Context, a::Ptr{Cvoid}, b::Ptr{Cvoid})
+    h = zeros(UInt64, 65536)
+    GC.@preserve h check(ctx, ccall(fptr(:gg_counts_spectrum_cn), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{UInt64}), a, b, h))
+    return permutedims(reshape(h, 256, 256))   # [count in a + 1, count in b + 1]
+end
+"reads in the 4-bit encoding of LongSequence{DNAAlphabet{4}}: 16 bases per word, offsets in bases"
+function dbg_from_reads_4bit(ctx::Context, data4::Vector{UInt64}, offs::Vector{UInt64}, k::Integer, min_freq::Integer)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve data4 offs begin
+        check(ctx, ccall(fptr(:gg_dbg_from_reads_4bit), Cint,
+                         (Ptr{Cvoid}, Ptr{UInt64}, Ptr{UInt64}, UInt64, Cint, UInt64, Ref{Ptr{Cvoid}}),
+                         ctx.h, data4, offs, length(offs) - 1, k, min_freq, out))
+    end
+    return out[]
+end
+graph_write_gfa1(ctx::Context, g::Ptr{Cvoid}, filename::AbstractString) =
+    check(ctx, ccall(fptr(:gg_graph_write_gfa1), Cint, (Ptr{Cvoid}, Cstring), g, filename))
+function graph_load_gfa1(ctx::Context, gfafile::AbstractString, fafile::AbstractString)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ctx, ccall(fptr(:gg_graph_load_gfa1), Cint, (Ptr{Cvoid}, Cstring, Cstring, Ref{Ptr{Cvoid}}), ctx.h, gfafile, fafile, out))
+    return out[]
+end
+function graph_from_arrays(ctx::Context, k::Integer, node_off::Vector{UInt64}, bases::Vector{UInt8}, link_row::Vector{UInt64}, tri::Vector{Int64})
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve node_off bases link_row tri begin
+        check(ctx, ccall(fptr(:gg_graph_from_arrays), Cint,
+                         (Ptr{Cvoid}, Cint, UInt64, Ptr{UInt64}, Ptr{UInt8}, Ptr{UInt64}, Ptr{Int64}, Ref{Ptr{Cvoid}}),
+                         ctx.h, k, length(node_off) - 1, node_off, bases, link_row, tri, out))
+    end
+    return out[]
+end
+function graph_find_tip_nodes(ctx::Context, g::Ptr{Cvoid}, min_size::Integer)
+    n = Ref{UInt64}(0)
+    check(ctx, ccall(fptr(:gg_graph_find_tip_nodes), Cint, (Ptr{Cvoid}, UInt64, Ptr{Int64}, Ref{UInt64}), g, min_size, C_NULL, n))
+    tips = Vector{Int64}(undef, n[])
+    GC.@preserve tips check(ctx, ccall(fptr(:gg_graph_find_tip_nodes), Cint, (Ptr{Cvoid}, UInt64, Ptr{Int64}, Ref{UInt64}), g, min_size, tips, n))
+    return tips
+end
+
 # ---- unique mer index -----------------------------------------------------------------------
 function unique_mer_index(ctx::Context, bases::Vector{UInt8}, offs::Vector{UInt64}, k::Integer)
     out = Ref{Ptr{Cvoid}}(C_NULL)
