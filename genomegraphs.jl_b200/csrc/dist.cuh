@@ -172,6 +172,29 @@ static void dist_alltoallv(gg_comm *cm, const void *send, const u64 *soff, const
     NCK(nc->GroupEnd());
 }
 
+// ---- error agreement -------------------------------------------------------------------------------
+// A failure that only one rank sees (out of memory, a CUDA error) must not leave the peers waiting in the next
+// collective: local phases run under dist_guard, which catches the failure, lets every rank learn the worst status
+// with ONE ncclAllReduce(min) and then throws on all ranks together.  `f` must not contain collectives.
+template <class F>
+static void dist_guard(gg_comm *cm, const char *what, F f) {
+    NcclApi *nc = nccl_api();
+    gg_ctx *ctx = cm->ctx;
+    GgError mine{GG_OK, ""};
+    try { f(); } catch (const GgError &e) { mine = e; cudaGetLastError(); } catch (const std::bad_alloc &) { mine = GgError{GG_ERR_OOM, "host allocation failed"}; }
+    if (!cm->agree) {   // one word of plain device memory outside the arena (the arena itself may be what failed)
+        if (cudaMalloc((void **)&cm->agree, sizeof(u64)) != cudaSuccess) GG_THROW(GG_ERR_OOM, "no memory for the status word");
+    }
+    const u64 ok = mine.code == GG_OK ? 1 : 0;
+    CK(cudaMemcpyAsync(cm->agree, &ok, sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    NCK(nc->AllReduce(cm->agree, cm->agree, 1, ncclUint64, ncclMin, cm->comm, ctx->stream));
+    u64 all = 0;
+    CK(cudaMemcpyAsync(&all, cm->agree, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (mine.code != GG_OK) throw mine;
+    if (!all) GG_THROW(GG_ERR_CUDA, "a peer rank failed in: %s", what);
+}
+
 // instances per child of this rank's bucket range, summed over the ranks' pass-A histograms
 __global__ void dist_child_hist_kernel(const u32 *__restrict__ all_hist, int P, u32 nbh, int hb, int bits, u32 child0, u32 nchild,
                                        u32 *__restrict__ out) {
@@ -212,10 +235,13 @@ static u64 dist_msd_count(gg_comm *cm, const PackedReads &pr, const u32 *valid, 
     const int est_shift = msd_est_shift(nbases_glob);
     mark();  // 1: size all-reduce done
     // ---- pass A on the local reads; histograms all-gathered, estimate maps merged ----
-    DBuf<u32> hist, all_hist(ctx, (u64)P * nbh);
+    DBuf<u32> hist, all_hist;
     DBuf<u8> est;
-    if constexpr (W == 1) msd_pass_a_launch(ctx, pr, valid, k, canonical, est_shift, hist, est);
-    else msdw_pass_a_launch<W>(ctx, pr, valid, k, canonical, est_shift, hist, est);
+    dist_guard(cm, "pass A", [&] {
+        all_hist.alloc(ctx, (u64)P * nbh);
+        if constexpr (W == 1) msd_pass_a_launch(ctx, pr, valid, k, canonical, est_shift, hist, est);
+        else msdw_pass_a_launch<W>(ctx, pr, valid, k, canonical, est_shift, hist, est);
+    });
     NCK(nc->AllGather(hist.p, all_hist.p, nbh, ncclUint32, cm->comm, ctx->stream));
     NCK(nc->AllReduce(est.p, est.p, 1ULL << EST_LOG, ncclUint8, ncclMax, cm->comm, ctx->stream));
     u64 N_loc = 0, dest = 0;
@@ -229,7 +255,10 @@ static u64 dist_msd_count(gg_comm *cm, const PackedReads &pr, const u32 *valid, 
     for (u32 v : h_all) N_glob += v;
     *n_instances_local = N_loc;
     *n_instances_global = N_glob;
-    if (N_loc >= 0xFFFFFFFFull) GG_THROW(GG_ERR_LIMIT, "%llu k-mer instances exceed the 2^32-1 per-GPU limit", (unsigned long long)N_loc);
+    // (a limit only this rank hits must reach the peers before the next collective)
+    dist_guard(cm, "instance count", [&] {
+        if (N_loc >= 0xFFFFFFFFull) GG_THROW(GG_ERR_LIMIT, "%llu k-mer instances exceed the 2^32-1 per-GPU limit", (unsigned long long)N_loc);
+    });
     const MsdPlan pl = msd_plan(dest, N_glob, k, tune, hb);
     const u32 nb0 = 1u << pl.b0, grp = 1u << (hb - pl.b0);
     // ---- per-rank histograms at level-0 resolution, owners of the buckets ----
@@ -277,9 +306,12 @@ static u64 dist_msd_count(gg_comm *cm, const PackedReads &pr, const u32 *valid, 
         }
     }
     h_vbeg.back() = (u32)N_recv;  // with a single source the virtual buckets are contiguous and vbeg doubles as an offset array
-    DBuf<u32> vbeg(ctx, h_vbeg.size()), vcnt(ctx, h_vcnt.size());
-    CK(cudaMemcpyAsync(vbeg.p, h_vbeg.data(), h_vbeg.size() * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(vcnt.p, h_vcnt.data(), h_vcnt.size() * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+    DBuf<u32> vbeg, vcnt;
+    dist_guard(cm, "bucket tables", [&] {
+        vbeg.alloc(ctx, h_vbeg.size()); vcnt.alloc(ctx, h_vcnt.size());
+        CK(cudaMemcpyAsync(vbeg.p, h_vbeg.data(), h_vbeg.size() * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(vcnt.p, h_vcnt.data(), h_vcnt.size() * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+    });
     DBuf<u32> hist0, bstart;
     DBuf<u64> A, Rtmp;
     u64 *R = nullptr;
@@ -299,7 +331,7 @@ static u64 dist_msd_count(gg_comm *cm, const PackedReads &pr, const u32 *valid, 
         DBuf<u64> tok(ctx, 1);
         CK(cudaMemcpyAsync(pcur.p, h_cur.data(), nb0 * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
         // the collectives of pass A ran after every rank's previous call on its stream: nobody still reads its buffer
-        msd_pass_b(ctx, pr, valid, k, canonical, pl, hist.p, N_loc, hist0, bstart, A, &pt, pcur.p);
+        dist_guard(cm, "pass B (peer scatter)", [&] { msd_pass_b(ctx, pr, valid, k, canonical, pl, hist.p, N_loc, hist0, bstart, A, &pt, pcur.p); });
         stage_end(ctx, ST_EXTRACT);
         mark();  // 3: pass B (scatter into the peers) done locally
         stage_begin(ctx, ST_SORT);
@@ -309,12 +341,14 @@ static u64 dist_msd_count(gg_comm *cm, const PackedReads &pr, const u32 *valid, 
         R = cm->R;
     } else {
         // ---- pass B locally (its output doubles as the send buffer), then one grouped ncclSend / ncclRecv exchange ----
-        if constexpr (W == 1) msd_pass_b(ctx, pr, valid, k, canonical, pl, hist.p, N_loc, hist0, bstart, A);
-        else msdw_pass_b<W>(ctx, pr, valid, k, canonical, pl, hist.p, N_loc, hist0, bstart, A);
+        dist_guard(cm, "pass B", [&] {
+            if constexpr (W == 1) msd_pass_b(ctx, pr, valid, k, canonical, pl, hist.p, N_loc, hist0, bstart, A);
+            else msdw_pass_b<W>(ctx, pr, valid, k, canonical, pl, hist.p, N_loc, hist0, bstart, A);
+            Rtmp.alloc(ctx, (N_recv ? N_recv : 1) * W);
+        });
         stage_end(ctx, ST_EXTRACT);
         mark();  // 3: pass B done
         stage_begin(ctx, ST_SORT);
-        Rtmp.alloc(ctx, (N_recv ? N_recv : 1) * W);
         dist_alltoallv(cm, A.p, soff.data(), scnt.data(), Rtmp.p, roff.data(), rcnt.data(), sizeof(u64) * W);
         CK(cudaStreamSynchronize(ctx->stream));  // h_vbeg / h_vcnt are read by the copies above; A is released next
         A.release();
@@ -330,37 +364,16 @@ static u64 dist_msd_count(gg_comm *cm, const PackedReads &pr, const u32 *valid, 
                first[me] << pl.b1, nchild, child_hist.p);
     }
     u64 U = 0;
-    if constexpr (W == 1) U = msd_finish(ctx, R, N_recv, vbeg.p, vcnt.p, nb_local, (u32)P, pl, tune, min_freq, ukeys, ucounts, child_hist.p);
-    else U = msdw_finish<W>(ctx, R, N_recv, vbeg.p, vcnt.p, nb_local, (u32)P, pl, tune, min_freq, ukeys, ucounts, child_hist.p);
+    dist_guard(cm, "level 1 + leaves", [&] {
+        if constexpr (W == 1) U = msd_finish(ctx, R, N_recv, vbeg.p, vcnt.p, nb_local, (u32)P, pl, tune, min_freq, ukeys, ucounts, child_hist.p);
+        else U = msdw_finish<W>(ctx, R, N_recv, vbeg.p, vcnt.p, nb_local, (u32)P, pl, tune, min_freq, ukeys, ucounts, child_hist.p);
+    });
     mark();  // 5: level 1 + leaves + gather done
     if (dbg)
         fprintf(stderr, "[dist rank %d] t0=%.3f size-allreduce %.2f | passA+allgather %.2f | passB %.2f | exchange %.2f (send %.1f MB, recv %.1f MB) | finish %.2f ms\n",
                 me, tmark[0], tmark[1] - tmark[0], tmark[2] - tmark[1], tmark[3] - tmark[2], tmark[4] - tmark[3],
                 (double)(N_loc - scnt[me]) * 8e-6 * W, (double)(N_recv - rcnt[me]) * 8e-6 * W, tmark[5] - tmark[4]);
     return U;
-}
-
-// ---- error agreement -------------------------------------------------------------------------------
-// A failure that only one rank sees (out of memory, a CUDA error) must not leave the peers waiting in the next
-// collective: local phases run under dist_guard, which catches the failure, lets every rank learn the worst status
-// with ONE ncclAllReduce(min) and then throws on all ranks together.  `f` must not contain collectives.
-template <class F>
-static void dist_guard(gg_comm *cm, const char *what, F f) {
-    NcclApi *nc = nccl_api();
-    gg_ctx *ctx = cm->ctx;
-    GgError mine{GG_OK, ""};
-    try { f(); } catch (const GgError &e) { mine = e; cudaGetLastError(); } catch (const std::bad_alloc &) { mine = GgError{GG_ERR_OOM, "host allocation failed"}; }
-    if (!cm->agree) {   // one word of plain device memory outside the arena (the arena itself may be what failed)
-        if (cudaMalloc((void **)&cm->agree, sizeof(u64)) != cudaSuccess) GG_THROW(GG_ERR_OOM, "no memory for the status word");
-    }
-    const u64 ok = mine.code == GG_OK ? 1 : 0;
-    CK(cudaMemcpyAsync(cm->agree, &ok, sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
-    NCK(nc->AllReduce(cm->agree, cm->agree, 1, ncclUint64, ncclMin, cm->comm, ctx->stream));
-    u64 all = 0;
-    CK(cudaMemcpyAsync(&all, cm->agree, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    if (mine.code != GG_OK) throw mine;
-    if (!all) GG_THROW(GG_ERR_CUDA, "a peer rank failed in: %s", what);
 }
 
 // ---- super-k-mer route over several GPUs (skm.cuh) -------------------------------------------------

@@ -1234,14 +1234,18 @@ static gg_counts *counts_allgather_impl(gg_comm *cm, gg_counts *c) {
     f->ctx = ctx; f->k = c->k; f->W = c->W; f->n_unique = total; f->n_instances = c->n_instances;
     try {
         const int W = c->W;
-        f->d_keys = dalloc<u64>(ctx, total * W);
-        f->d_counts = dalloc<u32>(ctx, total);
-        DBuf<u64> mk(ctx, maxn * W), pk(ctx, (u64)P * maxn * W);
-        DBuf<u32> mc(ctx, maxn), pc(ctx, (u64)P * maxn);
-        if (c->n_unique) {
-            CK(cudaMemcpyAsync(mk.p, c->d_keys, c->n_unique * W * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream));
-            CK(cudaMemcpyAsync(mc.p, c->d_counts, c->n_unique * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
-        }
+        DBuf<u64> mk, pk;
+        DBuf<u32> mc, pc;
+        dist_guard(cm, "gathered count table", [&] {   // an allocation failure on one rank must not leave the peers in the all-gather
+            f->d_keys = dalloc<u64>(ctx, total * W);
+            f->d_counts = dalloc<u32>(ctx, total);
+            mk.alloc(ctx, maxn * W); pk.alloc(ctx, (u64)P * maxn * W);
+            mc.alloc(ctx, maxn); pc.alloc(ctx, (u64)P * maxn);
+            if (c->n_unique) {
+                CK(cudaMemcpyAsync(mk.p, c->d_keys, c->n_unique * W * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream));
+                CK(cudaMemcpyAsync(mc.p, c->d_counts, c->n_unique * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
+            }
+        });
         NCK(nc->AllGather(mk.p, pk.p, maxn * W, ncclUint64, cm->comm, ctx->stream));
         NCK(nc->AllGather(mc.p, pc.p, maxn, ncclUint32, cm->comm, ctx->stream));
         LAUNCH(ctx, allgather_compact_kernel, (unsigned)(ctx->num_sms * 8), 256, 0, pk.p, pc.p, maxn, W, P, sz.p, sz.p + P, f->d_keys, f->d_counts);

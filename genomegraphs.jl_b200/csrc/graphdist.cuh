@@ -310,7 +310,7 @@ static gg_graph *build_graph_sharded(gg_ctx *ctx, const u64 *keys, u64 U, int k,
         // splitters: heads + a 2^-sl hash sample.  Fewer splitters shrink the reduced list (ranked on every rank) and make its
         // records cache-resident for the expansion, as long as every rank keeps >= ~2^18 walks in flight (measured on C2 / C3)
         int sl = 4;
-        while (sl < 7 && (nvp / (u64)P) >> (sl + 1) >= (1ULL << 18)) ++sl;
+        while (sl < 7 && (nvp / (u64)P) >> (sl + 1) >= (1ULL << (P > 1 ? 17 : 18))) ++sl;   // (the list is ranked on EVERY rank: keep it short)
         if (getenv("GG_SPLIT_LOG")) sl = atoi(getenv("GG_SPLIT_LOG"));
         // ---- K5: neighbour lookup of the own k-mers ----
         stage_begin(ctx, ST_LOOKUP);
