@@ -408,7 +408,24 @@ def main():
     # ---- parity of the benchmarked result + CPU baseline beside it ----
     parity = {"ok": True}
     cpu = None
-    if world > 1 and not args.no_parity:
+    if world > 1 and not args.no_parity and n_inst_total >= 2 ** 32 - 1:
+        # the whole job exceeds what ONE GPU builds (2^32 - 1 instances): size-independent properties instead -- every instance
+        # was seen, and the unitigs hold every kept k-mer exactly once: bases - (k - 1) * nodes = kept k-mers of the count table
+        import torch
+        ch, ng = C.c_void_p(), C.c_uint64()
+        N.check(H, L.gg_dist_count_kmers_dev(comm.h, d_seq, d_offs, nreads, nbytes, k, 1, min_freq, C.byref(ch), C.byref(ng)))
+        nu = C.c_uint64()
+        L.gg_counts_sizes(ch, C.byref(nu), None, None, None)
+        L.gg_counts_free(ch)
+        t = torch.tensor([nu.value], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t)
+        kept = int(t.item())
+        props = {"instances_seen_equal_reads_times_windows": ng.value == n_inst_total,
+                 "kmers_in_unitigs_equal_kept_kmers": sizes[1] - (k - 1) * sizes[0] == kept, "kept_kmers": kept}
+        parity.update({"n_gpu_vs_1_gpu": "skipped: %d instances exceed the one-GPU limit" % n_inst_total, "properties": props})
+        parity["ok"] = parity["ok"] and props["instances_seen_equal_reads_times_windows"] and props["kmers_in_unitigs_equal_kept_kmers"]
+        barrier()
+    elif world > 1 and not args.no_parity:
         # the same job once more on ONE GPU (rank 0, outside every timed region): checksum + sizes must equal the N-GPU result
         if rank == 0:
             da, do = C.c_void_p(), C.c_void_p()

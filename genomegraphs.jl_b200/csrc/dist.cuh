@@ -522,7 +522,17 @@ static u64 dist_skm_count(gg_comm *cm, const PackedReads &pr, const u32 *valid, 
     const u64 win_glob = read_scalar<u64>(ctx, sz.p);
     *n_instances_local = win_local;
     *n_instances_global = win_glob;
-    const SkmGeom g = skm_geom(win_glob, k, canonical, tune);
+    // rounds: leaf bins of ~bin_inst instances, at most 512 x 8192 of them per round -- larger jobs are counted in rounds over
+    // slices of the minimizer digit (every round rescans the reads and exchanges only its own slice's records)
+    u32 rounds = (u32)ceil_div(ceil_div(win_glob ? win_glob : 1, tune.bin_inst), (u64)SKM_MAX_NB0 * SKM_MAX_NB1 * 9 / 10);
+    if (const char *e = getenv("GG_SKM_ROUNDS")) rounds = (u32)atoi(e);   // tests
+    if (rounds < 1) rounds = 1;
+    std::vector<DBuf<u64>> round_keys(rounds);
+    std::vector<DBuf<u32>> round_counts(rounds);
+    std::vector<u64> round_n(rounds, 0);
+    for (u32 round = 0; round < rounds; ++round) {
+    SkmGeom g = skm_geom(win_glob / rounds + 1, k, canonical, tune);
+    g.rounds = rounds; g.round = round;
     const u32 nb0 = g.nb0, row = nb0 + SKM_DIST_TAIL;
     const u64 nleaf = (u64)nb0 * g.nb1;
     SkmFirst fs;
@@ -639,6 +649,31 @@ static u64 dist_skm_count(gg_comm *cm, const PackedReads &pr, const u32 *valid, 
         CK(cudaStreamSynchronize(ctx->stream));
     });
     rtmp.release();
+    round_keys[round] = std::move(uk); round_counts[round] = std::move(uc); round_n[round] = U;
+    }   // rounds
+    DBuf<u64> uk;
+    DBuf<u32> uc;
+    u64 U = round_n[0];
+    if (rounds == 1) { uk = std::move(round_keys[0]); uc = std::move(round_counts[0]); }
+    else {   // the rounds' tables are disjoint and each is sorted: one ordering pass over their concatenation
+        dist_guard(cm, "merge of the rounds", [&] {
+            U = 0;
+            for (u32 r = 0; r < rounds; ++r) U += round_n[r];
+            DBuf<u64> ck(ctx, U + 1);
+            DBuf<u32> cc(ctx, U + 1);
+            u64 at = 0;
+            for (u32 r = 0; r < rounds; ++r) {
+                if (round_n[r]) {
+                    CK(cudaMemcpyAsync(ck.p + at, round_keys[r].p, round_n[r] * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream));
+                    CK(cudaMemcpyAsync(cc.p + at, round_counts[r].p, round_n[r] * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
+                }
+                at += round_n[r];
+            }
+            CK(cudaStreamSynchronize(ctx->stream));
+            for (u32 r = 0; r < rounds; ++r) { round_keys[r].release(); round_counts[r].release(); }
+            U = skm_sort_pairs(ctx, ck.p, cc.p, U, U, k, uk, uc);
+        });
+    }
     stage_begin(ctx, ST_FILTER);   // the second exchange is booked under "filter" (with the all-gather of the graph stage)
     U = dist_range_repartition(cm, uk, uc, U, k, ukeys, ucounts);
     stage_end(ctx, ST_FILTER);

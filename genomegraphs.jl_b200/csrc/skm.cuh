@@ -50,6 +50,9 @@ __host__ __device__ __forceinline__ u32 skm_digits(u32 h) {
 struct SkmGeom {
     int k, canonical;
     u32 nb0, nb1;   // level-0 bins x leaf bins per level-0 bin (any counts: the digits are range-reduced by multiply-high)
+    // rounds > 1 (inputs whose leaf bins would outnumber 512 x 8192): a call handles the super-k-mers whose minimizer
+    // digit falls into slice `round` of `rounds` equal slices and skips the others; the rounds' tables are disjoint
+    u32 rounds = 1, round = 0;
 };
 // bins of a minimizer: d uniform in [0, 2^32) -> bin0 = floor(d * nb0 / 2^32); the low word of that product is uniform
 // again -> bin1 likewise; `rest` = what is left for further splits
@@ -247,10 +250,19 @@ __global__ void __launch_bounds__(SKM_THREADS, 2) skm_scan_kernel(const u64 *__r
             it0 = 0; it1 = 1;
             continue;
         }
-        tot_inst += n_inst; tot_rec += n_rec;
-        // ---------------- phase B: bin of every staged run ----------------
+        // ---------------- phase B: bin of every staged run (the hash is replaced by its bin digits; runs of other rounds
+        // are marked and skipped from here on) ----------------
         for (u32 i = threadIdx.x; i < ntot; i += SKM_THREADS) {
-            atomicAdd(&S.hist[__umulhi(skm_digits(S.dh[i]), nb0)], 1u);
+            u32 d = skm_digits(S.dh[i]);
+            if (g.rounds > 1) {
+                const u64 pr = (u64)d * g.rounds;
+                if ((u32)(pr >> 32) != g.round) { S.ds[i] = 0xFFFFFFFFu; continue; }
+                d = (u32)pr;   // the low word is uniform again
+            }
+            S.dh[i] = d;
+            tot_inst += (S.ds[i] & 31u) + 1u;
+            ++tot_rec;
+            atomicAdd(&S.hist[__umulhi(d, nb0)], 1u);
         }
         __syncthreads();
         if (MODE == 0) {
@@ -285,11 +297,12 @@ __global__ void __launch_bounds__(SKM_THREADS, 2) skm_scan_kernel(const u64 *__r
                     __syncthreads();
                     const bool staged = tot <= SKM_BULK_CAP;   // (uniform) otherwise this half goes out record by record
                     for (u32 i = threadIdx.x; i < ntot; i += SKM_THREADS) {
+                        const u32 dsv = S.ds[i];
+                        if (dsv == 0xFFFFFFFFu) continue;   // another round's run
                         u32 b, bin1, rest;
-                        skm_bins(skm_digits(S.dh[i]), nb0, g.nb1, b, bin1, rest);
+                        skm_bins(S.dh[i], nb0, g.nb1, b, bin1, rest);
                         if (b < h0 || b >= h0 + 256) continue;
                         const u32 r = atomicAdd(&S.hist[b], 1u);
-                        const u32 dsv = S.ds[i];
                         const u32 len = (dsv & 31u) + 1u;
                         const u32 meta = (len - 1u) | (bin1 << 5) | ((rest >> 18) << 18);
                         atomicAdd(&hist1[(u64)b * g.nb1 + bin1], 1u);
@@ -314,10 +327,11 @@ __global__ void __launch_bounds__(SKM_THREADS, 2) skm_scan_kernel(const u64 *__r
             // ---------------- phase D: records built and stored, grouped by bin ----------------
             const u64 tile_b0 = tile_w0 << 5;
             for (u32 i = threadIdx.x; i < ntot; i += SKM_THREADS) {
-                u32 b, bin1, rest;
-                skm_bins(skm_digits(S.dh[i]), nb0, g.nb1, b, bin1, rest);
-                const u32 p = S.gbase[b] + atomicAdd(&S.hist[b], 1u);
                 const u32 dsv = S.ds[i];
+                if (dsv == 0xFFFFFFFFu) continue;   // another round's run
+                u32 b, bin1, rest;
+                skm_bins(S.dh[i], nb0, g.nb1, b, bin1, rest);
+                const u32 p = S.gbase[b] + atomicAdd(&S.hist[b], 1u);
                 const u32 len = (dsv & 31u) + 1u;
                 const u32 meta = (len - 1u) | (bin1 << 5) | ((rest >> 18) << 18);
                 atomicAdd(&hist1[(u64)b * g.nb1 + bin1], 1u);

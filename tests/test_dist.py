@@ -26,10 +26,10 @@ def _free_port():
     return p
 
 
-def _launch(mode, world):
+def _launch(mode, world, env=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "dist_worker.py"), mode]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, cwd=ROOT)
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, cwd=ROOT, env=dict(os.environ, **(env or {})))
     assert r.returncode == 0 and ("DIST_OK " + mode) in r.stdout, r.stdout[-3000:]
 
 
@@ -80,3 +80,14 @@ def test_gpu_dist_world_n(pkg, world):
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     _launch("gpu", world)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [1, 2])
+def test_gpu_dist_rounds(pkg, world):
+    """GG_SKM_ROUNDS=3: the super-k-mer route counts in three rounds over slices of the minimizer digit (what a job
+    with more than 512 x 8192 leaf bins does) and merges the rounds' tables"""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    _launch("gpu", world, env={"GG_SKM_ROUNDS": "3"})
