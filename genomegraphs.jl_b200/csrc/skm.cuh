@@ -422,11 +422,24 @@ __global__ void __launch_bounds__(SKM_L1_THREADS) skm_l1_kernel(const ulonglong2
     const ulonglong2 *tp = in + tile0;
     for (u32 i = threadIdx.x; i < nb1; i += SKM_L1_THREADS) hist[i] = 0;
     __syncthreads();
+    // the tile's records stay in registers between the count and the placement (16 independent 128-bit loads per thread):
+    // a second sweep over the 128 KB tile missed L2 and doubled the kernel's DRAM reads (ncu, profiles/README.md)
+    constexpr int PER = SKM_ALIGN / SKM_L1_THREADS;
+    ulonglong2 rec[PER];
     u32 inst = 0;
-    for (u32 i = threadIdx.x; i < m; i += SKM_L1_THREADS) {
-        const u32 meta = (u32)tp[i].y;
-        atomicAdd(&hist[(meta >> 5) & (SKM_MAX_NB1 - 1u)], 1u);
-        inst += (meta & 31u) + 1u;
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        const u32 i = threadIdx.x + (u32)q * SKM_L1_THREADS;
+        rec[q] = i < m ? tp[i] : make_ulonglong2(0, 0);
+    }
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        const u32 i = threadIdx.x + (u32)q * SKM_L1_THREADS;
+        if (i < m) {
+            const u32 meta = (u32)rec[q].y;
+            atomicAdd(&hist[(meta >> 5) & (SKM_MAX_NB1 - 1u)], 1u);
+            inst += (meta & 31u) + 1u;
+        }
     }
     if (inst_total) {   // multi-GPU: the owner learns how many k-mer instances it received
         inst = warp_sum(inst);
@@ -439,10 +452,13 @@ __global__ void __launch_bounds__(SKM_L1_THREADS) skm_l1_kernel(const ulonglong2
         hist[i] = 0;
     }
     __syncthreads();
-    for (u32 i = threadIdx.x; i < m; i += SKM_L1_THREADS) {
-        const ulonglong2 rec = tp[i];
-        const u32 b = ((u32)rec.y >> 5) & (SKM_MAX_NB1 - 1u);
-        out[(u64)gpos[b] + atomicAdd(&hist[b], 1u)] = rec;
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        const u32 i = threadIdx.x + (u32)q * SKM_L1_THREADS;
+        if (i < m) {
+            const u32 b = ((u32)rec[q].y >> 5) & (SKM_MAX_NB1 - 1u);
+            out[(u64)gpos[b] + atomicAdd(&hist[b], 1u)] = rec[q];
+        }
     }
 }
 __global__ void skm_gather_strided_kernel(const u32 *__restrict__ in, u32 stride, u32 n, u32 *__restrict__ out) {
