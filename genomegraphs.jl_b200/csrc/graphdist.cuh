@@ -131,7 +131,7 @@ __global__ void gs_expand_kernel(const u64 *__restrict__ red_rec, const u32 *__r
     u32 i, back = 0;
     if (sel_bit(sel, v)) i = sel_rank(sel, v);
     else {
-        const u64 ol = ownloc[t];
+        const u64 ol = __ldcs(ownloc + t);
         i = (u32)(ol >> 32);
         back = (u32)ol;
     }
@@ -198,25 +198,31 @@ __global__ void gs_nodelen_kernel(const uint4 *__restrict__ ntab, u64 nn, u32 *_
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nn) len[i] = ntab[i].w;
 }
+// the node's first-base offset takes the place of its length: emission then needs ONE random access per vertex
+__global__ void gs_nodeoff_kernel(const u32 *__restrict__ off, u64 nn, uint4 *__restrict__ ntab) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nn) ntab[i].w = off[i];
+}
 // every own vertex of an emitted range writes its base(s)
 template <int W>
 __global__ void __launch_bounds__(256) gs_emit_kernel(const u64 *__restrict__ keys, const u64 *__restrict__ rec, const u32 *__restrict__ vhead,
                                                       const u32 *__restrict__ vrank, u32 v0, u32 nvl, int k, const u64 *__restrict__ nsel,
-                                                      const uint4 *__restrict__ ntab, const u32 *__restrict__ node_off, u32 *__restrict__ packed,
+                                                      const uint4 *__restrict__ ntab, u32 *__restrict__ packed,
                                                       u32 *__restrict__ node_first, u32 *__restrict__ node_last) {
     const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nvl) return;
-    const u32 head = vhead[t];
+    // (the per-vertex arrays are read once: streaming loads keep L2 for the node table, the rank structure and the packed bases)
+    const u32 head = __ldcs(vhead + t);
     if (head == V_NONE) return;
     const u32 v = v0 + t;
-    const u32 tail = ((u32)rec[t]) & ~V_TERM;
+    const u32 tail = ((u32)__ldcs(rec + t)) & ~V_TERM;
     const u32 id = sel_rank(nsel, min(head >> 1, tail >> 1));
-    const uint4 pr = ntab[id];   // (head, first emitted rank, emitted count, bases) of the node keyed here
+    const uint4 pr = ntab[id];   // (head, first emitted rank, emitted count, offset of the first base) of the node keyed here
     if (pr.x != head) return;    // the mirror orientation is the emitted one
-    const u32 rank = vrank[t], re = pr.y, cnt = pr.z;
+    const u32 rank = __ldcs(vrank + t), re = pr.y, cnt = pr.z;
     if (rank < re || rank - re >= cnt) return;
     const u32 j = rank - re;
-    const u64 off = node_off[id];
+    const u64 off = pr.w;
     const Kmer<W> x = vertex_kmer<W>(keys, v, k);
     // 2-bit codes OR-ed into a zeroed packed array (16 bases per word): the vertices of a node sit at random table
     // positions, and the packed array of all nodes is small enough to stay in L2, where the atomics are served
@@ -483,7 +489,8 @@ static gg_graph *build_graph_sharded(gg_ctx *ctx, const u64 *keys, u64 U, int k,
                 dfill(ctx, node_first.p, (nn + 1) * sizeof(u32), 0u);
                 dfill(ctx, node_last.p, (nn + 1) * sizeof(u32), 0u);
             }
-            LAUNCH(ctx, gs_emit_kernel<W>, (unsigned)ceil_div(nvl, 256), 256, 0, keys, rec.p, vhead.p, vrank.p, v0, nvl, k, nsel.p, ntab.p, node_off32.p,
+            if (nn) LAUNCH(ctx, gs_nodeoff_kernel, (unsigned)ceil_div(nn, 256), 256, 0, node_off32.p, nn, ntab.p);
+            LAUNCH(ctx, gs_emit_kernel<W>, (unsigned)ceil_div(nvl, 256), 256, 0, keys, rec.p, vhead.p, vrank.p, v0, nvl, k, nsel.p, ntab.p,
                    packed.p, node_first.p, node_last.p);
         };
         if (nc) dist_guard(cm, "node emission", local6); else local6();
