@@ -315,7 +315,7 @@ static u64 dist_msd_count(gg_comm *cm, const PackedReads &pr, const u32 *valid, 
     DBuf<u32> hist0, bstart;
     DBuf<u64> A, Rtmp;
     u64 *R = nullptr;
-    if (W == 1 && dist_ensure_recv(cm, need)) {
+    if (dist_ensure_recv(cm, need * W)) {
         // ---- pass B fused with the exchange: tiles are written into the owners' buffers over NVLink ----
         MsdPeers pt;
         memset(&pt, 0, sizeof(pt));
@@ -331,7 +331,10 @@ static u64 dist_msd_count(gg_comm *cm, const PackedReads &pr, const u32 *valid, 
         DBuf<u64> tok(ctx, 1);
         CK(cudaMemcpyAsync(pcur.p, h_cur.data(), nb0 * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
         // the collectives of pass A ran after every rank's previous call on its stream: nobody still reads its buffer
-        dist_guard(cm, "pass B (peer scatter)", [&] { msd_pass_b(ctx, pr, valid, k, canonical, pl, hist.p, N_loc, hist0, bstart, A, &pt, pcur.p); });
+        dist_guard(cm, "pass B (peer scatter)", [&] {
+            if constexpr (W == 1) msd_pass_b(ctx, pr, valid, k, canonical, pl, hist.p, N_loc, hist0, bstart, A, &pt, pcur.p);
+            else msdw_pass_b<W>(ctx, pr, valid, k, canonical, pl, hist.p, N_loc, hist0, bstart, A, &pt, pcur.p);
+        });
         stage_end(ctx, ST_EXTRACT);
         mark();  // 3: pass B (scatter into the peers) done locally
         stage_begin(ctx, ST_SORT);

@@ -119,10 +119,12 @@ __global__ void __launch_bounds__(256) msdw_hist_kernel(const u64 *__restrict__ 
 }
 
 // ---- pass B ---------------------------------------------------------------------------------------
-template <int W>
+// PEER (multi-GPU): the buckets are owned by ranks and the tile's runs are written straight into the owners' receive
+// buffers over NVLink (the cursors then hold key offsets inside those buffers): the level-0 scatter IS the exchange.
+template <int W, bool PEER>
 __global__ void __launch_bounds__(256, 2) msdw_scatter_kernel(const u64 *__restrict__ packed, const u32 *__restrict__ valid, u64 nwords,
                                                               int k, int canonical, int b0, u32 *__restrict__ cursor,
-                                                              u64 *__restrict__ out) {
+                                                              u64 *__restrict__ out, MsdPeers pt) {
     extern __shared__ __align__(16) u8 smem_raw[];
     u64 *skeys = reinterpret_cast<u64 *>(smem_raw);                                  // TILE_KEYS * W: keys grouped by bucket
     u64 *akeys = skeys + (size_t)MsdW<W>::TILE_KEYS * W;                             // STASH: TILE_KEYS * W keys as extracted
@@ -148,7 +150,8 @@ __global__ void __launch_bounds__(256, 2) msdw_scatter_kernel(const u64 *__restr
     __syncthreads();
     for (u32 i = threadIdx.x; i < total; i += 256) {
         const Kmer<W> key = km_load<W>(skeys, i);
-        km_store<W>(out, (u32)(delta[kw_bits<W>(key, lowbit, b0)] + i), key);
+        const u32 d = kw_bits<W>(key, lowbit, b0);
+        km_store<W>(PEER ? pt.ptr[msd_owner(pt, d)] : out, (u32)(delta[d] + i), key);
     }
 }
 
@@ -401,7 +404,7 @@ static void msdw_pass_a_launch(gg_ctx *ctx, const PackedReads &pr, const u32 *va
 // pass B: keys scattered into 2^b0 buckets of A (N * W words)
 template <int W>
 static void msdw_pass_b(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, int k, int canonical, const MsdPlan &pl, const u32 *hist, u64 N,
-                        DBuf<u32> &hist0, DBuf<u32> &bstart, DBuf<u64> &A) {
+                        DBuf<u32> &hist0, DBuf<u32> &bstart, DBuf<u64> &A, const MsdPeers *peers = nullptr, u32 *peer_cursor = nullptr) {
     const u32 nb0 = 1u << pl.b0;
     hist0.alloc(ctx, nb0 + 1);
     bstart.alloc(ctx, nb0 + 1);
@@ -409,13 +412,20 @@ static void msdw_pass_b(gg_ctx *ctx, const PackedReads &pr, const u32 *valid, in
     LAUNCH(ctx, msd_collapse_kernel, (unsigned)ceil_div(nb0 + 1, 256), 256, 0, hist, pl.hb, pl.b0, hist0.p);
     exclusive_scan_u32(ctx, hist0.p, bstart.p, nb0 + 1, nullptr);
     LAUNCH(ctx, msd_copy_u32_kernel, (unsigned)ceil_div(nb0, 256), 256, 0, bstart.p, (u64)nb0, cursor.p);
-    A.alloc(ctx, (N ? N : 1) * W);
+    A.alloc(ctx, ((N && !peers) ? N : 1) * W);
     if (N == 0) return;
     const size_t smemB = (MsdW<W>::STASH ? 2 : 1) * (size_t)MsdW<W>::TILE_KEYS * W * 8 + 2 * (size_t)(1 << MSDW_B0_MAX) * 4 + (size_t)MsdW<W>::TILE_KEYS * 2;
-    set_max_smem(ctx, msdw_scatter_kernel<W>, smemB);
+    set_max_smem(ctx, (msdw_scatter_kernel<W, false>), smemB);
+    set_max_smem(ctx, (msdw_scatter_kernel<W, true>), smemB);
     prof_bytes(ctx, 12.0 * (double)pr.nwords + 8.0 * W * (double)N);   // masks + packed words in, every key out once
-    LAUNCH(ctx, msdw_scatter_kernel<W>, (unsigned)ceil_div(pr.nwords, MsdW<W>::TILE_WORDS), 256, smemB, pr.packed.p, valid, pr.nwords, k,
-           canonical, pl.b0, cursor.p, A.p);
+    MsdPeers none;
+    memset(&none, 0, sizeof(none));
+    if (peers)
+        LAUNCH(ctx, (msdw_scatter_kernel<W, true>), (unsigned)ceil_div(pr.nwords, MsdW<W>::TILE_WORDS), 256, smemB, pr.packed.p, valid, pr.nwords, k,
+               canonical, pl.b0, peer_cursor, (u64 *)nullptr, *peers);
+    else
+        LAUNCH(ctx, (msdw_scatter_kernel<W, false>), (unsigned)ceil_div(pr.nwords, MsdW<W>::TILE_WORDS), 256, smemB, pr.packed.p, valid, pr.nwords, k,
+               canonical, pl.b0, cursor.p, A.p, none);
 }
 // Level-0 buckets -> sorted unique keys + counts (see msd_finish).  With nsrc > 1 (multi-GPU) level 1 always
 // runs (with b1 = 0 bits if need be): it merges the pieces of a bucket into one contiguous child.
