@@ -151,7 +151,6 @@ __global__ void __launch_bounds__(SKM_THREADS, 2) skm_scan_kernel(const u64 *__r
         __syncthreads();
         // ---------------- phase 1 ----------------
         u32 rl = 0, rh = 0, rslot = NOSLOT;   // open run: windows so far, minimizer hash, staging slot
-        u32 n_inst = 0, n_rec = 0;
 #pragma unroll 1
         for (int it = it0; it < it1; ++it) {
             const u64 t = tbase + it;
@@ -208,10 +207,8 @@ __global__ void __launch_bounds__(SKM_THREADS, 2) skm_scan_kernel(const u64 *__r
                 if (rl != 0) {                     // the carried run takes the leading continuation windows and ends in this word (WIN < 32)
                     rl += (u32)__ffs((int)~cm) - 1u;
                     if (rslot < SKM_STAGE_CAP) S.ds[rslot] += rl - 1u;
-                    n_inst += rl;
                     rl = 0;
                 }
-                n_rec += nq;
                 const u32 sbase = nq ? atomicAdd(&S.s_n, nq) : 0u;   // one reservation per thread and word
                 const u32 rel = (u32)(t - tile_w0) << 5;
                 u32 mask = nm, qi = 0;
@@ -228,19 +225,16 @@ __global__ void __launch_bounds__(SKM_THREADS, 2) skm_scan_kernel(const u64 *__r
                         rl = len; rh = hq; rslot = slot;
                     } else {
                         if (slot < SKM_STAGE_CAP) { S.dh[slot] = hq; S.ds[slot] = ((rel + (u32)j) << 5) | (len - 1u); }
-                        n_inst += len;
                     }
                 }
             } else if (rl != 0) {  // no k-mer starts in this word: the open run ends here
                 if (rslot < SKM_STAGE_CAP) S.ds[rslot] += rl - 1u;
-                n_inst += rl;
                 rl = 0;
             }
         }
         __syncwarp();
         if (rl != 0) {
             if (rslot < SKM_STAGE_CAP) S.ds[rslot] += rl - 1u;
-            n_inst += rl;
         }
         __syncthreads();
         const u32 ntot = S.s_n;
@@ -494,7 +488,6 @@ __global__ void __launch_bounds__(THREADS) skm_leaf_kernel(const ulonglong2 *__r
                                                            const u32 *__restrict__ lcnt, u32 nleaf, int k, int canonical, u32 min_freq,
                                                            u64 *__restrict__ okeys, u32 *__restrict__ ocnts, unsigned long long *kept_cursor,
                                                            u32 *__restrict__ ovf_list, u32 *ovf_n, u32 test_ovf_mod) {
-    constexpr int WIN = (1 << LOGW) + 1;
     constexpr u32 HT = 1u << LOG_HT, HM = HT - 1u, LIST = SkmLeafSmem<THREADS, LOG_HT>::LIST;
     extern __shared__ __align__(16) u8 smem_raw[];
     SkmLeafSmem<THREADS, LOG_HT> &S = *reinterpret_cast<SkmLeafSmem<THREADS, LOG_HT> *>(smem_raw);

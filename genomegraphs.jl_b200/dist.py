@@ -1,10 +1,12 @@
-"""Multi-GPU host layer: one process per GPU, k-mers range-partitioned over the ranks.
+"""Multi-GPU host layer: one process per GPU.
 
-Plays the role of KmerAnalysis `dist_mem` (re-exported by the reference at
-src/GenomeGraphs.jl:46-47): every rank counts on ITS shard of the reads and ends up owning a
-contiguous key range of the global sorted (k-mer, count) table.  The exchange itself is NCCL
-send/recv inside libggb200.so (csrc/dist.cuh); `torch.distributed` is only the host channel
-that ships the 128-byte NCCL unique id (any backend, gloo included).
+Plays the role of KmerAnalysis `dist_mem` (re-exported by the reference at src/GenomeGraphs.jl:46-47): every rank
+counts on ITS shard of the reads.  For 17 <= k <= 32 the super-k-mers are partitioned by minimizer bin and stored into
+the owner GPU's buffer over NVLink (bulk asynchronous copies), each rank counts its bins, and a second exchange
+range-partitions the kept k-mers, so that every rank ends up owning a contiguous key range of the global sorted
+(k-mer, count) table; other k partition W-word keys by range directly.  The graph stage is sharded by vertex range.
+All exchanges run inside libggb200.so (csrc/dist.cuh, csrc/graphdist.cuh: NCCL + CUDA IPC peer memory);
+`torch.distributed` is only the host channel that ships the 128-byte NCCL unique id (any backend, gloo included).
 """
 import ctypes as C
 
