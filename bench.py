@@ -76,7 +76,8 @@ def base_config(args, w, world):
             "l2_policy": "inputs (%.0f MB of reads per GPU per step) larger than the 126 MB L2; no flush needed" % (nreads_total * w["read_len"] / world / 1e6),
             "parallelism": ("1 GPU" if world == 1 else
                             "1 process per GPU; reads sharded by index; super-k-mers partitioned by minimizer hash and stored into the owner "
-                            "GPU's buffer over NVLink; kept k-mers range-partitioned in a second exchange; graph stage on the gathered table")}
+                            "GPU's buffer over NVLink (bulk asynchronous copies); kept k-mers range-partitioned in a second exchange; unitig stage "
+                            "sharded by vertex range over the all-gathered table; every rank returns the whole graph")}
 
 
 def cpu_sample(w):

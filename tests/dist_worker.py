@@ -63,6 +63,32 @@ def main():
             keys, counts = np.unique(mine, return_counts=True)
             keep = counts >= min_freq
             part = (keys[keep].reshape(-1, 1), counts[keep].astype(np.uint32))
+            # ---- the super-k-mer route's TWO exchanges, emulated on the same shard: (1) every canonical k-mer goes to the rank
+            # that owns its bin (any function of the k-mer stands in for the minimizer digit: equal k-mers meet in one bin; bins
+            # are owned in equal shares), the owner counts and filters; (2) the kept pairs, a hash subset of the table, are
+            # range-partitioned on a 14-bit digit histogram with gg_dist_splitters and merged.  Must equal `part`.
+            nb0 = 64
+            binof = ((km * np.uint64(0x9E3779B97F4A7C15)) >> np.uint64(58)).astype(np.int64)   # 0 .. 63
+            owner_first = [q * nb0 // world for q in range(world + 1)]
+            out1 = [km[(binof >= owner_first[p]) & (binof < owner_first[p + 1])] for p in range(world)]
+            ex1 = [None] * world
+            dist.all_gather_object(ex1, out1)
+            got = np.concatenate([ex1[p][rank] for p in range(world)])
+            k2, c2 = np.unique(got, return_counts=True)
+            k2, c2 = k2[c2 >= min_freq], c2[c2 >= min_freq].astype(np.uint32)
+            tb = min(14, 2 * k)
+            dig2 = (k2 >> np.uint64(2 * k - tb)).astype(np.int64)
+            h2 = np.bincount(dig2, minlength=1 << tb).astype(np.uint64)
+            hs2 = [None] * world
+            dist.all_gather_object(hs2, h2)
+            fb2 = D.splitters(np.sum(hs2, axis=0), world)
+            out2 = [(k2[(dig2 >= fb2[p]) & (dig2 < fb2[p + 1])], c2[(dig2 >= fb2[p]) & (dig2 < fb2[p + 1])]) for p in range(world)]
+            ex2 = [None] * world
+            dist.all_gather_object(ex2, out2)
+            rk = np.concatenate([ex2[p][rank][0] for p in range(world)])
+            rc = np.concatenate([ex2[p][rank][1] for p in range(world)])
+            order = np.argsort(rk, kind="stable")
+            part2 = (rk[order].reshape(-1, 1), rc[order])
         else:
             c = D.dist_mem(k, pkg.CANONICAL, comm, min_freq)((seq, offs))
             kk, c32, _ = c.export()
@@ -72,6 +98,10 @@ def main():
             graph = (ga.node_strings(), ga.link_lists())
         parts = [None] * world
         dist.all_gather_object(parts, part)
+        parts2 = None
+        if mode == "cpu":
+            parts2 = [None] * world
+            dist.all_gather_object(parts2, part2)
         graphs = [None] * world
         if mode == "gpu":
             dist.all_gather_object(graphs, graph)
@@ -83,6 +113,9 @@ def main():
             gc = np.concatenate([p[1] for p in parts])
             assert np.array_equal(gk, okeys), "k-mers differ (case seed %d)" % seed
             assert np.array_equal(gc, ocnt), "counts differ (case seed %d)" % seed
+            if parts2 is not None:   # minimizer-bin partition + range repartition: the same global table, cut at (possibly) other keys
+                assert np.array_equal(np.concatenate([p[0] for p in parts2]), okeys), "two-exchange k-mers differ (case seed %d)" % seed
+                assert np.array_equal(np.concatenate([p[1] for p in parts2]), ocnt), "two-exchange counts differ (case seed %d)" % seed
             if mode == "gpu":
                 og = O.dbg(okeys, k)
                 for g in graphs:
