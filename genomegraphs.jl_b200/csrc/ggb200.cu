@@ -1143,6 +1143,7 @@ int gg_comm_unique_id(uint8_t id[GG_COMM_ID_BYTES]) {
 int gg_comm_create(gg_ctx *ctx, const uint8_t id[GG_COMM_ID_BYTES], int rank, int world, gg_comm **out) {
     API_BEGIN(ctx)
     if (!out || !id || world < 1 || rank < 0 || rank >= world) GG_THROW(GG_ERR_ARG, "bad communicator arguments");
+    if (world > MSD_MAX_PEERS) GG_THROW(GG_ERR_LIMIT, "a communicator spans at most %d ranks (the GPUs of one box)", MSD_MAX_PEERS);
     *out = nullptr;
     NcclApi *nc = nccl_api();
     if (!nc) GG_THROW(GG_ERR_CUDA, "libnccl.so.2 could not be loaded");
