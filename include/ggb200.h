@@ -172,12 +172,17 @@ void gg_umi_free(gg_umi *u);
 /* ---- multi-GPU (one process per GPU) ------------------------------------------------------
  * Replaces the role of KmerAnalysis `dist_mem` (re-export src/GenomeGraphs.jl:46-47, prose
  * docs/src/man/assembly.md:108-117: workers count read ranges, sorted count vectors are
- * merged).  Every rank passes ITS shard of the reads; k-mers are range-partitioned over the
- * ranks on the all-gathered level-0 histogram and exchanged once (NCCL send/recv over
- * NVLink); rank r returns the r-th contiguous slice of the global sorted table, so the
- * concatenation over ranks equals the single-GPU gg_count_kmers result.  All k <= 128
- * (k <= 32 scatters straight into the peers' buffers over NVLink; longer k-mers use
- * ncclSend / ncclRecv); non-canonical counting at k = 32 is not covered (GG_ERR_LIMIT).
+ * merged).  Every rank passes ITS shard of the reads.  17 <= k <= 32: the super-k-mers are
+ * partitioned by minimizer bin and stored into the owner GPU's buffer over NVLink (bulk
+ * asynchronous copies; grouped ncclSend / ncclRecv without peer mapping), every rank counts
+ * its bins -- in rounds over slices of the minimizer digit for jobs beyond ~7.7e9 instances --
+ * and a second exchange range-partitions the kept k-mers.  Other k <= 128: W-word keys are
+ * range-partitioned on the all-gathered level-0 histogram, the level-0 scatter writing
+ * straight into the owners' buffers.  Either way rank r returns the r-th contiguous slice of
+ * the global sorted table, so the concatenation over ranks equals the single-GPU
+ * gg_count_kmers result.  A communicator spans at most 8 ranks (the GPUs of one box);
+ * non-canonical counting at k = 32 is not covered (GG_ERR_LIMIT).  A failure on one rank is
+ * agreed on before the next collective: every rank returns an error, none is left waiting.
  * Bootstrap: rank 0 calls gg_comm_unique_id and ships the bytes to the other ranks by any
  * host channel (the Python host uses torch.distributed, Julia would use Distributed / MPI);
  * every rank then calls gg_comm_create on its own context.  Collective calls must be made
@@ -197,8 +202,10 @@ int gg_dist_count_kmers_dev(gg_comm *comm, const uint8_t *d_seq_bytes, const uin
                             uint64_t *n_instances_global);
 /* slices of all ranks -> the whole sorted table on every rank */
 int gg_counts_allgather(gg_comm *comm, gg_counts *local, gg_counts **full);
-/* reads -> graph: distributed count + filter, all-gather of the kept k-mers, graph stage on
- * every rank (each rank returns the same graph). */
+/* reads -> graph: distributed count + filter, all-gather of the kept k-mers, unitig stage
+ * sharded by vertex range (lookups, successor pointers, list ranking, emission on the owner
+ * of each vertex; bitmaps / node table / packed bases summed over the ranks), link stage on
+ * every rank.  Each rank returns the same, whole graph.  At most 2^30 kept k-mers. */
 int gg_dist_dbg_from_reads_dev(gg_comm *comm, const uint8_t *d_seq_bytes, const uint64_t *d_read_offsets, uint64_t nreads,
                                uint64_t nbytes, int k, uint64_t min_freq, gg_graph **out, uint64_t *n_instances_global);
 
