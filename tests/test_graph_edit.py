@@ -1,0 +1,158 @@
+"""Tip removal (SURVEY section 8 f, rank 3): remove_node!, collapse_all_unitigs!, remove_tips!.
+
+CPU: the sequential restatement of the reference (oracle/graph_edit.py) against hand-checked cases and against the
+executable model of the data-parallel formulation (tests/collapse_model.py) on fuzzed graphs.
+GPU: the CUDA entry points (gg_graph_remove_nodes, gg_graph_collapse_all_unitigs, gg_graph_remove_tips) against the
+sequential restatement through the C ABI, bit-exact: node sequences, deleted nodes, per-node link order.
+"""
+import random
+
+import numpy as np
+import pytest
+
+import __graft_entry__ as G
+import collapse_model as M
+from oracle import graph_edit as E
+from oracle import oracle as O
+
+
+def _dbg_graph(seed, k=15, glen=3000, nreads=900, err=8000, min_freq=1, read_len=60):
+    seq, offs = O.synth_reads(seed, glen, nreads, read_len, True, 150, err)
+    keys, cnt = O.count_kmers(seq, offs, k)
+    og = O.dbg(O.filter_counts(keys, cnt, k, min_freq), k)
+    return og.nodes(), og.links()
+
+
+def _random_graph(rnd, nn, nl, dup=0.1):
+    """random sequences, random symmetric links made with add_link! (distances >= 0: no overlap to check), with
+    duplicate links, links between the two ends of one node, self links and deleted nodes"""
+    g = E.Graph(["".join(rnd.choice("ACGT") for _ in range(rnd.randint(1, 12))) for _ in range(nn)], [[] for _ in range(nn)])
+    for _ in range(nl):
+        a = rnd.randint(1, nn) * rnd.choice((1, -1))
+        b = rnd.randint(1, nn) * rnd.choice((1, -1))
+        g.add_link(a, b, rnd.randint(0, 5))
+        if rnd.random() < dup:
+            g.add_link(a, b, rnd.randint(0, 5))
+    for _ in range(rnd.randint(0, 2)):
+        g.remove_node(rnd.randint(1, nn))
+    return g.nodes, g.links
+
+
+def _chain_graph(rnd, k=5):
+    """sequences cut into overlapping pieces (paths and circles, pieces stored in either orientation, node ids
+    shuffled), linked by (k-1)-overlaps pushed in random order, plus a few branch links without overlap"""
+    pieces, joins = [], []          # joins: (piece index a, piece index b): end of a -> start of b
+    for _ in range(rnd.randint(1, 6)):
+        L = rnd.randint(k + 2, 60)
+        s = "".join(rnd.choice("ACGT") for _ in range(L))
+        circle = rnd.random() < 0.3
+        if circle:
+            s = s + s[:k - 1]
+        nk = len(s) - k + 1
+        cuts = sorted(rnd.sample(range(1, nk), min(rnd.randint(1, 5), nk - 1)))
+        first = len(pieces)
+        a = 0
+        for c in cuts + [nk]:
+            pieces.append(s[a:c + k - 1])       # k-mers a .. c-1
+            a = c
+        joins += [(i, i + 1) for i in range(first, len(pieces) - 1)]
+        if circle:
+            joins.append((len(pieces) - 1, first))
+    perm = list(range(len(pieces)))
+    rnd.shuffle(perm)                # piece i becomes node perm[i] + 1
+    sign = [rnd.choice((1, -1)) for _ in pieces]
+    nodes = [None] * len(pieces)
+    for i, p in enumerate(pieces):
+        nodes[perm[i]] = p if sign[i] > 0 else E.revcomp(p)
+    g = E.Graph(nodes, [[] for _ in nodes])
+    ident = lambda i: (perm[i] + 1) * sign[i]
+    rnd.shuffle(joins)
+    for a, b in joins:
+        if rnd.random() < 0.5:
+            g.add_link(-ident(a), ident(b), -(k - 1))
+        else:
+            g.add_link(ident(b), -ident(a), -(k - 1))
+    for _ in range(rnd.randint(0, 3)):
+        g.add_link(rnd.randint(1, len(nodes)) * rnd.choice((1, -1)), rnd.randint(1, len(nodes)) * rnd.choice((1, -1)), 3)
+    return g.nodes, g.links
+
+
+def _seq_collapse(nodes, links, min_nodes=2):
+    g = E.Graph(nodes, links)
+    new = g.collapse_all_unitigs(min_nodes, True)
+    return g.nodes, g.links, len(new)
+
+
+def test_restatement_small_cases():
+    # three nodes in a row, (k-1) = 2 overlaps: ACGT -> GTA -> TAC ; all collapse into one canonical node
+    g = E.Graph(["ACGT", "GTA", "TAC"], [[], [], []])
+    g.add_link(-1, 2, -2)
+    g.add_link(-2, 3, -2)
+    assert g.find_all_unitigs(2) == [[1, 2, 3]]
+    new = g.collapse_all_unitigs(2, True)
+    assert new == [4] and g.nodes == ["", "", "", "ACGTAC"] and g.links == [[], [], [], []]
+
+
+def test_restatement_tip_rules():
+    # src/Graphs.jl:778-802 on a fork: only a dead end next to a branching neighbour (or an isolated node) is a tip
+    g = E.Graph(["AAAC", "AACGGG", "AACT", "CGGGT", "TTTTT"], [[] for _ in range(5)])
+    g.add_link(-1, 2, -3)
+    g.add_link(-1, 3, -3)
+    g.add_link(-2, 4, -4)
+    # node 3: one backward link, no forward link, and node 1 has two forward links -> tip; node 5 isolated -> tip;
+    # node 4: its only neighbour (2) has one forward link -> not a tip; node 1: two forward links -> not a tip
+    assert g.find_tip_nodes(5) == [3, 5]
+    assert g.find_tip_nodes(4) == [3]        # node 5 is longer than min_size
+    passes, removed = g.remove_tips(4)
+    # after removing 3: 1 -> 2 -> 4 is one unitig AAACGGGT; canonical of AAACGGGT vs ACCCGTTT: AAAC.. < ACCC.. keep
+    assert (passes, removed) == (2, 1)
+    assert g.nodes == ["", "", "", "", "TTTTT", "AAACGGGT"] and all(not ls for ls in g.links)
+
+
+def test_model_equals_restatement_fuzz_random_links():
+    rnd = random.Random(5)
+    hits = 0
+    for trial in range(400):
+        nodes, links = _random_graph(rnd, rnd.randint(1, 14), rnd.randint(0, 14))
+        exp = _seq_collapse(nodes, links)
+        got = M.collapse_all_unitigs(nodes, links, 2)
+        assert got[0] == exp[0] and got[1] == exp[1] and got[2] == exp[2], (trial, nodes, links)
+        hits += exp[2] > 0
+    assert hits > 100
+
+
+def test_model_equals_restatement_fuzz_chains():
+    rnd = random.Random(9)
+    circles = 0
+    for trial in range(300):
+        nodes, links = _chain_graph(rnd)
+        for mn in (2, 3):
+            exp = _seq_collapse(nodes, links, mn)
+            got = M.collapse_all_unitigs(nodes, links, mn)
+            assert got[0] == exp[0] and got[1] == exp[1] and got[2] == exp[2], (trial, mn, nodes, links)
+        circles += any(len(ls) == 0 for ls in exp[1][len(nodes):])
+    assert circles > 10
+
+
+@pytest.mark.parametrize("seed,err,min_size", [(3, 8000, 45), (4, 20000, 30), (5, 3000, 10000), (6, 12000, 20)])
+def test_model_equals_restatement_remove_tips_dbg(seed, err, min_size):
+    nodes, links = _dbg_graph(seed, err=err)
+    g = E.Graph(nodes, links)
+    assert M.find_tip_nodes(nodes, links, min_size) == g.find_tip_nodes(min_size)
+    passes, removed = g.remove_tips(min_size)
+    n2, l2, p2, r2 = M.remove_tips(nodes, links, min_size)
+    assert (p2, r2) == (passes, removed) and n2 == g.nodes and l2 == g.links
+    if min_size >= 30:
+        assert removed > 0 and len(g.nodes) > len(nodes)
+
+
+def test_remove_nodes_model():
+    rnd = random.Random(2)
+    for _ in range(100):
+        nodes, links = _random_graph(rnd, rnd.randint(2, 10), rnd.randint(0, 12))
+        ids = [rnd.randint(1, len(nodes)) * rnd.choice((1, -1)) for _ in range(rnd.randint(0, 4))]
+        g = E.Graph(nodes, links)
+        for n in ids:
+            g.remove_node(n)
+        n2, l2 = M.remove_nodes(nodes, links, ids)
+        assert n2 == g.nodes and l2 == g.links
