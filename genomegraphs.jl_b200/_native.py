@@ -53,6 +53,9 @@ SIGNATURES = {
     "gg_count_kmers_4bit": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_int, C.c_int, vpp]),
     "gg_dbg_from_reads_4bit": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_int, C.c_uint64, vpp]),
     "gg_graph_find_tip_nodes": (C.c_int, [vp, C.c_uint64, vp, u64p]),
+    "gg_graph_remove_nodes": (C.c_int, [vp, vp, C.c_uint64, vpp]),
+    "gg_graph_collapse_all_unitigs": (C.c_int, [vp, C.c_uint64, vpp, u64p]),
+    "gg_graph_remove_tips": (C.c_int, [vp, C.c_uint64, vpp, u64p, u64p]),
     "gg_graph_write_gfa1": (C.c_int, [vp, C.c_char_p]),
     "gg_gfa1_write": (C.c_int, [C.c_char_p, C.c_uint64, vp, vp, vp, vp]),
     "gg_graph_load_gfa1": (C.c_int, [vp, C.c_char_p, C.c_char_p, vpp]),

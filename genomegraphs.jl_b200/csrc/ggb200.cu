@@ -10,6 +10,7 @@
 #include "dist.cuh"
 #include "graph.cuh"
 #include "graphdist.cuh"
+#include "graphedit.cuh"
 #include "umi.cuh"
 #include "synth.cuh"
 #include "gfa.cuh"
@@ -966,6 +967,82 @@ int gg_graph_find_tip_nodes(gg_graph *g, uint64_t min_size, int64_t *tips, uint6
         CK(cudaStreamSynchronize(_c->stream));
     }
     *n_tips = nt;
+    API_END
+}
+// remove_node! (src/Graphs.jl:459-466) for every id (+n and -n both name node n): a new handle, `g` stays as it is
+int gg_graph_remove_nodes(gg_graph *g, const int64_t *ids, uint64_t n_ids, gg_graph **out) {
+    if (!g) return GG_ERR_ARG;
+    API_BEGIN(g->ctx)
+    if (!out || (n_ids && !ids)) GG_THROW(GG_ERR_ARG, "null argument");
+    *out = nullptr;
+    CK(cudaSetDevice(_c->device));
+    const u64 nn = g->n_nodes;
+    for (u64 t = 0; t < n_ids; ++t) {
+        const i64 x = ids[t];
+        if (x == 0 || (u64)(x < 0 ? -x : x) > nn) GG_THROW(GG_ERR_ARG, "node id %lld outside 1..%llu", (long long)x, (unsigned long long)nn);
+    }
+    DBuf<u32> dead(_c, nn + 1);
+    CK(cudaMemsetAsync(dead.p, 0, (nn + 1) * sizeof(u32), _c->stream));
+    if (n_ids) {
+        DBuf<i64> d_ids(_c, n_ids);
+        CK(cudaMemcpyAsync(d_ids.p, ids, n_ids * sizeof(i64), cudaMemcpyHostToDevice, _c->stream));
+        LAUNCH(_c, ge_mark_ids_kernel, (unsigned)ceil_div(n_ids, 256), 256, 0, d_ids.p, (u64)n_ids, dead.p);
+        CK(cudaStreamSynchronize(_c->stream));   // ids is the caller's pageable memory
+    }
+    *out = ge_remove_dead(_c, g, dead.p);
+    API_END
+}
+// collapse_all_unitigs!(sg, min_nodes, consume = true) (src/Graphs.jl:528-539)
+int gg_graph_collapse_all_unitigs(gg_graph *g, uint64_t min_nodes, gg_graph **out, uint64_t *n_new_nodes) {
+    if (!g) return GG_ERR_ARG;
+    API_BEGIN(g->ctx)
+    if (!out) GG_THROW(GG_ERR_ARG, "null output");
+    *out = nullptr;
+    CK(cudaSetDevice(_c->device));
+    u64 m = 0;
+    *out = ge_collapse(_c, g, min_nodes, &m);
+    if (n_new_nodes) *n_new_nodes = m;
+    API_END
+}
+// remove_tips!(sdg, min_size) (src/remove_tips.jl:2-30): find the tips, remove them, collapse the paths that appear,
+// until no tip is left.  *n_passes counts like the reference's log (1 = nothing to do).
+int gg_graph_remove_tips(gg_graph *g, uint64_t min_size, gg_graph **out, uint64_t *n_passes, uint64_t *n_tips_removed) {
+    if (!g) return GG_ERR_ARG;
+    API_BEGIN(g->ctx)
+    if (!out) GG_THROW(GG_ERR_ARG, "null output");
+    *out = nullptr;
+    CK(cudaSetDevice(_c->device));
+    gg_graph *cur = nullptr, *mid = nullptr;
+    u64 passes = 1, removed = 0;
+    try {
+        for (;;) {
+            const gg_graph *src = cur ? cur : g;
+            const u64 nn = src->n_nodes;
+            if (nn == 0) break;
+            if (nn >= 0xFFFFFFFFull) GG_THROW(GG_ERR_LIMIT, "too many nodes");
+            DBuf<u32> flag(_c, nn + 1), scratch(_c, nn + 1);
+            DBuf<u64> tot(_c, 1);
+            LAUNCH(_c, tip_kernel, (unsigned)ceil_div(nn, 256), 256, 0, src->d_node_off, src->d_link_row, src->d_link_tri, nn, (u64)min_size, flag.p);
+            exclusive_scan_u32(_c, flag.p, scratch.p, nn, tot.p);
+            const u64 nt = read_scalar<u64>(_c, tot.p);
+            if (nt == 0) break;
+            mid = ge_remove_dead(_c, src, flag.p);
+            if (cur) { ge_free_graph(_c, cur); cur = nullptr; }
+            cur = ge_collapse(_c, mid, 2, nullptr);
+            ge_free_graph(_c, mid);
+            mid = nullptr;
+            removed += nt;
+            ++passes;
+        }
+        if (!cur) cur = ge_clone_graph(_c, g);
+    } catch (...) {
+        if (cur) ge_free_graph(_c, cur);
+        if (mid) ge_free_graph(_c, mid);
+        throw;
+    }
+    *out = cur;
+    if (n_passes) *n_passes = passes;
+    if (n_tips_removed) *n_tips_removed = removed;
     API_END
 }
 int gg_graph_sizes(gg_graph *g, uint64_t *n_nodes, uint64_t *total_bases, uint64_t *n_link_entries, int *k) {

@@ -365,6 +365,29 @@ class DeviceGraph:
         N.check(self.ctx.h, N.lib().gg_graph_find_tip_nodes(self.h, int(min_size), _ptr(out), C.byref(n2)))
         return out[:n2.value]
 
+    def remove_nodes(self, ids):
+        """remove_node! (src/Graphs.jl:459-466) for every id: a new DeviceGraph"""
+        a = np.ascontiguousarray(ids, dtype=np.int64)
+        h = C.c_void_p()
+        N.check(self.ctx.h, N.lib().gg_graph_remove_nodes(self.h, _ptr(a) if a.size else None, a.size, C.byref(h)))
+        return DeviceGraph(self.ctx, h)
+
+    def collapse_all_unitigs(self, min_nodes=2, consume=True):
+        """collapse_all_unitigs!(sg, min_nodes, consume) (src/Graphs.jl:528-539): (new DeviceGraph, number of new nodes)"""
+        if not consume:
+            raise ValueError("only consume = true (what remove_tips! uses) runs on the device")
+        h = C.c_void_p()
+        m = C.c_uint64(0)
+        N.check(self.ctx.h, N.lib().gg_graph_collapse_all_unitigs(self.h, int(min_nodes), C.byref(h), C.byref(m)))
+        return DeviceGraph(self.ctx, h), m.value
+
+    def remove_tips(self, min_size):
+        """remove_tips!(sdg, min_size) (src/remove_tips.jl:2-30): (new DeviceGraph, passes, tips removed)"""
+        h = C.c_void_p()
+        p, r = C.c_uint64(0), C.c_uint64(0)
+        N.check(self.ctx.h, N.lib().gg_graph_remove_tips(self.h, int(min_size), C.byref(h), C.byref(p), C.byref(r)))
+        return DeviceGraph(self.ctx, h), p.value, r.value
+
     def free(self):
         if self.h:
             N.lib().gg_graph_free(self.h)
@@ -470,6 +493,41 @@ def dbg_(sdg, kmers_or_counts, min_freq=None, k=None, ctx=None):
     for i, ls in enumerate(ga.link_lists()):
         sdg.links[i].extend(SDGLink(*t) for t in ls)
     return sdg
+
+
+def _sdg_arrays(sdg, k=0):
+    """SequenceDistanceGraph (Python objects) -> GraphArrays; deleted nodes are empty"""
+    seqs = ["" if n.deleted else n.seq for n in sdg.nodes]
+    node_off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    node_off[1:] = np.cumsum([len(x) for x in seqs], dtype=np.uint64)
+    bases = np.frombuffer("".join(seqs).encode(), dtype=np.uint8).copy()
+    link_row = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    link_row[1:] = np.cumsum([len(ls) for ls in sdg.links], dtype=np.uint64)
+    tri = np.array([l.astuple() for ls in sdg.links for l in ls], dtype=np.int64).reshape(-1)
+    return GraphArrays(k, node_off, bases, link_row, tri)
+
+
+def _sdg_assign(sdg, ga):
+    seqs = ga.node_strings()
+    sdg.nodes[:] = [SDGNode(x, len(x) == 0) for x in seqs]     # empty_node: deleted, no sequence (src/Graphs.jl:86-88)
+    sdg.links[:] = [[SDGLink(*t) for t in ls] for ls in ga.link_lists()]
+    return sdg
+
+
+def remove_tips_(sdg, min_size, ctx=None):
+    """remove_tips!(sdg, min_size) (src/remove_tips.jl:2-30) on the device; mutates and returns `sdg` like the reference.
+    Accepts a SequenceDistanceGraph (uploaded, edited, written back) or a DeviceGraph (a new DeviceGraph is returned)."""
+    if isinstance(sdg, DeviceGraph):
+        return sdg.remove_tips(min_size)[0]
+    dg = DeviceGraph.from_arrays(_sdg_arrays(sdg), ctx=ctx)
+    try:
+        out, _, _ = dg.remove_tips(min_size)
+        try:
+            return _sdg_assign(sdg, out.arrays())
+        finally:
+            out.free()
+    finally:
+        dg.free()
 
 
 def dbg_from_reads(reads, k, min_freq, ctx=None):

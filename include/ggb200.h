@@ -146,6 +146,20 @@ int gg_graph_checksum(gg_graph *g, uint64_t *checksum);
 /* find_tip_nodes(sg, min_size) (src/Graphs.jl:778-816) on the device-resident graph: ids of the tip nodes, ascending
  * (the reference returns a Set).  Call with tips == NULL to get *n_tips first; *n_tips = capacity on input. */
 int gg_graph_find_tip_nodes(gg_graph *g, uint64_t min_size, int64_t *tips, uint64_t *n_tips);
+/* Tip removal on the device-resident graph.  Each call returns a NEW handle and leaves `g` as it is; a removed /
+ * collapsed node keeps its id and becomes empty (zero bases, no links: the reference's empty_node), new nodes are
+ * appended.  Node ids, orientation (canonical) and the order of the link entries at every node equal the reference's.
+ * Links must be symmetric as add_link! (src/Graphs.jl:473-476) makes them (GG_ERR_ARG otherwise).
+ *   gg_graph_remove_nodes          remove_node! (src/Graphs.jl:459-466) for every id; +n and -n both name node n
+ *   gg_graph_collapse_all_unitigs  collapse_all_unitigs!(sg, min_nodes, consume = true) (src/Graphs.jl:528-539:
+ *                                  find_all_unitigs! :831-862, join_path! :1040-1088); min_nodes >= 2; an overlap
+ *                                  (dist <= 0) that the sequences do not have is GG_ERR_ARG ("Sequences do not
+ *                                  overlap.", src/Graphs.jl:1023)
+ *   gg_graph_remove_tips           remove_tips!(sdg, min_size) (src/remove_tips.jl:2-30); *n_passes as in its log
+ *                                  (1 = no tip found), *n_tips_removed over all passes */
+int gg_graph_remove_nodes(gg_graph *g, const int64_t *ids, uint64_t n_ids, gg_graph **out);
+int gg_graph_collapse_all_unitigs(gg_graph *g, uint64_t min_nodes, gg_graph **out, uint64_t *n_new_nodes);
+int gg_graph_remove_tips(gg_graph *g, uint64_t min_size, gg_graph **out, uint64_t *n_passes, uint64_t *n_tips_removed);
 /* persistence: write_to_gfa1 (src/Graphs.jl:892-926), <filename>.gfa + <filename>.fasta in the reference's format,
  * from a graph handle or straight from exported arrays (host only, no context needed); and a loader for that pair of
  * files (load_from_gfa1! is unfinished upstream, src/Graphs.jl:943-958): nodes by their seq<id> names, one add_link!

@@ -156,3 +156,124 @@ def test_remove_nodes_model():
             g.remove_node(n)
         n2, l2 = M.remove_nodes(nodes, links, ids)
         assert n2 == g.nodes and l2 == g.links
+
+
+# ------------------------------------------------ CUDA path through the C ABI -------------------------------------------
+@pytest.fixture(scope="module")
+def pkg():
+    return G.build()
+
+
+@pytest.fixture(scope="module")
+def ctx(pkg):
+    c = pkg.Context(0)
+    yield c
+    c.close()
+
+
+def _device_graph(pkg, ctx, nodes, links, k=0):
+    node_off = np.zeros(len(nodes) + 1, dtype=np.uint64)
+    node_off[1:] = np.cumsum([len(x) for x in nodes], dtype=np.uint64)
+    bases = np.frombuffer("".join(nodes).encode(), dtype=np.uint8).copy()
+    link_row = np.zeros(len(nodes) + 1, dtype=np.uint64)
+    link_row[1:] = np.cumsum([len(ls) for ls in links], dtype=np.uint64)
+    tri = np.array([t for ls in links for t in ls], dtype=np.int64).reshape(-1)
+    return pkg.DeviceGraph.from_arrays(pkg.GraphArrays(k, node_off, bases, link_row, tri), ctx=ctx)
+
+
+def _back(dg):
+    ga = dg.arrays()
+    return ga.node_strings(), ga.link_lists()
+
+
+@pytest.mark.gpu
+def test_gpu_collapse_fuzz(pkg, ctx):
+    """gg_graph_collapse_all_unitigs against join_path! one path after the other (random links, chains, circles)"""
+    rnd = random.Random(31)
+    hits = 0
+    for trial in range(120):
+        nodes, links = _chain_graph(rnd) if trial % 2 else _random_graph(rnd, rnd.randint(1, 16), rnd.randint(0, 18), dup=0.2)
+        for mn in (2, 3):
+            try:
+                exp = _seq_collapse(nodes, links, mn)
+            except ValueError:
+                exp = None
+            dg = _device_graph(pkg, ctx, nodes, links)
+            try:
+                if exp is None:
+                    with pytest.raises(ValueError):
+                        dg.collapse_all_unitigs(mn)
+                    continue
+                out, m = dg.collapse_all_unitigs(mn)
+                try:
+                    got = _back(out)
+                    assert m == exp[2] and got[0] == exp[0] and got[1] == exp[1], (trial, mn, nodes, links)
+                    hits += m > 0
+                finally:
+                    out.free()
+            finally:
+                dg.free()
+    assert hits > 60
+
+
+@pytest.mark.gpu
+def test_gpu_remove_nodes(pkg, ctx):
+    rnd = random.Random(32)
+    for _ in range(40):
+        nodes, links = _random_graph(rnd, rnd.randint(2, 12), rnd.randint(0, 14))
+        ids = [rnd.randint(1, len(nodes)) * rnd.choice((1, -1)) for _ in range(rnd.randint(0, 4))]
+        g = E.Graph(nodes, links)
+        for n in ids:
+            g.remove_node(n)
+        dg = _device_graph(pkg, ctx, nodes, links)
+        out = dg.remove_nodes(ids)
+        assert _back(out) == (g.nodes, g.links)
+        out.free()
+        with pytest.raises(ValueError):
+            dg.remove_nodes([len(nodes) + 1])
+        dg.free()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,err,min_size,k", [(3, 8000, 45, 15), (4, 20000, 30, 15), (5, 3000, 10000, 15), (6, 12000, 20, 15), (7, 10000, 70, 31)])
+def test_gpu_remove_tips_dbg(pkg, ctx, seed, err, min_size, k):
+    """reads -> graph on the device -> remove_tips! on the device, against the sequential restatement on the oracle's graph"""
+    seq, offs = O.synth_reads(seed, 3000, 900, 60, True, 150, err)
+    keys, cnt = O.count_kmers(seq, offs, k)
+    og = O.dbg(O.filter_counts(keys, cnt, k, 1), k)
+    g = E.Graph(og.nodes(), og.links())
+    passes, removed = g.remove_tips(min_size)
+    ga = pkg.dbg_from_reads((seq, offs), k, 1, ctx=ctx)
+    assert ga.node_strings() == og.nodes() and ga.link_lists() == og.links()
+    dg = pkg.DeviceGraph.from_arrays(ga, ctx=ctx)
+    out, p2, r2 = dg.remove_tips(min_size)
+    got = _back(out)
+    assert (p2, r2) == (passes, removed)
+    assert got[0] == g.nodes and got[1] == g.links
+    if min_size >= 30:
+        assert removed > 0 and len(g.nodes) > og.n_nodes
+    # the edited graph is a graph like any other: no tip of that size is left, the writer accepts it
+    assert out.find_tip_nodes(min_size).size == 0
+    out.free()
+    dg.free()
+    # the reference-named host entry mutates the Python graph
+    sdg = pkg.empty_graph()
+    for s in og.nodes():
+        sdg.add_node_(s)
+    for i, ls in enumerate(og.links()):
+        sdg.links[i].extend(pkg.SDGLink(*t) for t in ls)
+    assert pkg.remove_tips_(sdg, min_size, ctx=ctx) is sdg
+    assert [n.seq for n in sdg.nodes] == g.nodes and sdg.link_tuples() == g.links
+    assert all(n.deleted == (n.seq == "") for n in sdg.nodes)
+
+
+@pytest.mark.gpu
+def test_gpu_collapse_rejects_asymmetric_links(pkg, ctx):
+    dg = _device_graph(pkg, ctx, ["ACGT", "GTAA"], [[(-1, 2, -2)], []])
+    with pytest.raises(ValueError):
+        dg.collapse_all_unitigs(2)
+    dg.free()
+    dg = _device_graph(pkg, ctx, ["ACGT", "TTAA"], [[(-1, 2, -2)], [(2, -1, -2)]])
+    with pytest.raises(ValueError, match="do not overlap"):
+        dg.collapse_all_unitigs(2)
+    dg.free()
