@@ -14,6 +14,8 @@ def pytest_configure(config):
 
 
 def pytest_collection_modifyitems(config, items):
+    if os.environ.get("GG_HAS_GPU") == "1":   # skips the torch import (a minute on a fresh box) when the caller knows
+        return
     try:
         import torch
         has_gpu = torch.cuda.is_available()

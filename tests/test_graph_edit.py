@@ -277,3 +277,23 @@ def test_gpu_collapse_rejects_asymmetric_links(pkg, ctx):
     with pytest.raises(ValueError, match="do not overlap"):
         dg.collapse_all_unitigs(2)
     dg.free()
+
+
+@pytest.mark.gpu
+def test_gpu_remove_tips_large(pkg, ctx):
+    """a graph beyond the single-launch sizes of the scan and sort primitives (> 65,536 link entries)"""
+    k = 21
+    seq, offs = O.synth_reads(8, 150000, 30000, 100, True, 300, 10000)
+    ga = pkg.dbg_from_reads((seq, offs), k, 1, ctx=ctx)
+    nodes, links = ga.node_strings(), ga.link_lists()
+    assert len(ga.link_triples) // 3 > 100000
+    g = E.Graph(nodes, links)
+    passes, removed = g.remove_tips(60)
+    dg = pkg.DeviceGraph.from_arrays(ga, ctx=ctx)
+    out, p2, r2 = dg.remove_tips(60)
+    got = _back(out)
+    assert (p2, r2) == (passes, removed) and removed > 1000
+    assert got[0] == g.nodes and got[1] == g.links
+    c1, m = dg.collapse_all_unitigs(2)       # nothing to collapse in a fresh unitig graph
+    assert m == 0 and _back(c1) == (nodes, links)
+    c1.free(); out.free(); dg.free()
