@@ -290,10 +290,16 @@ def test_gpu_remove_tips_large(pkg, ctx):
     g = E.Graph(nodes, links)
     passes, removed = g.remove_tips(60)
     dg = pkg.DeviceGraph.from_arrays(ga, ctx=ctx)
+    import time
+    t0 = time.perf_counter()
     out, p2, r2 = dg.remove_tips(60)
+    dt = time.perf_counter() - t0
     got = _back(out)
+    print("remove_tips on the device: %d nodes, %d link entries -> %d nodes, %d passes, %d tips, %.1f ms (first call)"
+          % (len(nodes), len(ga.link_triples) // 3, len(got[0]), p2, r2, 1e3 * dt))
     assert (p2, r2) == (passes, removed) and removed > 1000
     assert got[0] == g.nodes and got[1] == g.links
-    c1, m = dg.collapse_all_unitigs(2)       # nothing to collapse in a fresh unitig graph
-    assert m == 0 and _back(c1) == (nodes, links)
+    c1, m = dg.collapse_all_unitigs(2)       # the few paths dbg! leaves open (its walk stops at used k-mers, src/dbg.jl:147-150)
+    exp = _seq_collapse(nodes, links)
+    assert m == exp[2] and _back(c1) == (exp[0], exp[1])
     c1.free(); out.free(); dg.free()
