@@ -15,7 +15,7 @@ export
     mer, freq, Canonical, NonCanonical, CANONICAL, NONCANONICAL, serial_mem, spectra,
     empty_graph,
     WorkSpace, add_mer_counts!, mer_counts,
-    dbg, dbg!,
+    dbg, dbg!, remove_tips!,
     # device-side counter (drop-in for serial_mem(M, CANONICAL))
     gpu_mem, GPUContext, DeviceGraph, load_from_gfa1
 

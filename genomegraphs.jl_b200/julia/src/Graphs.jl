@@ -91,5 +91,7 @@ end
 # generic functions the device-graph methods of ../dbg.jl extend (reference src/Graphs.jl:892, :814)
 function write_to_gfa1 end
 function find_tip_nodes end
+function remove_node! end            # reference src/Graphs.jl:459
+function collapse_all_unitigs! end   # reference src/Graphs.jl:528
 
 end # module Graphs

@@ -147,6 +147,46 @@ load_from_gfa1(gfafile::AbstractString, fafile::AbstractString; ctx::LibGG.Conte
     DeviceGraph(ctx, LibGG.graph_load_gfa1(ctx, gfafile, fafile))
 "`find_tip_nodes(sg, min_size)` (src/Graphs.jl:778-816) on the device graph; ids ascending."
 Graphs.find_tip_nodes(g::DeviceGraph, min_size::Integer) = Set{Graphs.NodeID}(LibGG.graph_find_tip_nodes(g.ctx, g.h, min_size))
+
+# ---- tip removal (reference src/remove_tips.jl:2-30) --------------------------------------------------------------
+# The device entry points return a NEW handle; the `!` methods below keep the reference's mutating contract by
+# swapping the handle inside the DeviceGraph (or by writing the result back into the host graph).
+function swap_handle!(g::DeviceGraph, h::Ptr{Cvoid})
+    LibGG.graph_free(g.h)
+    g.h = h
+    return g
+end
+"`remove_node!(sg, n)` (src/Graphs.jl:459-466); a vector of ids removes them all in one pass."
+Graphs.remove_node!(g::DeviceGraph, n::Graphs.NodeID) = swap_handle!(g, LibGG.graph_remove_nodes(g.ctx, g.h, Int64[n]))
+Graphs.remove_node!(g::DeviceGraph, ns::AbstractVector{<:Integer}) = swap_handle!(g, LibGG.graph_remove_nodes(g.ctx, g.h, collect(Int64, ns)))
+"`collapse_all_unitigs!(sg, min_nodes, consume)` (src/Graphs.jl:528-539); only `consume = true` runs on the device."
+function Graphs.collapse_all_unitigs!(g::DeviceGraph, min_nodes::Integer, consume::Bool)
+    consume || throw(ArgumentError("collapse_all_unitigs! on a DeviceGraph needs consume = true"))
+    h, _ = LibGG.graph_collapse_all_unitigs(g.ctx, g.h, min_nodes)
+    swap_handle!(g, h)
+    return nothing
+end
+"`remove_tips!(sdg, min_size)` (src/remove_tips.jl:2-30) on the device-resident graph."
+function remove_tips!(g::DeviceGraph, min_size::Integer)
+    @info "Beginning tip removal process"
+    h, passes, ntips = LibGG.graph_remove_tips(g.ctx, g.h, min_size)
+    swap_handle!(g, h)
+    @info string("Removed ", ntips, " tips")
+    @info string("Finished tip removal process in ", passes, " passes")
+    return g
+end
+"The reference's signature: the host graph is uploaded, edited on the device and replaced in place."
+function remove_tips!(sdg::GRAPH_TYPE, min_size::Integer; ctx::LibGG.Context = LibGG.default_context())
+    g = remove_tips!(DeviceGraph(sdg, 0; ctx = ctx), min_size)
+    node_off, bases, link_row, tri = LibGG.graph_export(g.ctx, g.h)
+    empty!(Graphs.nodes(sdg)); empty!(Graphs.links(sdg))
+    fill_graph!(sdg, node_off, bases, link_row, tri)
+    for (i, n) in enumerate(Graphs.nodes(sdg))      # an emptied node is the reference's empty_node (deleted = true)
+        isempty(n.seq) && (Graphs.nodes(sdg)[i] = Graphs.SDGNode{LongSequence{DNAAlphabet{4}}}(n.seq, true))
+    end
+    return sdg
+end
+
 "Device graph -> the reference's graph type."
 function Base.convert(::Type{GRAPH_TYPE}, g::DeviceGraph)
     return fill_graph!(empty_graph(LongSequence{DNAAlphabet{4}}), LibGG.graph_export(g.ctx, g.h)...)

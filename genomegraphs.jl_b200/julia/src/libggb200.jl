@@ -176,6 +176,25 @@ function graph_find_tip_nodes(ctx::Context, g::Ptr{Cvoid}, min_size::Integer)
     return tips
 end
 
+"remove_node! for every id (src/Graphs.jl:459-466): a new graph handle"
+function graph_remove_nodes(ctx::Context, g::Ptr{Cvoid}, ids::Vector{Int64})
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve ids check(ctx, ccall(fptr(:gg_graph_remove_nodes), Cint, (Ptr{Cvoid}, Ptr{Int64}, UInt64, Ref{Ptr{Cvoid}}), g, ids, length(ids), out))
+    return out[]
+end
+"collapse_all_unitigs!(sg, min_nodes, true) (src/Graphs.jl:528-539): (new graph handle, number of new nodes)"
+function graph_collapse_all_unitigs(ctx::Context, g::Ptr{Cvoid}, min_nodes::Integer)
+    out = Ref{Ptr{Cvoid}}(C_NULL); m = Ref{UInt64}(0)
+    check(ctx, ccall(fptr(:gg_graph_collapse_all_unitigs), Cint, (Ptr{Cvoid}, UInt64, Ref{Ptr{Cvoid}}, Ref{UInt64}), g, min_nodes, out, m))
+    return out[], Int(m[])
+end
+"remove_tips!(sdg, min_size) (src/remove_tips.jl:2-30): (new graph handle, passes, tips removed)"
+function graph_remove_tips(ctx::Context, g::Ptr{Cvoid}, min_size::Integer)
+    out = Ref{Ptr{Cvoid}}(C_NULL); p = Ref{UInt64}(0); r = Ref{UInt64}(0)
+    check(ctx, ccall(fptr(:gg_graph_remove_tips), Cint, (Ptr{Cvoid}, UInt64, Ref{Ptr{Cvoid}}, Ref{UInt64}, Ref{UInt64}), g, min_size, out, p, r))
+    return out[], Int(p[]), Int(r[])
+end
+
 # ---- unique mer index -----------------------------------------------------------------------
 function unique_mer_index(ctx::Context, bases::Vector{UInt8}, offs::Vector{UInt64}, k::Integer)
     out = Ref{Ptr{Cvoid}}(C_NULL)
