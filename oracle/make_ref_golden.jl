@@ -17,6 +17,10 @@
 #   read cases  : serial_mem(M, CANONICAL)(reads) (docs/src/man/assembly.md:126-128), then
 #                 dbg!(sg, counted_kmers, min_freq) src/dbg.jl:274-278, then
 #                 GraphIndexes.UniqueMerIndex{M}(sg) src/GraphIndexes.jl:62-102
+#   tip cases   : Graphs.find_tip_nodes(sg, min_size) src/Graphs.jl:778-816, Graphs.collapse_all_unitigs!(unitigs, newnodes,
+#                 sg, 2, true) src/Graphs.jl:528-539 and remove_tips!(sg, min_size) src/remove_tips.jl:2-30 on the graphs of
+#                 tests/golden/tips_golden.json (rebuilt node by node, link vectors filled in their stored order)
+#                 -> tests/golden/tips_golden_ref.json (--write replaces tips_golden.json)
 # Output: tests/golden/dbg_golden_ref.json (same schema as dbg_golden.json, "generator" names this
 # script and the package versions) and a line per case: OK / DIFF <field>.  With --write the committed
 # dbg_golden.json is replaced, after which `pytest tests/test_golden.py` checks the oracle and the CUDA
@@ -78,6 +82,52 @@ function run_reads_case(c)
                               "total_per_node" => Int.(idx.total_mers_per_node)))
 end
 
+# ---- tip removal ------------------------------------------------------------------------------------------------
+const SEQ4 = LongSequence{DNAAlphabet{4}}
+function graph_from_case(nodes, links)
+    sg = empty_graph(SEQ4)
+    for s in nodes
+        GG.Graphs.add_node!(sg, SEQ4(s))
+    end
+    for (i, s) in enumerate(nodes)     # an empty sequence is a removed node: the reference's empty_node (deleted = true)
+        isempty(s) && (GG.Graphs.nodes(sg)[i] = GG.Graphs.empty_node(SEQ4))
+    end
+    for (i, ls) in enumerate(links), l in ls
+        push!(GG.Graphs.linksof(sg, i), GG.Graphs.SequenceDistanceGraphLink(l[1], l[2], l[3]))
+    end
+    return sg
+end
+function edited_arrays(sg)   # deleted nodes print as "" (their sequence is empty)
+    nodes = String[string(GG.Graphs.node(sg, i).seq) for i in GG.Graphs.each_node_id(sg)]
+    links = [[[GG.Graphs.source(l), GG.Graphs.destination(l), GG.Graphs.distance(l)] for l in GG.Graphs.linksof(sg, i)]
+             for i in GG.Graphs.each_node_id(sg)]
+    return nodes, links
+end
+function run_tips_case(c)
+    r = Dict{String,Any}("name" => c["name"], "min_size" => c["min_size"], "nodes" => c["nodes"], "links" => c["links"])
+    sg = graph_from_case(c["nodes"], c["links"])
+    r["tips"] = sort!(collect(GG.Graphs.find_tip_nodes(sg, c["min_size"])))
+    try
+        utgs = Vector{GG.Graphs.SequenceDistanceGraphPath{typeof(sg)}}()
+        newnodes = Vector{GG.Graphs.NodeID}()
+        GG.Graphs.collapse_all_unitigs!(utgs, newnodes, sg, 2, true)
+        nodes, links = edited_arrays(sg)
+        r["collapse"] = Dict("new_nodes" => newnodes, "nodes" => nodes, "links" => links)
+    catch e
+        r["collapse"] = Dict("error" => sprint(showerror, e))
+    end
+    sg = graph_from_case(c["nodes"], c["links"])
+    try
+        remove_tips!(sg, c["min_size"])
+        nodes, links = edited_arrays(sg)
+        # passes / removed are only logged by the reference (src/remove_tips.jl:11-27): keep the committed numbers
+        r["remove_tips"] = Dict("passes" => c["remove_tips"]["passes"], "removed" => c["remove_tips"]["removed"], "nodes" => nodes, "links" => links)
+    catch e
+        r["remove_tips"] = Dict("error" => sprint(showerror, e))
+    end
+    return r
+end
+
 function diff_fields(a, b, fields)
     bad = String[]
     for f in fields
@@ -118,6 +168,26 @@ function main()
         JSON.print(io, out)
     end
     WRITE && cp(joinpath(GOLD, "dbg_golden_ref.json"), joinpath(GOLD, "dbg_golden.json"); force = true)
+    tips = JSON.parsefile(joinpath(GOLD, "tips_golden.json"))
+    tout = Dict{String,Any}("generator" => out["generator"], "cases" => Any[])
+    for c in tips["cases"]
+        r = run_tips_case(c)
+        bad = diff_fields(c, r, ["tips"])
+        for part in ("collapse", "remove_tips")
+            if haskey(c[part], "error") || haskey(r[part], "error")
+                haskey(c[part], "error") == haskey(r[part], "error") || push!(bad, part * ".error")
+            else
+                append!(bad, [part * "." * f for f in diff_fields(c[part], r[part], ["nodes", "links"])])
+            end
+        end
+        println(isempty(bad) ? "OK    " : "DIFF  ", c["name"], isempty(bad) ? "" : string("  ", bad))
+        ndiff += !isempty(bad)
+        push!(tout["cases"], r)
+    end
+    open(joinpath(GOLD, "tips_golden_ref.json"), "w") do io
+        JSON.print(io, tout)
+    end
+    WRITE && cp(joinpath(GOLD, "tips_golden_ref.json"), joinpath(GOLD, "tips_golden.json"); force = true)
     println(ndiff == 0 ? "all cases equal the committed vectors: the oracle is pinned to the reference" :
             string(ndiff, " case(s) differ from the committed vectors"))
     exit(ndiff == 0 ? 0 : 1)

@@ -16,6 +16,16 @@ from oracle import graph_edit as E
 from oracle import oracle as O
 
 
+import json
+import os
+
+TIPS_GOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tips_golden.json")))["cases"]
+
+
+def _tl(ls):
+    return [[tuple(t) for t in row] for row in ls]
+
+
 def _dbg_graph(seed, k=15, glen=3000, nreads=900, err=8000, min_freq=1, read_len=60):
     seq, offs = O.synth_reads(seed, glen, nreads, read_len, True, 150, err)
     keys, cnt = O.count_kmers(seq, offs, k)
@@ -156,6 +166,23 @@ def test_remove_nodes_model():
             g.remove_node(n)
         n2, l2 = M.remove_nodes(nodes, links, ids)
         assert n2 == g.nodes and l2 == g.links
+
+
+@pytest.mark.parametrize("case", TIPS_GOLD, ids=lambda c: c["name"])
+def test_tips_golden_restatement_and_model(case):
+    """committed vectors (tests/golden/make_tips_golden.py; oracle/make_ref_golden.jl regenerates them with the real
+    package) against the sequential restatement and the model of the device formulation"""
+    nodes, links = case["nodes"], _tl(case["links"])
+    g = E.Graph(nodes, links)
+    assert g.find_tip_nodes(case["min_size"]) == case["tips"] == M.find_tip_nodes(nodes, links, case["min_size"])
+    c = case["collapse"]
+    new = g.collapse_all_unitigs(2, True)
+    assert new == c["new_nodes"] and g.nodes == c["nodes"] and g.links == _tl(c["links"])
+    assert M.collapse_all_unitigs(nodes, links, 2) == (c["nodes"], _tl(c["links"]), len(c["new_nodes"]))
+    r = case["remove_tips"]
+    g = E.Graph(nodes, links)
+    assert g.remove_tips(case["min_size"]) == (r["passes"], r["removed"]) and g.nodes == r["nodes"] and g.links == _tl(r["links"])
+    assert M.remove_tips(nodes, links, case["min_size"]) == (r["nodes"], _tl(r["links"]), r["passes"], r["removed"])
 
 
 # ------------------------------------------------ CUDA path through the C ABI -------------------------------------------
@@ -303,3 +330,20 @@ def test_gpu_remove_tips_large(pkg, ctx):
     exp = _seq_collapse(nodes, links)
     assert m == exp[2] and _back(c1) == (exp[0], exp[1])
     c1.free(); out.free(); dg.free()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", TIPS_GOLD, ids=lambda c: c["name"])
+def test_gpu_tips_golden(pkg, ctx, case):
+    nodes, links = case["nodes"], _tl(case["links"])
+    dg = _device_graph(pkg, ctx, nodes, links)
+    assert dg.find_tip_nodes(case["min_size"]).tolist() == case["tips"]
+    c = case["collapse"]
+    out, m = dg.collapse_all_unitigs(2)
+    assert m == len(c["new_nodes"]) and _back(out) == (c["nodes"], _tl(c["links"]))
+    out.free()
+    r = case["remove_tips"]
+    out, passes, removed = dg.remove_tips(case["min_size"])
+    assert (passes, removed) == (r["passes"], r["removed"]) and _back(out) == (r["nodes"], _tl(r["links"]))
+    out.free()
+    dg.free()
