@@ -192,14 +192,30 @@ def csrc_sha():
     return h.hexdigest()[:16]
 
 
+# the files that hold the kernels of the counting + graph stages (the ones an ncu traffic table lists) and the host code
+# that launches them; ggb200.cu (ABI entry points) and the files of other routes are left out, so that adding an entry
+# point next to the path does not void a capture of kernels that did not change
+TRAFFIC_FILES = ("common.cuh", "prims.cuh", "pack.cuh", "sort.cuh", "skm.cuh", "graph.cuh", "graphdist.cuh")
+
+
+def kernel_files_sha(read=None):
+    """per-file hashes of TRAFFIC_FILES (read: name -> bytes, default: the working tree)"""
+    d = os.path.join(ROOT, "genomegraphs.jl_b200", "csrc")
+    read = read or (lambda f: open(os.path.join(d, f), "rb").read())
+    return {f: hashlib.sha256(read(f)).hexdigest()[:16] for f in TRAFFIC_FILES}
+
+
 def ncu_traffic(kernel, workload):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from an `ncu --set full` capture of THIS build
-    (profiles/ncu_traffic.json, written by scripts/ncu_summary.py --traffic with the csrc hash of the build it saw); else None"""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from an `ncu --set full` capture (profiles/ncu_traffic.json,
+    written by scripts/ncu_traffic.py): used only while every file that defines or launches the captured kernels
+    (TRAFFIC_FILES) is byte-identical to the build the capture saw; else None"""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
     except Exception:
         return None
-    if t.get("csrc_sha") != csrc_sha() or t.get("workload") != workload:
+    if t.get("workload") != workload:
+        return None
+    if t.get("files") != kernel_files_sha() and t.get("csrc_sha") != csrc_sha():
         return None
     return t.get("kernels", {}).get(kernel)
 

@@ -112,7 +112,8 @@ __global__ void ge_rec_init_kernel(const u32 *__restrict__ ptr, const u32 *__res
     if (v >= nv) return;
     rec[v] = make_uint4(ptr[v], (u32)v, 1u, wgt ? wgt[v] : 0u);
 }
-__global__ void ge_jump_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, u64 nv) {
+// `active` (optional): set when some pointer has not run out yet after this round
+__global__ void ge_jump_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, u64 nv, u32 *__restrict__ active) {
     const u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nv) return;
     uint4 a = in[v];
@@ -122,6 +123,7 @@ __global__ void ge_jump_kernel(const uint4 *__restrict__ in, uint4 *__restrict__
         a.y = a.y < b.y ? a.y : b.y;
         a.z += b.z;
         a.w += b.w;
+        if (active && a.x != GE_NIL) *active = 1u;
     }
     out[v] = a;
 }
@@ -432,11 +434,16 @@ static gg_graph *ge_remove_dead(gg_ctx *ctx, const gg_graph *g, const u32 *dead)
     return h;
 }
 
-static void ge_jump(gg_ctx *ctx, uint4 **a, uint4 **b, u64 nv, int rounds) {
+// `rounds` = ceil(log2(vertices)) covers the longest possible chain; every fourth round asks whether any pointer is still
+// running and stops when none is (paths of a unitig graph are short; only cycles keep their pointers for ever)
+static void ge_jump(gg_ctx *ctx, uint4 **a, uint4 **b, u64 nv, int rounds, u32 *d_active) {
     for (int r = 0; r < rounds; ++r) {
+        const bool ask = d_active && (r & 3) == 3 && r + 1 < rounds;
+        if (ask) CK(cudaMemsetAsync(d_active, 0, sizeof(u32), ctx->stream));
         prof_bytes(ctx, 48.0 * (double)nv);
-        LAUNCH(ctx, ge_jump_kernel, (unsigned)ceil_div(nv, 256), 256, 0, *a, *b, nv);
+        LAUNCH(ctx, ge_jump_kernel, (unsigned)ceil_div(nv, 256), 256, 0, *a, *b, nv, ask ? d_active : (u32 *)nullptr);
         std::swap(*a, *b);
+        if (ask && read_scalar<u32>(ctx, d_active) == 0) break;
     }
 }
 static void ge_raise(u32 e) {
@@ -475,17 +482,17 @@ static gg_graph *ge_collapse(gg_ctx *ctx, const gg_graph *g, u64 min_nodes, u64 
     uint4 *a = ra.p, *b = rb.p;
     // pass 1: cycles
     LAUNCH(ctx, ge_rec_init_kernel, (unsigned)ceil_div(nv, 256), 256, 0, succ.p, (const u32 *)nullptr, nv, a);
-    ge_jump(ctx, &a, &b, nv, rounds);
+    ge_jump(ctx, &a, &b, nv, rounds, err.p + 2);
     LAUNCH(ctx, ge_cut_kernel, (unsigned)ceil_div(nv, 256), 256, 0, a, nv, succ.p, pred.p);
     // pass 2: prefix and suffix aggregates of the paths
     DBuf<u32> trim(ctx, nv), wgt(ctx, nv);
     LAUNCH(ctx, ge_weight_kernel, (unsigned)ceil_div(nv, 256), 256, 0, g->d_node_off, pred.p, ddist.p, nv, trim.p, wgt.p);
     LAUNCH(ctx, ge_rec_init_kernel, (unsigned)ceil_div(nv, 256), 256, 0, succ.p, wgt.p, nv, a);
-    ge_jump(ctx, &a, &b, nv, rounds);
+    ge_jump(ctx, &a, &b, nv, rounds, err.p + 2);
     uint4 *rs = a;             // suffix records; b is scratch
     uint4 *c = rc.p;
     LAUNCH(ctx, ge_rec_init_kernel, (unsigned)ceil_div(nv, 256), 256, 0, pred.p, wgt.p, nv, b);
-    ge_jump(ctx, &b, &c, nv, rounds);
+    ge_jump(ctx, &b, &c, nv, rounds, err.p + 2);
     uint4 *rp = b;
     DBuf<u32> cmin(ctx, nv), coff(ctx, nv), flag(ctx, nn), uidx(ctx, nn), ulen(ctx, nn);
     DBuf<u64> tot(ctx, 2);

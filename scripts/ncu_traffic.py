@@ -1,13 +1,13 @@
 #!/usr/bin/env python
 """profiles/ncu_traffic.json from an `ncu --set full` capture of THIS build: dram__bytes_read.sum + dram__bytes_write.sum per
-launch of every captured kernel (bench.py's roofline.traffic reads it when the csrc hash and the workload match).
+launch of every captured kernel (bench.py's roofline.traffic reads it while the files that define and launch the captured kernels are unchanged and the workload matches).
 usage: scripts/ncu_traffic.py <rep> <workload> [more reps of the same build]"""
 import csv, io, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 workload = sys.argv[2]
-out = {"csrc_sha": bench.csrc_sha(), "workload": workload, "kernels": {}, "source": [os.path.basename(r) for r in [sys.argv[1]] + sys.argv[3:]]}
+out = {"csrc_sha": bench.csrc_sha(), "files": bench.kernel_files_sha(), "workload": workload, "kernels": {}, "source": [os.path.basename(r) for r in [sys.argv[1]] + sys.argv[3:]]}
 acc = {}
 for rep in [sys.argv[1]] + sys.argv[3:]:
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
