@@ -571,6 +571,12 @@ class WorkSpace:
         self.sdg = dbg_(SequenceDistanceGraph(), self.mer_counts(name), min_freq, ctx=self.ctx)
         return self
 
+    def remove_tips_(self, min_size):
+        """remove_tips!(ws, min_size) (the commented-out WorkSpace form at src/remove_tips.jl:1-5, :28-29): edits the
+        workspace graph on the device"""
+        remove_tips_(self.sdg, min_size, ctx=self.ctx)
+        return self
+
     def __repr__(self):
         lines = ["Graph Genome workspace", " Sequence distance graph (%d nodes)" % self.sdg.n_nodes(),
                  " Mer count stores: %d" % len(self.mer_count_stores)]

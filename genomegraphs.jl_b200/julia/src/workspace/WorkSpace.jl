@@ -26,6 +26,9 @@ end
 "`dbg!(ws, name, min_freq)`: build the workspace graph from a stored count table."
 dbg!(ws::WorkSpace, name::Symbol, min_freq::Integer) = (dbg!(ws.sdg, mer_counts(ws, name), min_freq); ws)
 
+"`remove_tips!(ws, min_size)`: the WorkSpace form the reference has commented out (src/remove_tips.jl:1-5, :28-29)."
+remove_tips!(ws::WorkSpace, min_size::Integer) = (remove_tips!(ws.sdg, min_size; ctx = ws.ctx); ws)
+
 function Base.show(io::IO, ws::WorkSpace)
     println(io, "Graph Genome workspace")
     println(io, " Sequence distance graph (", Graphs.n_nodes(ws.sdg), " nodes)")

@@ -55,6 +55,37 @@ G4 -- perfect circle pass (src/dbg.jl:160-181), paths numbered before circles, k
          node 2 = c!(AACAA) = min(AACAA, TTGTT) = AACAA
   overlaps: node 1 CCTC: in (CC, 1), last TC -> in (GA, -1); node 2 AACAA: in (AA, 2), last AA canonical -> out (AA, -2)
   merge: (AA,2) x (AA,-2) -> add_link!(2,-2,-2): both pushes land in links[2]
+
+T1 / T2 -- tip removal: src/Graphs.jl (find_tip_nodes! :778-802, find_all_unitigs! :831-862, join_path! :1040-1088, remove_node!
+  :459-466, remove_link! :487-495) and src/remove_tips.jl:2-30 executed by hand.  forward_links(n) = entries of links[|n|] with
+  source == -n, backward_links(n) = forward_links(-n) [:667-690].
+
+T1 (fork with a tip), nodes 1 AAAC, 2 AACGGG, 3 AACT, 4 CGGGT, 5 TTTTT; add_link!(-1,2,-3), (-1,3,-3), (-2,4,-4):
+  links[1] = [(-1,2), (-1,3)], links[2] = [(2,-1), (-2,4)], links[3] = [(3,-1)], links[4] = [(4,-2)], links[5] = []
+  find_tip_nodes(4): node 1: fw 2 links -> no rule applies; node 2 (6 bases > 4) skipped; node 3: fw 0, bw 1 (to -1),
+  forward_links(1) has 2 > 1 -> tip; node 4 (5 bases) skipped; node 5 (5 bases) skipped.  tips = {3}.
+  remove_node!(3): links[3] = [], links[1] = [(-1,2)].  collapse_all_unitigs!(.., 2, true): n = 1: fw [(-1,2)], dest 2,
+  backward_links(2) = [(2,-1)] (1) -> push 2; fw(2) = [(-2,4)], backward_links(4) = [(4,-2)] -> push 4; fw(4) = []; reversed
+  twice -> path [1, 2, 4] (node 5: alone).  sequence: AAAC + AACGGG[4:] (overlap AAC ok) = AAACGGG, + CGGGT[5:] (overlap CGGG
+  ok) = AAACGGGT; canonical (A < comp(T) = A? equal; A vs comp(G) = C: A < C) -> kept.  node 6 = AAACGGGT without links (first has
+  no backward, last no forward link); nodes 1, 2, 4 emptied.  Pass 2: node 6 has 8 bases > 4, node 5 has 5 > 4: no tip.
+
+T2 (two joined paths next to a hub: link ORDER), nodes 1 AC, 2 AAA, 3 C, 4 GG, 5 T, all distances 1 (no overlap);
+  add_link!(-1,2), (-1,4), (-2,3), (-4,5), (-3,-5), (-3,1):
+  links[1] = [(-1,2), (-1,4), (1,-3)]   links[2] = [(2,-1), (-2,3)]   links[3] = [(3,-2), (-3,-5), (-3,1)]
+  links[4] = [(4,-1), (-4,5)]           links[5] = [(5,-4), (-5,-3)]
+  find_all_unitigs!(2): n = 1: fw has 2 links; backwards: fw(-1) = [(1,-3)], backward_links(-3) = fw(3) has 2 -> stop: [1] alone.
+    n = 2: fw [(-2,3)], backward_links(3) = [(3,-2)] -> push 3; fw(3) has 2 -> stop; backwards: fw(-2) = [(2,-1)], node 1 consumed
+    -> stop: [2, 3].  n = 4: fw [(-4,5)], backward_links(5) = [(5,-4)] -> push 5; fw(5) = [(-5,-3)], node 3 consumed -> stop;
+    backwards: fw(-4) = [(4,-1)], node 1 consumed: [4, 5].
+  join [2, 3]: AAA + C = AAAC canonical (A < comp(C) = G); node 6.  backward_links(2) = [(2,-1)] -> add_link!(6,-1);
+    forward_links(3) = [(-3,-5), (-3,1)] -> add_link!(-6,-5), add_link!(-6,1).  Nodes 2, 3 removed with their entries:
+    links[1] = [(-1,4), (-1,6), (1,-6)]   links[4] = [(4,-1), (-4,5)]   links[5] = [(5,-4), (-5,-6)]
+    links[6] = [(6,-1), (-6,-5), (-6,1)]
+  join [4, 5]: GG + T = GGT, not canonical (comp(T) = A < G) -> ACC, path becomes [-5, -4]; node 7.
+    backward_links(-5) = entries of links[5] with source -5 = [(-5,-6)] -> add_link!(7,-6);
+    forward_links(-4) = entries of links[4] with source 4 = [(4,-1)] -> add_link!(-7,-1).  Nodes 4, 5 removed:
+    links[1] = [(-1,6), (1,-6), (-1,-7)]   links[6] = [(6,-1), (-6,1), (-6,7)]   links[7] = [(7,-6), (-7,-1)]
 """
 
 HAND_TRACED = [
@@ -70,4 +101,22 @@ HAND_TRACED = [
     dict(name="G4_circle_after_paths", k=3, kmers=["AAC", "ACA", "AGG", "CAA", "CTC"],
          nodes=["CCTC", "AACAA"],
          links=[[], [(2, -2, -2), (-2, 2, -2)]]),
+]
+
+# graph editing (see T1 / T2 above): input graph, min_size for remove_tips!, expected graph after
+# collapse_all_unitigs!(sg, 2, true) on the input ("collapse") and after remove_tips!(sg, min_size) ("remove_tips")
+TIPS_HAND_TRACED = [
+    dict(name="T1_fork_with_a_tip", min_size=4,
+         nodes=["AAAC", "AACGGG", "AACT", "CGGGT", "TTTTT"],
+         links=[[(-1, 2, -3), (-1, 3, -3)], [(2, -1, -3), (-2, 4, -4)], [(3, -1, -3)], [(4, -2, -4)], []],
+         tips=[3],
+         remove_tips=dict(passes=2, removed=1, nodes=["", "", "", "", "TTTTT", "AAACGGGT"], links=[[], [], [], [], [], []])),
+    dict(name="T2_two_paths_next_to_a_hub", min_size=0,
+         nodes=["AC", "AAA", "C", "GG", "T"],
+         links=[[(-1, 2, 1), (-1, 4, 1), (1, -3, 1)], [(2, -1, 1), (-2, 3, 1)], [(3, -2, 1), (-3, -5, 1), (-3, 1, 1)],
+                [(4, -1, 1), (-4, 5, 1)], [(5, -4, 1), (-5, -3, 1)]],
+         tips=[],
+         collapse=dict(nodes=["AC", "", "", "", "", "AAAC", "ACC"],
+                       links=[[(-1, 6, 1), (1, -6, 1), (-1, -7, 1)], [], [], [], [], [(6, -1, 1), (-6, 1, 1), (-6, 7, 1)],
+                              [(7, -6, 1), (-7, -1, 1)]])),
 ]

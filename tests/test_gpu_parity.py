@@ -389,3 +389,8 @@ def test_workspace(pkg, ctx):
     og = O.dbg(O.filter_counts(okeys, ocnt, 21, 2), 21)
     assert [n.seq for n in ws.graph().nodes] == og.nodes() and ws.graph().link_tuples() == og.links()
     assert "1 " not in repr(ws)[:5] and "workspace" in repr(ws)
+    from oracle import graph_edit as E
+    eg = E.Graph(og.nodes(), og.links())
+    eg.remove_tips(40)
+    ws.remove_tips_(40)
+    assert [n.seq for n in ws.graph().nodes] == eg.nodes and ws.graph().link_tuples() == eg.links

@@ -185,6 +185,28 @@ def test_tips_golden_restatement_and_model(case):
     assert M.remove_tips(nodes, links, case["min_size"]) == (r["nodes"], _tl(r["links"]), r["passes"], r["removed"])
 
 
+import sys
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+from hand_traced import TIPS_HAND_TRACED  # noqa: E402  (src/Graphs.jl + src/remove_tips.jl traced by hand)
+
+
+@pytest.mark.parametrize("case", TIPS_HAND_TRACED, ids=lambda c: c["name"])
+def test_tips_hand_traced_restatement_and_model(case):
+    nodes, links = case["nodes"], case["links"]
+    assert E.Graph(nodes, links).find_tip_nodes(case["min_size"]) == case["tips"]
+    if "collapse" in case:
+        c = case["collapse"]
+        g = E.Graph(nodes, links)
+        g.collapse_all_unitigs(2, True)
+        assert (g.nodes, g.links) == (c["nodes"], c["links"])
+        assert M.collapse_all_unitigs(nodes, links, 2)[:2] == (c["nodes"], c["links"])
+    if "remove_tips" in case:
+        r = case["remove_tips"]
+        g = E.Graph(nodes, links)
+        assert g.remove_tips(case["min_size"]) == (r["passes"], r["removed"]) and (g.nodes, g.links) == (r["nodes"], r["links"])
+        assert M.remove_tips(nodes, links, case["min_size"]) == (r["nodes"], r["links"], r["passes"], r["removed"])
+
+
 # ------------------------------------------------ CUDA path through the C ABI -------------------------------------------
 @pytest.fixture(scope="module")
 def pkg():
@@ -346,4 +368,21 @@ def test_gpu_tips_golden(pkg, ctx, case):
     out, passes, removed = dg.remove_tips(case["min_size"])
     assert (passes, removed) == (r["passes"], r["removed"]) and _back(out) == (r["nodes"], _tl(r["links"]))
     out.free()
+    dg.free()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", TIPS_HAND_TRACED, ids=lambda c: c["name"])
+def test_gpu_tips_hand_traced(pkg, ctx, case):
+    dg = _device_graph(pkg, ctx, case["nodes"], case["links"])
+    assert dg.find_tip_nodes(case["min_size"]).tolist() == case["tips"]
+    if "collapse" in case:
+        out, _ = dg.collapse_all_unitigs(2)
+        assert _back(out) == (case["collapse"]["nodes"], case["collapse"]["links"])
+        out.free()
+    if "remove_tips" in case:
+        r = case["remove_tips"]
+        out, passes, removed = dg.remove_tips(case["min_size"])
+        assert (passes, removed) == (r["passes"], r["removed"]) and _back(out) == (r["nodes"], r["links"])
+        out.free()
     dg.free()
