@@ -25,7 +25,8 @@
 //  * links: every old entry (s, d, dist) maps to (phi(s), phi(d), dist), phi = the new node's first / last end for the
 //    two outer ends of a path, identity for kept nodes; entries with an inner end and entries between two ends on the
 //    same side of one path disappear; an entry between the first and the last end of one path becomes a self link of
-//    the new node.  The place of an entry in its row follows from a closed form of the push order of join_path! (rows of
+//    the new node.  Entries between two kept nodes stay in place (a scan); the place of every other entry in its row
+//    follows from a closed form of the push order of join_path! (rows of
 //    kept nodes: old entries in place, then one block per joined path in joining order; rows of new nodes: first-end
 //    loop, last-end loop -- each over old entries, then entries pushed by earlier joins -- then blocks of later joins),
 //    packed into a 128-bit key and ordered with one stable radix sort.
@@ -279,7 +280,9 @@ struct GeEnds {
         return side == 0 ? id : -id;
     }
 };
-__global__ void ge_link_flag_kernel(const i64 *__restrict__ tri, u64 ne, GeEnds e, u32 *__restrict__ keep) {
+// class A (keep_a): entry between two kept nodes -- it stays in its row and the order among such entries is the old one;
+// class B (keep_b): every other surviving entry -- these get a key and are sorted
+__global__ void ge_link_flag_kernel(const i64 *__restrict__ tri, u64 ne, GeEnds e, u32 *__restrict__ keep_a, u32 *__restrict__ keep_b) {
     const u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= ne) return;
     u32 us, ss, ud, sd;
@@ -287,14 +290,16 @@ __global__ void ge_link_flag_kernel(const i64 *__restrict__ tri, u64 ne, GeEnds 
     u32 k = 1;
     if (ts == 2 || td == 2) k = 0;
     if (ts == 1 && td == 1 && us == ud && ss == sd) k = 0;
-    keep[q] = k;
+    const bool a = ts == 0 && td == 0;
+    keep_a[q] = (k && a) ? 1u : 0u;
+    keep_b[q] = (k && !a) ? 1u : 0u;
 }
 // key word 0 = row << 4 | seg << 3 | S << 2 | sub, word 1 = j << 32 | sx << 31 | sy << 30 | q  (see tests/collapse_model.py)
 __global__ void ge_link_emit_kernel(const u64 *__restrict__ row, const i64 *__restrict__ tri, const u32 *__restrict__ mirror, u64 ne, GeEnds e,
-                                    const u32 *__restrict__ keep, const u32 *__restrict__ pos, u64 *__restrict__ keys, u64 *__restrict__ pay,
+                                    const u32 *__restrict__ keep_b, const u32 *__restrict__ pos_b, u64 *__restrict__ keys, u64 *__restrict__ pay,
                                     i64 *__restrict__ tmp) {
     const u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= ne || !keep[q]) return;
+    if (q >= ne || !keep_b[q]) return;
     const i64 s = tri[3 * q], d = tri[3 * q + 1];
     const u64 i = (u64)(s < 0 ? -s : s) - 1;
     const u64 qs = q - row[i], qm = mirror[q];
@@ -303,29 +308,53 @@ __global__ void ge_link_emit_kernel(const u64 *__restrict__ row, const i64 *__re
     const i64 fs = e.phi(s, ts, us, ss), fd = e.phi(d, td, ud, sd);
     const u64 r = (u64)(fs < 0 ? -fs : fs) - 1;
     u64 seg = 0, S = 0, sub = 0, j = 0, sx = 0, sy = 0, qq = 0;
-    if (ts == 0) {
-        if (td == 0) { qq = qs; }                                       // old entry of a kept node: stays in place
-        else { seg = 1; j = ud; sx = sd; qq = qm; }                     // pushed when path ud is joined
-    } else if (td == 0) { S = ss; qq = qs; }                            // creation loops, old entries first
+    if (ts == 0) { seg = 1; j = ud; sx = sd; qq = qm; }                 // pushed to a kept node when path ud is joined
+    else if (td == 0) { S = ss; qq = qs; }                              // creation loops of the new node, old entries first
     else if (ud == us) { S = 1; sub = 2; j = ss == 0 ? qs : qm; qq = ss == 0 ? 1 : 0; }   // first end -- last end: (-N, N) then (N, -N)
     else if (ud < us) { S = ss; sub = 1; j = ud; sx = sd; qq = qm; }    // entries an earlier join had pushed
     else { seg = 1; j = ud; sx = sd; sy = ss; qq = qs; }                // pushed when the later path ud is joined
-    const u64 dst = pos[q];
+    const u64 dst = pos_b[q];
     keys[2 * dst] = (r << 4) | (seg << 3) | (S << 2) | sub;
     keys[2 * dst + 1] = (j << 32) | (sx << 31) | (sy << 30) | qq;
     pay[dst] = dst;
     tmp[3 * dst] = fs; tmp[3 * dst + 1] = fd; tmp[3 * dst + 2] = tri[3 * q + 2];
 }
-__global__ void ge_link_rows_kernel(const u64 *__restrict__ keys, const u64 *__restrict__ pay, const i64 *__restrict__ tmp, u64 nl, u64 nn2,
-                                    u64 *__restrict__ row, i64 *__restrict__ tri) {
-    const u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q > nl) return;
-    const u64 r1 = q < nl ? (keys[2 * q] >> 4) : nn2;          // rows (r0, r1] start at q
-    const u64 r0 = q > 0 ? (keys[2 * (q - 1)] >> 4) + 1 : 0;
-    for (u64 r = r0; r <= r1; ++r) row[r] = q;
-    if (q < nl) {
-        const u64 p = pay[q];
-        tri[3 * q] = tmp[3 * p]; tri[3 * q + 1] = tmp[3 * p + 1]; tri[3 * q + 2] = tmp[3 * p + 2];
+// first_b[r] = index of the first sorted class B entry of row r (r = 0 .. nn2)
+__global__ void ge_first_b_kernel(const u64 *__restrict__ keys, u64 nb, u64 nn2, u32 *__restrict__ first_b) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > nb) return;
+    const u64 r1 = t < nb ? (keys[2 * t] >> 4) : nn2;          // rows (r0 .. r1) start at t
+    const u64 r0 = t > 0 ? (keys[2 * (t - 1)] >> 4) + 1 : 0;
+    for (u64 r = r0; r <= r1; ++r) first_b[r] = (u32)t;
+}
+// row r of the new graph starts at (class A entries of the rows before r) + first_b[r]; its class A entries come first
+// in their old order, its sorted class B entries follow
+struct GePlace {
+    const u64 *row;       // old row offsets, nn + 1
+    const u32 *pos_a;     // exclusive scan of keep_a, ne
+    const u32 *first_b;   // nn2 + 1
+    u64 nn, ne, na;
+    __device__ __forceinline__ u64 a_before(u64 r) const {
+        if (r > nn) return na;
+        const u64 p = row[r];
+        return p < ne ? (u64)pos_a[p] : na;
+    }
+};
+__global__ void ge_link_place_kernel(GePlace g, const i64 *__restrict__ tri, const u32 *__restrict__ keep_a, const u64 *__restrict__ keys,
+                                     const u64 *__restrict__ pay, const i64 *__restrict__ tmp, u64 nb, u64 nn2, u64 *__restrict__ new_row,
+                                     i64 *__restrict__ out) {
+    const u64 x = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x <= nn2) new_row[x] = g.a_before(x) + g.first_b[x];
+    if (x < g.ne && keep_a[x]) {
+        const i64 s = tri[3 * x];
+        const u64 i = (u64)(s < 0 ? -s : s) - 1;
+        const u64 dst = (u64)g.first_b[i] + g.pos_a[x];
+        out[3 * dst] = s; out[3 * dst + 1] = tri[3 * x + 1]; out[3 * dst + 2] = tri[3 * x + 2];
+    }
+    if (x < nb) {
+        const u64 r = keys[2 * x] >> 4, p = pay[x];
+        const u64 dst = g.a_before(r + 1) + x;
+        out[3 * dst] = tmp[3 * p]; out[3 * dst + 1] = tmp[3 * p + 1]; out[3 * dst + 2] = tmp[3 * p + 2];
     }
 }
 
@@ -525,24 +554,33 @@ static gg_graph *ge_collapse(gg_ctx *ctx, const gg_graph *g, u64 min_nodes, u64 
         ge_raise(read_scalar<u32>(ctx, err.p));
         // ---- links
         GeEnds ends{cmin.p, pred.p, uidx.p, flip.p, nn};
-        DBuf<u32> keep(ctx, ne), pos(ctx, ne);
-        LAUNCH(ctx, ge_link_flag_kernel, (unsigned)ceil_div(ne, 256), 256, 0, g->d_link_tri, ne, ends, keep.p);
-        exclusive_scan_u32(ctx, keep.p, pos.p, ne, tot.p + 1);
-        const u64 nl = read_scalar<u64>(ctx, tot.p + 1);
+        DBuf<u32> keep_a(ctx, ne), keep_b(ctx, ne), pos_a(ctx, ne), pos_b(ctx, ne), first_b(ctx, nn2 + 1);
+        LAUNCH(ctx, ge_link_flag_kernel, (unsigned)ceil_div(ne, 256), 256, 0, g->d_link_tri, ne, ends, keep_a.p, keep_b.p);
+        exclusive_scan_u32(ctx, keep_a.p, pos_a.p, ne, tot.p);
+        exclusive_scan_u32(ctx, keep_b.p, pos_b.p, ne, tot.p + 1);
+        u64 hn[2];
+        CK(cudaMemcpyAsync(hn, tot.p, sizeof(hn), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        const u64 na = hn[0], nb2 = hn[1], nl = na + nb2;
         h->n_link_entries = nl;
         h->d_link_tri = dalloc<i64>(ctx, 3 * (nl ? nl : 1));
-        if (nl == 0) {
-            LAUNCH(ctx, fill_u64_kernel, (unsigned)ceil_div(nn2 + 1, 256), 256, 0, h->d_link_row, nn2 + 1, 0ULL);
-        } else {
-            DBuf<u64> keys(ctx, 2 * nl), keys_alt(ctx, 2 * nl), pay(ctx, nl), pay_alt(ctx, nl);
-            DBuf<i64> tmp(ctx, 3 * nl);
-            LAUNCH(ctx, ge_link_emit_kernel, (unsigned)ceil_div(ne, 256), 256, 0, g->d_link_row, g->d_link_tri, mirror.p, ne, ends, keep.p, pos.p, keys.p, pay.p, tmp.p);
+        DBuf<u64> keys(ctx, 2 * (nb2 + 1)), keys_alt(ctx, 2 * (nb2 + 1)), pay(ctx, nb2 + 1), pay_alt(ctx, nb2 + 1);
+        DBuf<i64> tmp(ctx, 3 * (nb2 + 1));
+        u64 *k0 = keys.p, *k1 = keys_alt.p, *p0 = pay.p, *p1 = pay_alt.p;
+        if (nb2) {
+            LAUNCH(ctx, ge_link_emit_kernel, (unsigned)ceil_div(ne, 256), 256, 0, g->d_link_row, g->d_link_tri, mirror.p, ne, ends, keep_b.p, pos_b.p, keys.p, pay.p, tmp.p);
             const u64 jmax = m > maxrow ? m : maxrow;
-            std::vector<BitRange> ranges = {{0, ilog2_ceil(maxrow + 2)}, {30, 32}, {32, 32 + ilog2_ceil(jmax + 2)}, {64, 64 + 4 + ilog2_ceil(nn2 + 1)}};
-            u64 *k0 = keys.p, *k1 = keys_alt.p, *p0 = pay.p, *p1 = pay_alt.p;
-            radix_sort<2>(ctx, &k0, &k1, &p0, &p1, nl, ranges);
-            LAUNCH(ctx, ge_link_rows_kernel, (unsigned)ceil_div(nl + 1, 256), 256, 0, k0, p0, tmp.p, nl, nn2, h->d_link_row, h->d_link_tri);
+            int qbits = ilog2_ceil(maxrow + 2);
+            if (qbits > 30) qbits = 30;
+            std::vector<BitRange> ranges = {{0, qbits}, {30, 32}, {32, 32 + ilog2_ceil(jmax + 2)}, {64, 64 + 4 + ilog2_ceil(nn2 + 1)}};
+            radix_sort<2>(ctx, &k0, &k1, &p0, &p1, nb2, ranges);
         }
+        if (nb2) LAUNCH(ctx, ge_first_b_kernel, (unsigned)ceil_div(nb2 + 1, 256), 256, 0, k0, nb2, nn2, first_b.p);
+        else dfill(ctx, first_b.p, (nn2 + 1) * sizeof(u32), 0u);
+        GePlace place{g->d_link_row, pos_a.p, first_b.p, nn, ne, na};
+        u64 span = nn2 + 1;
+        if (ne > span) span = ne;
+        LAUNCH(ctx, ge_link_place_kernel, (unsigned)ceil_div(span, 256), 256, 0, place, g->d_link_tri, keep_a.p, k0, p0, tmp.p, nb2, nn2, h->d_link_row, h->d_link_tri);
         CK(cudaStreamSynchronize(ctx->stream));
     } catch (...) {
         ge_free_graph(ctx, h);

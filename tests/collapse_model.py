@@ -224,45 +224,78 @@ def collapse_all_unitigs(nodes, links, min_nodes):
             return x
         return (nn + 1 + u) if side == 0 else -(nn + 1 + u)
 
-    # ---- ge_link_kernel: surviving entries with their (row, key); keys as packed in the CUDA code
-    items = []
+    # ---- ge_link_flag_kernel: class A = entry between two kept nodes (stays in its row, order given), class B = the rest
+    # of the surviving entries (get a key and are sorted)
+    cls = [0] * ne
+    for q in range(ne):
+        s, d, _ = tri[q]
+        ts, us, ss = end_type(s)
+        td, ud, sd = end_type(d)
+        if ts == 2 or td == 2:
+            continue
+        if ts == 1 and td == 1 and us == ud and ss == sd:
+            continue                # both at one end of one unitig: pushed to the old node only, gone with it
+        cls[q] = 1 if (ts == 0 and td == 0) else 2
+    pos_a, pos_b = [0] * ne, [0] * ne
+    n_a = n_b = 0
+    for q in range(ne):             # two exclusive scans
+        pos_a[q], pos_b[q] = n_a, n_b
+        n_a += cls[q] == 1
+        n_b += cls[q] == 2
+    # ---- ge_link_emit_kernel: keys of the class B entries, as packed in the CUDA code
+    items = [None] * n_b
     for i in range(nn):
         for q in range(row[i], row[i + 1]):
+            if cls[q] != 2:
+                continue
             s, d, ds = tri[q]
             qs = q - row[i]
             ts, us, ss = end_type(s)
             td, ud, sd = end_type(d)
-            if ts == 2 or td == 2:
-                continue
-            if ts == 1 and td == 1 and us == ud and ss == sd:
-                continue            # both at one end of one unitig: pushed to the old node only, gone with it
             fs, fd = phi(s, ts, us, ss), phi(d, td, ud, sd)
             r = abs(fs) - 1
             if ts == 0:
-                if td == 0:
-                    key = (0, 0, 0, 0, 0, 0, qs)
-                else:
-                    key = (1, 0, 0, ud, sd, 0, mirror[q])
+                key = (1, 0, 0, ud, sd, 0, mirror[q])        # pushed to a kept node when path ud is joined
+            elif td == 0:
+                key = (0, ss, 0, 0, 0, 0, qs)                # creation loops of the new node, old entries first
+            elif ud == us:
+                # first end -- last end of one unitig: the second loop of join_path! meets the entries the first
+                # loop has just pushed and links the new node to itself, (-N, N) then (N, -N) per link
+                key = (0, 1, 2, qs if ss == 0 else mirror[q], 0, 0, 1 if ss == 0 else 0)
+            elif ud < us:
+                key = (0, ss, 1, ud, sd, 0, mirror[q])       # entries an earlier join had pushed
             else:
-                if td == 0:
-                    key = (0, ss, 0, 0, 0, 0, qs)
-                elif ud == us:
-                    # first end -- last end of one unitig: the second loop of join_path! meets the entries the first
-                    # loop has just pushed and links the new node to itself, (-N, N) then (N, -N) per link
-                    key = (0, 1, 2, qs if ss == 0 else mirror[q], 0, 0, 1 if ss == 0 else 0)
-                elif ud < us:
-                    key = (0, ss, 1, ud, sd, 0, mirror[q])
-                else:
-                    key = (1, 0, 0, ud, sd, ss, qs)
+                key = (1, 0, 0, ud, sd, ss, qs)              # pushed when the later path ud is joined
             seg, S, sub, j, sx, sy, qq = key
             assert qq < (1 << 30)
             w0 = (r << 4) | (seg << 3) | (S << 2) | sub
             w1 = (j << 32) | (sx << 31) | (sy << 30) | qq
-            items.append((w0, w1, (fs, fd, ds)))
+            items[pos_b[q]] = (w0, w1, (fs, fd, ds))
     items.sort(key=lambda t: (t[0], t[1]))   # stable radix sort on the device
-    links2 = [[] for _ in range(nn + m)]
-    for w0, _, t in items:
-        links2[w0 >> 4].append(t)
+    # ---- ge_link_place_kernel: first_b[r] = first sorted class B entry of row r; class A entries before row r =
+    # pos_a[row[r]] (all of them for the new rows); row r starts at a_before(r) + first_b[r], its class A entries
+    # come first (kept rows: old entries in place), then its class B entries
+    nn2 = nn + m
+    first_b = [0] * (nn2 + 1)
+    for t in range(n_b + 1):
+        r1 = (items[t][0] >> 4) if t < n_b else nn2
+        r0 = (items[t - 1][0] >> 4) + 1 if t > 0 else 0
+        for r in range(r0, r1 + 1):
+            first_b[r] = t
+
+    def a_before(r):
+        return pos_a[row[r]] if (r <= nn and row[r] < ne) else n_a
+    row2 = [a_before(r) + first_b[r] for r in range(nn2 + 1)]
+    tri2 = [None] * (n_a + n_b)
+    for q in range(ne):
+        if cls[q] == 1:
+            i = abs(tri[q][0]) - 1
+            tri2[first_b[i] + pos_a[q]] = tri[q]
+    for t in range(n_b):
+        r = items[t][0] >> 4
+        tri2[a_before(r + 1) + t] = items[t][2]
+    assert all(x is not None for x in tri2) and row2[nn2] == n_a + n_b
+    links2 = [tri2[row2[r]:row2[r + 1]] for r in range(nn2)]
     return nodes2, links2, m
 
 
