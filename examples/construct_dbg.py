@@ -2,7 +2,7 @@
 """De Bruijn graph construction with the B200 path: the recipe of the reference's
 examples/construct_dbg.jl / docs/src/man/assembly.md:126-216 through the Python host mirror.
 
-    python examples/construct_dbg.py reads.fastq [more.fastq ...] [-k 31] [--min-freq 2] [--gfa out]
+    python examples/construct_dbg.py reads.fastq [more.fastq ...] [-k 31] [--min-freq 2] [--remove-tips 200] [--gfa out]
 
 Without input files a synthetic stand-in for the reference's (absent) ecoli-ref.fasta /
 pe-reads.fastq pair is generated: 4,641,652 bp uniform genome, 50x 150 bp paired reads.
@@ -23,6 +23,8 @@ def main():
     ap.add_argument("reads", nargs="*")
     ap.add_argument("-k", type=int, default=31)
     ap.add_argument("--min-freq", type=int, default=2)
+    ap.add_argument("--remove-tips", type=int, default=None, metavar="MIN_SIZE",
+                    help="remove_tips!(ws, MIN_SIZE) after the build (docs/src/man/assembly.md:234-275)")
     ap.add_argument("--gfa", default=None, help="write <gfa>.gfa + <gfa>.fasta (write_to_gfa1)")
     args = ap.parse_args()
     gg = G.build()
@@ -44,6 +46,12 @@ def main():
     print("k-mer spectrum, counts 1..10:", spectrum[1:11].tolist())
     graph = gg.dbg_(gg.empty_graph(), counts, args.min_freq)       # dbg!(graph, counts, min_freq)
     print("graph: %d nodes, %d link entries, %.2f s" % (graph.n_nodes(), sum(len(l) for l in graph.links), time.perf_counter() - t0))
+    if args.remove_tips is not None:
+        t1 = time.perf_counter()
+        gg.remove_tips_(graph, args.remove_tips)                   # remove_tips!(ws, 200)
+        live = sum(1 for n in graph.nodes if not n.deleted)
+        print("after remove_tips!(%d): %d nodes (%d live), %d link entries, %.2f s"
+              % (args.remove_tips, graph.n_nodes(), live, sum(len(l) for l in graph.links), time.perf_counter() - t1))
     if args.gfa:
         graph.write_to_gfa1(args.gfa)
 
