@@ -386,3 +386,25 @@ def test_gpu_tips_hand_traced(pkg, ctx, case):
         assert (passes, removed) == (r["passes"], r["removed"]) and _back(out) == (r["nodes"], r["links"])
         out.free()
     dg.free()
+
+
+def test_gfa1_of_an_edited_graph_skips_the_emptied_nodes(tmp_path):
+    """write_to_gfa1 (src/Graphs.jl:892-926) skips deleted nodes: the array writer of libggb200 (host code, no GPU) on a
+    tip-removed graph against the Python transliteration of the reference writer"""
+    pkg = G.build()
+    nodes, links = _dbg_graph(3)
+    g = E.Graph(nodes, links)
+    g.remove_tips(45)
+    assert "" in g.nodes
+    sdg = pkg.empty_graph()
+    for s in g.nodes:
+        sdg.add_node_(pkg.SDGNode(s, s == ""))
+    for i, ls in enumerate(g.links):
+        sdg.links[i].extend(pkg.SDGLink(*t) for t in ls)
+    a, b = str(tmp_path / "a"), str(tmp_path / "b")
+    from genomegraphs_b200.host import _sdg_arrays
+    pkg.write_gfa1_arrays(a, _sdg_arrays(sdg, 15))
+    sdg.write_to_gfa1(b)
+    assert open(a + ".fasta").read() == open(b + ".fasta").read()
+    ga, gb = open(a + ".gfa").read().replace(a + ".fasta", "F"), open(b + ".gfa").read().replace(b + ".fasta", "F")
+    assert ga == gb and ga.count("\nS\t") == sum(1 for s in g.nodes if s)
