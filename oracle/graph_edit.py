@@ -205,3 +205,88 @@ class Graph:
             passes += 1
             tips = self.find_tip_nodes(min_size)
         return passes, removed
+
+
+class CGraph:
+    """The same functions in plain C (oracle/graph_edit.c, part of libggoracle.so): for graphs of millions of nodes,
+    where this module's Python loops are too slow, and as the CPU path that is timed next to the CUDA one.  Arrays in
+    the layout of the C ABI: node_off (n + 1), bases (ASCII), link_row (n + 1), link_tri (3 per entry)."""
+
+    def __init__(self, node_off, bases, link_row, link_tri):
+        import ctypes as C
+        import numpy as np
+        from . import oracle as O
+        self._C, self._np, self._O = C, np, O
+        node_off = np.ascontiguousarray(node_off, dtype=np.uint64)
+        link_row = np.ascontiguousarray(link_row, dtype=np.uint64)
+        bases = np.ascontiguousarray(bases if len(bases) else np.zeros(1, dtype=np.uint8), dtype=np.uint8)
+        link_tri = np.ascontiguousarray(link_tri if len(link_tri) else np.zeros(3, dtype=np.int64), dtype=np.int64)
+        self.h = O.lib().ggo_edit_graph_new(len(node_off) - 1, O._p(node_off, C.c_uint64), O._p(bases, C.c_uint8), O._p(link_row, C.c_uint64),
+                                            O._p(link_tri, C.c_int64))
+
+    @classmethod
+    def from_lists(cls, nodes, links):
+        import numpy as np
+        node_off = np.zeros(len(nodes) + 1, dtype=np.uint64)
+        node_off[1:] = np.cumsum([len(x) for x in nodes], dtype=np.uint64)
+        link_row = np.zeros(len(nodes) + 1, dtype=np.uint64)
+        link_row[1:] = np.cumsum([len(ls) for ls in links], dtype=np.uint64)
+        return cls(node_off, np.frombuffer("".join(nodes).encode(), dtype=np.uint8), link_row,
+                   np.array([t for ls in links for t in ls], dtype=np.int64).reshape(-1))
+
+    def sizes(self):
+        C = self._C
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._O.lib().ggo_edit_graph_sizes(self.h, C.byref(a), C.byref(b), C.byref(c))
+        return a.value, b.value, c.value
+
+    def arrays(self):
+        C, np, O = self._C, self._np, self._O
+        nn, nb, nl = self.sizes()
+        node_off, link_row = np.zeros(nn + 1, dtype=np.uint64), np.zeros(nn + 1, dtype=np.uint64)
+        bases, tri = np.zeros(max(nb, 1), dtype=np.uint8), np.zeros(max(3 * nl, 3), dtype=np.int64)
+        O.lib().ggo_edit_graph_export(self.h, O._p(node_off, C.c_uint64), O._p(bases, C.c_uint8), O._p(link_row, C.c_uint64), O._p(tri, C.c_int64))
+        return node_off, bases[:nb], link_row, tri[:3 * nl]
+
+    def lists(self):
+        node_off, bases, link_row, tri = self.arrays()
+        b = bases.tobytes().decode()
+        t = tri.reshape(-1, 3)
+        nodes = [b[int(node_off[i]):int(node_off[i + 1])] for i in range(len(node_off) - 1)]
+        links = [[tuple(int(x) for x in t[j]) for j in range(int(link_row[i]), int(link_row[i + 1]))] for i in range(len(node_off) - 1)]
+        return nodes, links
+
+    def find_tip_nodes(self, min_size):
+        C, np, O = self._C, self._np, self._O
+        out = np.zeros(max(self.sizes()[0], 1), dtype=np.int64)
+        n = O.lib().ggo_edit_find_tips(self.h, int(min_size), O._p(out, C.c_int64))
+        return out[:n].tolist()
+
+    def remove_nodes(self, ids):
+        C, np, O = self._C, self._np, self._O
+        a = np.ascontiguousarray(ids if len(ids) else [0], dtype=np.int64)
+        O.lib().ggo_edit_remove_nodes(self.h, O._p(a, C.c_int64), len(ids))
+
+    @staticmethod
+    def _raise(rc):
+        if rc < 0:
+            raise ValueError("Sequences do not overlap." if rc == -1 else "This path is not a valid path.")
+
+    def collapse_all_unitigs(self, min_nodes=2):
+        rc = self._O.lib().ggo_edit_collapse(self.h, int(min_nodes))
+        self._raise(rc)
+        return rc
+
+    def remove_tips(self, min_size):
+        C = self._C
+        p, r = C.c_uint64(), C.c_uint64()
+        self._raise(self._O.lib().ggo_edit_remove_tips(self.h, int(min_size), C.byref(p), C.byref(r)))
+        return p.value, r.value
+
+    def free(self):
+        if self.h:
+            self._O.lib().ggo_edit_graph_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.free()

@@ -16,7 +16,7 @@ _LIB = None
 
 def build(force=False):
     so = os.path.join(_HERE, "libggoracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("gg_oracle.c", "oracle_impl.h", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("gg_oracle.c", "oracle_impl.h", "graph_edit.c", "Makefile")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-B", "libggoracle.so"], stdout=subprocess.DEVNULL)
     return so
@@ -49,6 +49,23 @@ def lib():
         L.ggo_synth_reads_range.restype = C.c_int
         L.ggo_synth_reads_range.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32,
                                             C.c_uint32, u8p, C.c_int]
+        # graph_edit.c: sequential restatement of remove_tips! and what it calls
+        L.ggo_edit_graph_new.restype = C.c_void_p
+        L.ggo_edit_graph_new.argtypes = [C.c_uint64, u64p, u8p, u64p, i64p]
+        L.ggo_edit_graph_free.restype = None
+        L.ggo_edit_graph_free.argtypes = [C.c_void_p]
+        L.ggo_edit_graph_sizes.restype = None
+        L.ggo_edit_graph_sizes.argtypes = [C.c_void_p, u64p, u64p, u64p]
+        L.ggo_edit_graph_export.restype = None
+        L.ggo_edit_graph_export.argtypes = [C.c_void_p, u64p, u8p, u64p, i64p]
+        L.ggo_edit_find_tips.restype = C.c_uint64
+        L.ggo_edit_find_tips.argtypes = [C.c_void_p, C.c_uint64, i64p]
+        L.ggo_edit_remove_nodes.restype = None
+        L.ggo_edit_remove_nodes.argtypes = [C.c_void_p, i64p, C.c_uint64]
+        L.ggo_edit_collapse.restype = C.c_int64
+        L.ggo_edit_collapse.argtypes = [C.c_void_p, C.c_uint64]
+        L.ggo_edit_remove_tips.restype = C.c_int64
+        L.ggo_edit_remove_tips.argtypes = [C.c_void_p, C.c_uint64, u64p, u64p]
         _LIB = L
     return _LIB
 

@@ -408,3 +408,57 @@ def test_gfa1_of_an_edited_graph_skips_the_emptied_nodes(tmp_path):
     assert open(a + ".fasta").read() == open(b + ".fasta").read()
     ga, gb = open(a + ".gfa").read().replace(a + ".fasta", "F"), open(b + ".gfa").read().replace(b + ".fasta", "F")
     assert ga == gb and ga.count("\nS\t") == sum(1 for s in g.nodes if s)
+
+
+# ------------------------------------------- the C restatement (oracle/graph_edit.c) ------------------------------------
+def test_c_restatement_equals_python_restatement_fuzz():
+    rnd = random.Random(41)
+    errors = 0
+    for trial in range(500):
+        nodes, links = _chain_graph(rnd) if trial % 2 else _random_graph(rnd, rnd.randint(1, 16), rnd.randint(0, 18), dup=0.2)
+        assert E.CGraph.from_lists(nodes, links).lists() == (list(nodes), [list(ls) for ls in links])
+        assert E.CGraph.from_lists(nodes, links).find_tip_nodes(7) == E.Graph(nodes, links).find_tip_nodes(7)
+        ids = [rnd.randint(1, len(nodes)) * rnd.choice((1, -1)) for _ in range(rnd.randint(0, 3))]
+        g, c = E.Graph(nodes, links), E.CGraph.from_lists(nodes, links)
+        for n in ids:
+            g.remove_node(n)
+        c.remove_nodes(ids)
+        assert c.lists() == (g.nodes, g.links)
+        for mn in (2, 3):
+            g, c = E.Graph(nodes, links), E.CGraph.from_lists(nodes, links)
+            try:
+                new = g.collapse_all_unitigs(mn, True)
+            except ValueError:
+                errors += 1
+                with pytest.raises(ValueError):
+                    c.collapse_all_unitigs(mn)
+                continue
+            assert c.collapse_all_unitigs(mn) == len(new) and c.lists() == (g.nodes, g.links), (trial, mn)
+        g, c = E.Graph(nodes, links), E.CGraph.from_lists(nodes, links)
+        try:
+            exp = g.remove_tips(8)
+        except ValueError:
+            continue
+        assert c.remove_tips(8) == exp and c.lists() == (g.nodes, g.links), trial
+
+
+@pytest.mark.parametrize("case", TIPS_GOLD, ids=lambda c: c["name"])
+def test_c_restatement_golden(case):
+    nodes, links = case["nodes"], _tl(case["links"])
+    assert E.CGraph.from_lists(nodes, links).find_tip_nodes(case["min_size"]) == case["tips"]
+    c = E.CGraph.from_lists(nodes, links)
+    assert c.collapse_all_unitigs(2) == len(case["collapse"]["new_nodes"]) and c.lists() == (case["collapse"]["nodes"], _tl(case["collapse"]["links"]))
+    c = E.CGraph.from_lists(nodes, links)
+    r = case["remove_tips"]
+    assert c.remove_tips(case["min_size"]) == (r["passes"], r["removed"]) and c.lists() == (r["nodes"], _tl(r["links"]))
+
+
+def test_c_restatement_dbg_graph_arrays():
+    """array interface (the layout of the C ABI) on a graph of a few thousand nodes"""
+    seq, offs = O.synth_reads(8, 60000, 12000, 100, True, 300, 10000)
+    keys, cnt = O.count_kmers(seq, offs, 21)
+    og = O.dbg(O.filter_counts(keys, cnt, 21, 1), 21)
+    c = E.CGraph(og.node_off, og.bases, og.link_row, og.link_tri)
+    g = E.Graph(og.nodes(), og.links())
+    assert c.remove_tips(60) == g.remove_tips(60)
+    assert c.lists() == (g.nodes, g.links) and c.sizes()[0] == len(g.nodes)
