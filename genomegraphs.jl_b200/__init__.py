@@ -11,4 +11,4 @@ from .host import *  # noqa: F401,F403
 from .host import (CANONICAL, NONCANONICAL, Context, DeviceGraph, GraphArrays, GraphStrandPosition, MerCounts, SDGLink, SDGNode,  # noqa: F401
                    SequenceDistanceGraph, UniqueMerIndex, WorkSpace, dbg_, dbg_arrays, dbg_from_reads, empty_graph, extract_kmers, freq,
                    mer, pack_reads, read_sequences, serial_mem, spectra, synth_genome, synth_reads,
-                   count_kmers_4bit, dbg_from_reads_4bit, pack_4bit, remove_tips_, spectra_cn, write_gfa1_arrays)
+                   count_kmers_4bit, dbg_from_reads_4bit, pack_4bit, remove_tips_, spectra_cn, write_gfa1_arrays, PairedReads, read_datastore, FwRv, RvFw)

@@ -9,6 +9,8 @@ The Julia host files that `ccall` the same ABI are under genomegraphs.jl_b200/ju
 """
 import ctypes as C
 
+import os
+
 import numpy as np
 
 from . import _native as N
@@ -175,6 +177,8 @@ def serial_mem(k, mode=CANONICAL, ctx=None):
 
     def counter(reads):
         c = ctx or Context.default()
+        if isinstance(reads, PairedReads):     # the read store's own 4-bit encoding goes to the device as it is
+            return count_kmers_4bit(reads.data4, reads.base_offsets, k, mode, ctx=c)
         seq, offs = _as_reads(reads)
         h = C.c_void_p()
         N.check(c.h, N.lib().gg_count_kmers(c.h, _ptr(seq) if seq.size else None, _ptr(offs), len(offs) - 1, int(k), int(mode), C.byref(h)))
@@ -495,6 +499,91 @@ def dbg_(sdg, kmers_or_counts, min_freq=None, k=None, ctx=None):
     return sdg
 
 
+FwRv, RvFw = "FwRv", "RvFw"     # PairedReadOrientation of ReadDatastores (docs/src/man/assembly.md:96-100)
+_PRSEQ_MAGIC = b"GGB200PRSEQ\x00\x00\x00\x00\x01"     # 16 bytes: everything behind it stays 8-byte aligned
+
+
+class PairedReads:
+    """The paired-read datastore `read_datastore(...)` makes (src/GenomeGraphs.jl:79-83: `PairedReads{DNAAlphabet{4}}(fwq, rvq,
+    name, name, minlen, maxlen, insertlen, mode)`), held the way this path consumes it: the reads' 4-bit encoding (the
+    encoding of LongSequence{DNAAlphabet{4}}, 16 bases per uint64) + base offsets, reads 2i / 2i+1 = R1 / R2 of pair i.
+    The file `<name>.prseq` is this repository's own container for that payload (header, offsets, 4-bit words; little
+    endian) -- ReadDatastores.jl is not vendored in the reference, so its on-disk layout is not restated; what is kept is
+    the content and the documented filter: a pair is dropped when either read is shorter than minlen, longer reads are
+    cut to maxlen (docs/src/man/assembly.md:86-88).  Opened stores are memory-mapped: the words go from the page cache
+    straight into the pinned staging of gg_count_kmers_4bit / gg_dbg_from_reads_4bit."""
+
+    def __init__(self, data4, base_offsets, name, minlen, maxlen, insertlen, orientation, path=None):
+        self.data4, self.base_offsets = data4, base_offsets
+        self.name, self.minlen, self.maxlen, self.insertlen, self.orientation, self.path = name, minlen, maxlen, insertlen, orientation, path
+
+    def __len__(self):
+        return len(self.base_offsets) - 1
+
+    def n_pairs(self):
+        return len(self) // 2
+
+    def __getitem__(self, i):
+        """read i as a string (N for every ambiguous code)"""
+        if not 0 <= i < len(self):
+            raise IndexError(i)
+        lo, hi = int(self.base_offsets[i]), int(self.base_offsets[i + 1])
+        idx = np.arange(lo, hi, dtype=np.uint64)
+        nib = (np.asarray(self.data4)[(idx >> np.uint64(4)).astype(np.int64)] >> ((idx & np.uint64(15)) * np.uint64(4))) & np.uint64(15)
+        lut = np.full(16, ord("N"), dtype=np.uint8)
+        lut[[1, 2, 4, 8]] = [ord(x) for x in "ACGT"]
+        return lut[nib.astype(np.int64)].tobytes().decode()
+
+    def write(self, path):
+        hdr = np.array([len(self), int(self.base_offsets[-1]), len(self.data4), self.minlen, self.maxlen, self.insertlen,
+                        0 if self.orientation == FwRv else 1], dtype="<u8")
+        nm = self.name.encode()
+        with open(path, "wb") as f:
+            f.write(_PRSEQ_MAGIC)
+            f.write(hdr.tobytes())
+            f.write(np.array([len(nm)], dtype="<u8").tobytes())
+            f.write(nm + b"\x00" * ((-len(nm)) % 8))
+            f.write(np.ascontiguousarray(self.base_offsets, dtype="<u8").tobytes())
+            f.write(np.ascontiguousarray(self.data4, dtype="<u8").tobytes())
+        self.path = str(path)
+        return self
+
+    @classmethod
+    def open(cls, path):
+        """open(PairedReads, "name.prseq"): header parsed, offsets and 4-bit words memory-mapped"""
+        with open(path, "rb") as f:
+            if f.read(len(_PRSEQ_MAGIC)) != _PRSEQ_MAGIC:
+                raise ValueError("%s is not a paired read datastore of this package" % path)
+            nreads, nbases, nwords, minlen, maxlen, insertlen, orient = (int(x) for x in np.frombuffer(f.read(56), dtype="<u8"))
+            ln = int(np.frombuffer(f.read(8), dtype="<u8")[0])
+            name = f.read(ln + ((-ln) % 8))[:ln].decode()
+            pos = f.tell()
+        offs = np.memmap(path, dtype="<u8", mode="r", offset=pos, shape=(nreads + 1,))
+        data = np.memmap(path, dtype="<u8", mode="r", offset=pos + 8 * (nreads + 1), shape=(nwords,)) if nwords else np.zeros(0, dtype=np.uint64)
+        if int(offs[-1]) != nbases or nwords != (nbases + 15) // 16:
+            raise ValueError("%s: header and payload disagree" % path)
+        return cls(data, offs, name, minlen, maxlen, insertlen, FwRv if orient == 0 else RvFw, str(path))
+
+
+def read_datastore(r1file, r2file, name, minlen, maxlen, insertlen=0, mode=FwRv):
+    """read_datastore(R1file, R2file, name, minlen, maxlen, insertlen, mode) (src/GenomeGraphs.jl:79-83): the two FASTQ
+    files are read pair by pair, a pair is dropped when either read is shorter than `minlen`, reads longer than `maxlen`
+    are cut (docs/src/man/assembly.md:86-88); the store is written to `<name>.prseq` and returned memory-mapped."""
+    (s1, o1), (s2, o2) = read_sequences(r1file), read_sequences(r2file)
+    if len(o1) != len(o2):
+        raise ValueError("the two FASTQ files hold different numbers of reads")
+    l1, l2 = np.diff(o1.astype(np.int64)), np.diff(o2.astype(np.int64))
+    keep = (l1 >= minlen) & (l2 >= minlen)
+    reads = []
+    for i in np.nonzero(keep)[0]:
+        reads.append(s1[int(o1[i]):int(o1[i]) + min(int(l1[i]), maxlen)].tobytes())
+        reads.append(s2[int(o2[i]):int(o2[i]) + min(int(l2[i]), maxlen)].tobytes())
+    data4, offs = pack_4bit(pack_reads(reads))
+    path = name if str(name).endswith(".prseq") else str(name) + ".prseq"
+    PairedReads(data4, offs, os.path.basename(str(name)), int(minlen), int(maxlen), int(insertlen), mode).write(path)
+    return PairedReads.open(path)
+
+
 def _sdg_arrays(sdg, k=0):
     """SequenceDistanceGraph (Python objects) -> GraphArrays; deleted nodes are empty"""
     seqs = ["" if n.deleted else n.seq for n in sdg.nodes]
@@ -533,6 +622,8 @@ def remove_tips_(sdg, min_size, ctx=None):
 def dbg_from_reads(reads, k, min_freq, ctx=None):
     """reads -> graph arrays in one device pipeline (count, filter, build)."""
     c = ctx or Context.default()
+    if isinstance(reads, PairedReads):
+        return dbg_from_reads_4bit(reads.data4, reads.base_offsets, k, min_freq, ctx=c)
     seq, offs = _as_reads(reads)
     gh = C.c_void_p()
     N.check(c.h, N.lib().gg_dbg_from_reads(c.h, _ptr(seq) if seq.size else None, _ptr(offs), len(offs) - 1, int(k), int(min_freq), C.byref(gh)))
