@@ -138,3 +138,16 @@ def test_bench_shard_range_matches_package(pkg):
     for n, world in [(101, 3), (20000000, 8), (6, 4), (0, 2)]:
         for r in range(world):
             assert bench.shard_range(n, r, world, 2) == pkg.dist.shard_range(n, r, world, 2)
+
+
+def test_graph_entry_points_reject_a_null_handle(pkg):
+    """no device is needed to be told that there is no graph: every gg_graph_* entry returns GG_ERR_ARG for NULL"""
+    import ctypes as C
+    L, N = pkg._native.lib(), pkg._native
+    out, a, b = C.c_void_p(), C.c_uint64(), C.c_uint64()
+    assert L.gg_graph_remove_nodes(None, None, 0, C.byref(out)) == N.GG_ERR_ARG
+    assert L.gg_graph_collapse_all_unitigs(None, 2, C.byref(out), C.byref(a)) == N.GG_ERR_ARG
+    assert L.gg_graph_remove_tips(None, 200, C.byref(out), C.byref(a), C.byref(b)) == N.GG_ERR_ARG
+    assert L.gg_graph_find_tip_nodes(None, 200, None, C.byref(a)) == N.GG_ERR_ARG
+    assert L.gg_graph_checksum(None, C.byref(a)) == N.GG_ERR_ARG
+    assert out.value is None
