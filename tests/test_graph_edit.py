@@ -462,3 +462,31 @@ def test_c_restatement_dbg_graph_arrays():
     g = E.Graph(og.nodes(), og.links())
     assert c.remove_tips(60) == g.remove_tips(60)
     assert c.lists() == (g.nodes, g.links) and c.sizes()[0] == len(g.nodes)
+
+
+def test_overlap_errors_agree_in_all_statements():
+    """a base changed inside an overlap: "Sequences do not overlap." (src/Graphs.jl:1023) exactly when the pair sits in a
+    collapsed path -- the Python restatement, the C restatement and the model raise together or agree on the result"""
+    rnd = random.Random(77)
+    raised = fine = 0
+    for trial in range(300):
+        nodes, links = _chain_graph(rnd)
+        nodes = list(nodes)
+        i = rnd.randrange(len(nodes))
+        s = nodes[i]
+        p = rnd.choice([rnd.randrange(0, min(4, len(s))), len(s) - 1 - rnd.randrange(0, min(4, len(s)))])
+        nodes[i] = s[:p] + rnd.choice([c for c in "ACGT" if c != s[p]]) + s[p + 1:]
+        try:
+            exp = _seq_collapse(nodes, links)
+        except ValueError:
+            raised += 1
+            with pytest.raises(ValueError):
+                M.collapse_all_unitigs(nodes, links, 2)
+            with pytest.raises(ValueError):
+                E.CGraph.from_lists(nodes, links).collapse_all_unitigs(2)
+            continue
+        fine += 1
+        assert M.collapse_all_unitigs(nodes, links, 2) == exp
+        c = E.CGraph.from_lists(nodes, links)
+        assert c.collapse_all_unitigs(2) == exp[2] and c.lists() == (exp[0], exp[1])
+    assert raised > 50 and fine > 50
