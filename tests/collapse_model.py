@@ -59,7 +59,7 @@ def jump(rec, rounds):
     return rec
 
 
-def collapse_all_unitigs(nodes, links, min_nodes):
+def collapse_all_unitigs(nodes, links, min_nodes, stats=None):
     """collapse_all_unitigs!(sg, min_nodes, consume = true): returns (nodes, links, number of new nodes)"""
     assert min_nodes >= 2
     nn = len(nodes)
@@ -242,6 +242,8 @@ def collapse_all_unitigs(nodes, links, min_nodes):
         pos_a[q], pos_b[q] = n_a, n_b
         n_a += cls[q] == 1
         n_b += cls[q] == 2
+    if stats is not None:
+        stats.update(entries=ne, class_a=n_a, class_b=n_b, new_nodes=m)
     # ---- ge_link_emit_kernel: keys of the class B entries, as packed in the CUDA code
     items = [None] * n_b
     for i in range(nn):

@@ -330,7 +330,8 @@ def test_gpu_collapse_rejects_asymmetric_links(pkg, ctx):
 
 @pytest.mark.gpu
 def test_gpu_remove_tips_large(pkg, ctx):
-    """a graph beyond the single-launch sizes of the scan and sort primitives (> 65,536 link entries)"""
+    """a graph beyond the single-launch sizes of the scan and sort primitives: 151,278 link entries, and 36,992 entries that
+    touch a collapsed path in the first pass (> 32,768: the multi-pass radix sort of the 128-bit keys, not the rank sort)"""
     k = 21
     seq, offs = O.synth_reads(8, 150000, 30000, 100, True, 300, 10000)
     ga = pkg.dbg_from_reads((seq, offs), k, 1, ctx=ctx)
